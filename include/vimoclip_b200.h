@@ -1,0 +1,154 @@
+/*
+ * vimoclip_b200 -- C-ABI of the B200-native ViMoCLIP per-frame encoding hot path.
+ *
+ * The reference (MarcosRodrigoT/VIMO-CLIP) is pure Python: its "plugin API" for this
+ * path is the nn.Module call surface.  This header is the boundary a
+ * maintainer binds from Python (ctypes): plain pointers and
+ * sizes, no torch types.  Each entry cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every entry returns int: 0 ok, <0 argument/shape/alignment error,
+ *     >0 a cudaError_t; vmc_last_error() gives the thread-local message;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation; the caller owns all buffers including the workspace;
+ *   - there is NO CPU fallback: host pointers are undefined behaviour.
+ */
+#ifndef VIMOCLIP_B200_H_
+#define VIMOCLIP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMC_ABI_VERSION 1
+
+/* ---- runtime ---------------------------------------------------------------- */
+const char* vmc_last_error(void);
+int vmc_abi_version(void);
+int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* kernels launched by this library since the last reset (bench.py "gpu_launches") */
+long long vmc_launch_count(void);
+void vmc_reset_launch_count(void);
+
+/* ---- P1: uint8 prologue -------------------------------------------------------
+ * Replaces the per-frame PIL loop of models/student_model.py:74-81 (to_pil_image ->
+ * Resize/CenterCrop (identity at 224x224) -> ToTensor -> Normalize) and the
+ * cv2.cvtColor + cv2.absdiff of utils/generate_frame_diff_video.py:37,46,49.
+ */
+enum {
+  VMC_SRC_U8 = 0,      /* uint8 pixels 0..255 taken as-is (HF processor path, extract_embeddings.py:91) */
+  VMC_SRC_U8_WRAP = 1, /* regime A: uint8 -> .float() -> to_pil_image: u8 = (-x) mod 256 (student_model.py:74,78) */
+  VMC_SRC_F32_WRAP = 2, /* regimes B/C: float input, u8 = (int64)trunc(x*255f) mod 256 */
+  VMC_SRC_F32_NORM = 3  /* already-normalised fp32 pixel_values (get_image_features input): patchify + bf16 only */
+};
+enum {
+  VMC_DST_U8 = 0,         /* wrapped uint8 [F,3,H,W] (bit-exact integer check) */
+  VMC_DST_F32_NCHW = 1,   /* (u8/255 - mean)/std fp32 [F,3,H,W]: what the reference feeds the ViT */
+  VMC_DST_BF16_PATCH = 2  /* same value rounded to bf16, patchified [F*(H/p)*(W/p), ld] (GEMM A operand) */
+};
+/* frames: [F,3,H,W] planar (src_kind u8 or f32).  dst per dst_kind.  ld_patch >= 3*p*p, multiple of 8;
+ * pad columns [3*p*p, ld_patch) are zero-filled. */
+int vmc_prologue(const void* frames, int src_kind, void* dst, int dst_kind, int F, int H, int W,
+                 int patch, int ld_patch, void* stream);
+/* BGR uint8 clips [clips, T+1, H, W, 3] (OpenCV layout) -> gray (9798 R + 19235 G + 3735 B + 16384) >> 15
+ * -> |gray[t+1]-gray[t]| -> diff_u8 [clips, T, H, W] (may be NULL) and/or the student prologue on the
+ * diff replicated to 3 channels (regime A wrap): dst per dst_kind as above with F = clips*T. */
+int vmc_frame_diff_prologue(const uint8_t* bgr, uint8_t* diff_u8, void* dst, int dst_kind, int clips,
+                            int T, int H, int W, int patch, int ld_patch, void* stream);
+
+/* ---- G: tcgen05/TMEM GEMM fed by TMA ------------------------------------------
+ * out[orow, n] = alpha * act(sum_k A[m,k] * W[n,k] + bias[n]) + resid[rrow, n]
+ * A [M,K] bf16 row-major (lda), W [N,K] bf16 row-major (ldw) == nn.Linear.weight layout.
+ * Replaces nn.Conv2d patch embed / nn.Linear / in_proj / out_proj / c_fc / c_proj / @proj
+ * reached from models/student_model.py:84 and extract_embeddings.py:94.
+ */
+enum { VMC_ACT_NONE = 0, VMC_ACT_QUICKGELU = 1, VMC_ACT_GELU_ERF = 2, VMC_ACT_RELU = 3 };
+typedef struct vmc_gemm_epilogue {
+  const float* bias;  /* [N] fp32 or NULL */
+  const float* resid; /* fp32 matrix added after activation, or NULL; may alias out */
+  long long ldr;      /* row stride of resid in elements */
+  void* out;          /* bf16 or fp32 */
+  long long ldo;      /* row stride of out in elements */
+  int out_bf16;       /* 1: out is bf16, 0: fp32 */
+  int act;            /* VMC_ACT_* */
+  float alpha;
+  int row_group;      /* 0: orow = rrow = m.  g > 0 (patch embed): f = m / g, orow = m + f + 1,
+                         rrow = m - f*g + 1 (token rows of frame f skip the CLS row; resid = pos-emb) */
+} vmc_gemm_epilogue;
+int vmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                  const vmc_gemm_epilogue* epi, void* stream);
+
+/* ---- E1: LayerNorm (fp32 statistics, eps inside sqrt) ---------------------------
+ * y = (x - mean) / sqrt(var + eps) * gamma + beta per row of width d (d % 4 == 0, d <= 4096).
+ * x fp32 rows at stride ldx (elements).  Outputs (either may be NULL): y32 fp32 (ld32), y16 bf16 (ld16).
+ * If cls_every > 0, rows r with r % cls_every == 0 take their input from cls_row[d] instead of x
+ * (CLS token = class_embedding + positional_embedding[0], OpenAI VisionTransformer.forward).
+ * Replaces ln_pre / ln_1 / ln_2 / ln_post and TFAM norm_self / norm_cross / norm_ffn / classifier.0.
+ */
+int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+                  float* y32, long long ld32, void* y16, long long ld16, int rows, int d,
+                  const float* cls_row, int cls_every, void* stream);
+
+/* ---- A1: ViT self-attention (no mask), head_dim 64 ------------------------------
+ * qkv bf16 [F*L, 3*d] (q | k | v, heads contiguous inside each), out bf16 [F*L, d].
+ * softmax(q k^T / 8) v per (frame, head); QK^T and PV on tcgen05, S/O in TMEM.
+ * Replaces nn.MultiheadAttention inside OpenAI ResidualAttentionBlock / HF CLIPAttention.
+ */
+int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream);
+
+/* ---- small masked attention (TFAM), fp32 in, bf16 out ---------------------------
+ * q [B*Tq, ldq], k/v [B*Tk, ldk/ldv] fp32 (heads*64 columns used starting at the pointer),
+ * key_valid uint8/bool [B, Tk]: 1 = real frame, 0 = padding (the mask_rgb / mask_flow of
+ * collate_fn_pad, TFAM/data/dataset.py:86-103, i.e. the inverse of the key_padding_mask built at
+ * TFAM/models/AMO_CLIP.py:125-126) or NULL for no mask.
+ * out bf16 [B*Tq, ldo].  Replaces self_attn / cross_attn of AttentionLayer (AMO_CLIP.py:39,44).
+ */
+int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk, const float* v,
+                         long long ldv, const uint8_t* key_valid, void* out, long long ldo, int B, int Tq,
+                         int Tk, int heads, void* stream);
+
+/* ---- utilities -------------------------------------------------------------- */
+/* fp32 [rows, d] (ldx) -> bf16 [rows, d] (ldy) */
+int vmc_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int d, void* stream);
+/* temporal mean: x fp32 [B, T, d] -> y32 fp32 [B, d] and/or y16 bf16 [B, d] (mean over ALL T rows,
+ * models/student_model.py:93, AMO_CLIP.py:170) */
+int vmc_mean_rows(const float* x, float* y32, void* y16, int B, int T, int d, void* stream);
+/* cosine distillation loss of losses.py:27-40: mean over rows of 1 - clamp(cos(s,t)); out: 1 fp32 */
+int vmc_cosine_distill_loss(const float* s, const float* t, int rows, int d, float* out, void* stream);
+
+/* ---- whole ViT tower -----------------------------------------------------------
+ * Replaces self.visual_encoder(x) (models/student_model.py:84) and
+ * clip_model.get_image_features(pixel_values) (extract_embeddings.py:94).
+ * All weights are device pointers packed by the host side (bf16 [N,K] row-major for GEMM
+ * operands, fp32 for LN / bias / embeddings).
+ */
+typedef struct vmc_vit_layer {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const void* w_qkv;  const float* b_qkv;   /* [3d, d] bf16, [3d] */
+  const void* w_out;  const float* b_out;   /* [d, d], [d] */
+  const void* w_fc1;  const float* b_fc1;   /* [4d, d], [4d] */
+  const void* w_fc2;  const float* b_fc2;   /* [d, 4d], [d] */
+} vmc_vit_layer;
+typedef struct vmc_vit_model {
+  int image, patch, width, layers, heads, out_dim;
+  int ld_patch;             /* row stride of the patchified A operand / conv weight (>= 3*p*p, %8) */
+  const void* w_patch;      /* [width, ld_patch] bf16 = conv1.weight.reshape(width, 3*p*p) */
+  const float* cls_pos0;    /* [width] = class_embedding + positional_embedding[0] */
+  const float* pos;         /* [L, width] fp32 positional_embedding */
+  const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+  const void* w_proj;       /* [out_dim, width] bf16 = proj.T */
+  const vmc_vit_layer* layer; /* HOST array of `layers` entries */
+} vmc_vit_model;
+/* bytes of workspace needed for F frames in flight */
+long long vmc_vit_workspace_bytes(const vmc_vit_model* m, int F);
+/* patches: bf16 [F*n, ld_patch] from vmc_prologue / vmc_frame_diff_prologue; out fp32 [F, out_dim] */
+int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int F, void* workspace,
+                    long long workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIMOCLIP_B200_H_ */

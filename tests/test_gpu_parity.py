@@ -1,0 +1,375 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): bit-exact for the integer prologue / frame difference / indexing and
+for the fp32 normalised tensor; per-frame embedding cosine >= 0.9995 and logit max-abs <= 1e-2 for
+the bf16 stages.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import vimoclip_b200 as vmc
+from oracle import clip_shim, losses as olosses, prologue, student as ostudent, tfam as otfam, weights
+from vimoclip_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.9995  # north_star: per-frame embedding cosine
+LOGIT_TOL = 1e-2  # north_star: logit max-abs
+
+
+def _cos_min(a, b):
+    return float(torch.nn.functional.cosine_similarity(a.double().cpu(), b.double().cpu(), dim=-1).min())
+
+
+# ------------------------------------------------------------------------------------------------
+# P1 prologue / frame difference: bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_loaded_native_library(cuda_device):
+    sm, major, minor = ops.device_info()
+    assert major == 10, f"expected a Blackwell sm_100 device, got sm_{major}{minor}"
+    assert sm > 0
+
+
+def test_prologue_bit_exact_all_regimes(cuda_device, golden):
+    g = golden("prologue.npz")
+    u8 = torch.from_numpy(g["frame_u8"])[None].to(cuda_device)
+    # regime A (uint8 input): integer wrap and fp32 normalise
+    assert np.array_equal(ops.prologue(u8, wrap=True, dst="u8").cpu().numpy()[0], g["wrapA_u8"])
+    assert np.array_equal(ops.prologue(u8, wrap=True, dst="f32").cpu().numpy()[0].view(np.uint32), g["normA"].view(np.uint32))
+    # regime B (float [0,1]) and C (already normalised floats)
+    fB = (u8.float() / 255.0).contiguous()
+    assert np.array_equal(ops.prologue(fB, wrap=True, dst="u8").cpu().numpy(), u8.cpu().numpy())
+    assert np.array_equal(ops.prologue(fB, wrap=True, dst="f32").cpu().numpy()[0].view(np.uint32), g["normB"].view(np.uint32))
+    fC = torch.from_numpy(g["normB"])[None].to(cuda_device)
+    assert np.array_equal(ops.prologue(fC, wrap=True, dst="u8").cpu().numpy()[0], g["wrapC_u8"])
+    assert np.array_equal(ops.prologue(fC, wrap=True, dst="f32").cpu().numpy()[0].view(np.uint32), g["normC"].view(np.uint32))
+    # no-wrap uint8 (HF processor path): (u8/255 - mean)/std
+    ref = prologue.normalise_u8(g["frame_u8"][None])
+    assert np.array_equal(ops.prologue(u8, wrap=False, dst="f32").cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("patch", [32, 16, 14])
+def test_prologue_patchify_bf16(cuda_device, patch):
+    gen = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (3, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    got = ops.prologue(u8.to(cuda_device), wrap=True, dst="patch", patch=patch).cpu()
+    ref32 = prologue.patchify(prologue.preprocess_frames(u8.numpy()), patch)
+    ref = torch.from_numpy(ref32).to(torch.bfloat16)  # bf16 round-to-nearest-even of the bit-exact fp32 value
+    k = 3 * patch * patch
+    assert got.shape == (3 * (224 // patch) ** 2, ops.patch_ld(patch))
+    assert torch.equal(got[:, :k].view(torch.int16), ref.view(torch.int16))
+    assert torch.count_nonzero(got[:, k:]) == 0
+    # float wrap regimes through the patch path
+    fB = (u8.float() / 255.0).to(cuda_device)
+    gotB = ops.prologue(fB, wrap=True, dst="patch", patch=patch).cpu()
+    refB = torch.from_numpy(prologue.patchify(prologue.preprocess_frames(fB.cpu().numpy()), patch)).to(torch.bfloat16)
+    assert torch.equal(gotB[:, :k].view(torch.int16), refB.view(torch.int16))
+
+
+def test_frame_difference_bit_exact(cuda_device, golden):
+    g = golden("framediff.npz")
+    frames = torch.from_numpy(g["frames"])[None].to(cuda_device)  # [1,5,48,64,3]
+    diff, u8 = ops.frame_diff(frames, dst="u8")
+    assert np.array_equal(diff.cpu().numpy()[0], g["diff"])
+    want = prologue.to_pil_u8(np.repeat(g["diff"][:, None], 3, axis=1))  # 3 identical channels, regime A wrap
+    assert np.array_equal(u8.cpu().numpy(), want)
+    # random 224x224 clips, fp32 + patch outputs against the oracle
+    rng = np.random.default_rng(11)
+    bgr = rng.integers(0, 256, size=(2, 4, 224, 224, 3), dtype=np.uint8)
+    d_ref = np.stack([prologue.frame_difference(c) for c in bgr])  # [2,3,224,224]
+    diff, f32 = ops.frame_diff(torch.from_numpy(bgr).to(cuda_device), dst="f32")
+    assert np.array_equal(diff.cpu().numpy(), d_ref)
+    rep = np.repeat(d_ref.reshape(6, 1, 224, 224), 3, axis=1)
+    n_ref = prologue.preprocess_frames(rep)
+    assert np.array_equal(f32.cpu().numpy().view(np.uint32), n_ref.view(np.uint32))
+    _, pt = ops.frame_diff(torch.from_numpy(bgr).to(cuda_device), dst="patch", patch=32, want_diff=False)
+    assert torch.equal(pt.cpu().view(torch.int16), torch.from_numpy(prologue.patchify(n_ref, 32)).to(torch.bfloat16).view(torch.int16))
+
+
+def test_prologue_full_size_properties(cuda_device):
+    """BASELINE-size batch (256 clips x 16 frames): size-independent integer properties."""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    u8 = torch.randint(0, 256, (1024, 3, 224, 224), dtype=torch.uint8, device=cuda_device, generator=gen)
+    w = ops.prologue(u8, wrap=True, dst="u8")
+    assert torch.equal(ops.prologue(w, wrap=True, dst="u8"), u8)  # (-(-x)) mod 256 == x
+    assert int(w.long().sum()) == int(((256 - u8.long()) % 256).sum())  # checksum of the closed form
+    bgr = torch.randint(0, 256, (8, 17, 224, 224, 3), dtype=torch.uint8, device=cuda_device, generator=gen)
+    same = bgr[:, :1].expand(-1, 17, -1, -1, -1).contiguous()
+    d0, _ = ops.frame_diff(same)
+    assert int(d0.max()) == 0  # identical frames -> zero difference
+    d1, _ = ops.frame_diff(bgr)
+    d2, _ = ops.frame_diff(bgr.flip(1).contiguous())
+    assert torch.equal(d1, d2.flip(1))  # |a-b| is symmetric under time reversal
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM
+# ------------------------------------------------------------------------------------------------
+def _ref_gemm(a, w, bias, act, alpha, resid):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == ops.ACT_QUICKGELU:
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == ops.ACT_GELU_ERF:
+        y = torch.nn.functional.gelu(y)
+    elif act == ops.ACT_RELU:
+        y = torch.relu(y)
+    y = y * alpha
+    if resid is not None:
+        y = y + resid
+    return y
+
+
+GEMM_CASES = [
+    # M, N, K, act, bias, resid, out_dtype
+    (128, 128, 64, ops.ACT_NONE, False, False, torch.float32),
+    (100, 64, 128, ops.ACT_NONE, True, False, torch.float32),
+    (333, 768, 768, ops.ACT_NONE, True, True, torch.float32),
+    (1000, 2304, 768, ops.ACT_NONE, True, False, torch.bfloat16),
+    (1576, 3072, 768, ops.ACT_QUICKGELU, True, False, torch.bfloat16),
+    (1576, 768, 3072, ops.ACT_NONE, True, True, torch.float32),
+    (40000, 768, 768, ops.ACT_NONE, True, False, torch.bfloat16),  # 128x256 tiles, several tiles per CTA
+    (512, 140, 256, ops.ACT_NONE, True, False, torch.float32),  # ragged N
+    (512, 512, 512, ops.ACT_GELU_ERF, True, False, torch.bfloat16),
+    (64, 256, 512, ops.ACT_RELU, True, False, torch.bfloat16),
+]
+
+
+@pytest.mark.parametrize("M,N,K,act,use_bias,use_resid,odt", GEMM_CASES)
+def test_gemm_against_fp32(cuda_device, M, N, K, act, use_bias, use_resid, odt):
+    gen = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = (torch.randn(M, K, device=cuda_device, generator=gen)).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=cuda_device, generator=gen) * K**-0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=cuda_device, generator=gen) if use_bias else None
+    resid = torch.randn(M, N, device=cuda_device, generator=gen) if use_resid else None
+    alpha = 0.5 if use_resid else 1.0
+    got = ops.gemm(a, w, bias=bias, act=act, alpha=alpha, resid=resid, out_dtype=odt).float()
+    ref = _ref_gemm(a, w, bias, act, alpha, resid)
+    tol = 2e-2 if odt == torch.bfloat16 else 2e-4
+    err = (got - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+def test_gemm_patch_embed_rowgroup_and_padded_k(cuda_device):
+    """Patch-embed epilogue: token rows scattered past each frame's CLS row, pos-emb added; K = 588 (ViT-L/14)."""
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    F_, n, d, K, ld = 3, 256, 1024, 588, 592
+    a = torch.zeros(F_ * n, ld, device=cuda_device, dtype=torch.bfloat16)
+    a[:, :K] = torch.randn(F_ * n, K, device=cuda_device, generator=gen).to(torch.bfloat16)
+    a[:, K:] = 7.0  # pad columns must be ignored: K < ld
+    w = torch.zeros(d, ld, device=cuda_device, dtype=torch.bfloat16)
+    w[:, :K] = (torch.randn(d, K, device=cuda_device, generator=gen) * K**-0.5).to(torch.bfloat16)
+    w[:, K:] = 3.0
+    pos = torch.randn(n + 1, d, device=cuda_device, generator=gen)
+    x = torch.full((F_ * (n + 1), d), -5.0, device=cuda_device)
+    ops.gemm(a, w, resid=pos, out=x, k=K, row_group=n)
+    ref = (a[:, :K].float() @ w[:, :K].float().t()).view(F_, n, d) + pos[1:][None]
+    xv = x.view(F_, n + 1, d)
+    assert torch.all(xv[:, 0] == -5.0)  # CLS rows untouched
+    assert (xv[:, 1:] - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_linearity_full_size(cuda_device):
+    """BASELINE-size GEMM (64 frames x 197 tokens, fc1): G(a1 + a2) == G(a1) + G(a2) on exactly representable inputs."""
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    M, N, K = 64 * 197, 3072, 768
+    a1 = torch.randint(-4, 5, (M, K), device=cuda_device, generator=gen).to(torch.bfloat16)
+    a2 = torch.randint(-4, 5, (M, K), device=cuda_device, generator=gen).to(torch.bfloat16)
+    w = torch.randint(-2, 3, (N, K), device=cuda_device, generator=gen).to(torch.bfloat16)
+    y1 = ops.gemm(a1, w, out_dtype=torch.float32)
+    y2 = ops.gemm(a2, w, out_dtype=torch.float32)
+    y12 = ops.gemm((a1 + a2), w, out_dtype=torch.float32)
+    assert torch.equal(y12, y1 + y2)  # small integers: every product and sum is exact in fp32
+    assert torch.equal(y1, a1.float() @ w.float().t())
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm / attention / small kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [512, 768, 1024])
+def test_layernorm(cuda_device, d):
+    gen = torch.Generator(device="cuda").manual_seed(d)
+    x = torch.randn(777, d, device=cuda_device, generator=gen) * 3 + 1
+    g_ = torch.randn(d, device=cuda_device, generator=gen)
+    b_ = torch.randn(d, device=cuda_device, generator=gen)
+    y32, y16 = ops.layernorm(x, g_, b_, want32=True, want16=True)
+    ref = torch.nn.functional.layer_norm(x, (d,), g_, b_, 1e-5)
+    assert (y32 - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert torch.equal(y16, y32.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("L,heads,F_", [(50, 12, 5), (197, 12, 3), (257, 16, 2), (128, 2, 2), (16, 1, 1)])
+def test_attention_vit(cuda_device, L, heads, F_):
+    gen = torch.Generator(device="cuda").manual_seed(L)
+    d = heads * 64
+    qkv = (torch.randn(F_ * L, 3 * d, device=cuda_device, generator=gen) * 1.5).to(torch.bfloat16)
+    got = ops.attention_vit(qkv, F_, L, heads).float().view(F_, L, heads, 64)
+    q, k, v = qkv.float().view(F_, L, 3, heads, 64).unbind(2)
+    s = torch.einsum("flhd,fmhd->fhlm", q, k) / 8.0
+    ref = torch.einsum("fhlm,fmhd->flhd", torch.softmax(s, -1), v)
+    err = (got - ref).abs().max().item()
+    assert err < 2e-2, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("B,Tq,Tk", [(2, 16, 15), (3, 40, 100), (1, 5, 70)])
+def test_attention_masked(cuda_device, B, Tq, Tk):
+    gen = torch.Generator(device="cuda").manual_seed(Tk)
+    h, d = 8, 512
+    q = torch.randn(B * Tq, d, device=cuda_device, generator=gen)
+    kv = torch.randn(B * Tk, 2 * d, device=cuda_device, generator=gen)
+    valid = torch.rand(B, Tk, device=cuda_device, generator=gen) > 0.3
+    valid[:, 0] = True
+    got = ops.attention_masked(q, kv[:, :d], kv[:, d:], valid, B, Tq, Tk, h).float()
+    qh = q.view(B, Tq, h, 64).transpose(1, 2)
+    kh = kv[:, :d].reshape(B, Tk, h, 64).transpose(1, 2)
+    vh = kv[:, d:].reshape(B, Tk, h, 64).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) / 8.0
+    s = s.masked_fill(~valid[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * Tq, d)
+    assert (got - ref).abs().max().item() < 1e-2  # bf16 output rounding
+    got2 = ops.attention_masked(q, kv[:, :d], kv[:, d:], None, B, Tq, Tk, h).float()
+    ref2 = (torch.softmax((qh @ kh.transpose(-1, -2)) / 8.0, -1) @ vh).transpose(1, 2).reshape(B * Tq, d)
+    assert (got2 - ref2).abs().max().item() < 1e-2
+
+
+def test_small_kernels(cuda_device, golden):
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(6, 16, 512, device=cuda_device, generator=gen)
+    m32, m16 = ops.mean_rows(x, want32=True, want16=True)
+    assert (m32 - x.mean(1)).abs().max().item() < 1e-6
+    assert torch.equal(m16, m32.to(torch.bfloat16))
+    assert torch.equal(ops.cast_bf16(x.view(-1, 512)), x.view(-1, 512).to(torch.bfloat16))
+    g = golden("losses.npz")
+    s, t, t2 = (torch.from_numpy(g[k]).to(cuda_device) for k in ("s", "t", "t2"))
+    assert abs(float(vmc.distillation_loss(s, t, "cosine")) - float(g["cos"])) < 1e-5
+    assert abs(float(vmc.distillation_loss(s, t2, "cosine")) - float(g["cos2"])) < 1e-5
+    assert abs(float(olosses.distillation_loss(s.cpu(), t.cpu(), "cosine")) - float(g["cos"])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# whole towers / drop-in modules against the oracle and the golden fixtures
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,nframes", [("ViT-B/32", 3), ("ViT-B/16", 2), ("ViT-L/14", 1)])
+def test_vit_tower_against_oracle_and_hf_golden(cuda_device, golden, name, nframes):
+    g = golden("vit_hf.npz")
+    tag = name.replace("/", "").replace("-", "").lower()
+    oracle = clip_shim.build_visual(name, seed=0)
+    feats = vmc.CLIPVisionFeatures(name)
+    feats.visual.load_state_dict(oracle.state_dict(), strict=True)
+    feats = feats.to(cuda_device)
+    gen = torch.Generator().manual_seed(4321)
+    u8 = torch.randint(0, 256, (nframes, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    got = feats.get_image_features_u8(u8.to(cuda_device))
+    ref = torch.from_numpy(g[tag + "_hf"])  # HF CLIPVisionModelWithProjection output (fp32, CPU)
+    assert _cos_min(got, ref) >= COS_MIN, _cos_min(got, ref)
+    x = torch.from_numpy(prologue.normalise_u8(u8.numpy()))
+    with torch.no_grad():
+        ref2 = oracle(x)
+    assert _cos_min(got, ref2) >= COS_MIN
+    # the reference-facing call: already-normalised fp32 pixel_values
+    got2 = feats.get_image_features(x.to(cuda_device))
+    assert _cos_min(got2, ref) >= COS_MIN
+    assert (got - ref).abs().max().item() < 0.05 * ref.abs().max().item()
+
+
+def test_student_config1_against_reference_golden(cuda_device, golden):
+    g = golden("student.npz")
+    oracle = ostudent.StudentOracle("ViT-B/32", seed=0)
+    weights.randomise_heads_(oracle, 0)
+    ours = vmc.FrameDiffStudentModel("ViT-B/32", device=cuda_device, num_classes=140, alpha=0.1)
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    gen = torch.Generator().manual_seed(1234)
+    frames = torch.randint(0, 256, (2, 16, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    emb, dis, logits = ours(frames)  # CPU uint8 input, like the reference's loaders hand over
+    assert emb.shape == (2, 16, 512) and dis.shape == (2, 16, 512) and logits.shape == (2, 140)
+    assert _cos_min(emb, torch.from_numpy(g["fd_b32_emb"])) >= COS_MIN
+    assert _cos_min(dis, torch.from_numpy(g["fd_b32_distill"])) >= COS_MIN
+    assert (logits.cpu() - torch.from_numpy(g["fd_b32_logits"])).abs().max().item() <= LOGIT_TOL
+    # float regimes B and C
+    gen = torch.Generator().manual_seed(99)
+    u8 = torch.randint(0, 256, (1, 2, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    embB, _, logB = ours(u8.float() / 255.0)
+    assert _cos_min(embB, torch.from_numpy(g["regB_emb"])) >= COS_MIN
+    assert (logB.cpu() - torch.from_numpy(g["regB_logits"])).abs().max().item() <= LOGIT_TOL
+    mean = torch.tensor(clip_shim.CLIP_MEAN).view(1, 1, 3, 1, 1)
+    std = torch.tensor(clip_shim.CLIP_STD).view(1, 1, 3, 1, 1)
+    embC, _, logC = ours((u8.float() / 255.0 - mean) / std)
+    assert _cos_min(embC, torch.from_numpy(g["regC_emb"])) >= COS_MIN
+    assert (logC.cpu() - torch.from_numpy(g["regC_logits"])).abs().max().item() <= LOGIT_TOL
+    with pytest.raises(NotImplementedError):
+        ours(torch.zeros(1, 1, 3, 360, 640, dtype=torch.uint8))
+
+
+MODES = {
+    "cross": dict(),
+    "cross_pe": dict(use_pe=True),
+    "rgb_only": dict(use_only_rgb=True),
+    "flow_only": dict(use_only_flow=True),
+    "concat_t": dict(use_cross_attention=False, concat_dim=1),
+    "concat_e": dict(use_cross_attention=False, concat_dim=-1),
+}
+
+
+@pytest.mark.parametrize("tag", list(MODES))
+def test_tfam_config1_against_reference_golden(cuda_device, golden, tag):
+    g = golden("tfam.npz")
+    oracle = otfam.TfamOracle(**MODES[tag]).eval()
+    weights.randomise_tfam_(oracle, 0)
+    ours = vmc.AMO_CLIP(device=cuda_device, **MODES[tag])
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    ours = ours.to(cuda_device).eval()
+    rgb, mot = torch.from_numpy(g["rgb"]).to(cuda_device), torch.from_numpy(g["motion"]).to(cuda_device)
+    mr, mm = torch.from_numpy(g["mask_rgb"]).to(cuda_device), torch.from_numpy(g["mask_mot"]).to(cuda_device)
+    logits = ours(rgb.clone(), mot.clone(), mr, mm)
+    err = (logits.cpu() - torch.from_numpy(g[tag + "_logits"])).abs().max().item()
+    assert logits.shape == (2, 140) and err <= LOGIT_TOL, f"{tag}: logit max-abs {err}"
+
+
+def test_tfam_no_mask_and_larger_batch(cuda_device, golden):
+    g = golden("tfam.npz")
+    oracle = otfam.TfamOracle().eval()
+    weights.randomise_tfam_(oracle, 0)
+    ours = vmc.AMO_CLIP(device=cuda_device)
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    ours = ours.to(cuda_device).eval()
+    out = ours(torch.from_numpy(g["nomask_rgb"]).to(cuda_device), torch.from_numpy(g["nomask_motion"]).to(cuda_device))
+    assert (out.cpu() - torch.from_numpy(g["nomask_logits"])).abs().max().item() <= LOGIT_TOL
+    # batch 64 x T 16/15 with ragged lengths against the oracle
+    gen = torch.Generator().manual_seed(8)
+    rgb, mot = torch.randn(64, 16, 512, generator=gen), torch.randn(64, 15, 512, generator=gen)
+    lr = torch.randint(1, 17, (64,), generator=gen)
+    lm = torch.randint(1, 16, (64,), generator=gen)
+    mr = torch.arange(16)[None] < lr[:, None]
+    mm = torch.arange(15)[None] < lm[:, None]
+    ref = oracle(rgb, mot, mr, mm)
+    out = ours(rgb.to(cuda_device), mot.to(cuda_device), mr.to(cuda_device), mm.to(cuda_device))
+    assert (out.cpu() - ref).abs().max().item() <= LOGIT_TOL
+
+
+def test_full_pipeline_small(cuda_device):
+    """Config-4 chain in memory on 3 clips: RGB tower + student + TFAM against the oracle chain."""
+    torch.manual_seed(0)
+    pipe = vmc.ViMoCLIPPipeline("ViT-B/16", "ViT-B/32", device=cuda_device, clips_per_step=2)
+    o_rgb = clip_shim.build_visual("ViT-B/16", seed=1)
+    o_st = ostudent.StudentOracle("ViT-B/32", seed=2)
+    weights.randomise_heads_(o_st, 2)
+    o_tf = otfam.TfamOracle().eval()
+    weights.randomise_tfam_(o_tf, 3)
+    pipe.rgb.visual.load_state_dict(o_rgb.state_dict())
+    pipe.student.load_state_dict(o_st.state_dict())
+    pipe.tfam.load_state_dict(o_tf.state_dict())
+    gen = torch.Generator().manual_seed(21)
+    rgb = torch.randint(0, 256, (3, 4, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    mot = torch.randint(0, 256, (3, 3, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    logits, er, em = pipe(rgb, mot)
+    with torch.no_grad():
+        er_ref = o_rgb(torch.from_numpy(prologue.normalise_u8(rgb.reshape(12, 3, 224, 224).numpy()))).view(3, 4, -1)
+        em_ref, _, _ = o_st(mot)
+        lg_ref = o_tf(er_ref, em_ref)
+    assert _cos_min(er, er_ref) >= COS_MIN and _cos_min(em, em_ref) >= COS_MIN
+    assert (logits.cpu() - lg_ref).abs().max().item() <= LOGIT_TOL
+    assert math.isfinite(float(logits.abs().sum()))

@@ -1,0 +1,142 @@
+"""CPU: host-side logic of the product package, the C-ABI surface and the drop-in contracts."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import vimoclip_b200 as vmc
+from oracle import indexing as oidx, student as ostudent, tfam as otfam
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "vimoclip_b200.h")).read()
+    declared = set(re.findall(r"\b(vmc_[a-z0-9_]+)\s*\(", header))
+    lib = ctypes.CDLL(vmc._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(vmc._lib.EXPORTED_SYMBOLS), declared ^ set(vmc._lib.EXPORTED_SYMBOLS)
+    assert vmc._lib.lib().vmc_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(vmc._lib.VmcError):
+        vmc.ops.prologue(torch.zeros(1, 3, 224, 224, dtype=torch.uint8), wrap=True, dst="u8")
+    with pytest.raises(vmc._lib.VmcError):
+        vmc.ops.gemm(torch.zeros(8, 64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16))
+    tower = vmc.VisionTower(32, 128, 1, 2, 64)
+    with pytest.raises(vmc._lib.VmcError):
+        tower(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(vmc._lib.VmcError):
+        vmc.AMO_CLIP(device="cpu").eval()(torch.zeros(1, 4, 512), torch.zeros(1, 4, 512))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vimo-clip_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+            assert "/root/reference" not in src, fn
+
+
+def test_state_dict_layouts_match_reference_names():
+    ours = vmc.FlowStudentModel("ViT-B/32", device="cpu")
+    ref = ostudent.StudentOracle("ViT-B/32")
+    a = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert a == b
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    # DataParallel-style "module." checkpoints (train.py:167) load through the wrapper
+    wrapped = torch.nn.DataParallel(vmc.FrameDiffStudentModel("ViT-B/32", device="cpu"))
+    wrapped.load_state_dict({"module." + k: v for k, v in ref.state_dict().items()}, strict=True)
+    t_ours = vmc.AMO_CLIP(device="cpu")
+    t_ref = otfam.TfamOracle()
+    assert {k: tuple(v.shape) for k, v in t_ours.state_dict().items()} == {k: tuple(v.shape) for k, v in t_ref.state_dict().items()}
+    t_ours.load_state_dict(t_ref.state_dict(), strict=True)
+    assert ours.visual_encoder.output_dim == 512 and len(ours.preprocess.transforms) == 5
+
+
+def test_reference_module_paths_resolve():
+    from models.student_model import FlowStudentModel
+    from models.student_model_frame_diff import FrameDiffStudentModel
+    from TFAM.models import AMO_CLIP
+    import losses
+
+    assert FlowStudentModel is vmc.FlowStudentModel and FrameDiffStudentModel is vmc.FrameDiffStudentModel
+    assert AMO_CLIP is vmc.AMO_CLIP and losses.distillation_loss is vmc.distillation_loss
+
+
+def test_indexing_bit_exact_with_oracle(golden):
+    g = golden("indexing.npz")
+    for key in g.files:
+        if key.startswith("sparse_"):
+            _, T, n = key.split("_")
+            emb = torch.arange(int(T), dtype=torch.float32)[:, None]
+            assert np.array_equal(vmc.indexing.sparse_sampling(emb, int(n))[:, 0].long().numpy(), g[key])
+    batch = [{"video_id": str(i), "embeddings": torch.from_numpy(g[f"collate_in_rgb{i}"]),
+              "flow_embeddings": torch.from_numpy(g[f"collate_in_flow{i}"]), "labels": torch.zeros(4)} for i in range(3)]
+    col = vmc.indexing.collate_fn_pad(batch)
+    assert np.array_equal(col["embeddings"].numpy(), g["collate_rgb"])
+    assert np.array_equal(col["mask_rgb"].numpy(), g["collate_mask_rgb"])
+    assert np.array_equal(col["mask_flow"].numpy(), g["collate_mask_flow"])
+    for total, mx in [(10, None), (10, 16), (100, 16), (451, 32), (33, 32)]:
+        assert np.array_equal(vmc.indexing.sample_frame_indices(total, mx), oidx.sample_frame_indices(total, mx))
+    assert vmc.indexing.segment_frame_indices(7, 3) == oidx.segment_indices(7, 3)
+
+
+def test_shard_index_math_round_trips():
+    for n, w in [(256, 8), (10, 4), (7, 2), (3, 8), (1, 1)]:
+        per = vmc.indexing.padded_per_rank(n, w)
+        cat = np.full(w * per, -1)
+        for r in range(w):
+            ids = vmc.indexing.shard_ids(n, r, w)
+            assert np.array_equal(ids, oidx.shard_clips(n, r, w)[0])
+            cat[r * per: r * per + len(ids)] = ids
+        assert np.array_equal(cat[vmc.indexing.unshard_order(n, w)], np.arange(n))
+
+
+def test_losses_cpu_semantics(golden):
+    g = golden("losses.npz")
+    s, t = torch.from_numpy(g["s"]), torch.from_numpy(g["t"])
+    assert np.isclose(float(vmc.distillation_loss(s, t, "cosine")), float(g["cos"]), atol=1e-6)
+    assert np.isclose(float(vmc.distillation_loss(s, t, "mse")), float(g["mse"]), atol=1e-6)
+    lg, tg = torch.from_numpy(g["logits"]), torch.from_numpy(g["targets"])
+    assert np.isclose(float(vmc.classification_loss(lg, tg, positive_weight=3)), float(g["bce_pw"]), atol=1e-6)
+    with pytest.raises(ValueError):
+        vmc.distillation_loss(s, t, "l1")
+
+
+def test_gather_clips_world2_gloo():
+    """N>1 host path on CPU: two gloo ranks shard 7 clips r::2 and gather them back in order."""
+    code = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import vimoclip_b200 as vmc
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=int(os.environ["RANK"]), world_size=2)
+n = 7
+ids = vmc.sharding.local_clip_ids(n)
+local = torch.tensor(ids, dtype=torch.float32)[:, None].repeat(1, 3) * 10 + torch.arange(3)
+out = vmc.sharding.gather_clips(local, n)
+exp = torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 3) * 10 + torch.arange(3)
+assert torch.equal(out, exp), out
+dist.destroy_process_group()
+print("ok")
+''' % ROOT
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=dict(os.environ, RANK=str(r), PORT=str(port)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0 and b"ok" in out, out.decode()

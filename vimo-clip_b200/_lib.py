@@ -1,0 +1,105 @@
+"""ctypes binding of ``libvimoclip_b200.so`` (the C-ABI declared in ``include/vimoclip_b200.h``).
+
+There is no CPU fallback: if the shared library is missing this module raises at first use, and
+every op raises on non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvimoclip_b200.so")
+
+# enums of include/vimoclip_b200.h
+SRC_U8, SRC_U8_WRAP, SRC_F32_WRAP, SRC_F32_NORM = 0, 1, 2, 3
+DST_U8, DST_F32_NCHW, DST_BF16_PATCH = 0, 1, 2
+ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
+ABI_VERSION = 1
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p),
+        ("ldr", C.c_longlong),
+        ("out", C.c_void_p),
+        ("ldo", C.c_longlong),
+        ("out_bf16", C.c_int),
+        ("act", C.c_int),
+        ("alpha", C.c_float),
+        ("row_group", C.c_int),
+    ]
+
+
+class VitLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_out", "b_out", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+class VitModel(C.Structure):
+    _fields_ = [
+        ("image", C.c_int), ("patch", C.c_int), ("width", C.c_int), ("layers", C.c_int), ("heads", C.c_int),
+        ("out_dim", C.c_int), ("ld_patch", C.c_int),
+        ("w_patch", C.c_void_p), ("cls_pos0", C.c_void_p), ("pos", C.c_void_p),
+        ("ln_pre_g", C.c_void_p), ("ln_pre_b", C.c_void_p), ("ln_post_g", C.c_void_p), ("ln_post_b", C.c_void_p),
+        ("w_proj", C.c_void_p), ("layer", C.POINTER(VitLayer)),
+    ]
+
+
+_SIGNATURES = {
+    "vmc_last_error": (C.c_char_p, []),
+    "vmc_abi_version": (C.c_int, []),
+    "vmc_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "vmc_launch_count": (C.c_longlong, []),
+    "vmc_reset_launch_count": (None, []),
+    "vmc_prologue": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vmc_frame_diff_prologue": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vmc_gemm_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), C.c_void_p]),
+    "vmc_layernorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "vmc_attention_vit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vmc_attention_masked": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vmc_cast_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "vmc_mean_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vmc_cosine_distill_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vmc_vit_workspace_bytes": (C.c_longlong, [C.POINTER(VitModel), C.c_int]),
+    "vmc_vit_forward": (C.c_int, [C.POINTER(VitModel), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class VmcError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the shared library once (thread-safe: DataParallel calls forward from several threads)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise VmcError(
+                        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(or `make -C vimo-clip_b200/csrc`). There is no CPU fallback."
+                    )
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                if handle.vmc_abi_version() != ABI_VERSION:
+                    raise VmcError("libvimoclip_b200.so ABI version mismatch; rebuild the library")
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().vmc_last_error().decode("utf-8", "replace")
+        raise VmcError(f"{what} failed (code {rc}): {msg}")

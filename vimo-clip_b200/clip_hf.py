@@ -1,0 +1,53 @@
+"""Stage 1: CLIP image features, the call surface ``extract_embeddings.py`` uses from HF ``CLIPModel``:
+
+    clip_model = CLIPModel.from_pretrained(...).eval().to(device)          # extract_embeddings.py:17
+    embeddings = clip_model.get_image_features(pixel_values)               # :94  -> Tensor [T, D]
+
+``CLIPVisionFeatures`` keeps that surface (``get_image_features`` returns a plain tensor like the
+pinned transformers 4.53.2) and loads HF-named weights (``vision_model.*``, ``visual_projection``).
+``get_image_features_u8`` is the fused entry: raw uint8 frames, normalisation inside the P1 kernel,
+so the fp32 ``pixel_values`` tensor of ``CLIPImageProcessor`` (extract_embeddings.py:89-93) never exists.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .vit import VisionTower, load_hf_vision_state_dict
+
+_HF_NAMES = {
+    "openai/clip-vit-base-patch16": "ViT-B/16",
+    "openai/clip-vit-base-patch32": "ViT-B/32",
+    "openai/clip-vit-large-patch14": "ViT-L/14",
+}
+
+
+class CLIPVisionFeatures(nn.Module):
+    def __init__(self, name: str = "openai/clip-vit-base-patch16", **tower_kw):
+        super().__init__()
+        self.visual = VisionTower.from_name(_HF_NAMES.get(name, name), **tower_kw)
+
+    @classmethod
+    def from_hf_state_dict(cls, name: str, state_dict: dict, **kw) -> "CLIPVisionFeatures":
+        m = cls(name, **kw)
+        load_hf_vision_state_dict(m.visual, state_dict)
+        return m
+
+    @torch.no_grad()
+    def get_image_features(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """pixel_values fp32 [F,3,224,224] (already normalised) -> [F, D] fp32, NOT L2-normalised."""
+        return self.visual(pixel_values)
+
+    @torch.no_grad()
+    def get_image_features_u8(self, frames_u8: torch.Tensor) -> torch.Tensor:
+        """frames uint8 [F,3,224,224] (RGB, as decord/PIL hand them over) -> [F, D] fp32."""
+        if frames_u8.dtype != torch.uint8:
+            raise TypeError("get_image_features_u8 expects uint8 frames")
+        dev = self.visual.proj.device
+        if dev.type != "cuda":
+            raise _lib.VmcError("CLIPVisionFeatures runs on CUDA only (no CPU fallback)")
+        patches = ops.prologue(frames_u8.to(dev, non_blocking=True), wrap=False, dst="patch", patch=self.visual.patch_size)
+        return self.visual.forward_patches(patches, frames_u8.shape[0])
+
+    forward = get_image_features

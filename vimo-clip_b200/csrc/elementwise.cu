@@ -1,0 +1,485 @@
+// HBM-bound kernels of the path: the uint8 prologue (P1), frame difference (a1),
+// LayerNorm (E1), temporal mean, casts and the cosine distillation loss (E2).
+// All are plain coalesced / 16-byte vectorised kernels: there is no data reuse, so
+// no shared-memory staging; grids are sized from the data, in 256-thread blocks.
+#include "common.cuh"
+#include "vimoclip_b200.h"
+
+namespace {
+
+using namespace vmc;
+
+// CLIP normalisation constants (clip/clip.py::_transform; HF CLIPImageProcessor defaults)
+__constant__ float c_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+__constant__ float c_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+
+// (float32(u8) / 255 - mean) / std with IEEE round-to-nearest divisions and no FMA contraction:
+// bit-for-bit torchvision ToTensor + Normalize (models/student_model.py:78 via clip _transform).
+__device__ __forceinline__ float normalise_px(uint32_t u8, int c) {
+  const float t = __fdiv_rn(static_cast<float>(u8), 255.0f);
+  return __fdiv_rn(__fsub_rn(t, c_mean[c]), c_std[c]);
+}
+
+// to_pil_image(float CHW) = pic.mul(255).byte(): fp32 multiply, then float -> uint8 through
+// int64 truncation, keeping the low 8 bits.
+__device__ __forceinline__ uint32_t wrap_f32(float x) {
+  const float y = __fmul_rn(x, 255.0f);
+  const long long i = static_cast<long long>(y);  // cvt.rzi.s64.f32 (truncation)
+  return static_cast<uint32_t>(i) & 255u;
+}
+
+// Store 16 horizontally consecutive values (channel c, row y, columns x0..x0+15) of frame f,
+// either as fp32 NCHW or as bf16 in the patchified GEMM-operand layout.
+__device__ __forceinline__ void store_f16px(void* dst, int dst_kind, int f, int c, int y, int x0,
+                                            const float (&v)[16], int H, int W, int p, int ld) {
+  if (dst_kind == VMC_DST_F32_NCHW) {
+    float* d = reinterpret_cast<float*>(dst) + (((size_t)f * 3 + c) * H + y) * W + x0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      reinterpret_cast<float4*>(d)[i] =
+          make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    return;
+  }
+  // VMC_DST_BF16_PATCH: row = f*n + (y/p)*(W/p) + x/p ; col = c*p*p + (y%p)*p + x%p
+  const int gw = W / p;
+  const int n = (H / p) * gw;
+  const int py = y / p, iy = y - py * p;
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(dst);
+  if ((p & 15) == 0) {
+    const int px = x0 / p, ix = x0 - px * p;
+    __nv_bfloat16* d =
+        base + ((size_t)f * n + (size_t)py * gw + px) * ld + (size_t)c * p * p + iy * p + ix;
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]);
+    o0.y = pack_bf16x2(v[2], v[3]);
+    o0.z = pack_bf16x2(v[4], v[5]);
+    o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]);
+    o1.y = pack_bf16x2(v[10], v[11]);
+    o1.z = pack_bf16x2(v[12], v[13]);
+    o1.w = pack_bf16x2(v[14], v[15]);
+    reinterpret_cast<uint4*>(d)[0] = o0;
+    reinterpret_cast<uint4*>(d)[1] = o1;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int x = x0 + i;
+      const int px = x / p, ix = x - px * p;
+      base[((size_t)f * n + (size_t)py * gw + px) * ld + (size_t)c * p * p + iy * p + ix] =
+          __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
+// Store 16 horizontally consecutive uint8 pixels per dst_kind (wrapped u8 / normalised fp32 / bf16 patches).
+__device__ __forceinline__ void store_px16(void* dst, int dst_kind, int f, int c, int y, int x0,
+                                           const uint32_t (&u)[16], int H, int W, int p, int ld) {
+  if (dst_kind == VMC_DST_U8) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      w[i] = u[4 * i] | (u[4 * i + 1] << 8) | (u[4 * i + 2] << 16) | (u[4 * i + 3] << 24);
+    uint8_t* d = reinterpret_cast<uint8_t*>(dst) + (((size_t)f * 3 + c) * H + y) * W + x0;
+    *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+    return;
+  }
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = normalise_px(u[i], c);
+  store_f16px(dst, dst_kind, f, c, y, x0, v, H, W, p, ld);
+}
+
+__global__ void __launch_bounds__(256)
+prologue_kernel(const void* __restrict__ src, int src_kind, void* __restrict__ dst, int dst_kind,
+                int F, int H, int W, int p, int ld) {
+  const int wv = W / 16;
+  const size_t total = (size_t)F * 3 * H * wv;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int xv = idx % wv;
+    size_t r = idx / wv;
+    const int y = r % H;
+    r /= H;
+    const int c = r % 3;
+    const int f = r / 3;
+    const size_t off = (((size_t)f * 3 + c) * H + y) * W + (size_t)xv * 16;
+    uint32_t u[16];
+    if (src_kind == VMC_SRC_F32_NORM) {
+      // already-normalised pixel_values (HF get_image_features input): layout change + bf16 only
+      const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 q = __ldg(s + i);
+        v[4 * i + 0] = q.x;
+        v[4 * i + 1] = q.y;
+        v[4 * i + 2] = q.z;
+        v[4 * i + 3] = q.w;
+      }
+      store_f16px(dst, dst_kind, f, c, y, xv * 16, v, H, W, p, ld);
+      continue;
+    }
+    if (src_kind == VMC_SRC_F32_WRAP) {
+      const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 q = __ldg(s + i);
+        u[4 * i + 0] = wrap_f32(q.x);
+        u[4 * i + 1] = wrap_f32(q.y);
+        u[4 * i + 2] = wrap_f32(q.z);
+        u[4 * i + 3] = wrap_f32(q.w);
+      }
+    } else {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + off));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 255u;
+        // regime A: uint8 -> float 0..255 -> *255 -> int64 -> low 8 bits == (-x) mod 256
+        if (src_kind == VMC_SRC_U8_WRAP) b = (0u - b) & 255u;
+        u[i] = b;
+      }
+    }
+    store_px16(dst, dst_kind, f, c, y, xv * 16, u, H, W, p, ld);
+  }
+}
+
+// OpenCV 8-bit BGR2GRAY: (B*3735 + G*19235 + R*9798 + (1<<14)) >> 15
+// (utils/generate_frame_diff_video.py:37,46; exhaustively verified)
+__device__ __forceinline__ uint32_t bgr_gray(uint32_t b, uint32_t g, uint32_t r) {
+  return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(256)
+frame_diff_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ diff_u8,
+                  void* __restrict__ dst, int dst_kind, int clips, int T, int H, int W, int p,
+                  int ld) {
+  const int wv = W / 16;
+  const size_t total = (size_t)clips * T * H * wv;
+  const size_t frame_bytes = (size_t)H * W * 3;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int xv = idx % wv;
+    size_t r = idx / wv;
+    const int y = r % H;
+    r /= H;
+    const int t = r % T;
+    const int clip = r / T;
+    const size_t f0 = (size_t)clip * (T + 1) + t;  // previous frame; current = f0 + 1
+    const size_t off = f0 * frame_bytes + ((size_t)y * W + (size_t)xv * 16) * 3;
+    const uint4* s0 = reinterpret_cast<const uint4*>(bgr + off);
+    const uint4* s1 = reinterpret_cast<const uint4*>(bgr + off + frame_bytes);
+    uint32_t w0[12], w1[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint4 a = __ldg(s0 + i);
+      const uint4 b = __ldg(s1 + i);
+      w0[4 * i] = a.x; w0[4 * i + 1] = a.y; w0[4 * i + 2] = a.z; w0[4 * i + 3] = a.w;
+      w1[4 * i] = b.x; w1[4 * i + 1] = b.y; w1[4 * i + 2] = b.z; w1[4 * i + 3] = b.w;
+    }
+    uint32_t d[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint32_t c0[3], c1[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int byte = 3 * i + k;
+        c0[k] = (w0[byte >> 2] >> (8 * (byte & 3))) & 255u;
+        c1[k] = (w1[byte >> 2] >> (8 * (byte & 3))) & 255u;
+      }
+      const int g0 = (int)bgr_gray(c0[0], c0[1], c0[2]);
+      const int g1 = (int)bgr_gray(c1[0], c1[1], c1[2]);
+      d[i] = (uint32_t)(g1 > g0 ? g1 - g0 : g0 - g1);  // cv2.absdiff(curr, prev)
+    }
+    const size_t fo = (size_t)clip * T + t;
+    if (diff_u8 != nullptr) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        w[i] = d[4 * i] | (d[4 * i + 1] << 8) | (d[4 * i + 2] << 16) | (d[4 * i + 3] << 24);
+      *reinterpret_cast<uint4*>(diff_u8 + (fo * H + y) * W + (size_t)xv * 16) =
+          make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (dst != nullptr) {
+      // the student sees uint8 frames with three identical channels (regime A wrap)
+      uint32_t u[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) u[i] = (0u - d[i]) & 255u;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) store_px16(dst, dst_kind, (int)fo, c, y, xv * 16, u, H, W, p, ld);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row cached in registers, fp32 two-pass statistics.
+// ---------------------------------------------------------------------------------------
+template <int NV>  // float4 per lane; supports d <= NV * 128
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, float* y32, long long ld32,
+                 __nv_bfloat16* y16, long long ld16, int rows, int d,
+                 const float* __restrict__ cls_row, int cls_every) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * ldx;
+  if (cls_every > 0 && (row % cls_every) == 0) xr = cls_row;
+  const int nv = d >> 2;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nv) {
+      v[i] = reinterpret_cast<const float4*>(xr)[j];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + j);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (y32 != nullptr) reinterpret_cast<float4*>(y32 + (size_t)row * ld32)[j] = o;
+      if (y16 != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(y16 + (size_t)row * ld16)[j] = pk;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                 long long ldy, int rows, int d) {
+  const int nv = d >> 2;
+  const size_t total = (size_t)rows * nv;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = idx % nv;
+    const size_t r = idx / nv;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + j);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(y + r * ldy)[j] = pk;
+  }
+}
+
+// mean over T rows: thread per (b, 4 columns)
+__global__ void __launch_bounds__(256)
+mean_rows_kernel(const float* __restrict__ x, float* y32, __nv_bfloat16* y16, int B, int T, int d) {
+  const int nv = d >> 2;
+  const size_t total = (size_t)B * nv;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = idx % nv;
+  const size_t b = idx / nv;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < T; ++t) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (b * T + t) * d) + j);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const float inv = 1.0f / (float)T;
+  s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+  if (y32 != nullptr) reinterpret_cast<float4*>(y32 + b * d)[j] = s;
+  if (y16 != nullptr) {
+    uint2 pk;
+    pk.x = pack_bf16x2(s.x, s.y);
+    pk.y = pack_bf16x2(s.z, s.w);
+    reinterpret_cast<uint2*>(y16 + b * d)[j] = pk;
+  }
+}
+
+// losses.py:27-40 -- one warp per row, atomicAdd of (1 - cos) / rows
+__global__ void __launch_bounds__(256)
+cosine_loss_kernel(const float* __restrict__ s, const float* __restrict__ t, int rows, int d,
+                   float* out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float ss = 0.f, tt = 0.f, st = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float a = s[(size_t)row * d + j], b = t[(size_t)row * d + j];
+    ss += a * a;
+    tt += b * b;
+    st += a * b;
+  }
+  ss = warp_sum(ss);
+  tt = warp_sum(tt);
+  st = warp_sum(st);
+  if (lane == 0) {
+    const float eps = 1e-5f;
+    const float ns = fmaxf(sqrtf(ss), eps), nt = fmaxf(sqrtf(tt), eps);
+    float c = st / (ns * nt);
+    c = fminf(fmaxf(c, -1.0f + eps), 1.0f - eps);
+    atomicAdd(out, (1.0f - c) / (float)rows);
+  }
+}
+
+int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = (size_t)vmc_num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int check_geometry(const char* who, int H, int W, int patch, int ld_patch, int dst_kind) {
+  VMC_CHECK_ARG(H > 0 && W > 0 && (W % 16) == 0, VMC_ERR_SHAPE,
+                "%s: W must be a positive multiple of 16 (H=%d W=%d)", who, H, W);
+  VMC_CHECK_ARG(dst_kind >= VMC_DST_U8 && dst_kind <= VMC_DST_BF16_PATCH, VMC_ERR_ARG,
+                "%s: unknown dst_kind %d", who, dst_kind);
+  if (dst_kind == VMC_DST_BF16_PATCH) {
+    VMC_CHECK_ARG(patch > 0 && (H % patch) == 0 && (W % patch) == 0, VMC_ERR_SHAPE,
+                  "%s: H,W must be multiples of patch %d (no resize in this path: the reference's "
+                  "Resize/CenterCrop is the identity only at the model resolution)",
+                  who, patch);
+    VMC_CHECK_ARG(ld_patch >= 3 * patch * patch && (ld_patch % 8) == 0, VMC_ERR_ALIGN,
+                  "%s: ld_patch must be >= 3*p*p and a multiple of 8", who);
+  }
+  return VMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vmc_prologue(const void* frames, int src_kind, void* dst, int dst_kind, int F, int H, int W,
+                 int patch, int ld_patch, void* stream) {
+  VMC_CHECK_ARG(frames && dst, VMC_ERR_ARG, "vmc_prologue: null pointer");
+  VMC_CHECK_ARG(src_kind >= VMC_SRC_U8 && src_kind <= VMC_SRC_F32_NORM, VMC_ERR_ARG,
+                "vmc_prologue: unknown src_kind %d", src_kind);
+  VMC_CHECK_ARG(src_kind != VMC_SRC_F32_NORM || dst_kind == VMC_DST_BF16_PATCH, VMC_ERR_ARG,
+                "vmc_prologue: VMC_SRC_F32_NORM only feeds VMC_DST_BF16_PATCH");
+  VMC_CHECK_ARG(F > 0, VMC_ERR_SHAPE, "vmc_prologue: F must be positive");
+  VMC_TRY(check_geometry("vmc_prologue", H, W, patch, ld_patch, dst_kind));
+  VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(frames) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                VMC_ERR_ALIGN, "vmc_prologue: pointers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dst_kind == VMC_DST_BF16_PATCH && ld_patch != 3 * patch * patch) {
+    const size_t n = (size_t)F * (H / patch) * (W / patch);
+    VMC_CUDA(cudaMemsetAsync(dst, 0, n * ld_patch * 2, st));
+  }
+  const size_t total = (size_t)F * 3 * H * (W / 16);
+  prologue_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, src_kind, dst, dst_kind, F, H, W,
+                                                        patch, ld_patch);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_frame_diff_prologue(const uint8_t* bgr, uint8_t* diff_u8, void* dst, int dst_kind,
+                            int clips, int T, int H, int W, int patch, int ld_patch, void* stream) {
+  VMC_CHECK_ARG(bgr && (diff_u8 || dst), VMC_ERR_ARG, "vmc_frame_diff_prologue: null pointer");
+  VMC_CHECK_ARG(clips > 0 && T > 0, VMC_ERR_SHAPE, "vmc_frame_diff_prologue: empty input");
+  if (dst) VMC_TRY(check_geometry("vmc_frame_diff_prologue", H, W, patch, ld_patch, dst_kind));
+  VMC_CHECK_ARG(H > 0 && W > 0 && (W % 16) == 0, VMC_ERR_SHAPE,
+                "vmc_frame_diff_prologue: W must be a positive multiple of 16");
+  VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(bgr) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(diff_u8) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                VMC_ERR_ALIGN, "vmc_frame_diff_prologue: pointers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dst && dst_kind == VMC_DST_BF16_PATCH && ld_patch != 3 * patch * patch) {
+    const size_t n = (size_t)clips * T * (H / patch) * (W / patch);
+    VMC_CUDA(cudaMemsetAsync(dst, 0, n * ld_patch * 2, st));
+  }
+  const size_t total = (size_t)clips * T * H * (W / 16);
+  frame_diff_kernel<<<grid_for(total, 256), 256, 0, st>>>(bgr, diff_u8, dst, dst_kind, clips, T, H,
+                                                          W, patch, ld_patch);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+                  float* y32, long long ld32, void* y16, long long ld16, int rows, int d,
+                  const float* cls_row, int cls_every, void* stream) {
+  VMC_CHECK_ARG(x && gamma && beta && (y32 || y16), VMC_ERR_ARG, "vmc_layernorm: null pointer");
+  VMC_CHECK_ARG(rows > 0 && d > 0 && (d % 4) == 0 && d <= 4096, VMC_ERR_SHAPE,
+                "vmc_layernorm: need d %% 4 == 0 and d <= 4096 (rows=%d d=%d)", rows, d);
+  VMC_CHECK_ARG((ldx % 4) == 0 && (!y32 || (ld32 % 4) == 0) && (!y16 || (ld16 % 4) == 0),
+                VMC_ERR_ALIGN, "vmc_layernorm: row strides must be multiples of 4 elements");
+  VMC_CHECK_ARG(cls_every <= 0 || cls_row != nullptr, VMC_ERR_ARG,
+                "vmc_layernorm: cls_every set without cls_row");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (rows + 7) / 8;
+  __nv_bfloat16* y16b = reinterpret_cast<__nv_bfloat16*>(y16);
+#define LN_LAUNCH(NV)                                                                            \
+  layernorm_kernel<NV><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, y32, ld32, y16b, ld16,    \
+                                             rows, d, cls_row, cls_every)
+  if (d <= 512) LN_LAUNCH(4);
+  else if (d <= 768) LN_LAUNCH(6);
+  else if (d <= 1024) LN_LAUNCH(8);
+  else if (d <= 2048) LN_LAUNCH(16);
+  else LN_LAUNCH(32);
+#undef LN_LAUNCH
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int d,
+                  void* stream) {
+  VMC_CHECK_ARG(x && y, VMC_ERR_ARG, "vmc_cast_bf16: null pointer");
+  VMC_CHECK_ARG(rows > 0 && d > 0 && (d % 4) == 0 && (ldx % 4) == 0 && (ldy % 4) == 0,
+                VMC_ERR_SHAPE, "vmc_cast_bf16: d and strides must be multiples of 4");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)rows * (d / 4);
+  cast_bf16_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(y),
+                                                         ldy, rows, d);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_mean_rows(const float* x, float* y32, void* y16, int B, int T, int d, void* stream) {
+  VMC_CHECK_ARG(x && (y32 || y16), VMC_ERR_ARG, "vmc_mean_rows: null pointer");
+  VMC_CHECK_ARG(B > 0 && T > 0 && d > 0 && (d % 4) == 0, VMC_ERR_SHAPE,
+                "vmc_mean_rows: bad shape B=%d T=%d d=%d", B, T, d);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)B * (d / 4);
+  mean_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      x, y32, reinterpret_cast<__nv_bfloat16*>(y16), B, T, d);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_cosine_distill_loss(const float* s, const float* t, int rows, int d, float* out,
+                            void* stream) {
+  VMC_CHECK_ARG(s && t && out, VMC_ERR_ARG, "vmc_cosine_distill_loss: null pointer");
+  VMC_CHECK_ARG(rows > 0 && d > 0, VMC_ERR_SHAPE, "vmc_cosine_distill_loss: empty input");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VMC_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  cosine_loss_kernel<<<(rows + 7) / 8, 256, 0, st>>>(s, t, rows, d, out);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+}  // extern "C"

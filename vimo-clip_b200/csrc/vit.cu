@@ -1,0 +1,160 @@
+// Whole CLIP vision tower (OpenAI VisionTransformer == HF CLIPVisionTransformer +
+// visual_projection under the weight mapping of SURVEY.md Appendix A), orchestrated on
+// one stream from the kernels of this library.  No host synchronisation.
+//
+// Data layout in HBM for F frames in flight, L = (image/patch)^2 + 1 tokens, d = width:
+//   x     fp32 [F*L, d]      residual stream (fp32 so 12-24 pre-LN blocks stay within tolerance)
+//   xn    bf16 [F*L, d]      LayerNorm output / attention output (A operand of the next GEMM)
+//   big   bf16 [F*L, 4d]     qkv ([F*L, 3d]) and MLP hidden ([F*L, 4d]) share this buffer
+//   cls   bf16 [F, d]        ln_post(CLS rows)
+// Reference: models/student_model.py:84 (self.visual_encoder(x)), extract_embeddings.py:94
+// (clip_model.get_image_features(pixel_values)).
+#include "common.cuh"
+#include "vimoclip_b200.h"
+
+namespace {
+
+inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  float* x;
+  void* xn;
+  void* big;
+  void* cls;
+  long long total;
+};
+
+Workspace carve(const vmc_vit_model* m, int F, void* base) {
+  const int g = m->image / m->patch;
+  const long long L = (long long)g * g + 1;
+  const long long rows = (long long)F * L;
+  const long long d = m->width;
+  Workspace w;
+  long long off = 0;
+  char* p = reinterpret_cast<char*>(base);
+  w.x = reinterpret_cast<float*>(p + off);
+  off += align_up(rows * d * 4, 1024);
+  w.xn = p + off;
+  off += align_up(rows * d * 2, 1024);
+  w.big = p + off;
+  off += align_up(rows * 4 * d * 2, 1024);
+  w.cls = p + off;
+  off += align_up((long long)F * d * 2, 1024);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+long long vmc_vit_workspace_bytes(const vmc_vit_model* m, int F) {
+  if (!m || F <= 0 || m->patch <= 0) return -1;
+  return carve(m, F, nullptr).total;
+}
+
+int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int F,
+                    void* workspace, long long workspace_bytes, void* stream) {
+  VMC_CHECK_ARG(m && patches && out && workspace, VMC_ERR_ARG, "vmc_vit_forward: null pointer");
+  VMC_CHECK_ARG(F > 0, VMC_ERR_SHAPE, "vmc_vit_forward: F must be positive");
+  VMC_CHECK_ARG(m->patch > 0 && m->image % m->patch == 0 && m->width == m->heads * 64 &&
+                    m->layers > 0 && m->layer != nullptr,
+                VMC_ERR_SHAPE, "vmc_vit_forward: unsupported model geometry (head_dim must be 64)");
+  VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, VMC_ERR_ALIGN,
+                "vmc_vit_forward: workspace must be 1024-byte aligned");
+  const Workspace w = carve(m, F, workspace);
+  VMC_CHECK_ARG(workspace_bytes >= w.total, VMC_ERR_WORKSPACE,
+                "vmc_vit_forward: workspace too small (%lld < %lld bytes)", workspace_bytes,
+                w.total);
+  const int g = m->image / m->patch;
+  const int n = g * g;
+  const int L = n + 1;
+  const int d = m->width;
+  const int rows = F * L;
+  const int kpatch = 3 * m->patch * m->patch;
+
+  // conv1 as a GEMM over patchified frames; epilogue adds positional_embedding[1 + token] and
+  // scatters token rows past each frame's CLS row.
+  {
+    vmc_gemm_epilogue e = {};
+    e.resid = m->pos;
+    e.ldr = d;
+    e.out = w.x;
+    e.ldo = d;
+    e.out_bf16 = 0;
+    e.act = VMC_ACT_NONE;
+    e.alpha = 1.0f;
+    e.row_group = n;
+    VMC_TRY(vmc_gemm_bf16(patches, m->ld_patch, m->w_patch, m->ld_patch, F * n, d, kpatch, &e,
+                          stream));
+  }
+  // ln_pre in place on the residual stream; CLS rows are sourced from class_embedding + pos[0].
+  VMC_TRY(vmc_layernorm(w.x, d, m->ln_pre_g, m->ln_pre_b, 1e-5f, w.x, d, nullptr, 0, rows, d,
+                        m->cls_pos0, L, stream));
+
+  for (int i = 0; i < m->layers; ++i) {
+    const vmc_vit_layer& ly = m->layer[i];
+    // x = x + out_proj(attn(ln_1(x)))
+    VMC_TRY(vmc_layernorm(w.x, d, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr, 0, w.xn, d, rows, d, nullptr,
+                          0, stream));
+    {
+      vmc_gemm_epilogue e = {};
+      e.bias = ly.b_qkv;
+      e.out = w.big;
+      e.ldo = 3 * d;
+      e.out_bf16 = 1;
+      e.alpha = 1.0f;
+      VMC_TRY(vmc_gemm_bf16(w.xn, d, ly.w_qkv, d, rows, 3 * d, d, &e, stream));
+    }
+    VMC_TRY(vmc_attention_vit(w.big, w.xn, F, L, m->heads, stream));
+    {
+      vmc_gemm_epilogue e = {};
+      e.bias = ly.b_out;
+      e.resid = w.x;
+      e.ldr = d;
+      e.out = w.x;
+      e.ldo = d;
+      e.out_bf16 = 0;
+      e.alpha = 1.0f;
+      VMC_TRY(vmc_gemm_bf16(w.xn, d, ly.w_out, d, rows, d, d, &e, stream));
+    }
+    // x = x + c_proj(QuickGELU(c_fc(ln_2(x))))
+    VMC_TRY(vmc_layernorm(w.x, d, ly.ln2_g, ly.ln2_b, 1e-5f, nullptr, 0, w.xn, d, rows, d, nullptr,
+                          0, stream));
+    {
+      vmc_gemm_epilogue e = {};
+      e.bias = ly.b_fc1;
+      e.out = w.big;
+      e.ldo = 4 * d;
+      e.out_bf16 = 1;
+      e.act = VMC_ACT_QUICKGELU;
+      e.alpha = 1.0f;
+      VMC_TRY(vmc_gemm_bf16(w.xn, d, ly.w_fc1, d, rows, 4 * d, d, &e, stream));
+    }
+    {
+      vmc_gemm_epilogue e = {};
+      e.bias = ly.b_fc2;
+      e.resid = w.x;
+      e.ldr = d;
+      e.out = w.x;
+      e.ldo = d;
+      e.out_bf16 = 0;
+      e.alpha = 1.0f;
+      VMC_TRY(vmc_gemm_bf16(w.big, 4 * d, ly.w_fc2, 4 * d, rows, d, 4 * d, &e, stream));
+    }
+  }
+  // ln_post on the CLS rows (row stride L*d), then @ proj (no bias), fp32 out.
+  VMC_TRY(vmc_layernorm(w.x, (long long)L * d, m->ln_post_g, m->ln_post_b, 1e-5f, nullptr, 0, w.cls,
+                        d, F, d, nullptr, 0, stream));
+  {
+    vmc_gemm_epilogue e = {};
+    e.out = out;
+    e.ldo = m->out_dim;
+    e.out_bf16 = 0;
+    e.alpha = 1.0f;
+    VMC_TRY(vmc_gemm_bf16(w.cls, d, m->w_proj, d, F, m->out_dim, d, &e, stream));
+  }
+  return VMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+"""Tensor-level wrappers over the C-ABI.  PyTorch is used only for device memory and streams.
+
+Every function enqueues hand-written sm_100a kernels on the current CUDA stream and returns
+device tensors.  CPU tensors raise: there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_QUICKGELU, ACT_RELU  # noqa: F401  (re-exported)
+
+
+def _need_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.VmcError("vimoclip_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _p(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(_lib.lib().vmc_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.lib().vmc_reset_launch_count()
+
+
+def device_info():
+    sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib().vmc_device_info(C.byref(sm), C.byref(major), C.byref(minor)), "vmc_device_info")
+    return sm.value, major.value, minor.value
+
+
+# ---------------------------------------------------------------------------------------------
+# P1 prologue
+# ---------------------------------------------------------------------------------------------
+def patch_ld(patch: int) -> int:
+    """Row stride of the patchified GEMM operand: 3*p*p rounded up to 8 elements (16 bytes)."""
+    k = 3 * patch * patch
+    return (k + 7) // 8 * 8
+
+
+def prologue(frames: torch.Tensor, *, wrap: bool, dst: str, patch: int = 0, normalised: bool = False) -> torch.Tensor:
+    """frames [F,3,H,W] uint8 or float32 -> 'u8' | 'f32' | 'patch' output.
+
+    ``wrap=True`` reproduces the student's in-forward ``.float()`` + ``to_pil_image`` wrap
+    (models/student_model.py:74,78); ``wrap=False`` takes uint8 pixels as they are (the HF
+    ``CLIPImageProcessor`` path of extract_embeddings.py:91).  Float input always wraps.
+    """
+    _need_cuda(frames)
+    if frames.dim() != 4 or frames.shape[1] != 3:
+        raise ValueError("frames must be [F,3,H,W]")
+    frames = frames.contiguous()
+    F_, _, H, W = frames.shape
+    if frames.dtype == torch.uint8:
+        src_kind = _lib.SRC_U8_WRAP if wrap else _lib.SRC_U8
+    elif frames.dtype == torch.float32:
+        # normalised=True: the tensor already holds (u8/255 - mean)/std (get_image_features input)
+        src_kind = _lib.SRC_F32_NORM if normalised else _lib.SRC_F32_WRAP
+    else:
+        raise TypeError("frames must be uint8 or float32")
+    ld = 0
+    if dst == "u8":
+        out = torch.empty((F_, 3, H, W), dtype=torch.uint8, device=frames.device)
+        kind = _lib.DST_U8
+    elif dst == "f32":
+        out = torch.empty((F_, 3, H, W), dtype=torch.float32, device=frames.device)
+        kind = _lib.DST_F32_NCHW
+    elif dst == "patch":
+        if patch <= 0 or H % patch or W % patch:
+            raise ValueError("H and W must be multiples of the patch size")
+        ld = patch_ld(patch)
+        out = torch.empty((F_ * (H // patch) * (W // patch), ld), dtype=torch.bfloat16, device=frames.device)
+        kind = _lib.DST_BF16_PATCH
+    else:
+        raise ValueError(dst)
+    with torch.cuda.device(frames.device):
+        _lib.check(_lib.lib().vmc_prologue(_p(frames), src_kind, _p(out), kind, F_, H, W, patch, ld, _stream()), "vmc_prologue")
+    return out
+
+
+def frame_diff(bgr: torch.Tensor, *, dst: str | None = None, patch: int = 0, want_diff: bool = True):
+    """bgr [clips, T+1, H, W, 3] uint8 -> (diff_u8 [clips,T,H,W] | None, student prologue output | None).
+
+    utils/generate_frame_diff_video.py:37,46,49 fused with the student prologue of the diff frames.
+    """
+    _need_cuda(bgr)
+    if bgr.dtype != torch.uint8 or bgr.dim() != 5 or bgr.shape[-1] != 3:
+        raise ValueError("bgr must be uint8 [clips, T+1, H, W, 3]")
+    bgr = bgr.contiguous()
+    clips, T1, H, W, _ = bgr.shape
+    T = T1 - 1
+    if T < 1:
+        raise ValueError("need at least two frames per clip")
+    diff = torch.empty((clips, T, H, W), dtype=torch.uint8, device=bgr.device) if want_diff else None
+    out, kind, ld = None, 0, 0
+    Fo = clips * T
+    if dst == "u8":
+        out, kind = torch.empty((Fo, 3, H, W), dtype=torch.uint8, device=bgr.device), _lib.DST_U8
+    elif dst == "f32":
+        out, kind = torch.empty((Fo, 3, H, W), dtype=torch.float32, device=bgr.device), _lib.DST_F32_NCHW
+    elif dst == "patch":
+        ld = patch_ld(patch)
+        out = torch.empty((Fo * (H // patch) * (W // patch), ld), dtype=torch.bfloat16, device=bgr.device)
+        kind = _lib.DST_BF16_PATCH
+    elif dst is not None:
+        raise ValueError(dst)
+    with torch.cuda.device(bgr.device):
+        _lib.check(
+            _lib.lib().vmc_frame_diff_prologue(_p(bgr), _p(diff), _p(out), kind, clips, T, H, W, patch, ld, _stream()),
+            "vmc_frame_diff_prologue",
+        )
+    return diff, out
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM / LayerNorm / attention
+# ---------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, alpha: float = 1.0, resid=None,
+         out: torch.Tensor | None = None, out_dtype=torch.bfloat16, n: int | None = None, k: int | None = None,
+         row_group: int = 0, out_rows: int | None = None) -> torch.Tensor:
+    """out = alpha * act(a @ w.T + bias) + resid.  a [M, lda] bf16, w [N, ldw] bf16 (nn.Linear layout)."""
+    _need_cuda(a, w, bias, resid, out)
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise TypeError("gemm operands must be bf16")
+    if a.stride(-1) != 1 or w.stride(-1) != 1:
+        raise ValueError("gemm operands must be row-major")
+    M = a.shape[0]
+    K = a.shape[1] if k is None else k
+    N = w.shape[0] if n is None else n
+    if out is None:
+        rows = M if out_rows is None else out_rows
+        out = torch.empty((rows, N), dtype=out_dtype, device=a.device)
+    e = _lib.GemmEpilogue()
+    e.bias = 0 if bias is None else bias.data_ptr()
+    e.resid = 0 if resid is None else resid.data_ptr()
+    e.ldr = 0 if resid is None else resid.stride(0)
+    e.out = out.data_ptr()
+    e.ldo = out.stride(0)
+    e.out_bf16 = 1 if out.dtype == torch.bfloat16 else 0
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("gemm output must be bf16 or fp32")
+    if bias is not None and bias.dtype != torch.float32 or resid is not None and resid.dtype != torch.float32:
+        raise TypeError("bias / resid must be fp32")
+    e.act = act
+    e.alpha = alpha
+    e.row_group = row_group
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().vmc_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, C.byref(e), _stream()), "vmc_gemm_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5, want32: bool = False,
+              want16: bool = True, out32: torch.Tensor | None = None):
+    """x fp32 [rows, d] -> (y32 | None, y16 | None)."""
+    _need_cuda(x, gamma, beta, out32)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("layernorm input must be fp32 [rows, d] row-major")
+    rows, d = x.shape
+    y32 = out32 if out32 is not None else (torch.empty((rows, d), dtype=torch.float32, device=x.device) if want32 else None)
+    y16 = torch.empty((rows, d), dtype=torch.bfloat16, device=x.device) if want16 else None
+    with torch.cuda.device(x.device):
+        _lib.check(
+            _lib.lib().vmc_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), eps, _p(y32), 0 if y32 is None else y32.stride(0),
+                                     _p(y16), 0 if y16 is None else y16.stride(0), rows, d, None, 0, _stream()),
+            "vmc_layernorm",
+        )
+    return y32, y16
+
+
+def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int) -> torch.Tensor:
+    """qkv bf16 [F*L, 3*heads*64] -> bf16 [F*L, heads*64]; softmax(q k^T / 8) v per (frame, head)."""
+    _need_cuda(qkv)
+    d = heads * 64
+    if qkv.dtype != torch.bfloat16 or tuple(qkv.shape) != (F_ * L, 3 * d) or not qkv.is_contiguous():
+        raise ValueError("qkv must be contiguous bf16 [F*L, 3*d]")
+    out = torch.empty((F_ * L, d), dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _lib.check(_lib.lib().vmc_attention_vit(_p(qkv), _p(out), F_, L, heads, _stream()), "vmc_attention_vit")
+    return out
+
+
+def attention_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_valid, B: int, Tq: int, Tk: int, heads: int) -> torch.Tensor:
+    """q [B*Tq, *], k/v [B*Tk, *] fp32 views (row-major, heads*64 columns) -> bf16 [B*Tq, heads*64]."""
+    _need_cuda(q, k, v, key_valid)
+    for t in (q, k, v):
+        if t.dtype != torch.float32 or t.stride(1) != 1:
+            raise ValueError("attention_masked inputs must be fp32 row-major")
+    if key_valid is not None:
+        if key_valid.dtype not in (torch.bool, torch.uint8) or tuple(key_valid.shape) != (B, Tk) or not key_valid.is_contiguous():
+            raise TypeError("key_valid must be a contiguous bool/uint8 [B, Tk] tensor (True = real frame)")
+    out = torch.empty((B * Tq, heads * 64), dtype=torch.bfloat16, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(
+            _lib.lib().vmc_attention_masked(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(key_valid), _p(out),
+                                            out.stride(0), B, Tq, Tk, heads, _stream()),
+            "vmc_attention_masked",
+        )
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("cast_bf16 input must be fp32 [rows, d] row-major")
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_cast_bf16(_p(x), x.stride(0), _p(y), y.stride(0), x.shape[0], x.shape[1], _stream()), "vmc_cast_bf16")
+    return y
+
+
+def mean_rows(x: torch.Tensor, *, want32: bool = True, want16: bool = False):
+    """x fp32 [B, T, d] contiguous -> mean over T (ALL rows, padded ones included)."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("mean_rows input must be contiguous fp32 [B, T, d]")
+    B, T, d = x.shape
+    y32 = torch.empty((B, d), dtype=torch.float32, device=x.device) if want32 else None
+    y16 = torch.empty((B, d), dtype=torch.bfloat16, device=x.device) if want16 else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_mean_rows(_p(x), _p(y32), _p(y16), B, T, d, _stream()), "vmc_mean_rows")
+    return y32, y16
+
+
+def cosine_distill_loss(student: torch.Tensor, teacher: torch.Tensor) -> torch.Tensor:
+    """losses.py:27-40: mean(1 - clamp(cos)) over rows, fp32 scalar on device."""
+    _need_cuda(student, teacher)
+    s = student.reshape(-1, student.shape[-1]).contiguous().float()
+    t = teacher.reshape(-1, teacher.shape[-1]).contiguous().float()
+    if s.shape != t.shape:
+        raise ValueError("student / teacher shapes differ")
+    out = torch.empty((1,), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib().vmc_cosine_distill_loss(_p(s), _p(t), s.shape[0], s.shape[1], _p(out), _stream()), "vmc_cosine_distill_loss")
+    return out[0]

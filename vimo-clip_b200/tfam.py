@@ -1,0 +1,195 @@
+"""TFAM fusion block: drop-in for ``TFAM/models/AMO_CLIP.py`` (same constructor, forward signature
+and state_dict keys: ``layers.{i}.{self_attn,cross_attn}.{in_proj_weight,in_proj_bias,out_proj.*}``,
+``layers.{i}.ffn.{0,3}.*``, ``layers.{i}.{norm_self,norm_cross,norm_ffn}.*``, ``classifier.{0,1,4}.*``,
+``projection_layer.*``).
+
+Inference forward on the sm_100a kernels (dropout is inactive in eval, AMO_CLIP.py:27,35):
+  post-LN layer (AMO_CLIP.py:37-51):  x = LN(x + SelfMHA(x));  x = LN(x + CrossMHA(x, motion));
+                                      x = LN(x + W2 relu(W1 x))
+  head (AMO_CLIP.py:170):             logits = classifier(mean over ALL T rows, padded ones included)
+GEMMs run on the tcgen05 kernel with fp32 accumulation and fp32 outputs; the residual stream, the
+LayerNorms, the attention scores/softmax and the pooling stay fp32 so logits hold max-abs <= 1e-2.
+
+The ``nn.MultiheadAttention`` / ``nn.Sequential`` members are parameter containers only (their
+``forward`` is never called): they give the reference's key names and initialisation.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+class AttentionLayer(nn.Module):
+    def __init__(self, d_model: int, num_heads: int, dim_feedforward: int, dropout: float = 0.1, activation: str = "relu"):
+        super().__init__()
+        assert d_model % num_heads == 0, f"d_model ({d_model}) debe ser divisible por num_heads ({num_heads})"
+        if d_model // num_heads != 64:
+            raise ValueError("the attention kernel is specialised for head_dim 64 (d_model=512, nhead=8)")
+        self.activation = activation
+        self.self_attn = nn.MultiheadAttention(d_model, num_heads, dropout=dropout, batch_first=True)
+        self.cross_attn = nn.MultiheadAttention(d_model, num_heads, dropout=dropout, batch_first=True)
+        self.ffn = nn.Sequential(
+            nn.Linear(d_model, dim_feedforward),
+            nn.GELU() if activation == "gelu" else nn.ReLU(),
+            nn.Dropout(dropout),
+            nn.Linear(dim_feedforward, d_model),
+            nn.Dropout(dropout),
+        )
+        self.norm_self = nn.LayerNorm(d_model)
+        self.norm_cross = nn.LayerNorm(d_model)
+        self.norm_ffn = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+
+
+class AMO_CLIP(nn.Module):
+    def __init__(
+        self,
+        d_model=512,
+        nhead=8,
+        num_layers=4,
+        dim_feedforward=2048,
+        num_classes=140,
+        use_cross_attention=True,
+        use_pe=False,
+        use_only_rgb=False,
+        use_only_flow=False,
+        concat_dim=1,
+        dropout=0.1,
+        mlp_dropout=0.3,
+        device="cuda",
+    ):
+        super().__init__()
+        self.use_cross_attention = use_cross_attention
+        self.use_pe = use_pe
+        self.use_only_rgb = use_only_rgb
+        self.use_only_flow = use_only_flow
+        self.concat_dim = concat_dim
+        self.d_model = d_model
+        self.nhead = nhead
+        self.device = device
+        self.layers = nn.ModuleList([AttentionLayer(d_model, nhead, dim_feedforward, dropout=dropout) for _ in range(num_layers)])
+        self.classifier = nn.Sequential(
+            nn.LayerNorm(d_model), nn.Linear(d_model, d_model // 2), nn.GELU(), nn.Dropout(mlp_dropout), nn.Linear(d_model // 2, num_classes)
+        )
+        self.projection_layer = nn.Linear(2 * self.d_model, self.d_model)
+        self._cache = None
+
+    def positional_encoding(self, seq_len, device=None):
+        """Sinusoidal PE, AMO_CLIP.py:88-97 (host-side table build; added in place by forward)."""
+        device = device if device is not None else self.classifier[0].weight.device
+        position = torch.arange(seq_len, device=device).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, self.d_model, 2, device=device) * (-math.log(10000.0) / self.d_model))
+        pe = torch.zeros(seq_len, self.d_model, device=device)
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        return pe
+
+    # ---- packed weights (bf16 GEMM operands, fp32 vectors), rebuilt when parameters change ----
+    def _packed(self):
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._cache is not None and self._cache[0] == sig:
+            return self._cache[1]
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()  # noqa: E731
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        layers = []
+        for ly in self.layers:
+            layers.append(dict(
+                w_sin=bf(ly.self_attn.in_proj_weight), b_sin=f32(ly.self_attn.in_proj_bias),
+                w_sout=bf(ly.self_attn.out_proj.weight), b_sout=f32(ly.self_attn.out_proj.bias),
+                w_cin=bf(ly.cross_attn.in_proj_weight), b_cin=f32(ly.cross_attn.in_proj_bias),
+                w_cout=bf(ly.cross_attn.out_proj.weight), b_cout=f32(ly.cross_attn.out_proj.bias),
+                w1=bf(ly.ffn[0].weight), b1=f32(ly.ffn[0].bias), w2=bf(ly.ffn[3].weight), b2=f32(ly.ffn[3].bias),
+                ns=(f32(ly.norm_self.weight), f32(ly.norm_self.bias), ly.norm_self.eps),
+                nc=(f32(ly.norm_cross.weight), f32(ly.norm_cross.bias), ly.norm_cross.eps),
+                nf=(f32(ly.norm_ffn.weight), f32(ly.norm_ffn.bias), ly.norm_ffn.eps),
+                act=ops.ACT_GELU_ERF if ly.activation == "gelu" else ops.ACT_RELU,
+            ))
+        c = self.classifier
+        head = dict(ln=(f32(c[0].weight), f32(c[0].bias), c[0].eps), w1=bf(c[1].weight), b1=f32(c[1].bias),
+                    w2=bf(c[4].weight), b2=f32(c[4].bias),
+                    wp=bf(self.projection_layer.weight), bp=f32(self.projection_layer.bias))
+        self._cache = (sig, (layers, head))
+        return self._cache[1]
+
+    @staticmethod
+    def _ln(y, norm):
+        g, b, eps = norm
+        return ops.layernorm(y, g, b, eps=eps, want32=True, want16=True)
+
+    def _layer(self, x32, x16, B, T, w, key_valid, cross16=None, Tm=0, cross_valid=None):
+        d, h = self.d_model, self.nhead
+        # self-attention block (AMO_CLIP.py:39-40)
+        qkv = ops.gemm(x16, w["w_sin"], bias=w["b_sin"], out_dtype=torch.float32)
+        a16 = ops.attention_masked(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], key_valid, B, T, T, h)
+        y = ops.gemm(a16, w["w_sout"], bias=w["b_sout"], resid=x32, out_dtype=torch.float32)
+        x32, x16 = self._ln(y, w["ns"])
+        # cross-attention block (AMO_CLIP.py:43-45)
+        if cross16 is not None:
+            q = ops.gemm(x16, w["w_cin"][:d], bias=w["b_cin"][:d], out_dtype=torch.float32)
+            kv = ops.gemm(cross16, w["w_cin"][d:], bias=w["b_cin"][d:], out_dtype=torch.float32)
+            a16 = ops.attention_masked(q, kv[:, :d], kv[:, d:], cross_valid, B, T, Tm, h)
+            y = ops.gemm(a16, w["w_cout"], bias=w["b_cout"], resid=x32, out_dtype=torch.float32)
+            x32, x16 = self._ln(y, w["nc"])
+        # feed-forward block (AMO_CLIP.py:48-49)
+        hdn = ops.gemm(x16, w["w1"], bias=w["b1"], act=w["act"])
+        y = ops.gemm(hdn, w["w2"], bias=w["b2"], resid=x32, out_dtype=torch.float32)
+        return self._ln(y, w["nf"])
+
+    @staticmethod
+    def _valid(mask, dev):
+        if mask is None:
+            return None
+        return mask.to(device=dev, dtype=torch.bool).contiguous()
+
+    @torch.no_grad()
+    def forward(self, rgb_emb, motion_emb, mask_rgb=None, mask_flow=None):
+        """rgb_emb [B,T_r,d], motion_emb [B,T_m,d], masks bool [B,T] (True = real frame) -> logits [B,C]."""
+        dev = self.classifier[0].weight.device
+        if dev.type != "cuda":
+            raise _lib.VmcError("AMO_CLIP runs on CUDA only (no CPU fallback); call .to('cuda') first")
+        if self.training:
+            raise _lib.VmcError("this drop-in implements the inference forward; call .eval() (training is SURVEY.md 8f rank 2)")
+        layers, head = self._packed()
+        d = self.d_model
+        if self.use_pe:  # AMO_CLIP.py:129-134: added IN PLACE to the caller's tensors
+            rgb_emb += self.positional_encoding(rgb_emb.size(1), rgb_emb.device).unsqueeze(0)
+            motion_emb += self.positional_encoding(motion_emb.size(1), motion_emb.device).unsqueeze(0)
+        rgb = rgb_emb.to(dev).float()
+        mot = motion_emb.to(dev).float()
+        v_rgb, v_mot = self._valid(mask_rgb, dev), self._valid(mask_flow, dev)
+        B = rgb.shape[0]
+        cross16, Tm, cross_valid = None, 0, None
+        if self.use_only_rgb:
+            x, valid = rgb, v_rgb
+        elif self.use_only_flow:
+            x, valid = mot, v_mot
+        elif self.use_cross_attention:
+            x, valid = rgb, v_rgb
+            Tm = mot.shape[1]
+            cross16 = ops.cast_bf16(mot.reshape(B * Tm, d).contiguous())
+            cross_valid = v_mot
+        else:
+            rgb = rgb[:, :-1, :]  # AMO_CLIP.py:153-154 (masks are indexed: None is an error there too)
+            v_rgb = v_rgb[:, :-1]
+            if self.concat_dim == 1:
+                valid = torch.cat([v_rgb, v_mot], dim=1).contiguous()
+                x = torch.cat([rgb, mot], dim=1)
+            elif self.concat_dim == -1:
+                valid = v_mot
+                cat16 = ops.cast_bf16(torch.cat([rgb, mot], dim=-1).reshape(B * mot.shape[1], 2 * d).contiguous())
+                x = ops.gemm(cat16, head["wp"], bias=head["bp"], out_dtype=torch.float32).view(B, mot.shape[1], d)
+            else:
+                raise ValueError("concat_dim must be 1 or -1")
+        T = x.shape[1]
+        x32 = x.reshape(B * T, d).contiguous()
+        x16 = ops.cast_bf16(x32)
+        for w in layers:
+            x32, x16 = self._layer(x32, x16, B, T, w, valid, cross16, Tm, cross_valid)
+        pooled, _ = ops.mean_rows(x32.view(B, T, d))
+        _, p16 = ops.layernorm(pooled, head["ln"][0], head["ln"][1], eps=head["ln"][2], want32=False, want16=True)
+        hid = ops.gemm(p16, head["w1"], bias=head["b1"], act=ops.ACT_GELU_ERF)
+        return ops.gemm(hid, head["w2"], bias=head["b2"], out_dtype=torch.float32)
