@@ -1,0 +1,322 @@
+"""Benchmark of the ViMoCLIP per-frame encoding hot path (BASELINE.json metric: frames/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--clips C]
+
+Workload (BASELINE config 4, "Full ViMoCLIP inference"): per GPU and per step, C clips (default 256) of
+16 RGB frames + 15 motion frames, 224x224 uint8, through CLIP ViT-B/16 (RGB) + MoCLIP ViT-B/32 student
+(motion) + TFAM cross-attention fusion -> logits [C,140]; synthetic data, seeded random weights.
+One JSON line is printed by rank 0.  `value` = RGB frames/s with inputs resident in HBM; `e2e` = the same
+metric through the public `ViMoCLIPPipeline.forward` with pinned HOST inputs (H2D of every frame and D2H of
+logits + embeddings inside the timed region).  For N > 1 (torchrun, one rank per GPU) clips are sharded,
+every rank runs the same per-GPU batch (weak scaling), and the timed step ends with the NCCL all-gather
+of logits and embeddings.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_RGB, T_MOT, RES, NUM_CLASSES = 16, 15, 224, 140
+# SURVEY.md section 8d / BASELINE.md section 3: algorithmic FLOPs (2*MAC)
+FLOPS_B16, FLOPS_B32 = 35.127e9, 8.818e9
+FLOPS_TFAM_CLIP = 0.5371e9  # T_rgb 16, T_mot 15
+FLOPS_HEADS_CLIP = 0.0171e9
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        # median over the samples taken under load (upper half)
+        sm_sorted = sorted(sm)
+        under_load = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": statistics.median(under_load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's algorithm (oracle restatement, fp32 PyTorch) on host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, clips: int):
+    import torch
+
+    from oracle import clip_shim, prologue, student as ostudent, tfam as otfam, weights
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rgb_tower = clip_shim.build_visual("ViT-B/16", seed=0)
+    student = ostudent.StudentOracle("ViT-B/32", seed=0)
+    weights.randomise_heads_(student, 0)
+    tfam = otfam.TfamOracle().eval()
+    weights.randomise_tfam_(tfam, 0)
+    gen = torch.Generator().manual_seed(1234)
+    rgb = torch.randint(0, 256, (clips, T_RGB, 3, RES, RES), dtype=torch.uint8, generator=gen)
+    mot = torch.randint(0, 256, (clips, T_MOT, 3, RES, RES), dtype=torch.uint8, generator=gen)
+
+    def step():
+        with torch.no_grad():
+            x = torch.from_numpy(prologue.normalise_u8(rgb.reshape(-1, 3, RES, RES).numpy()))
+            er = rgb_tower(x).view(clips, T_RGB, -1)
+            em, _, _ = student(mot)
+            return tfam(er, em)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    fps = clips * T_RGB / (ms / 1e3)
+    return fps, ms, cores, torch.get_num_threads()
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    clips = args.ref_clips
+    fps, ms, cores, threads = cpu_reference_run(args.steps, max(args.warmup, 1), clips)
+    line = {
+        "impl": "reference", "metric": "frames/sec (CLIP ViT+MoCLIP+TFAM)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.clips),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{clips} clip(s) x ({T_RGB} RGB + {T_MOT} motion) frames per step of the same workload; oracle restatement of the reference "
+                                   f"(fp32 PyTorch CPU, {threads} threads of {cores} cores); vectorised numpy preprocessing instead of the reference's per-frame PIL loop"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(clips):
+    return {"workload": f"config4: full ViMoCLIP inference (CLIP ViT-B/16 on RGB + MoCLIP ViT-B/32 student on motion + TFAM), {clips} clips x "
+                        f"({T_RGB} RGB + {T_MOT} motion) frames x {RES}x{RES} uint8 per GPU per step, {NUM_CLASSES} classes",
+            "clips_per_gpu": clips, "frames_per_clip": T_RGB, "motion_frames_per_clip": T_MOT, "parallelism": "clip-sharded, weights replicated",
+            "l2": "inputs (1.19 GB/step) and activations (>8 GB) are larger than the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def ours_main(args):
+    import torch
+    import torch.distributed as dist
+
+    import vimoclip_b200 as vmc
+    from vimoclip_b200 import _lib, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clips = args.clips
+    torch.manual_seed(0)
+    pipe = vmc.ViMoCLIPPipeline("openai/clip-vit-base-patch16", "ViT-B/32", num_classes=NUM_CLASSES, device=dev, clips_per_step=args.chunk)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    rgb_dev = torch.randint(0, 256, (clips, T_RGB, 3, RES, RES), dtype=torch.uint8, device=dev, generator=gen)
+    mot_dev = torch.randint(0, 256, (clips, T_MOT, 3, RES, RES), dtype=torch.uint8, device=dev, generator=gen)
+    total_clips = clips * world
+
+    def step_resident():
+        lg, er, em = pipe(rgb_dev, mot_dev)
+        if world > 1:
+            lg = vmc.sharding.gather_clips(lg, total_clips)
+            er = vmc.sharding.gather_clips(er, total_clips)
+            em = vmc.sharding.gather_clips(em, total_clips)
+        return lg, er, em
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    # ---- device-resident throughput (`value`) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms_step = timed(step_resident, args.steps, args.warmup)
+    launches = ops.launch_count() // (args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    fps = total_clips * T_RGB / (ms_step / 1e3)
+
+    # ---- end to end through the public API with pinned host inputs (`e2e`) ----
+    rgb_host = torch.empty(rgb_dev.shape, dtype=torch.uint8).pin_memory()
+    mot_host = torch.empty(mot_dev.shape, dtype=torch.uint8).pin_memory()
+    rgb_host.copy_(rgb_dev)
+    mot_host.copy_(mot_dev)
+    out_host = None
+
+    def step_e2e():
+        nonlocal out_host
+        lg, er, em = pipe(rgb_host, mot_host)  # H2D of every frame inside the call
+        if world > 1:
+            lg = vmc.sharding.gather_clips(lg, total_clips)
+            er = vmc.sharding.gather_clips(er, total_clips)
+            em = vmc.sharding.gather_clips(em, total_clips)
+        out_host = (lg.cpu(), er[:clips].cpu() if world > 1 else er.cpu(), em[:clips].cpu() if world > 1 else em.cpu())
+
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e = timed(step_e2e, e2e_steps, 1)
+    fps_e2e = total_clips * T_RGB / (ms_e2e / 1e3)
+    h2d = rgb_host.numel() + mot_host.numel()
+    d2h = sum(t.numel() * t.element_size() for t in out_host)
+
+    # ---- per-kernel-class profile of one extra step (roofline of the dominant kernel) ----
+    L = _lib.lib()
+    L.vmc_profile_begin()
+    step_resident()
+    n = 6
+    ms_c, fl_c, by_c, la_c = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
+    _lib.check(L.vmc_profile_end(ms_c, fl_c, by_c, la_c, n), "vmc_profile_end")
+    names = ["prologue", "gemm_tcgen05", "attention_vit", "layernorm", "attention_tfam", "other"]
+    classes = {names[i]: {"ms": ms_c[i], "launches": la_c[i], "tflops": (fl_c[i] / (ms_c[i] * 1e9) if ms_c[i] > 0 else None),
+                          "gbs": (by_c[i] / (ms_c[i] * 1e6) if ms_c[i] > 0 else None)} for i in range(n)}
+    peaks = load_peaks()
+    gemm = classes["gemm_tcgen05"]
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": gemm["tflops"], "peak": peaks["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": (gemm["tflops"] / peaks["bf16_sustained"]) if gemm["tflops"] else None, "traffic": None,
+                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
+                "share_of_step": gemm["ms"] / sum(c["ms"] for c in classes.values()),
+                "hbm_kernels": {k: {"gbs": classes[k]["gbs"], "frac_of_hbm_peak": (classes[k]["gbs"] / peaks["hbm"]) if classes[k]["gbs"] else None}
+                                for k in ("prologue", "layernorm")}}
+    flops_step = clips * (T_RGB * FLOPS_B16 + T_MOT * FLOPS_B32 + FLOPS_TFAM_CLIP + FLOPS_HEADS_CLIP)
+    step_tflops = flops_step / (ms_step * 1e9)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cfps, cms, cores, threads = cpu_reference_run(1, 1, args.ref_clips)
+        cpu = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{args.ref_clips} clip(s) x ({T_RGB}+{T_MOT}) frames of the same workload, 1 warm-up + 1 timed pass ({cms / 1e3:.1f} s), oracle restatement "
+                         f"of the reference in fp32 PyTorch on {threads} threads"}
+
+    line = {
+        "metric": "frames/sec (CLIP ViT+MoCLIP+TFAM)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(clips),
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps},
+        "gpu_launches": launches * args.steps,
+        "gpu_launches_per_step": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "step_tflops": step_tflops,
+        "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
+        "kernel_classes": classes,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=256, help="clips per GPU per step")
+    ap.add_argument("--chunk", type=int, default=64, help="clips per tower call (frames in flight = chunk*16)")
+    ap.add_argument("--ref-clips", type=int, default=2, help="clips per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_main(args)
+    return ours_main(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

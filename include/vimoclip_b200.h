@@ -32,6 +32,12 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* kernels launched by this library since the last reset (bench.py "gpu_launches") */
 long long vmc_launch_count(void);
 void vmc_reset_launch_count(void);
+/* Per-kernel-class timing for the roofline lines of bench.py: while a profile is open every launch is
+ * bracketed by CUDA events on its own stream.  Classes: 0 prologue, 1 tcgen05 GEMM, 2 ViT attention,
+ * 3 LayerNorm, 4 small (TFAM) attention, 5 other.  vmc_profile_end synchronises the device and fills
+ * per-class milliseconds, algorithmic FLOPs, algorithmic bytes and launch counts (arrays of >= 6). */
+void vmc_profile_begin(void);
+int vmc_profile_end(double* ms, double* flops, double* bytes, long long* launches, int ncat);
 
 /* ---- P1: uint8 prologue -------------------------------------------------------
  * Replaces the per-frame PIL loop of models/student_model.py:74-81 (to_pil_image ->
@@ -86,10 +92,13 @@ int vmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, in
  * x fp32 rows at stride ldx (elements).  Outputs (either may be NULL): y32 fp32 (ld32), y16 bf16 (ld16).
  * If cls_every > 0, rows r with r % cls_every == 0 take their input from cls_row[d] instead of x
  * (CLS token = class_embedding + positional_embedding[0], OpenAI VisionTransformer.forward).
+ * y16_split = 1 writes the bf16 output as the 3*d-column "split" operand [hi | lo | hi] (hi = bf16(y),
+ * lo = bf16(y - hi)) that, multiplied against weights packed [Whi | Whi | Wlo], gives a near-fp32 GEMM
+ * on the bf16 tensor cores (used by the TFAM block to hold logit max-abs <= 1e-2).
  * Replaces ln_pre / ln_1 / ln_2 / ln_post and TFAM norm_self / norm_cross / norm_ffn / classifier.0.
  */
 int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
-                  float* y32, long long ld32, void* y16, long long ld16, int rows, int d,
+                  float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows, int d,
                   const float* cls_row, int cls_every, void* stream);
 
 /* ---- A1: ViT self-attention (no mask), head_dim 64 ------------------------------
@@ -104,15 +113,16 @@ int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void*
  * key_valid uint8/bool [B, Tk]: 1 = real frame, 0 = padding (the mask_rgb / mask_flow of
  * collate_fn_pad, TFAM/data/dataset.py:86-103, i.e. the inverse of the key_padding_mask built at
  * TFAM/models/AMO_CLIP.py:125-126) or NULL for no mask.
- * out bf16 [B*Tq, ldo].  Replaces self_attn / cross_attn of AttentionLayer (AMO_CLIP.py:39,44).
+ * out bf16 (out_f32 = 0) or fp32 (out_f32 = 1) [B*Tq, ldo].  Replaces self_attn / cross_attn of AttentionLayer (AMO_CLIP.py:39,44).
  */
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk, const float* v,
-                         long long ldv, const uint8_t* key_valid, void* out, long long ldo, int B, int Tq,
-                         int Tk, int heads, void* stream);
+                         long long ldv, const uint8_t* key_valid, void* out, int out_f32, long long ldo,
+                         int B, int Tq, int Tk, int heads, void* stream);
 
 /* ---- utilities -------------------------------------------------------------- */
-/* fp32 [rows, d] (ldx) -> bf16 [rows, d] (ldy) */
-int vmc_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int d, void* stream);
+/* fp32 [rows, d] (ldx) -> bf16 [rows, d] (ldy), or with split = 1 -> bf16 [rows, 3*d] = [hi | lo | hi] */
+int vmc_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int d, int split,
+                  void* stream);
 /* temporal mean: x fp32 [B, T, d] -> y32 fp32 [B, d] and/or y16 bf16 [B, d] (mean over ALL T rows,
  * models/student_model.py:93, AMO_CLIP.py:170) */
 int vmc_mean_rows(const float* x, float* y32, void* y16, int B, int T, int d, void* stream);

@@ -1,0 +1,67 @@
+"""Per-shape timing of the hot kernels with CUDA events (not part of bench.py; for tuning)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vimoclip_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+F_ = int(os.environ.get("KB_FRAMES", "1024"))
+which = os.environ.get("KB_WHICH", "gemm,attn,ln").split(",")
+iters = int(os.environ.get("KB_ITERS", "10"))
+
+
+def timeit(fn, iters=iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+gen = torch.Generator(device="cuda").manual_seed(0)
+if "gemm" in which:
+    for L, d in [(197, 768), (50, 768)]:
+        M = F_ * L
+        x = torch.randn(M, d, device=dev, generator=gen).to(torch.bfloat16)
+        h = torch.randn(M, 4 * d, device=dev, generator=gen).to(torch.bfloat16)
+        res = torch.randn(M, d, device=dev, generator=gen)
+        for name, a, N, K, kw in [
+            ("qkv", x, 3 * d, d, dict(out_dtype=torch.bfloat16)),
+            ("out+res", x, d, d, dict(resid=res, out=res)),
+            ("fc1+qgelu", x, 4 * d, d, dict(act=ops.ACT_QUICKGELU, out_dtype=torch.bfloat16)),
+            ("fc1 plain", x, 4 * d, d, dict(out_dtype=torch.bfloat16)),
+            ("fc2+res", h, d, 4 * d, dict(resid=res, out=res)),
+            ("fc2 plain bf16", h, d, 4 * d, dict(out_dtype=torch.bfloat16)),
+        ]:
+            w = (torch.randn(N, K, device=dev, generator=gen) * K**-0.5).to(torch.bfloat16)
+            b = torch.randn(N, device=dev, generator=gen)
+            out = kw.pop("out", None)
+            if out is None:
+                out = torch.empty(M, N, device=dev, dtype=kw.pop("out_dtype"))
+            ms = timeit(lambda: ops.gemm(a, w, bias=b, out=out, **kw))
+            print(f"gemm {name:16s} M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+if "attn" in which:
+    for L, heads in [(197, 12), (50, 12), (257, 16)]:
+        d = heads * 64
+        Fa = F_ if L != 257 else F_ // 2
+        qkv = torch.randn(Fa * L, 3 * d, device=dev, generator=gen).to(torch.bfloat16)
+        ms = timeit(lambda: ops.attention_vit(qkv, Fa, L, heads))
+        fl = 4.0 * Fa * heads * L * L * 64
+        print(f"attn L={L} heads={heads} F={Fa}: {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s  {ms * 1e3 / (Fa * heads):.2f} us/(frame,head)/148SM={ms*1e3*148/(Fa*heads):.1f} us per CTA", flush=True)
+if "ln" in which:
+    x = torch.randn(F_ * 197, 768, device=dev, generator=gen)
+    g_ = torch.ones(768, device=dev)
+    ms = timeit(lambda: ops.layernorm(x, g_, g_))
+    print(f"layernorm rows={F_ * 197} d=768: {ms:.3f} ms  {x.numel() * 6 / ms / 1e6:.0f} GB/s")
+    u8 = torch.randint(0, 256, (F_, 3, 224, 224), dtype=torch.uint8, device=dev, generator=gen)
+    for p in (16, 32):
+        ms = timeit(lambda: ops.prologue(u8, wrap=True, dst="patch", patch=p))
+        print(f"prologue p={p} F={F_}: {ms:.3f} ms  {u8.numel() * 3 / ms / 1e6:.0f} GB/s")

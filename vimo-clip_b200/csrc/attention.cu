@@ -222,8 +222,8 @@ constexpr int KB = 64;
 __global__ void __launch_bounds__(128)
 attention_masked_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k,
                         long long ldk, const float* __restrict__ v, long long ldv,
-                        const uint8_t* __restrict__ key_valid, __nv_bfloat16* __restrict__ out,
-                        long long ldo, int Tq, int Tk) {
+                        const uint8_t* __restrict__ key_valid, void* __restrict__ out_v,
+                        int out_f32, long long ldo, int Tq, int Tk) {
   __shared__ float sq[QB][HD];
   __shared__ float sk[KB][HD + 1];
   __shared__ float sv[KB][HD];
@@ -293,9 +293,16 @@ attention_masked_kernel(const float* __restrict__ q, long long ldq, const float*
     if (r < Tq) {
       // all keys masked: torch's softmax over an all -inf row yields NaN; keep that behaviour
       const float inv = 1.0f / l[i];
-      __nv_bfloat16* orow = out + ((size_t)b * Tq + r) * ldo + h * HD;
-      orow[lane] = __float2bfloat16_rn(o0[i] * inv);
-      orow[lane + 32] = __float2bfloat16_rn(o1[i] * inv);
+      const size_t off = ((size_t)b * Tq + r) * ldo + h * HD;
+      if (out_f32) {
+        float* orow = reinterpret_cast<float*>(out_v) + off;
+        orow[lane] = o0[i] * inv;
+        orow[lane + 32] = o1[i] * inv;
+      } else {
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(out_v) + off;
+        orow[lane] = __float2bfloat16_rn(o0[i] * inv);
+        orow[lane + 32] = __float2bfloat16_rn(o1[i] * inv);
+      }
     }
   }
 }
@@ -336,7 +343,11 @@ int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void*
   VMC_CHECK_ARG(smem <= 227 * 1024, VMC_ERR_SHAPE, "vmc_attention_vit: L=%d needs %u B of smem", L,
                 smem);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  attention_vit_kernel<<<(unsigned)((long long)F * heads), 128, smem, st>>>(tm, a);
+  {
+    const double fl = 4.0 * F * heads * (double)L * L * HD;
+    VmcProfScope prof(VMC_K_ATTN_VIT, st, fl, 8.0 * F * L * d);
+    attention_vit_kernel<<<(unsigned)((long long)F * heads), 128, smem, st>>>(tm, a);
+  }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
   return VMC_OK;
@@ -344,15 +355,20 @@ int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void*
 
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk,
                          const float* v, long long ldv, const uint8_t* key_valid, void* out,
-                         long long ldo, int B, int Tq, int Tk, int heads, void* stream) {
+                         int out_f32, long long ldo, int B, int Tq, int Tk, int heads,
+                         void* stream) {
   VMC_CHECK_ARG(q && k && v && out, VMC_ERR_ARG, "vmc_attention_masked: null pointer");
   VMC_CHECK_ARG(B > 0 && Tq > 0 && Tk > 0 && heads > 0 && B <= 65535 && heads <= 65535,
                 VMC_ERR_SHAPE, "vmc_attention_masked: bad shape B=%d Tq=%d Tk=%d heads=%d", B, Tq,
                 Tk, heads);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((Tq + QB - 1) / QB, heads, B);
-  attention_masked_kernel<<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, key_valid,
-                                                reinterpret_cast<__nv_bfloat16*>(out), ldo, Tq, Tk);
+  {
+    VmcProfScope prof(VMC_K_ATTN_SMALL, st, 4.0 * B * heads * (double)Tq * Tk * HD,
+                      4.0 * B * heads * HD * (Tq + 2.0 * Tk) + 2.0 * B * Tq * heads * HD);
+    attention_masked_kernel<<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, key_valid,
+                                                  out, out_f32, ldo, Tq, Tk);
+  }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
   return VMC_OK;

@@ -63,6 +63,18 @@ int vmc_num_sms();
 // Count of kernels this library has launched (bench.py's "gpu_launches").
 void vmc_count_launch(int n = 1);
 
+// Optional per-kernel-class timing (bench.py roofline): CUDA events recorded around each launch on
+// the launching stream while a profile is open (vmc_profile_begin / vmc_profile_end).
+enum { VMC_K_PROLOGUE = 0, VMC_K_GEMM = 1, VMC_K_ATTN_VIT = 2, VMC_K_LAYERNORM = 3, VMC_K_ATTN_SMALL = 4,
+       VMC_K_OTHER = 5, VMC_K_COUNT = 6 };
+struct VmcProfScope {
+  int cat;
+  cudaStream_t stream;
+  void* rec;
+  VmcProfScope(int cat, cudaStream_t stream, double flops, double bytes);
+  ~VmcProfScope();
+};
+
 // Host: encode a tiled TMA tensor map (bf16, up to 3 dims, 128B swizzle).
 // dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int vmc_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank,

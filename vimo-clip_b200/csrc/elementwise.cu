@@ -211,6 +211,23 @@ frame_diff_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ diff_u8
   }
 }
 
+// bf16 "split" operand for near-fp32 GEMMs on the bf16 tensor cores: x = hi + lo with hi = bf16(x),
+// lo = bf16(x - hi).  Rows are written as [hi | lo | hi] (3*d columns) and multiplied against weights
+// packed as [Whi | Whi | Wlo], i.e. x W^T ~= hi Whi^T + lo Whi^T + hi Wlo^T in ONE K = 3d GEMM.
+__device__ __forceinline__ void store_split4(__nv_bfloat16* row, int d, int j, float4 o) {
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(o.x, o.y), h23 = __floats2bfloat162_rn(o.z, o.w);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(o.x - __low2float(h01), o.y - __high2float(h01));
+  const __nv_bfloat162 l23 = __floats2bfloat162_rn(o.z - __low2float(h23), o.w - __high2float(h23));
+  uint2 hi, lo;
+  hi.x = *reinterpret_cast<const uint32_t*>(&h01);
+  hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+  lo.x = *reinterpret_cast<const uint32_t*>(&l01);
+  lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+  reinterpret_cast<uint2*>(row)[j] = hi;
+  reinterpret_cast<uint2*>(row + d)[j] = lo;
+  reinterpret_cast<uint2*>(row + 2 * d)[j] = hi;
+}
+
 // ---------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row cached in registers, fp32 two-pass statistics.
 // ---------------------------------------------------------------------------------------
@@ -218,7 +235,7 @@ template <int NV>  // float4 per lane; supports d <= NV * 128
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* y32, long long ld32,
-                 __nv_bfloat16* y16, long long ld16, int rows, int d,
+                 __nv_bfloat16* y16, long long ld16, int y16_split, int rows, int d,
                  const float* __restrict__ cls_row, int cls_every) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -262,10 +279,14 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
       if (y32 != nullptr) reinterpret_cast<float4*>(y32 + (size_t)row * ld32)[j] = o;
       if (y16 != nullptr) {
-        uint2 pk;
-        pk.x = pack_bf16x2(o.x, o.y);
-        pk.y = pack_bf16x2(o.z, o.w);
-        reinterpret_cast<uint2*>(y16 + (size_t)row * ld16)[j] = pk;
+        if (y16_split) {
+          store_split4(y16 + (size_t)row * ld16, d, j, o);
+        } else {
+          uint2 pk;
+          pk.x = pack_bf16x2(o.x, o.y);
+          pk.y = pack_bf16x2(o.z, o.w);
+          reinterpret_cast<uint2*>(y16 + (size_t)row * ld16)[j] = pk;
+        }
       }
     }
   }
@@ -273,7 +294,7 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
-                 long long ldy, int rows, int d) {
+                 long long ldy, int rows, int d, int split) {
   const int nv = d >> 2;
   const size_t total = (size_t)rows * nv;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -281,10 +302,14 @@ cast_bf16_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __re
     const int j = idx % nv;
     const size_t r = idx / nv;
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + j);
-    uint2 pk;
-    pk.x = pack_bf16x2(v.x, v.y);
-    pk.y = pack_bf16x2(v.z, v.w);
-    reinterpret_cast<uint2*>(y + r * ldy)[j] = pk;
+    if (split) {
+      store_split4(y + r * ldy, d, j, v);
+    } else {
+      uint2 pk;
+      pk.x = pack_bf16x2(v.x, v.y);
+      pk.y = pack_bf16x2(v.z, v.w);
+      reinterpret_cast<uint2*>(y + r * ldy)[j] = pk;
+    }
   }
 }
 
@@ -385,8 +410,14 @@ int vmc_prologue(const void* frames, int src_kind, void* dst, int dst_kind, int 
     VMC_CUDA(cudaMemsetAsync(dst, 0, n * ld_patch * 2, st));
   }
   const size_t total = (size_t)F * 3 * H * (W / 16);
-  prologue_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, src_kind, dst, dst_kind, F, H, W,
-                                                        patch, ld_patch);
+  {
+    const double px = (double)F * 3 * H * W;
+    const double in_b = (src_kind == VMC_SRC_F32_WRAP || src_kind == VMC_SRC_F32_NORM) ? 4.0 : 1.0;
+    const double out_b = dst_kind == VMC_DST_U8 ? 1.0 : (dst_kind == VMC_DST_F32_NCHW ? 4.0 : 2.0);
+    VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * (in_b + out_b));
+    prologue_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, src_kind, dst, dst_kind, F, H, W,
+                                                          patch, ld_patch);
+  }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
   return VMC_OK;
@@ -409,16 +440,22 @@ int vmc_frame_diff_prologue(const uint8_t* bgr, uint8_t* diff_u8, void* dst, int
     VMC_CUDA(cudaMemsetAsync(dst, 0, n * ld_patch * 2, st));
   }
   const size_t total = (size_t)clips * T * H * (W / 16);
-  frame_diff_kernel<<<grid_for(total, 256), 256, 0, st>>>(bgr, diff_u8, dst, dst_kind, clips, T, H,
-                                                          W, patch, ld_patch);
+  {
+    const double px = (double)clips * T * H * W;
+    const double out_b = !dst ? 0.0 : (dst_kind == VMC_DST_U8 ? 3.0 : (dst_kind == VMC_DST_F32_NCHW ? 12.0 : 6.0));
+    // each BGR frame is read twice (as "previous" and as "current") except at clip ends
+    VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * (6.0 + (diff_u8 ? 1.0 : 0.0) + out_b));
+    frame_diff_kernel<<<grid_for(total, 256), 256, 0, st>>>(bgr, diff_u8, dst, dst_kind, clips, T, H,
+                                                            W, patch, ld_patch);
+  }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
   return VMC_OK;
 }
 
 int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
-                  float* y32, long long ld32, void* y16, long long ld16, int rows, int d,
-                  const float* cls_row, int cls_every, void* stream) {
+                  float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows,
+                  int d, const float* cls_row, int cls_every, void* stream) {
   VMC_CHECK_ARG(x && gamma && beta && (y32 || y16), VMC_ERR_ARG, "vmc_layernorm: null pointer");
   VMC_CHECK_ARG(rows > 0 && d > 0 && (d % 4) == 0 && d <= 4096, VMC_ERR_SHAPE,
                 "vmc_layernorm: need d %% 4 == 0 and d <= 4096 (rows=%d d=%d)", rows, d);
@@ -431,7 +468,9 @@ int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float
   __nv_bfloat16* y16b = reinterpret_cast<__nv_bfloat16*>(y16);
 #define LN_LAUNCH(NV)                                                                            \
   layernorm_kernel<NV><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, y32, ld32, y16b, ld16,    \
-                                             rows, d, cls_row, cls_every)
+                                             y16_split, rows, d, cls_row, cls_every)
+  VmcProfScope prof(VMC_K_LAYERNORM, st, 0.0,
+                    (double)rows * d * (4.0 + (y32 ? 4.0 : 0.0) + (y16 ? 2.0 : 0.0)));
   if (d <= 512) LN_LAUNCH(4);
   else if (d <= 768) LN_LAUNCH(6);
   else if (d <= 1024) LN_LAUNCH(8);
@@ -444,14 +483,15 @@ int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float
 }
 
 int vmc_cast_bf16(const float* x, long long ldx, void* y, long long ldy, int rows, int d,
-                  void* stream) {
+                  int split, void* stream) {
   VMC_CHECK_ARG(x && y, VMC_ERR_ARG, "vmc_cast_bf16: null pointer");
   VMC_CHECK_ARG(rows > 0 && d > 0 && (d % 4) == 0 && (ldx % 4) == 0 && (ldy % 4) == 0,
                 VMC_ERR_SHAPE, "vmc_cast_bf16: d and strides must be multiples of 4");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t total = (size_t)rows * (d / 4);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
   cast_bf16_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(y),
-                                                         ldy, rows, d);
+                                                         ldy, rows, d, split);
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
   return VMC_OK;
@@ -463,6 +503,7 @@ int vmc_mean_rows(const float* x, float* y32, void* y16, int B, int T, int d, vo
                 "vmc_mean_rows: bad shape B=%d T=%d d=%d", B, T, d);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t total = (size_t)B * (d / 4);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
   mean_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
       x, y32, reinterpret_cast<__nv_bfloat16*>(y16), B, T, d);
   VMC_LAUNCH_CHECK();
@@ -476,6 +517,7 @@ int vmc_cosine_distill_loss(const float* s, const float* t, int rows, int d, flo
   VMC_CHECK_ARG(rows > 0 && d > 0, VMC_ERR_SHAPE, "vmc_cosine_distill_loss: empty input");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VMC_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
   cosine_loss_kernel<<<(rows + 7) / 8, 256, 0, st>>>(s, t, rows, d, out);
   VMC_LAUNCH_CHECK();
   vmc_count_launch();

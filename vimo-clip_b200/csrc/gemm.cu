@@ -28,7 +28,6 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
 
 struct GemmArgs {
   int M, N, K;
@@ -306,16 +305,17 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
   g.tiles_m = (M + BM - 1) / BM;
   g.tiles_n = (N + BN - 1) / BN;
   g.epi = *epi;
-  static bool attr_set[2] = {false, false};
-  const int which = (BN == 256) ? 1 : 0;
-  if (!attr_set[which]) {
-    VMC_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set[which] = true;
-  }
+  // per device/context attribute; cheap enough to set on every launch (DataParallel: several devices)
+  VMC_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int tiles = g.tiles_m * g.tiles_n;
   const int grid = tiles < vmc_num_sms() ? tiles : vmc_num_sms();
-  gemm_bf16_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  {
+    const double out_b = (double)M * N * (epi->out_bf16 ? 2 : 4);
+    VmcProfScope prof(VMC_K_GEMM, stream, 2.0 * M * N * K,
+                      2.0 * ((double)M * K + (double)N * K) + out_b + (epi->resid ? 4.0 * M * N : 0.0));
+    gemm_bf16_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
   return VMC_OK;

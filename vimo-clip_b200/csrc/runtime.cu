@@ -37,6 +37,38 @@ int vmc_num_sms() {
   return cached[dev];
 }
 
+// ---- per-kernel-class event profile -------------------------------------------------------
+#include <vector>
+namespace {
+struct ProfRec {
+  int cat;
+  cudaEvent_t e0, e1;
+  double flops, bytes;
+};
+std::mutex g_prof_mu;
+std::atomic<bool> g_prof_on{false};
+std::vector<ProfRec*> g_prof;
+}  // namespace
+
+VmcProfScope::VmcProfScope(int c, cudaStream_t s, double flops, double bytes) : cat(c), stream(s), rec(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec* r = new ProfRec;
+  r->cat = c;
+  r->flops = flops;
+  r->bytes = bytes;
+  cudaEventCreate(&r->e0);
+  cudaEventCreate(&r->e1);
+  cudaEventRecord(r->e0, s);
+  rec = r;
+}
+VmcProfScope::~VmcProfScope() {
+  if (!rec) return;
+  ProfRec* r = static_cast<ProfRec*>(rec);
+  cudaEventRecord(r->e1, stream);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back(r);
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -93,6 +125,45 @@ int vmc_abi_version(void) { return VMC_ABI_VERSION; }
 long long vmc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void vmc_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+void vmc_profile_begin(void) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (ProfRec* r : g_prof) {
+    cudaEventDestroy(r->e0);
+    cudaEventDestroy(r->e1);
+    delete r;
+  }
+  g_prof.clear();
+  g_prof_on.store(true);
+}
+
+int vmc_profile_end(double* ms, double* flops, double* bytes, long long* launches, int ncat) {
+  g_prof_on.store(false);
+  VMC_CHECK_ARG(ms && flops && bytes && launches && ncat >= VMC_K_COUNT, VMC_ERR_ARG,
+                "vmc_profile_end: need %d-entry arrays", (int)VMC_K_COUNT);
+  VMC_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < ncat; ++i) {
+    ms[i] = 0;
+    flops[i] = 0;
+    bytes[i] = 0;
+    launches[i] = 0;
+  }
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (ProfRec* r : g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r->e0, r->e1) == cudaSuccess) {
+      ms[r->cat] += t;
+      flops[r->cat] += r->flops;
+      bytes[r->cat] += r->bytes;
+      launches[r->cat] += 1;
+    }
+    cudaEventDestroy(r->e0);
+    cudaEventDestroy(r->e1);
+    delete r;
+  }
+  g_prof.clear();
+  return VMC_OK;
+}
 
 int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

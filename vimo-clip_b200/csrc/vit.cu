@@ -89,13 +89,13 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
                           stream));
   }
   // ln_pre in place on the residual stream; CLS rows are sourced from class_embedding + pos[0].
-  VMC_TRY(vmc_layernorm(w.x, d, m->ln_pre_g, m->ln_pre_b, 1e-5f, w.x, d, nullptr, 0, rows, d,
+  VMC_TRY(vmc_layernorm(w.x, d, m->ln_pre_g, m->ln_pre_b, 1e-5f, w.x, d, nullptr, 0, 0, rows, d,
                         m->cls_pos0, L, stream));
 
   for (int i = 0; i < m->layers; ++i) {
     const vmc_vit_layer& ly = m->layer[i];
     // x = x + out_proj(attn(ln_1(x)))
-    VMC_TRY(vmc_layernorm(w.x, d, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr, 0, w.xn, d, rows, d, nullptr,
+    VMC_TRY(vmc_layernorm(w.x, d, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr, 0, w.xn, d, 0, rows, d, nullptr,
                           0, stream));
     {
       vmc_gemm_epilogue e = {};
@@ -119,7 +119,7 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
       VMC_TRY(vmc_gemm_bf16(w.xn, d, ly.w_out, d, rows, d, d, &e, stream));
     }
     // x = x + c_proj(QuickGELU(c_fc(ln_2(x))))
-    VMC_TRY(vmc_layernorm(w.x, d, ly.ln2_g, ly.ln2_b, 1e-5f, nullptr, 0, w.xn, d, rows, d, nullptr,
+    VMC_TRY(vmc_layernorm(w.x, d, ly.ln2_g, ly.ln2_b, 1e-5f, nullptr, 0, w.xn, d, 0, rows, d, nullptr,
                           0, stream));
     {
       vmc_gemm_epilogue e = {};
@@ -145,7 +145,7 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
   }
   // ln_post on the CLS rows (row stride L*d), then @ proj (no bias), fp32 out.
   VMC_TRY(vmc_layernorm(w.x, (long long)L * d, m->ln_post_g, m->ln_post_b, 1e-5f, nullptr, 0, w.cls,
-                        d, F, d, nullptr, 0, stream));
+                        d, 0, F, d, nullptr, 0, stream));
   {
     vmc_gemm_epilogue e = {};
     e.out = out;

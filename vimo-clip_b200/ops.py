@@ -161,18 +161,18 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, al
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5, want32: bool = False,
-              want16: bool = True, out32: torch.Tensor | None = None):
-    """x fp32 [rows, d] -> (y32 | None, y16 | None)."""
+              want16: bool = True, out32: torch.Tensor | None = None, split16: bool = False):
+    """x fp32 [rows, d] -> (y32 | None, y16 | None).  split16: y16 is the [rows, 3d] split operand [hi|lo|hi]."""
     _need_cuda(x, gamma, beta, out32)
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("layernorm input must be fp32 [rows, d] row-major")
     rows, d = x.shape
     y32 = out32 if out32 is not None else (torch.empty((rows, d), dtype=torch.float32, device=x.device) if want32 else None)
-    y16 = torch.empty((rows, d), dtype=torch.bfloat16, device=x.device) if want16 else None
+    y16 = torch.empty((rows, 3 * d if split16 else d), dtype=torch.bfloat16, device=x.device) if want16 else None
     with torch.cuda.device(x.device):
         _lib.check(
             _lib.lib().vmc_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), eps, _p(y32), 0 if y32 is None else y32.stride(0),
-                                     _p(y16), 0 if y16 is None else y16.stride(0), rows, d, None, 0, _stream()),
+                                     _p(y16), 0 if y16 is None else y16.stride(0), 1 if split16 else 0, rows, d, None, 0, _stream()),
             "vmc_layernorm",
         )
     return y32, y16
@@ -190,8 +190,9 @@ def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int) -> torch.Tenso
     return out
 
 
-def attention_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_valid, B: int, Tq: int, Tk: int, heads: int) -> torch.Tensor:
-    """q [B*Tq, *], k/v [B*Tk, *] fp32 views (row-major, heads*64 columns) -> bf16 [B*Tq, heads*64]."""
+def attention_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_valid, B: int, Tq: int, Tk: int, heads: int,
+                     out_dtype=torch.bfloat16) -> torch.Tensor:
+    """q [B*Tq, *], k/v [B*Tk, *] fp32 views (row-major, heads*64 columns) -> bf16 or fp32 [B*Tq, heads*64]."""
     _need_cuda(q, k, v, key_valid)
     for t in (q, k, v):
         if t.dtype != torch.float32 or t.stride(1) != 1:
@@ -199,24 +200,38 @@ def attention_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_vali
     if key_valid is not None:
         if key_valid.dtype not in (torch.bool, torch.uint8) or tuple(key_valid.shape) != (B, Tk) or not key_valid.is_contiguous():
             raise TypeError("key_valid must be a contiguous bool/uint8 [B, Tk] tensor (True = real frame)")
-    out = torch.empty((B * Tq, heads * 64), dtype=torch.bfloat16, device=q.device)
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("attention_masked output must be bf16 or fp32")
+    out = torch.empty((B * Tq, heads * 64), dtype=out_dtype, device=q.device)
     with torch.cuda.device(q.device):
         _lib.check(
             _lib.lib().vmc_attention_masked(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(key_valid), _p(out),
-                                            out.stride(0), B, Tq, Tk, heads, _stream()),
+                                            1 if out_dtype == torch.float32 else 0, out.stride(0), B, Tq, Tk, heads, _stream()),
             "vmc_attention_masked",
         )
     return out
 
 
-def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+def cast_bf16(x: torch.Tensor, split: bool = False) -> torch.Tensor:
+    """fp32 [rows, d] -> bf16 [rows, d], or the split operand [rows, 3d] = [hi | lo | hi] (see ``split_weight``)."""
     _need_cuda(x)
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("cast_bf16 input must be fp32 [rows, d] row-major")
-    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    rows, d = x.shape
+    y = torch.empty((rows, 3 * d if split else d), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().vmc_cast_bf16(_p(x), x.stride(0), _p(y), y.stride(0), x.shape[0], x.shape[1], _stream()), "vmc_cast_bf16")
+        _lib.check(_lib.lib().vmc_cast_bf16(_p(x), x.stride(0), _p(y), y.stride(0), rows, d, 1 if split else 0, _stream()), "vmc_cast_bf16")
     return y
+
+
+def split_weight(w: torch.Tensor) -> torch.Tensor:
+    """One-time packing of an fp32 nn.Linear weight [N, K] as bf16 [N, 3K] = [Whi | Whi | Wlo] so that
+    ``gemm(cast_bf16(x, split=True), split_weight(w))`` ~= x @ w.T to ~2^-16 relative (three bf16 MMAs in one
+    K = 3K GEMM, fp32 accumulation in TMEM).  Weight packing happens at load time, not on the hot path."""
+    w = w.detach().float()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
 
 
 def mean_rows(x: torch.Tensor, *, want32: bool = True, want16: bool = False):

@@ -16,7 +16,7 @@ from .tfam import AMO_CLIP
 
 class ViMoCLIPPipeline(nn.Module):
     def __init__(self, rgb_model: str = "openai/clip-vit-base-patch16", student_model: str = "ViT-B/32", num_classes: int = 140,
-                 frame_diff: bool = False, device="cuda", clips_per_step: int = 64):
+                 frame_diff: bool = False, device="cuda", clips_per_step: int = 256):
         super().__init__()
         self.rgb = CLIPVisionFeatures(rgb_model).to(device)
         cls = FrameDiffStudentModel if frame_diff else FlowStudentModel
@@ -26,22 +26,24 @@ class ViMoCLIPPipeline(nn.Module):
         self.device = device
 
     @torch.no_grad()
-    def forward(self, rgb_u8: torch.Tensor, motion_u8: torch.Tensor):
-        """rgb_u8 [N,T,3,224,224] uint8 RGB frames; motion_u8 [N,T_m,3,224,224] uint8 flow / frame-diff frames.
-        Returns (logits [N,C], rgb_emb [N,T,D], motion_emb [N,T_m,D]) on the device."""
+    def forward(self, rgb_u8: torch.Tensor, motion_u8: torch.Tensor, mask_rgb=None, mask_flow=None):
+        """rgb_u8 [N,T,3,224,224] uint8 RGB frames; motion_u8 [N,T_m,3,224,224] uint8 flow / frame-diff frames
+        (host or device).  Returns (logits [N,C], rgb_emb [N,T,D], motion_emb [N,T_m,D]) on the device.
+
+        Host inputs are copied clip-chunk by clip-chunk (``clips_per_step``) so the H2D copy of chunk i+1
+        is queued behind the kernels of chunk i on the same stream; the towers batch every frame of a chunk."""
         N, T = rgb_u8.shape[:2]
-        Tm = motion_u8.shape[1]
-        logits, e_rgb, e_mot = [], [], []
+        e_rgb, e_mot = [], []
         for c0 in range(0, N, self.clips_per_step):
             r = rgb_u8[c0:c0 + self.clips_per_step].to(self.device, non_blocking=True)
             m = motion_u8[c0:c0 + self.clips_per_step].to(self.device, non_blocking=True)
             n = r.shape[0]
-            er = self.rgb.get_image_features_u8(r.reshape(n * T, *r.shape[2:])).view(n, T, -1)
-            em, _, _ = self.student(m)
-            logits.append(self.tfam(er, em))
-            e_rgb.append(er)
-            e_mot.append(em)
-        return torch.cat(logits), torch.cat(e_rgb), torch.cat(e_mot)
+            e_rgb.append(self.rgb.get_image_features_u8(r.reshape(n * T, *r.shape[2:])).view(n, T, -1))
+            e_mot.append(self.student(m)[0])
+        er = e_rgb[0] if len(e_rgb) == 1 else torch.cat(e_rgb)
+        em = e_mot[0] if len(e_mot) == 1 else torch.cat(e_mot)
+        logits = self.tfam(er, em, mask_rgb, mask_flow)
+        return logits, er, em
 
     @torch.no_grad()
     def forward_sharded(self, rgb_u8_local, motion_u8_local, num_clips: int):
