@@ -107,6 +107,9 @@ int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float
  * Replaces nn.MultiheadAttention inside OpenAI ResidualAttentionBlock / HF CLIPAttention.
  */
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream);
+/* same, selecting the implementation: 2 = P kept in TMEM as the A operand of the PV MMA (default),
+ * 1 = P staged through shared memory (first version; kept as a cross-check in the tests) */
+int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, int impl, void* stream);
 
 /* ---- small masked attention (TFAM), fp32 in, bf16 out ---------------------------
  * q [B*Tq, ldq], k/v [B*Tk, ldk/ldv] fp32 (heads*64 columns used starting at the pointer),

@@ -202,12 +202,13 @@ def test_layernorm(cuda_device, d):
     assert torch.equal(y16, y32.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("L,heads,F_", [(50, 12, 5), (197, 12, 3), (257, 16, 2), (128, 2, 2), (16, 1, 1)])
-def test_attention_vit(cuda_device, L, heads, F_):
+@pytest.mark.parametrize("impl", [2, 1])
+@pytest.mark.parametrize("L,heads,F_", [(50, 12, 5), (197, 12, 3), (257, 16, 2), (128, 2, 2), (16, 1, 1), (129, 3, 2), (272, 1, 1)])
+def test_attention_vit(cuda_device, L, heads, F_, impl):
     gen = torch.Generator(device="cuda").manual_seed(L)
     d = heads * 64
     qkv = (torch.randn(F_ * L, 3 * d, device=cuda_device, generator=gen) * 1.5).to(torch.bfloat16)
-    got = ops.attention_vit(qkv, F_, L, heads).float().view(F_, L, heads, 64)
+    got = ops.attention_vit(qkv, F_, L, heads, impl=impl).float().view(F_, L, heads, 64)
     q, k, v = qkv.float().view(F_, L, 3, heads, 64).unbind(2)
     s = torch.einsum("flhd,fmhd->fhlm", q, k) / 8.0
     ref = torch.einsum("fhlm,fmhd->flhd", torch.softmax(s, -1), v)

@@ -53,9 +53,11 @@ if "attn" in which:
         d = heads * 64
         Fa = F_ if L != 257 else F_ // 2
         qkv = torch.randn(Fa * L, 3 * d, device=dev, generator=gen).to(torch.bfloat16)
-        ms = timeit(lambda: ops.attention_vit(qkv, Fa, L, heads))
-        fl = 4.0 * Fa * heads * L * L * 64
-        print(f"attn L={L} heads={heads} F={Fa}: {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s  {ms * 1e3 / (Fa * heads):.2f} us/(frame,head)/148SM={ms*1e3*148/(Fa*heads):.1f} us per CTA", flush=True)
+        for impl in (1, 2):
+            ms = timeit(lambda: ops.attention_vit(qkv, Fa, L, heads, impl=impl))
+            fl = 4.0 * Fa * heads * L * L * 64
+            print(f"attn impl={impl} L={L} heads={heads} F={Fa}: {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s  "
+                  f"{ms * 1e3 * 148 / (Fa * heads):.1f} us per (frame,head) per SM", flush=True)
 if "ln" in which:
     x = torch.randn(F_ * 197, 768, device=dev, generator=gen)
     g_ = torch.ones(768, device=dev)

@@ -27,11 +27,25 @@ struct AttnArgs {
   int F, L, heads, d;
   int n_mt;     // ceil(L / 128)
   int lk16;     // ceil(L / 16) * 16
-  int n_pkb;    // 16 KB blocks of P: ceil(ceil32(lk16) / 64)
+  int n_pkb;    // 16 KB blocks of P in smem (0 when P lives in TMEM)
+  int o_col;    // TMEM column of the O accumulator
   uint32_t tmem_cols;
   __nv_bfloat16* out;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// kPTmem = true : P (bf16) is written back into TMEM over the dead S columns and the PV MMA takes
+//                 its A operand from TMEM (tcgen05.mma ... [d], [a], b-desc): 96 KB of smem and 256
+//                 TMEM columns per CTA at L = 197, so two CTAs share an SM and overlap each other's
+//                 load / MMA / softmax phases.
+// kPTmem = false: P goes through shared memory in the K-major 128B-swizzled layout (first version,
+//                 kept as a cross-check of the TMEM-operand path).
+template <bool kPTmem>
 __global__ void __launch_bounds__(128)
 attention_vit_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,7 +152,7 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs a) {
         float p[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float e = exp2f(fmaf(__uint_as_float(r[j]), sc, -mxs));
+          const float e = ex2_approx(fmaf(__uint_as_float(r[j]), sc, -mxs));
           p[j] = (c0 + j < a.L) ? e : 0.f;
         }
         // round to bf16 first so the normaliser matches what the PV MMA actually sums
@@ -149,18 +163,35 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs a) {
           sum += __low2float(h2) + __high2float(h2);
           pk[j] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        // K-major SW128 layout: block kb = c/2 (64 columns), row tid, 16-byte chunk ((c&1)*4 + i)
-        uint8_t* prow = sP_generic + (c >> 1) * TILE + (tid >> 3) * 1024 + (tid & 7) * 128;
+        if constexpr (kPTmem) {
+          // P[row, 32c .. 32c+31] as 16 packed columns at TMEM cols [16c, 16c+16): these alias S
+          // columns this thread has already consumed (chunk c/2 <= c), lane-private.
+          uint32_t lo8[8], hi8[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = ((c & 1) * 4 + i) ^ (tid & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) =
-              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          for (int j = 0; j < 8; ++j) {
+            lo8[j] = pk[j];
+            hi8[j] = pk[8 + j];
+          }
+          tmem_st_32x32b_x8(tmem_base + lane_addr + uint32_t(c * 16), lo8);
+          tmem_st_32x32b_x8(tmem_base + lane_addr + uint32_t(c * 16 + 8), hi8);
+        } else {
+          // K-major SW128 layout: block kb = c/2 (64 columns), row tid, 16-byte chunk ((c&1)*4 + i)
+          uint8_t* prow = sP_generic + (c >> 1) * TILE + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int chunk = ((c & 1) * 4 + i) ^ (tid & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) =
+                make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
         }
       }
       row_sum = sum;
     }
-    fence_proxy_async_smem();
+    if constexpr (kPTmem) {
+      tmem_st_wait();
+    } else {
+      fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
 
@@ -170,9 +201,14 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs a) {
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);  // B (V) is MN-major
       const int nkk = a.lk16 / 16;
       for (int kk = 0; kk < nkk; ++kk) {
-        const uint64_t dp = umma_desc_sw128(sP + (kk >> 2) * TILE) + uint64_t(2 * (kk & 3));
         const uint64_t dv = umma_desc_sw128(sV + kk * 2048);
-        umma_ss(tmem_base, dp, dv, idesc_pv, kk != 0);
+        if constexpr (kPTmem) {
+          // A from TMEM: 16 bf16 of K = 8 packed 32-bit columns per step
+          umma_ts(tmem_base + uint32_t(a.o_col), tmem_base + uint32_t(kk * 8), dv, idesc_pv, kk != 0);
+        } else {
+          const uint64_t dp = umma_desc_sw128(sP + (kk >> 2) * TILE) + uint64_t(2 * (kk & 3));
+          umma_ss(tmem_base + uint32_t(a.o_col), dp, dv, idesc_pv, kk != 0);
+        }
       }
       umma_commit(bar_mma);
     }
@@ -187,7 +223,7 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs a) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_addr + uint32_t(half * 32), r);
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + uint32_t(a.o_col + half * 32), r);
         tmem_ld_wait();
         if (row < a.L) {
 #pragma unroll
@@ -317,11 +353,14 @@ uint32_t pow2_at_least(uint32_t v) {
 
 extern "C" {
 
-int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream) {
+int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, int impl,
+                           void* stream) {
   VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit: null pointer");
   VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 272, VMC_ERR_SHAPE,
                 "vmc_attention_vit: need 0 < L <= 272 tokens (L=%d)", L);
+  VMC_CHECK_ARG(impl == 1 || impl == 2, VMC_ERR_ARG, "vmc_attention_vit: impl must be 1 or 2");
   const int d = heads * HD;
+  const bool p_tmem = impl == 2;
   AttnArgs a;
   a.F = F;
   a.L = L;
@@ -329,8 +368,17 @@ int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void*
   a.d = d;
   a.n_mt = (L + 127) / 128;
   a.lk16 = ((L + 15) / 16) * 16;
-  a.n_pkb = (((a.lk16 + 31) / 32) * 32 + 63) / 64;
-  a.tmem_cols = pow2_at_least(a.lk16 > 64 ? a.lk16 : 64);
+  const int lk32 = ((a.lk16 + 31) / 32) * 32;
+  if (p_tmem) {
+    a.n_pkb = 0;
+    a.o_col = ((lk32 / 2 + 31) / 32) * 32;  // first 32-aligned column past the packed P
+    const int need = lk32 > a.o_col + HD ? lk32 : a.o_col + HD;
+    a.tmem_cols = pow2_at_least(need);
+  } else {
+    a.n_pkb = (lk32 + 63) / 64;
+    a.o_col = 0;
+    a.tmem_cols = pow2_at_least(lk32 > 64 ? lk32 : 64);
+  }
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   CUtensorMap tm;
   const uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)F};
@@ -338,19 +386,29 @@ int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void*
   const uint32_t box[3] = {HD, 128, 1};
   VMC_TRY(vmc_encode_tmap_bf16(&tm, qkv, 3, dims, strides, box));
   const uint32_t smem = (3 * a.n_mt + a.n_pkb) * TILE + 64 + 1024;
-  VMC_CUDA(cudaFuncSetAttribute(attention_vit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                227 * 1024));
   VMC_CHECK_ARG(smem <= 227 * 1024, VMC_ERR_SHAPE, "vmc_attention_vit: L=%d needs %u B of smem", L,
                 smem);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  {
-    const double fl = 4.0 * F * heads * (double)L * L * HD;
+  const double fl = 4.0 * F * heads * (double)L * L * HD;
+  const unsigned grid = (unsigned)((long long)F * heads);
+  if (p_tmem) {
+    VMC_CUDA(cudaFuncSetAttribute(attention_vit_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VmcProfScope prof(VMC_K_ATTN_VIT, st, fl, 8.0 * F * L * d);
-    attention_vit_kernel<<<(unsigned)((long long)F * heads), 128, smem, st>>>(tm, a);
+    attention_vit_kernel<true><<<grid, 128, smem, st>>>(tm, a);
+  } else {
+    VMC_CUDA(cudaFuncSetAttribute(attention_vit_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VmcProfScope prof(VMC_K_ATTN_VIT, st, fl, 8.0 * F * L * d);
+    attention_vit_kernel<false><<<grid, 128, smem, st>>>(tm, a);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
   return VMC_OK;
+}
+
+int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream) {
+  return vmc_attention_vit_impl(qkv, out, F, L, heads, 2, stream);
 }
 
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk,

@@ -6,10 +6,11 @@
 // operands are TMA-loaded as 128B-swizzled [rows x 64] boxes and consumed by
 // tcgen05.mma.kind::f16 (UMMA 128 x BN x 16) with the fp32 accumulator in TMEM.
 //
-// Warp roles (192 threads, one CTA per SM, grid = min(#SM, #tiles)):
+// Warp roles (320 threads, one CTA per SM, grid = min(#SM, #tiles)):
 //   warp 0      TMA producer  (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/act/residual -> global
+//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/act/residual -> global
+//               (two warps per TMEM lane quarter, each owning half of the tile's columns)
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -27,7 +28,7 @@ using namespace vmc;
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 
 struct GemmArgs {
   int M, N, K;
@@ -42,7 +43,8 @@ struct Cfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr uint32_t BAR_BYTES = 256;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr uint32_t BIAS_BYTES = BN * 4 * 4;  // 8 epilogue warps x BN/2 floats
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two)
 };
 
@@ -93,7 +95,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -167,9 +169,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (8) =====================
+    // Warps 2..9: TMEM lane quarter = warp & 3 (hardware rule), column half = (warp - 2) >> 2.
+    // Per tile each warp (a) stages its half of the bias vector in shared memory BEFORE the
+    // accumulator is ready, (b) software-prefetches the residual of chunk c+1 while chunk c is
+    // processed, so no global-load latency sits between tcgen05.ld and the stores.
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int HALF_N = BN / 2;
+    constexpr int CH = HALF_N / 32;  // 32-column chunks per warp
     const vmc_gemm_epilogue& e = g.epi;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + C::BAR_BYTES - raw_addr)) + ew * HALF_N;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -183,84 +194,109 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         orow = (long long)m + f + 1;
         rrow = m - f * e.row_group + 1;
       }
+      const int n_base = n_blk * BN + half * HALF_N;
+      // (a) bias -> smem (zero beyond N), one float4 (or one float for BN = 128... HALF_N/32 floats) per lane
+      __syncwarp();
+#pragma unroll
+      for (int j = lane * 4; j < HALF_N; j += 128) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias != nullptr) {
+          if (n_base + j + 4 <= g.N) {
+            b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n_base + j));
+          } else {
+            if (n_base + j + 0 < g.N) b4.x = __ldg(e.bias + n_base + j + 0);
+            if (n_base + j + 1 < g.N) b4.y = __ldg(e.bias + n_base + j + 1);
+            if (n_base + j + 2 < g.N) b4.z = __ldg(e.bias + n_base + j + 2);
+          }
+        }
+        *reinterpret_cast<float4*>(bias_s + j) = b4;
+      }
+      __syncwarp();
+      const float* rbase = (e.resid != nullptr && row_ok) ? e.resid + rrow * e.ldr + n_base : nullptr;
+      float4 res[2][8];
+      if (rbase != nullptr && n_base + 32 <= g.N) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res[0][j] = reinterpret_cast<const float4*>(rbase)[j];
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= g.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[32];
+      const uint32_t t_acc =
+          tmem_base + uint32_t(acc * BN + half * HALF_N) + (uint32_t(quarter * 32) << 16);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (n0 + 32 <= g.N) {
-          if (e.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(e.bias + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(bp + j);
-              v[4 * j + 0] += b.x;
-              v[4 * j + 1] += b.y;
-              v[4 * j + 2] += b.z;
-              v[4 * j + 3] += b.w;
-            }
-          }
-          if (e.act != VMC_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act);
-          }
-          if (e.alpha != 1.0f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
-          }
-          if (e.resid != nullptr) {
-            const float4* rp = reinterpret_cast<const float4*>(e.resid + rrow * e.ldr + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = rp[j];
-              v[4 * j + 0] += b.x;
-              v[4 * j + 1] += b.y;
-              v[4 * j + 2] += b.z;
-              v[4 * j + 3] += b.w;
-            }
-          }
-          if (e.out_bf16) {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) +
-                                                 orow * e.ldo + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              op[j] = o;
-            }
-          } else {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) +
-                                                   orow * e.ldo + n0);
+      for (int c = 0; c < CH; ++c) {
+        const int n0 = n_base + c * 32;
+        if (n0 < g.N) {  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
+          // (b) prefetch the next chunk's residual while this one is in flight
+          if (c + 1 < CH && rbase != nullptr && n0 + 64 <= g.N) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              op[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              res[(c + 1) & 1][j] = reinterpret_cast<const float4*>(rbase + (c + 1) * 32)[j];
           }
-        } else {
-          // ragged last column chunk: scalar path
+          tmem_ld_wait();
+          if (row_ok) {
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            if (n < g.N) {
-              float x = v[j];
-              if (e.bias != nullptr) x += __ldg(e.bias + n);
-              x = apply_act(x, e.act) * e.alpha;
-              if (e.resid != nullptr) x += e.resid[rrow * e.ldr + n];
-              if (e.out_bf16)
-                reinterpret_cast<__nv_bfloat16*>(e.out)[orow * e.ldo + n] = __float2bfloat16_rn(x);
-              else
-                reinterpret_cast<float*>(e.out)[orow * e.ldo + n] = x;
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * j);
+              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+            }
+            if (e.act != VMC_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act);
+            }
+            if (e.alpha != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+            }
+            if (n0 + 32 <= g.N) {
+              if (e.resid != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = res[c & 1][j];
+                  v[4 * j + 0] += b.x;
+                  v[4 * j + 1] += b.y;
+                  v[4 * j + 2] += b.z;
+                  v[4 * j + 3] += b.w;
+                }
+              }
+              if (e.out_bf16) {
+                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) +
+                                                     orow * e.ldo + n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 o;
+                  o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                  o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                  o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                  o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                  op[j] = o;
+                }
+              } else {
+                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) +
+                                                       orow * e.ldo + n0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  op[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+            } else {
+              // ragged last column chunk: scalar path (residual read directly)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int n = n0 + j;
+                if (n < g.N) {
+                  float x = v[j];
+                  if (e.resid != nullptr) x += e.resid[rrow * e.ldr + n];
+                  if (e.out_bf16)
+                    reinterpret_cast<__nv_bfloat16*>(e.out)[orow * e.ldo + n] = __float2bfloat16_rn(x);
+                  else
+                    reinterpret_cast<float*>(e.out)[orow * e.ldo + n] = x;
+                }
+              }
             }
           }
         }

@@ -178,7 +178,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
     return y32, y16
 
 
-def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int) -> torch.Tensor:
+def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int, impl: int = 2) -> torch.Tensor:
     """qkv bf16 [F*L, 3*heads*64] -> bf16 [F*L, heads*64]; softmax(q k^T / 8) v per (frame, head)."""
     _need_cuda(qkv)
     d = heads * 64
@@ -186,7 +186,7 @@ def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int) -> torch.Tenso
         raise ValueError("qkv must be contiguous bf16 [F*L, 3*d]")
     out = torch.empty((F_ * L, d), dtype=torch.bfloat16, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        _lib.check(_lib.lib().vmc_attention_vit(_p(qkv), _p(out), F_, L, heads, _stream()), "vmc_attention_vit")
+        _lib.check(_lib.lib().vmc_attention_vit_impl(_p(qkv), _p(out), F_, L, heads, impl, _stream()), "vmc_attention_vit")
     return out
 
 
