@@ -136,11 +136,21 @@ GEMM_CASES = [
     (512, 140, 256, ops.ACT_NONE, True, False, torch.float32),  # ragged N
     (512, 512, 512, ops.ACT_GELU_ERF, True, False, torch.bfloat16),
     (64, 256, 512, ops.ACT_RELU, True, False, torch.bfloat16),
+    (129, 768, 64, ops.ACT_NONE, True, True, torch.float32),  # second CTA of the pair owns a single row
+    (50000, 2304, 768, ops.ACT_NONE, True, False, torch.bfloat16),  # many pair tiles per cluster
+    (1000, 36, 128, ops.ACT_NONE, True, True, torch.float32),  # ragged 32-column chunk
 ]
 
 
+@pytest.fixture(params=[2, 1], ids=["pair", "single"])
+def gemm_impl(request):
+    ops.set_option(vmc._lib.OPT_GEMM_IMPL, request.param)
+    yield request.param
+    ops.set_option(vmc._lib.OPT_GEMM_IMPL, 0)
+
+
 @pytest.mark.parametrize("M,N,K,act,use_bias,use_resid,odt", GEMM_CASES)
-def test_gemm_against_fp32(cuda_device, M, N, K, act, use_bias, use_resid, odt):
+def test_gemm_against_fp32(cuda_device, gemm_impl, M, N, K, act, use_bias, use_resid, odt):
     gen = torch.Generator(device="cuda").manual_seed(M * 7 + N)
     a = (torch.randn(M, K, device=cuda_device, generator=gen)).to(torch.bfloat16)
     w = (torch.randn(N, K, device=cuda_device, generator=gen) * K**-0.5).to(torch.bfloat16)
@@ -154,7 +164,7 @@ def test_gemm_against_fp32(cuda_device, M, N, K, act, use_bias, use_resid, odt):
     assert err <= tol * max(1.0, ref.abs().max().item()), f"max abs err {err}"
 
 
-def test_gemm_patch_embed_rowgroup_and_padded_k(cuda_device):
+def test_gemm_patch_embed_rowgroup_and_padded_k(cuda_device, gemm_impl):
     """Patch-embed epilogue: token rows scattered past each frame's CLS row, pos-emb added; K = 588 (ViT-L/14)."""
     gen = torch.Generator(device="cuda").manual_seed(1)
     F_, n, d, K, ld = 3, 256, 1024, 588, 592
@@ -173,7 +183,7 @@ def test_gemm_patch_embed_rowgroup_and_padded_k(cuda_device):
     assert (xv[:, 1:] - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
 
 
-def test_gemm_linearity_full_size(cuda_device):
+def test_gemm_linearity_full_size(cuda_device, gemm_impl):
     """BASELINE-size GEMM (64 frames x 197 tokens, fc1): G(a1 + a2) == G(a1) + G(a2) on exactly representable inputs."""
     gen = torch.Generator(device="cuda").manual_seed(9)
     M, N, K = 64 * 197, 3072, 768

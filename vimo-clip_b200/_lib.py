@@ -17,6 +17,7 @@ SRC_U8, SRC_U8_WRAP, SRC_F32_WRAP, SRC_F32_NORM = 0, 1, 2, 3
 DST_U8, DST_F32_NCHW, DST_BF16_PATCH = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
 ABI_VERSION = 1
+OPT_GEMM_IMPL, OPT_ATTN_IMPL = 0, 1
 
 
 class GemmEpilogue(C.Structure):
@@ -51,6 +52,7 @@ class VitModel(C.Structure):
 _SIGNATURES = {
     "vmc_last_error": (C.c_char_p, []),
     "vmc_abi_version": (C.c_int, []),
+    "vmc_set_option": (C.c_int, [C.c_int, C.c_int]),
     "vmc_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "vmc_launch_count": (C.c_longlong, []),
     "vmc_reset_launch_count": (None, []),

@@ -351,6 +351,8 @@ uint32_t pow2_at_least(uint32_t v) {
 
 }  // namespace
 
+int vmc_get_option(int option);
+
 extern "C" {
 
 int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, int impl,
@@ -408,7 +410,8 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
 }
 
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream) {
-  return vmc_attention_vit_impl(qkv, out, F, L, heads, 2, stream);
+  return vmc_attention_vit_impl(qkv, out, F, L, heads, vmc_get_option(VMC_OPT_ATTN_IMPL) == 1 ? 1 : 2,
+                                stream);
 }
 
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk,

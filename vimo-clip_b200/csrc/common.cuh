@@ -106,6 +106,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// no memory ordering implied: for barriers that only hand TMEM / smem slots back (ordered by
+// tcgen05.fence / bar.sync already), avoids the MEMBAR a release arrive compiles to
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");

@@ -9,8 +9,8 @@
 // Warp roles (320 threads, one CTA per SM, grid = min(#SM, #tiles)):
 //   warp 0      TMA producer  (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> bias/act/residual -> global
-//               (two warps per TMEM lane quarter, each owning half of the tile's columns)
+//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns -> smem transpose -> bias/act/residual
+//               -> coalesced global stores (two warps per TMEM lane quarter, half the columns each)
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM double buffer full/empty
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -42,9 +42,9 @@ struct Cfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t STG_BYTES = 8 * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
   static constexpr uint32_t BAR_BYTES = 256;
-  static constexpr uint32_t BIAS_BYTES = BN * 4 * 4;  // 8 epilogue warps x BN/2 floats
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two)
 };
 
@@ -71,7 +71,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = base + STAGES * C::STAGE_BYTES + C::STG_BYTES;
   // barrier layout (8 B each): full[STAGES] | empty[STAGES] | tfull[2] | tempty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -171,131 +171,121 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   } else {
     // ===================== epilogue warps (8) =====================
     // Warps 2..9: TMEM lane quarter = warp & 3 (hardware rule), column half = (warp - 2) >> 2.
-    // Per tile each warp (a) stages its half of the bias vector in shared memory BEFORE the
-    // accumulator is ready, (b) software-prefetches the residual of chunk c+1 while chunk c is
-    // processed, so no global-load latency sits between tcgen05.ld and the stores.
+    // tcgen05.ld hands each thread one ROW of the accumulator (32 consecutive columns).  Writing
+    // that straight to global memory makes every warp store touch 32 different 128-byte lines
+    // (measured: the epilogue, not the MMA, bounded the K = 768 GEMMs).  So each warp transposes
+    // its 32 x 32 fp32 chunk through a private 4 KB, XOR-swizzled shared-memory tile and then
+    // reads/writes global memory with 8 lanes per 128-byte row segment (4 full lines per warp
+    // instruction): residual loads, bias and the stores are all coalesced.
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;
     constexpr int HALF_N = BN / 2;
     constexpr int CH = HALF_N / 32;  // 32-column chunks per warp
     const vmc_gemm_epilogue& e = g.epi;
-    float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + C::BAR_BYTES - raw_addr)) + ew * HALF_N;
+    uint8_t* stg = smem_raw + (base + STAGES * C::STAGE_BYTES - raw_addr) + ew * 4096;
+    const int lr = lane >> 3;  // row within a group of 4 rows
+    const int lc = lane & 7;   // 16-byte column chunk within the 128-byte row segment
+    const bool has_res = e.resid != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_blk = t % g.tiles_n;
       const int m_blk = t / g.tiles_n;
-      const int m = m_blk * BM + quarter * 32 + lane;
-      const bool row_ok = m < g.M;
-      long long orow = m, rrow = m;
-      if (e.row_group > 0) {
-        const int f = m / e.row_group;
-        orow = (long long)m + f + 1;
-        rrow = m - f * e.row_group + 1;
-      }
+      const int row0 = m_blk * BM + quarter * 32;
       const int n_base = n_blk * BN + half * HALF_N;
-      // (a) bias -> smem (zero beyond N), one float4 (or one float for BN = 128... HALF_N/32 floats) per lane
-      __syncwarp();
-#pragma unroll
-      for (int j = lane * 4; j < HALF_N; j += 128) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias != nullptr) {
-          if (n_base + j + 4 <= g.N) {
-            b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n_base + j));
-          } else {
-            if (n_base + j + 0 < g.N) b4.x = __ldg(e.bias + n_base + j + 0);
-            if (n_base + j + 1 < g.N) b4.y = __ldg(e.bias + n_base + j + 1);
-            if (n_base + j + 2 < g.N) b4.z = __ldg(e.bias + n_base + j + 2);
-          }
-        }
-        *reinterpret_cast<float4*>(bias_s + j) = b4;
-      }
-      __syncwarp();
-      const float* rbase = (e.resid != nullptr && row_ok) ? e.resid + rrow * e.ldr + n_base : nullptr;
-      float4 res[2][8];
-      if (rbase != nullptr && n_base + 32 <= g.N) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res[0][j] = reinterpret_cast<const float4*>(rbase)[j];
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_acc =
           tmem_base + uint32_t(acc * BN + half * HALF_N) + (uint32_t(quarter * 32) << 16);
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < CH; ++c) {
         const int n0 = n_base + c * 32;
-        if (n0 < g.N) {  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
-          // (b) prefetch the next chunk's residual while this one is in flight
-          if (c + 1 < CH && rbase != nullptr && n0 + 64 <= g.N) {
+        if (n0 >= g.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
+        // coalesced-layout operands of this chunk, issued before the TMEM load is waited for
+        const int col = n0 + lc * 4;
+        const bool col_full = col + 4 <= g.N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias != nullptr && col_full) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+        float4 res[8];
+        long long ooff[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              res[(c + 1) & 1][j] = reinterpret_cast<const float4*>(rbase + (c + 1) * 32)[j];
+        for (int i = 0; i < 8; ++i) {
+          const int m = row0 + i * 4 + lr;
+          long long orow = m, rrow = m;
+          if (e.row_group > 0) {
+            const int f = m / e.row_group;
+            orow = (long long)m + f + 1;
+            rrow = m - f * e.row_group + 1;
           }
-          tmem_ld_wait();
-          if (row_ok) {
-            float v[32];
+          ooff[i] = (m < g.M) ? orow * e.ldo + col : -1;
+          res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && m < g.M && col_full)
+            res[i] = *reinterpret_cast<const float4*>(e.resid + rrow * e.ldr + col);
+        }
+        tmem_ld_wait();
+        // transpose through the swizzled staging tile: row = lane, 16-byte chunk j at (j ^ (lane & 7))
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * j);
-              v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
-            }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        float4 w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + lr;
+          w[i] = *reinterpret_cast<const float4*>(stg + rl * 128 + ((lc ^ (rl & 7)) << 4));
+        }
+        __syncwarp();
+        if (col_full) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (ooff[i] < 0) continue;
+            float4 v = w[i];
+            v.x += b4.x;
+            v.y += b4.y;
+            v.z += b4.z;
+            v.w += b4.w;
             if (e.act != VMC_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act);
+              v.x = apply_act(v.x, e.act);
+              v.y = apply_act(v.y, e.act);
+              v.z = apply_act(v.z, e.act);
+              v.w = apply_act(v.w, e.act);
             }
-            if (e.alpha != 1.0f) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
-            }
-            if (n0 + 32 <= g.N) {
-              if (e.resid != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 b = res[c & 1][j];
-                  v[4 * j + 0] += b.x;
-                  v[4 * j + 1] += b.y;
-                  v[4 * j + 2] += b.z;
-                  v[4 * j + 3] += b.w;
-                }
-              }
-              if (e.out_bf16) {
-                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) +
-                                                     orow * e.ldo + n0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 o;
-                  o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                  o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                  o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                  o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                  op[j] = o;
-                }
-              } else {
-                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) +
-                                                       orow * e.ldo + n0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  op[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              }
+            v.x = fmaf(v.x, e.alpha, res[i].x);
+            v.y = fmaf(v.y, e.alpha, res[i].y);
+            v.z = fmaf(v.z, e.alpha, res[i].z);
+            v.w = fmaf(v.w, e.alpha, res[i].w);
+            if (e.out_bf16) {
+              uint2 o;
+              o.x = pack_bf16x2(v.x, v.y);
+              o.y = pack_bf16x2(v.z, v.w);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + ooff[i]) = o;
             } else {
-              // ragged last column chunk: scalar path (residual read directly)
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + ooff[i]) = v;
+            }
+          }
+        } else if (col < g.N) {
+          // ragged last columns (N not a multiple of 4 or of the chunk): scalar path
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int n = n0 + j;
-                if (n < g.N) {
-                  float x = v[j];
-                  if (e.resid != nullptr) x += e.resid[rrow * e.ldr + n];
-                  if (e.out_bf16)
-                    reinterpret_cast<__nv_bfloat16*>(e.out)[orow * e.ldo + n] = __float2bfloat16_rn(x);
-                  else
-                    reinterpret_cast<float*>(e.out)[orow * e.ldo + n] = x;
-                }
+          for (int i = 0; i < 8; ++i) {
+            if (ooff[i] < 0) continue;
+            const float wv[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+            const int m = row0 + i * 4 + lr;
+            long long rrow = m;
+            if (e.row_group > 0) rrow = m - (m / e.row_group) * e.row_group + 1;
+            for (int q = 0; q < 4; ++q) {
+              if (col + q < g.N) {
+                float x = wv[q];
+                if (e.bias != nullptr) x += __ldg(e.bias + col + q);
+                x = apply_act(x, e.act) * e.alpha;
+                if (has_res) x += e.resid[rrow * e.ldr + col + q];
+                if (e.out_bf16)
+                  reinterpret_cast<__nv_bfloat16*>(e.out)[ooff[i] + q] = __float2bfloat16_rn(x);
+                else
+                  reinterpret_cast<float*>(e.out)[ooff[i] + q] = x;
               }
             }
           }
@@ -303,7 +293,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive_relaxed(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -359,6 +349,10 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
 
 }  // namespace
 
+int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ldw, int M, int N,
+                       int K, const vmc_gemm_epilogue* epi, cudaStream_t stream);
+int vmc_get_option(int option);
+
 extern "C" int vmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
                              int N, int K, const vmc_gemm_epilogue* epi, void* stream) {
   VMC_CHECK_ARG(A && W && epi && epi->out, VMC_ERR_ARG, "vmc_gemm_bf16: null pointer");
@@ -381,7 +375,9 @@ extern "C" int vmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   VMC_CHECK_ARG(epi->act >= VMC_ACT_NONE && epi->act <= VMC_ACT_RELU, VMC_ERR_ARG,
                 "vmc_gemm_bf16: unknown activation %d", epi->act);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // 128x256 tiles when there are enough of them to fill the machine twice; 128x128 otherwise.
+  if (vmc_get_option(VMC_OPT_GEMM_IMPL) != 1)  // default: CTA-pair kernel (gemm2.cu)
+    return vmc_gemm2_dispatch(A, lda, W, ldw, M, N, K, epi, st);
+  // single-CTA kernel: 128x256 tiles when there are enough to fill the machine twice; 128x128 otherwise.
   const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
   if (N > 128 && tiles256 >= 2LL * vmc_num_sms())
     return launch_gemm<256>(A, lda, W, ldw, M, N, K, epi, st);

@@ -1,0 +1,527 @@
+// G-family, second generation: CTA-pair (cta_group::2) tcgen05 GEMM.
+//
+// Why a pair: with one CTA per 128 x 256 tile, every k-step moves A (4 KB) + B (8 KB) into shared
+// memory by TMA and out again into the tensor core, 192 B/cycle/SM at the full MMA rate against a
+// 128 B/cycle shared-memory pipe -- measured: the single-CTA kernel (gemm.cu) saturates at ~65 % of
+// the MMA rate with the tensor pipe waiting on operands.  Two CTAs on the two SMs of a TPC share one
+// 256 x 256 tile: each holds its own 128 rows of A and HALF of B (128 rows), the tensor cores read
+// the other half from the peer's shared memory, so per SM the traffic is 128 B/cycle.
+//
+//   cluster (2,1,1); CTA rank r owns rows [m0 + 128 r, +128) of the pair tile
+//   warp 0      TMA producer in BOTH CTAs (own A rows, own half of B); all transaction bytes are
+//               signalled on the LEADER's (rank 0) full barrier
+//   warp 1      TMEM allocator (both CTAs, cta_group::2); MMA issuer in the leader only:
+//               tcgen05.mma.cta_group::2 (UMMA 256 x BN x 16), commits multicast to both CTAs
+//   warps 2..9  epilogue in both CTAs on their own 128 TMEM lanes; accumulator-free signal goes to
+//               the leader's tempty barrier (remote mbarrier arrive)
+// Epilogue: tcgen05.ld gives a thread one accumulator ROW; the chunk is transposed through a private
+// XOR-swizzled 4 KB shared-memory tile so global loads (residual, bias) and stores are issued with 8
+// lanes per 128-byte row segment (4 full lines per warp instruction).
+#include "common.cuh"
+#include "vimoclip_b200.h"
+
+namespace {
+
+using namespace vmc;
+
+constexpr int BM = 128;  // rows per CTA (pair tile: 256)
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 320;
+
+struct Gemm2Args {
+  int M, N, K;
+  int tiles_m, tiles_n;  // pair tiles
+  vmc_gemm_epilogue epi;
+};
+
+template <int BN>
+struct Cfg2 {
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of B
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr uint32_t STG_BYTES = 8 * 4096;
+  static constexpr uint32_t BAR_BYTES = 256;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // relaxed: the barrier only orders TMEM reuse (tcgen05.wait::ld + tcgen05.fence before it); a
+  // release here makes ptxas emit MEMBAR.ALL.GPU, which waited for every epilogue store to drain
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* m,
+                                                uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_ss_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive(1) on the barrier at this offset in BOTH CTAs of the pair when all prior MMAs retire
+__device__ __forceinline__ void umma_commit_mc2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+__device__ __forceinline__ float act2(float v, int act) {
+  switch (act) {
+    case VMC_ACT_QUICKGELU:
+      return __fdividef(v, 1.0f + __expf(-1.702f * v));
+    case VMC_ACT_GELU_ERF:
+      return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    case VMC_ACT_RELU:
+      return fmaxf(v, 0.0f);
+    default:
+      return v;
+  }
+}
+
+// x * sigmoid(1.702 x) with sigmoid(z) = 0.5 + 0.5 tanh(z / 2): one MUFU per element instead of two
+__device__ __forceinline__ float quickgelu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+
+// Specialised epilogues for the shapes that carry the ViT (row_group == 0, bias present, alpha == 1,
+// N a multiple of 32): all row addressing is hoisted to one pointer + stride per tile.
+//   MODE 1: bf16 out = acc + bias            (qkv)
+//   MODE 2: bf16 out = QuickGELU(acc + bias) (mlp.c_fc)
+//   MODE 3: fp32 out = resid + acc + bias    (attn.out_proj, mlp.c_proj; out may alias resid)
+template <int MODE, int HALF_N>
+__device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M, int N, int row0,
+                                              int n_base, uint32_t t_acc, uint8_t* stg, int lane) {
+  const int lr = lane >> 3, lc = lane & 7;
+  const int m_first = row0 + lr;
+  int nvalid = (M - m_first + 3) >> 2;  // rows m_first + 4 i, i < nvalid, are inside the matrix
+  nvalid = nvalid < 0 ? 0 : (nvalid > 8 ? 8 : nvalid);
+  constexpr int ESZ = (MODE == 3) ? 4 : 2;
+  char* optr = reinterpret_cast<char*>(e.out) + ((long long)m_first * e.ldo + n_base + lc * 4) * ESZ;
+  const long long ostride = 4 * e.ldo * ESZ;
+  const char* rptr = nullptr;
+  long long rstride = 0;
+  if constexpr (MODE == 3) {
+    rptr = reinterpret_cast<const char*>(e.resid) + ((long long)m_first * e.ldr + n_base + lc * 4) * 4;
+    rstride = 4 * e.ldr * 4;
+  }
+  const float* bptr = e.bias + n_base + lc * 4;
+#pragma unroll 1
+  for (int c = 0; c < HALF_N / 32; ++c) {
+    if (n_base + c * 32 >= N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + c * 32));
+    float4 res[8];
+    if constexpr (MODE == 3) {
+      const char* rp = rptr + c * 128;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nvalid) res[i] = *reinterpret_cast<const float4*>(rp);
+        rp += rstride;
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+          make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    float4 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = i * 4 + lr;
+      w[i] = *reinterpret_cast<const float4*>(stg + rl * 128 + ((lc ^ (rl & 7)) << 4));
+    }
+    __syncwarp();
+    char* op = optr + c * 32 * ESZ;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = w[i];
+      v.x += b4.x;
+      v.y += b4.y;
+      v.z += b4.z;
+      v.w += b4.w;
+      if constexpr (MODE == 2) {
+        v.x = quickgelu_fast(v.x);
+        v.y = quickgelu_fast(v.y);
+        v.z = quickgelu_fast(v.z);
+        v.w = quickgelu_fast(v.w);
+      }
+      if constexpr (MODE == 3) {
+        v.x += res[i].x;
+        v.y += res[i].y;
+        v.z += res[i].z;
+        v.w += res[i].w;
+        if (i < nvalid) *reinterpret_cast<float4*>(op) = v;
+      } else {
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        if (i < nvalid) *reinterpret_cast<uint2*>(op) = o;
+      }
+      op += ostride;
+    }
+  }
+}
+
+template <int BN, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                          const __grid_constant__ CUtensorMap tmB, const Gemm2Args g) {
+  using C = Cfg2<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t stg_base = base + STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = stg_base + C::STG_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_kb = (g.K + BK - 1) / BK;
+  const int num_tiles = g.tiles_m * g.tiles_n;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);   // leader's producer arrive (+ both CTAs' transaction bytes)
+      mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);    // multicast tcgen05.commit
+      mbar_init(tempty_bar(a), 16);  // 8 epilogue warps x 2 CTAs (used in the leader only)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_ptr_addr, C::TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int n_blk = t % g.tiles_n;
+        const int m_blk = t / g.tiles_n;
+        const int m_row = m_blk * (2 * BM) + (int)rank * BM;
+        const int n_row = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint32_t full_leader = mapa_rank(full_bar(stage), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * C::STAGE_BYTES);
+          tma_load_2d_cg2(sa, &tmA, full_leader, kb * BK, m_row);
+          tma_load_2d_cg2(sb, &tmB, full_leader, kb * BK, n_row);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_ss_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          umma_commit_mc2(empty_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_mc2(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (8, both CTAs) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int HALF_N = BN / 2;
+    const vmc_gemm_epilogue& e = g.epi;
+    uint8_t* stg = smem_raw + (stg_base - raw_addr) + ew * 4096;
+    const int lr = lane >> 3;
+    const int lc = lane & 7;
+    const bool has_res = e.resid != nullptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int n_blk = t % g.tiles_n;
+      const int m_blk = t / g.tiles_n;
+      const int row0 = m_blk * (2 * BM) + (int)rank * BM + quarter * 32;
+      const int n_base = n_blk * BN + half * HALF_N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc =
+          tmem_base + uint32_t(acc * BN + half * HALF_N) + (uint32_t(quarter * 32) << 16);
+      if constexpr (MODE != 0) {
+        epilogue_fast<MODE, HALF_N>(e, g.M, g.N, row0, n_base, t_acc, stg, lane);
+      } else {
+        // ---- generic path: any activation / alpha / ragged N / patch-embed row remap ----
+#pragma unroll 1
+        for (int c = 0; c < HALF_N / 32; ++c) {
+          const int n0 = n_base + c * 32;
+          if (n0 >= g.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
+          const int col = n0 + lc * 4;
+          const bool col_full = col + 4 <= g.N;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.bias != nullptr && col_full) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+          float4 res[8];
+          long long ooff[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = row0 + i * 4 + lr;
+            long long orow = m, rrow = m;
+            if (e.row_group > 0) {
+              const int f = m / e.row_group;
+              orow = (long long)m + f + 1;
+              rrow = m - f * e.row_group + 1;
+            }
+            ooff[i] = (m < g.M) ? orow * e.ldo + col : -1;
+            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res && m < g.M && col_full)
+              res[i] = *reinterpret_cast<const float4*>(e.resid + rrow * e.ldr + col);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          float4 w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + lr;
+            w[i] = *reinterpret_cast<const float4*>(stg + rl * 128 + ((lc ^ (rl & 7)) << 4));
+          }
+          __syncwarp();
+          if (col_full) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (ooff[i] < 0) continue;
+              float4 v = w[i];
+              v.x += b4.x;
+              v.y += b4.y;
+              v.z += b4.z;
+              v.w += b4.w;
+              if (e.act != VMC_ACT_NONE) {
+                v.x = act2(v.x, e.act);
+                v.y = act2(v.y, e.act);
+                v.z = act2(v.z, e.act);
+                v.w = act2(v.w, e.act);
+              }
+              v.x = fmaf(v.x, e.alpha, res[i].x);
+              v.y = fmaf(v.y, e.alpha, res[i].y);
+              v.z = fmaf(v.z, e.alpha, res[i].z);
+              v.w = fmaf(v.w, e.alpha, res[i].w);
+              if (e.out_bf16) {
+                uint2 o;
+                o.x = pack_bf16x2(v.x, v.y);
+                o.y = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + ooff[i]) = o;
+              } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + ooff[i]) = v;
+              }
+            }
+          } else if (col < g.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (ooff[i] < 0) continue;
+              const float wv[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+              const int m = row0 + i * 4 + lr;
+              long long rrow = m;
+              if (e.row_group > 0) rrow = m - (m / e.row_group) * e.row_group + 1;
+              for (int q = 0; q < 4; ++q) {
+                if (col + q < g.N) {
+                  float x = wv[q];
+                  if (e.bias != nullptr) x += __ldg(e.bias + col + q);
+                  x = act2(x, e.act) * e.alpha;
+                  if (has_res) x += e.resid[rrow * e.ldr + col + q];
+                  if (e.out_bf16)
+                    reinterpret_cast<__nv_bfloat16*>(e.out)[ooff[i] + q] = __float2bfloat16_rn(x);
+                  else
+                    reinterpret_cast<float*>(e.out)[ooff[i] + q] = x;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, int MODE>
+int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                 const vmc_gemm_epilogue* epi, cudaStream_t stream) {
+  using C = Cfg2<BN>;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)lda * 2};
+    const uint32_t box[2] = {BK, BM};
+    VMC_TRY(vmc_encode_tmap_bf16(&tmA, A, 2, dims, strides, box));
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t strides[1] = {(uint64_t)ldw * 2};
+    const uint32_t box[2] = {BK, BN / 2};
+    VMC_TRY(vmc_encode_tmap_bf16(&tmB, W, 2, dims, strides, box));
+  }
+  Gemm2Args g;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.tiles_m = (M + 2 * BM - 1) / (2 * BM);
+  g.tiles_n = (N + BN - 1) / BN;
+  g.epi = *epi;
+  VMC_CUDA(cudaFuncSetAttribute(gemm2_bf16_tcgen05_kernel<BN, MODE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int tiles = g.tiles_m * g.tiles_n;
+  const int max_pairs = vmc_num_sms() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  {
+    const double out_b = (double)M * N * (epi->out_bf16 ? 2 : 4);
+    VmcProfScope prof(VMC_K_GEMM, stream, 2.0 * M * N * K,
+                      2.0 * ((double)M * K + (double)N * K) + out_b + (epi->resid ? 4.0 * M * N : 0.0));
+    gemm2_bf16_tcgen05_kernel<BN, MODE><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, g);
+  }
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+}  // namespace
+
+// Called by vmc_gemm_bf16 (gemm.cu) after argument validation.
+int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ldw, int M, int N,
+                       int K, const vmc_gemm_epilogue* epi, cudaStream_t stream) {
+  const long long tiles256 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+  const bool big = N > 128 && tiles256 >= (long long)vmc_num_sms();
+  // specialised epilogues (see epilogue_fast): the four GEMMs of every ViT block
+  const bool fast_ok = epi->row_group == 0 && epi->bias != nullptr && epi->alpha == 1.0f && (N % 32) == 0;
+  int mode = 0;
+  if (fast_ok) {
+    if (epi->out_bf16 && !epi->resid && epi->act == VMC_ACT_NONE) mode = 1;
+    else if (epi->out_bf16 && !epi->resid && epi->act == VMC_ACT_QUICKGELU) mode = 2;
+    else if (!epi->out_bf16 && epi->resid && epi->act == VMC_ACT_NONE) mode = 3;
+  }
+#define VMC_G2(BN_, MODE_) return launch_gemm2<BN_, MODE_>(A, lda, W, ldw, M, N, K, epi, stream)
+  if (big) {
+    switch (mode) {
+      case 1: VMC_G2(256, 1);
+      case 2: VMC_G2(256, 2);
+      case 3: VMC_G2(256, 3);
+      default: VMC_G2(256, 0);
+    }
+  }
+  switch (mode) {
+    case 1: VMC_G2(128, 1);
+    case 2: VMC_G2(128, 2);
+    case 3: VMC_G2(128, 3);
+    default: VMC_G2(128, 0);
+  }
+#undef VMC_G2
+}

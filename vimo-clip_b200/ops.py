@@ -35,6 +35,11 @@ def reset_launch_count() -> None:
     _lib.lib().vmc_reset_launch_count()
 
 
+def set_option(option: int, value: int) -> None:
+    """Select an implementation variant (``_lib.OPT_GEMM_IMPL`` / ``_lib.OPT_ATTN_IMPL``); 0 = default."""
+    _lib.check(_lib.lib().vmc_set_option(option, value), "vmc_set_option")
+
+
 def device_info():
     sm, major, minor = C.c_int(), C.c_int(), C.c_int()
     _lib.check(_lib.lib().vmc_device_info(C.byref(sm), C.byref(major), C.byref(minor)), "vmc_device_info")
