@@ -23,20 +23,46 @@ class ViMoCLIPPipeline(nn.Module):
         self.student = cls(student_model, device=device, num_classes=num_classes)
         self.tfam = AMO_CLIP(num_classes=num_classes, device=device).to(device).eval()
         self.clips_per_step = clips_per_step
-        self.device = device
+        self.device = torch.device(device)
+        self._copy_stream = None
+
+    def _stage(self, rgb_u8, motion_u8, c0):
+        """Queue the host->device copy of one clip chunk on the copy stream; returns (rgb, motion, event)."""
+        r = rgb_u8[c0:c0 + self.clips_per_step]
+        m = motion_u8[c0:c0 + self.clips_per_step]
+        if r.is_cuda and m.is_cuda:
+            return r, m, None
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            r = r.to(self.device, non_blocking=True)
+            m = m.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        # the buffers are produced on the copy stream and consumed on the compute stream
+        r.record_stream(compute)
+        m.record_stream(compute)
+        return r, m, ev
 
     @torch.no_grad()
     def forward(self, rgb_u8: torch.Tensor, motion_u8: torch.Tensor, mask_rgb=None, mask_flow=None):
         """rgb_u8 [N,T,3,224,224] uint8 RGB frames; motion_u8 [N,T_m,3,224,224] uint8 flow / frame-diff frames
         (host or device).  Returns (logits [N,C], rgb_emb [N,T,D], motion_emb [N,T_m,D]) on the device.
 
-        Host inputs are copied clip-chunk by clip-chunk (``clips_per_step``) so the H2D copy of chunk i+1
-        is queued behind the kernels of chunk i on the same stream; the towers batch every frame of a chunk."""
+        Host inputs (ideally pinned) are copied clip-chunk by clip-chunk (``clips_per_step``) on a separate
+        copy stream, one chunk ahead of the compute stream, so the H2D transfer of chunk i+1 overlaps the
+        kernels of chunk i; the towers batch every frame of a chunk."""
         N, T = rgb_u8.shape[:2]
         e_rgb, e_mot = [], []
-        for c0 in range(0, N, self.clips_per_step):
-            r = rgb_u8[c0:c0 + self.clips_per_step].to(self.device, non_blocking=True)
-            m = motion_u8[c0:c0 + self.clips_per_step].to(self.device, non_blocking=True)
+        starts = list(range(0, N, self.clips_per_step))
+        staged = self._stage(rgb_u8, motion_u8, starts[0])
+        for k, c0 in enumerate(starts):
+            r, m, ev = staged
+            if k + 1 < len(starts):
+                staged = self._stage(rgb_u8, motion_u8, starts[k + 1])
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
             n = r.shape[0]
             e_rgb.append(self.rgb.get_image_features_u8(r.reshape(n * T, *r.shape[2:])).view(n, T, -1))
             e_mot.append(self.student(m)[0])
