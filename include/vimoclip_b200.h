@@ -32,7 +32,7 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel,
  * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/2 = P in TMEM, 1 = P through shared memory.
  * Both implementations of each op are kept so the tests can cross-check them. */
-enum { VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1 };
+enum { VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* 2 = band (smem-staged) kernel, else direct kernel */ };
 int vmc_set_option(int option, int value);
 /* kernels launched by this library since the last reset (bench.py "gpu_launches") */
 long long vmc_launch_count(void);

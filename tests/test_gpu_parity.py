@@ -51,8 +51,15 @@ def test_prologue_bit_exact_all_regimes(cuda_device, golden):
     assert np.array_equal(ops.prologue(u8, wrap=False, dst="f32").cpu().numpy().view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.fixture(params=[0, 2], ids=["direct", "band"])
+def prologue_impl(request):
+    ops.set_option(vmc._lib.OPT_PROLOGUE_IMPL, request.param)
+    yield request.param
+    ops.set_option(vmc._lib.OPT_PROLOGUE_IMPL, 0)
+
+
 @pytest.mark.parametrize("patch", [32, 16, 14])
-def test_prologue_patchify_bf16(cuda_device, patch):
+def test_prologue_patchify_bf16(cuda_device, prologue_impl, patch):
     gen = torch.Generator().manual_seed(5)
     u8 = torch.randint(0, 256, (3, 3, 224, 224), dtype=torch.uint8, generator=gen)
     got = ops.prologue(u8.to(cuda_device), wrap=True, dst="patch", patch=patch).cpu()
@@ -69,7 +76,7 @@ def test_prologue_patchify_bf16(cuda_device, patch):
     assert torch.equal(gotB[:, :k].view(torch.int16), refB.view(torch.int16))
 
 
-def test_frame_difference_bit_exact(cuda_device, golden):
+def test_frame_difference_bit_exact(cuda_device, golden, prologue_impl):
     g = golden("framediff.npz")
     frames = torch.from_numpy(g["frames"])[None].to(cuda_device)  # [1,5,48,64,3]
     diff, u8 = ops.frame_diff(frames, dst="u8")

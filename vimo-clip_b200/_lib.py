@@ -17,7 +17,7 @@ SRC_U8, SRC_U8_WRAP, SRC_F32_WRAP, SRC_F32_NORM = 0, 1, 2, 3
 DST_U8, DST_F32_NCHW, DST_BF16_PATCH = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
 ABI_VERSION = 1
-OPT_GEMM_IMPL, OPT_ATTN_IMPL = 0, 1
+OPT_GEMM_IMPL, OPT_ATTN_IMPL, OPT_PROLOGUE_IMPL = 0, 1, 2
 
 
 class GemmEpilogue(C.Structure):

@@ -13,11 +13,27 @@ using namespace vmc;
 __constant__ float c_mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
 __constant__ float c_std[3] = {0.26862954f, 0.26130258f, 0.27577711f};
 
-// (float32(u8) / 255 - mean) / std with IEEE round-to-nearest divisions and no FMA contraction:
-// bit-for-bit torchvision ToTensor + Normalize (models/student_model.py:78 via clip _transform).
+// RN(1/std_c) and RN(1/255) as fp32 bit patterns (numpy float32 division, correctly rounded)
+__constant__ float c_rstd[3] = {3.7226030826568604f /*0x406e3f0e*/, 3.8269808292388916f /*0x4074ed41*/,
+                                3.6261167526245117f /*0x4068124c*/};
+#define VMC_R255 0.0039215688593685627f /* 0x3b808081 */
+
+// Correctly rounded a / b from the correctly rounded reciprocal rb = RN(1/b):
+// q0 = a*rb; r = fma(-q0, b, a); q = fma(r, rb, q0).  Verified EXHAUSTIVELY (exact rational
+// arithmetic) to equal the IEEE division for every operand pair this file feeds it: u/255 for the
+// 256 byte values and (u/255 - mean_c)/std_c for the 768 (u, c) pairs.  Three FMA-pipe instructions
+// instead of the ~10-instruction IEEE division sequence, which made the first prologue compute-bound.
+__device__ __forceinline__ float div_by_const(float a, float b, float rb) {
+  const float q0 = __fmul_rn(a, rb);
+  const float r = __fmaf_rn(-q0, b, a);
+  return __fmaf_rn(r, rb, q0);
+}
+
+// (float32(u8) / 255 - mean) / std, bit-for-bit torchvision ToTensor + Normalize
+// (models/student_model.py:78 via clip _transform): fp32, true division semantics, no contraction.
 __device__ __forceinline__ float normalise_px(uint32_t u8, int c) {
-  const float t = __fdiv_rn(static_cast<float>(u8), 255.0f);
-  return __fdiv_rn(__fsub_rn(t, c_mean[c]), c_std[c]);
+  const float t = div_by_const(static_cast<float>(u8), 255.0f, VMC_R255);
+  return div_by_const(__fsub_rn(t, c_mean[c]), c_std[c], c_rstd[c]);
 }
 
 // to_pil_image(float CHW) = pic.mul(255).byte(): fp32 multiply, then float -> uint8 through
@@ -89,58 +105,184 @@ __device__ __forceinline__ void store_px16(void* dst, int dst_kind, int f, int c
   store_f16px(dst, dst_kind, f, c, y, x0, v, H, W, p, ld);
 }
 
+template <int UNROLL>
 __global__ void __launch_bounds__(256)
 prologue_kernel(const void* __restrict__ src, int src_kind, void* __restrict__ dst, int dst_kind,
                 int F, int H, int W, int p, int ld) {
   const int wv = W / 16;
   const size_t total = (size_t)F * 3 * H * wv;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int xv = idx % wv;
-    size_t r = idx / wv;
-    const int y = r % H;
-    r /= H;
-    const int c = r % 3;
-    const int f = r / 3;
-    const size_t off = (((size_t)f * 3 + c) * H + y) * W + (size_t)xv * 16;
-    uint32_t u[16];
-    if (src_kind == VMC_SRC_F32_NORM) {
-      // already-normalised pixel_values (HF get_image_features input): layout change + bf16 only
-      const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
-      float v[16];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const bool f32_src = src_kind == VMC_SRC_F32_WRAP || src_kind == VMC_SRC_F32_NORM;
+  for (size_t idx0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += UNROLL * stride) {
+    // issue all UNROLL 16-byte loads first: ~4x the bytes in flight per thread (HBM latency hiding)
+    uint4 q[UNROLL];
+    if (!f32_src) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 q = __ldg(s + i);
-        v[4 * i + 0] = q.x;
-        v[4 * i + 1] = q.y;
-        v[4 * i + 2] = q.z;
-        v[4 * i + 3] = q.w;
+      for (int k = 0; k < UNROLL; ++k) {
+        const size_t idx = idx0 + k * stride;
+        if (idx < total)
+          q[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + idx * 16));
       }
-      store_f16px(dst, dst_kind, f, c, y, xv * 16, v, H, W, p, ld);
-      continue;
     }
-    if (src_kind == VMC_SRC_F32_WRAP) {
-      const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 q = __ldg(s + i);
-        u[4 * i + 0] = wrap_f32(q.x);
-        u[4 * i + 1] = wrap_f32(q.y);
-        u[4 * i + 2] = wrap_f32(q.z);
-        u[4 * i + 3] = wrap_f32(q.w);
+    for (int k = 0; k < UNROLL; ++k) {
+      const size_t idx = idx0 + k * stride;
+      if (idx >= total) break;
+      // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div/mod cost more than the pixels
+      const uint32_t i32 = (uint32_t)idx;
+      const uint32_t row = i32 / (uint32_t)wv;
+      const int xv = (int)(i32 - row * (uint32_t)wv);
+      const uint32_t plane = row / (uint32_t)H;
+      const int y = (int)(row - plane * (uint32_t)H);
+      const int f = (int)(plane / 3u);
+      const int c = (int)(plane - 3u * (uint32_t)f);
+      const size_t off = idx * 16;  // == (((f*3 + c)*H + y)*W + xv*16): the source is contiguous
+      uint32_t u[16];
+      if (src_kind == VMC_SRC_F32_NORM) {
+        // already-normalised pixel_values (HF get_image_features input): layout change + bf16 only
+        const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = __ldg(s + i);
+          v[4 * i + 0] = t.x;
+          v[4 * i + 1] = t.y;
+          v[4 * i + 2] = t.z;
+          v[4 * i + 3] = t.w;
+        }
+        store_f16px(dst, dst_kind, f, c, y, xv * 16, v, H, W, p, ld);
+        continue;
       }
+      if (src_kind == VMC_SRC_F32_WRAP) {
+        const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = __ldg(s + i);
+          u[4 * i + 0] = wrap_f32(t.x);
+          u[4 * i + 1] = wrap_f32(t.y);
+          u[4 * i + 2] = wrap_f32(t.z);
+          u[4 * i + 3] = wrap_f32(t.w);
+        }
+      } else {
+        const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 255u;
+          // regime A: uint8 -> float 0..255 -> *255 -> int64 -> low 8 bits == (-x) mod 256
+          if (src_kind == VMC_SRC_U8_WRAP) b = (0u - b) & 255u;
+          u[i] = b;
+        }
+      }
+      store_px16(dst, dst_kind, f, c, y, xv * 16, u, H, W, p, ld);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Patch-matrix prologue, coalesced on both sides.  One block iteration = one "band": the p image
+// rows of one (frame, channel, patch-row), which are p*W CONTIGUOUS source bytes.  The band is
+// loaded with 16-byte coalesced loads, normalised, scattered into shared memory in patch-major
+// order (element (iy, x) -> patch x/p, offset iy*p + x%p), and written out as W/p contiguous
+// p*p-element runs (512 B at p = 16, 2 KB at p = 32) of the bf16 patch matrix.
+// The first version (prologue_kernel) stored 32 bytes per thread 1.5 KB apart: 30 % of HBM peak.
+// ---------------------------------------------------------------------------------------
+template <typename LoadPx>
+__device__ __forceinline__ void band_to_patches(LoadPx load16, __nv_bfloat16* __restrict__ tile,
+                                                __nv_bfloat16* __restrict__ dst, int f, int c, int py,
+                                                int H, int W, int p, int ld) {
+  const int gw = W / p;
+  const int n = (H / p) * gw;
+  const int pp = p * p;
+  const int chunks_in = p * (W / 16);  // 16-pixel chunks of the band
+  for (int q = threadIdx.x; q < chunks_in; q += blockDim.x) {
+    const int iy = q / (W / 16);
+    const int x0 = (q - iy * (W / 16)) * 16;
+    float v[16];
+    load16(iy, x0, v);
+    if ((p & 15) == 0) {
+      const int px = x0 / p, ix = x0 - px * p;
+      uint4 o0, o1;
+      o0.x = pack_bf16x2(v[0], v[1]);
+      o0.y = pack_bf16x2(v[2], v[3]);
+      o0.z = pack_bf16x2(v[4], v[5]);
+      o0.w = pack_bf16x2(v[6], v[7]);
+      o1.x = pack_bf16x2(v[8], v[9]);
+      o1.y = pack_bf16x2(v[10], v[11]);
+      o1.z = pack_bf16x2(v[12], v[13]);
+      o1.w = pack_bf16x2(v[14], v[15]);
+      uint4* t = reinterpret_cast<uint4*>(tile + px * pp + iy * p + ix);
+      t[0] = o0;
+      t[1] = o1;
     } else {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + off));
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        uint32_t b = (w[i >> 2] >> (8 * (i & 3))) & 255u;
-        // regime A: uint8 -> float 0..255 -> *255 -> int64 -> low 8 bits == (-x) mod 256
-        if (src_kind == VMC_SRC_U8_WRAP) b = (0u - b) & 255u;
-        u[i] = b;
+        const int x = x0 + i;
+        const int px = x / p, ix = x - px * p;
+        tile[px * pp + iy * p + ix] = __float2bfloat16_rn(v[i]);
       }
     }
-    store_px16(dst, dst_kind, f, c, y, xv * 16, u, H, W, p, ld);
+  }
+  __syncthreads();
+  __nv_bfloat16* drow = dst + ((size_t)f * n + (size_t)py * gw) * ld + (size_t)c * pp;
+  if ((pp & 7) == 0) {
+    const int per_patch = pp / 8;  // 16-byte chunks per patch-channel run
+    for (int q = threadIdx.x; q < gw * per_patch; q += blockDim.x) {
+      const int px = q / per_patch, w = q - px * per_patch;
+      reinterpret_cast<uint4*>(drow + (size_t)px * ld)[w] = reinterpret_cast<const uint4*>(tile + px * pp)[w];
+    }
+  } else {
+    const int per_patch = pp / 4;  // 8-byte chunks (p = 14: 196 elements per run)
+    for (int q = threadIdx.x; q < gw * per_patch; q += blockDim.x) {
+      const int px = q / per_patch, w = q - px * per_patch;
+      reinterpret_cast<uint2*>(drow + (size_t)px * ld)[w] = reinterpret_cast<const uint2*>(tile + px * pp)[w];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+prologue_patch_kernel(const void* __restrict__ src, int src_kind, __nv_bfloat16* __restrict__ dst,
+                      int F, int H, int W, int p, int ld) {
+  extern __shared__ __align__(16) uint8_t smem_tile[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem_tile);
+  const int gh = H / p;
+  const int bands = F * 3 * gh;
+  for (int b = blockIdx.x; b < bands; b += gridDim.x) {
+    const int py = b % gh;
+    const int c = (b / gh) % 3;
+    const int f = b / (3 * gh);
+    const size_t off = (((size_t)f * 3 + c) * H + (size_t)py * p) * W;
+    if (src_kind == VMC_SRC_U8 || src_kind == VMC_SRC_U8_WRAP) {
+      const uint8_t* s = reinterpret_cast<const uint8_t*>(src) + off;
+      const bool wrap = src_kind == VMC_SRC_U8_WRAP;
+      band_to_patches(
+          [&](int iy, int x0, float (&v)[16]) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(s + (size_t)iy * W + x0));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              uint32_t u = (w[i >> 2] >> (8 * (i & 3))) & 255u;
+              if (wrap) u = (0u - u) & 255u;
+              v[i] = normalise_px(u, c);
+            }
+          },
+          tile, dst, f, c, py, H, W, p, ld);
+    } else {
+      const float* s = reinterpret_cast<const float*>(src) + off;
+      const bool norm = src_kind == VMC_SRC_F32_NORM;
+      band_to_patches(
+          [&](int iy, int x0, float (&v)[16]) {
+            const float4* q4 = reinterpret_cast<const float4*>(s + (size_t)iy * W + x0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 q = __ldg(q4 + i);
+              const float in[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[4 * i + k] = norm ? in[k] : normalise_px(wrap_f32(in[k]), c);
+            }
+          },
+          tile, dst, f, c, py, H, W, p, ld);
+    }
   }
 }
 
@@ -159,12 +301,13 @@ frame_diff_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ diff_u8
   const size_t frame_bytes = (size_t)H * W * 3;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    const int xv = idx % wv;
-    size_t r = idx / wv;
-    const int y = r % H;
-    r /= H;
-    const int t = r % T;
-    const int clip = r / T;
+    const uint32_t i32 = (uint32_t)idx;
+    const uint32_t row = i32 / (uint32_t)wv;
+    const int xv = (int)(i32 - row * (uint32_t)wv);
+    const uint32_t fr = row / (uint32_t)H;
+    const int y = (int)(row - fr * (uint32_t)H);
+    const int clip = (int)(fr / (uint32_t)T);
+    const int t = (int)(fr - (uint32_t)clip * (uint32_t)T);
     const size_t f0 = (size_t)clip * (T + 1) + t;  // previous frame; current = f0 + 1
     const size_t off = f0 * frame_bytes + ((size_t)y * W + (size_t)xv * 16) * 3;
     const uint4* s0 = reinterpret_cast<const uint4*>(bgr + off);
@@ -207,6 +350,76 @@ frame_diff_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ diff_u8
       for (int i = 0; i < 16; ++i) u[i] = (0u - d[i]) & 255u;
 #pragma unroll
       for (int c = 0; c < 3; ++c) store_px16(dst, dst_kind, (int)fo, c, y, xv * 16, u, H, W, p, ld);
+    }
+  }
+}
+
+// Frame difference -> student patch matrix, band-wise (see band_to_patches).  The grey difference of
+// the band is computed once into shared memory (uint8), then emitted for the 3 identical channels.
+__global__ void __launch_bounds__(256)
+frame_diff_patch_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ diff_u8,
+                        __nv_bfloat16* __restrict__ dst, int clips, int T, int H, int W, int p, int ld) {
+  extern __shared__ __align__(16) uint8_t smem_tile[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem_tile);
+  uint8_t* dband = smem_tile + (size_t)p * W * 2;  // p*W wrapped-diff bytes
+  const int gh = H / p;
+  const int bands = clips * T * gh;
+  const size_t frame_bytes = (size_t)H * W * 3;
+  for (int b = blockIdx.x; b < bands; b += gridDim.x) {
+    const int py = b % gh;
+    const int t = (b / gh) % T;
+    const int clip = b / (gh * T);
+    const size_t f0 = (size_t)clip * (T + 1) + t;
+    const size_t fo = (size_t)clip * T + t;
+    const uint8_t* s0 = bgr + f0 * frame_bytes + (size_t)py * p * W * 3;
+    const uint8_t* s1 = s0 + frame_bytes;
+    for (int q = threadIdx.x; q < p * (W / 16); q += blockDim.x) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(s0 + (size_t)q * 48);
+      const uint4* b4 = reinterpret_cast<const uint4*>(s1 + (size_t)q * 48);
+      uint32_t w0[12], w1[12];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const uint4 a = __ldg(a4 + i);
+        const uint4 bb = __ldg(b4 + i);
+        w0[4 * i] = a.x; w0[4 * i + 1] = a.y; w0[4 * i + 2] = a.z; w0[4 * i + 3] = a.w;
+        w1[4 * i] = bb.x; w1[4 * i + 1] = bb.y; w1[4 * i + 2] = bb.z; w1[4 * i + 3] = bb.w;
+      }
+      uint32_t d[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t c0[3], c1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int byte = 3 * i + k;
+          c0[k] = (w0[byte >> 2] >> (8 * (byte & 3))) & 255u;
+          c1[k] = (w1[byte >> 2] >> (8 * (byte & 3))) & 255u;
+        }
+        const int g0 = (int)bgr_gray(c0[0], c0[1], c0[2]);
+        const int g1 = (int)bgr_gray(c1[0], c1[1], c1[2]);
+        d[i] = (uint32_t)(g1 > g0 ? g1 - g0 : g0 - g1);
+      }
+      uint32_t wd[4], ww[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        wd[i] = d[4 * i] | (d[4 * i + 1] << 8) | (d[4 * i + 2] << 16) | (d[4 * i + 3] << 24);
+        ww[i] = ((0u - d[4 * i]) & 255u) | (((0u - d[4 * i + 1]) & 255u) << 8) |
+                (((0u - d[4 * i + 2]) & 255u) << 16) | (((0u - d[4 * i + 3]) & 255u) << 24);
+      }
+      if (diff_u8 != nullptr)
+        *reinterpret_cast<uint4*>(diff_u8 + (fo * H + (size_t)py * p) * W + (size_t)q * 16) =
+            make_uint4(wd[0], wd[1], wd[2], wd[3]);
+      *reinterpret_cast<uint4*>(dband + (size_t)q * 16) = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+    }
+    __syncthreads();
+    for (int c = 0; c < 3; ++c) {
+      band_to_patches(
+          [&](int iy, int x0, float (&v)[16]) {
+            const uint4 q = *reinterpret_cast<const uint4*>(dband + (size_t)iy * W + x0);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = normalise_px((w[i >> 2] >> (8 * (i & 3))) & 255u, c);
+          },
+          tile, dst, (int)fo, c, py, H, W, p, ld);
     }
   }
 }
@@ -364,6 +577,10 @@ cosine_loss_kernel(const float* __restrict__ s, const float* __restrict__ t, int
   }
 }
 
+}  // namespace
+int vmc_get_option(int option);
+namespace {
+
 int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = (size_t)vmc_num_sms() * 16;
@@ -410,13 +627,22 @@ int vmc_prologue(const void* frames, int src_kind, void* dst, int dst_kind, int 
     VMC_CUDA(cudaMemsetAsync(dst, 0, n * ld_patch * 2, st));
   }
   const size_t total = (size_t)F * 3 * H * (W / 16);
-  {
+  VMC_CHECK_ARG(total < (1ull << 31), VMC_ERR_SHAPE, "vmc_prologue: too many frames in one call (F=%d)", F);
+  if (dst_kind == VMC_DST_BF16_PATCH && vmc_get_option(VMC_OPT_PROLOGUE_IMPL) == 2) {
+    const double px = (double)F * 3 * H * W;
+    const double in_b = (src_kind == VMC_SRC_F32_WRAP || src_kind == VMC_SRC_F32_NORM) ? 4.0 : 1.0;
+    const int bands = F * 3 * (H / patch);
+    const int grid = bands < vmc_num_sms() * 8 ? bands : vmc_num_sms() * 8;
+    VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * (in_b + 2.0));
+    prologue_patch_kernel<<<grid, 256, (size_t)patch * W * 2, st>>>(
+        frames, src_kind, reinterpret_cast<__nv_bfloat16*>(dst), F, H, W, patch, ld_patch);
+  } else {
     const double px = (double)F * 3 * H * W;
     const double in_b = (src_kind == VMC_SRC_F32_WRAP || src_kind == VMC_SRC_F32_NORM) ? 4.0 : 1.0;
     const double out_b = dst_kind == VMC_DST_U8 ? 1.0 : (dst_kind == VMC_DST_F32_NCHW ? 4.0 : 2.0);
     VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * (in_b + out_b));
-    prologue_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, src_kind, dst, dst_kind, F, H, W,
-                                                          patch, ld_patch);
+    prologue_kernel<4><<<grid_for((total + 3) / 4, 256), 256, 0, st>>>(frames, src_kind, dst, dst_kind,
+                                                                       F, H, W, patch, ld_patch);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
@@ -440,7 +666,15 @@ int vmc_frame_diff_prologue(const uint8_t* bgr, uint8_t* diff_u8, void* dst, int
     VMC_CUDA(cudaMemsetAsync(dst, 0, n * ld_patch * 2, st));
   }
   const size_t total = (size_t)clips * T * H * (W / 16);
-  {
+  VMC_CHECK_ARG(total < (1ull << 31), VMC_ERR_SHAPE, "vmc_frame_diff_prologue: too many frames in one call");
+  if (dst && dst_kind == VMC_DST_BF16_PATCH && vmc_get_option(VMC_OPT_PROLOGUE_IMPL) == 2) {
+    const double px = (double)clips * T * H * W;
+    const int bands = clips * T * (H / patch);
+    const int grid = bands < vmc_num_sms() * 8 ? bands : vmc_num_sms() * 8;
+    VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * (6.0 + (diff_u8 ? 1.0 : 0.0) + 6.0));
+    frame_diff_patch_kernel<<<grid, 256, (size_t)patch * W * 3, st>>>(
+        bgr, diff_u8, reinterpret_cast<__nv_bfloat16*>(dst), clips, T, H, W, patch, ld_patch);
+  } else {
     const double px = (double)clips * T * H * W;
     const double out_b = !dst ? 0.0 : (dst_kind == VMC_DST_U8 ? 3.0 : (dst_kind == VMC_DST_F32_NCHW ? 12.0 : 6.0));
     // each BGR frame is read twice (as "previous" and as "current") except at clip ends
