@@ -30,10 +30,11 @@ const char* vmc_last_error(void);
 int vmc_abi_version(void);
 int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel,
- * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/2 = P in TMEM, 1 = P through shared memory.
+ * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
  * Both implementations of each op are kept so the tests can cross-check them. */
-enum { VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* 2 = band (smem-staged) kernel, else direct kernel */ };
-int vmc_set_option(int option, int value);
+enum { VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
+       VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* 2 = band (smem-staged) kernel, else direct kernel */ };
+int vmc_set_option(int option, long long value);
 /* kernels launched by this library since the last reset (bench.py "gpu_launches") */
 long long vmc_launch_count(void);
 void vmc_reset_launch_count(void);
@@ -112,7 +113,8 @@ int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float
  * Replaces nn.MultiheadAttention inside OpenAI ResidualAttentionBlock / HF CLIPAttention.
  */
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream);
-/* same, selecting the implementation: 2 = P kept in TMEM as the A operand of the PV MMA (default),
+/* same, selecting the implementation: 3 = persistent, pipelined kernel with 8 softmax warps (default for
+ * 128 < L <= 256; other L fall back to 2), 4 = the same pipeline with 16 softmax warps (measured slower), 2 = one CTA per (frame, head) with P kept in TMEM as the A operand of the PV MMA,
  * 1 = P staged through shared memory (first version; kept as a cross-check in the tests) */
 int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, int impl, void* stream);
 

@@ -51,11 +51,11 @@ if "gemm" in which:
             ms = timeit(lambda: ops.gemm(a, w, bias=b, out=out, **kw))
             print(f"gemm {name:16s} M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
 if "attn" in which:
-    for L, heads in [(197, 12), (50, 12), (257, 16)]:
+    for L, heads in [(197, 12), (50, 12), (257, 16)][: int(os.environ.get("KB_ATTN_SHAPES", "3"))]:
         d = heads * 64
         Fa = F_ if L != 257 else F_ // 2
         qkv = torch.randn(Fa * L, 3 * d, device=dev, generator=gen).to(torch.bfloat16)
-        for impl in (1, 2):
+        for impl in [int(x) for x in os.environ.get("KB_ATTN_IMPLS", "2,3,4").split(",")]:
             ms = timeit(lambda: ops.attention_vit(qkv, Fa, L, heads, impl=impl))
             fl = 4.0 * Fa * heads * L * L * 64
             print(f"attn impl={impl} L={L} heads={heads} F={Fa}: {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s  "

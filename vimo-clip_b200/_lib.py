@@ -52,7 +52,7 @@ class VitModel(C.Structure):
 _SIGNATURES = {
     "vmc_last_error": (C.c_char_p, []),
     "vmc_abi_version": (C.c_int, []),
-    "vmc_set_option": (C.c_int, [C.c_int, C.c_int]),
+    "vmc_set_option": (C.c_int, [C.c_int, C.c_longlong]),
     "vmc_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "vmc_launch_count": (C.c_longlong, []),
     "vmc_reset_launch_count": (None, []),

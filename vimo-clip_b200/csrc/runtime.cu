@@ -116,15 +116,18 @@ int vmc_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uin
   return VMC_OK;
 }
 
-static std::atomic<int> g_options[8];
+static std::atomic<long long> g_options[8];
 
 int vmc_get_option(int option) {
+  return (option >= 0 && option < 8) ? (int)g_options[option].load(std::memory_order_relaxed) : 0;
+}
+long long vmc_get_option64(int option) {
   return (option >= 0 && option < 8) ? g_options[option].load(std::memory_order_relaxed) : 0;
 }
 
 extern "C" {
 
-int vmc_set_option(int option, int value) {
+int vmc_set_option(int option, long long value) {
   VMC_CHECK_ARG(option >= 0 && option < 8, VMC_ERR_ARG, "vmc_set_option: unknown option %d", option);
   g_options[option].store(value, std::memory_order_relaxed);
   return VMC_OK;
