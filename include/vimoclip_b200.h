@@ -71,6 +71,15 @@ int vmc_prologue(const void* frames, int src_kind, void* dst, int dst_kind, int 
 int vmc_frame_diff_prologue(const uint8_t* bgr, uint8_t* diff_u8, void* dst, int dst_kind, int clips,
                             int T, int H, int W, int patch, int ld_patch, void* stream);
 
+/* Non-224x224 frames: Resize(224, BICUBIC) -> CenterCrop(224) of clip's _transform (models/student_model.py:77-78),
+ * i.e. Pillow's 8-bit bicubic resampler (22-bit fixed-point coefficients, horizontal then vertical pass, each
+ * clipped to uint8) with torchvision's size / crop rules; bit-exact.  The student's to_pil_image wrap (src_kind)
+ * is applied to the source pixels first, as in the reference.  frames [F,3,H,W] (u8 or f32), out uint8
+ * [F,3,size,size], tmp uint8 [F,3,H,size] scratch.  Feed `out` to vmc_prologue with VMC_SRC_U8. */
+int vmc_resize_geometry(int H, int W, int size, int* new_h, int* new_w, int* top, int* left);
+int vmc_resize_center_crop(const void* frames, int src_kind, uint8_t* out, uint8_t* tmp, int F, int H, int W,
+                           int size, void* stream);
+
 /* ---- G: tcgen05/TMEM GEMM fed by TMA ------------------------------------------
  * out[orow, n] = alpha * act(sum_k A[m,k] * W[n,k] + bias[n]) + resid[rrow, n]
  * A [M,K] bf16 row-major (lda), W [N,K] bf16 row-major (ldw) == nn.Linear.weight layout.

@@ -15,6 +15,7 @@ a checksum stored in the fixture):
   tfam.npz         reference ``TFAM/models/AMO_CLIP.py`` logits, BASELINE config 1 + every fusion mode
   indexing.npz     reference ``sparse_sampling`` / ``collate_fn_pad`` (TFAM/data/dataset.py)
   losses.npz       reference ``losses.py``
+  resize.npz       PIL / torchvision bicubic Resize(224) + CenterCrop(224); reference student on 640x360 frames
 """
 from __future__ import annotations
 
@@ -260,6 +261,34 @@ def golden_indexing():
     print("indexing.npz", len(out), "arrays")
 
 
+def golden_resize():
+    """PIL / torchvision Resize(224, BICUBIC) + CenterCrop(224) on seeded frames, and the reference student file on
+    640x360 frames (wrap -> resize -> crop -> normalise -> ViT)."""
+    from PIL import Image
+    from torchvision.transforms import CenterCrop, Compose, InterpolationMode, Resize
+
+    tf = Compose([Resize(224, interpolation=InterpolationMode.BICUBIC), CenterCrop(224)])
+    out = {}
+    for tag, (H, W) in {"360x640": (360, 640), "240x320": (240, 320), "500x375": (500, 375)}.items():
+        img = np.random.default_rng(len(tag) * 7 + H).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        out["pil_" + tag] = np.asarray(tf(Image.fromarray(img))).transpose(2, 0, 1)
+        out["seed_" + tag] = np.int64(len(tag) * 7 + H)
+    clip_shim.install()
+    sys.path.insert(0, REF)
+    mod = load_ref_module("ref_fd_resize", "models/student_model_frame_diff.py")
+    clip_shim.set_seed(0)
+    model = mod.FrameDiffStudentModel("ViT-B/32", device="cpu", num_classes=140)
+    weights.randomise_heads_(model, 0)
+    model.eval()
+    g = torch.Generator().manual_seed(31)
+    frames = torch.randint(0, 256, (1, 2, 3, 360, 640), dtype=torch.uint8, generator=g)
+    with torch.no_grad():
+        emb, dis, logits = model(frames)
+    out.update(student_emb=emb.numpy(), student_logits=logits.numpy())
+    np.savez_compressed(os.path.join(OUT, "resize.npz"), **out)
+    print("resize.npz", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
 def golden_losses():
     ref = load_ref_module("ref_losses", "losses.py")
     g = torch.Generator().manual_seed(11)
@@ -280,6 +309,6 @@ def golden_losses():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
-    which = sys.argv[1:] or ["prologue", "framediff", "student", "vit_hf", "tfam", "indexing", "losses"]
+    which = sys.argv[1:] or ["prologue", "framediff", "student", "vit_hf", "tfam", "indexing", "losses", "resize"]
     for w in which:
         globals()["golden_" + w]()

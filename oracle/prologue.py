@@ -32,9 +32,14 @@ def normalise_u8(u8: np.ndarray) -> np.ndarray:
 
 
 def preprocess_frames(frames: np.ndarray) -> np.ndarray:
-    """[F,3,224,224] uint8 (regime A) or float (regimes B, C) -> normalised fp32 fed to the ViT."""
-    assert frames.shape[-1] == 224 and frames.shape[-2] == 224, "resize path is out of scope (SURVEY 8f rank 1)"
-    return normalise_u8(to_pil_u8(frames))
+    """[F,3,H,W] uint8 (regime A) or float (regimes B, C) -> normalised fp32 [F,3,224,224] fed to the ViT:
+    to_pil_image wrap -> Resize(224, bicubic) -> CenterCrop(224) (identities at 224x224) -> ToTensor -> Normalize."""
+    u8 = to_pil_u8(frames)
+    if u8.shape[-1] != 224 or u8.shape[-2] != 224:
+        from .resize import resize_center_crop_u8
+
+        u8 = resize_center_crop_u8(u8, 224)
+    return normalise_u8(u8)
 
 
 def bgr2gray(bgr: np.ndarray) -> np.ndarray:

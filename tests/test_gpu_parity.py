@@ -96,6 +96,29 @@ def test_frame_difference_bit_exact(cuda_device, golden, prologue_impl):
     assert torch.equal(pt.cpu().view(torch.int16), torch.from_numpy(prologue.patchify(n_ref, 32)).to(torch.bfloat16).view(torch.int16))
 
 
+@pytest.mark.parametrize("H,W", [(360, 640), (240, 320), (500, 375), (224, 224), (300, 224), (1080, 1920)])
+def test_resize_center_crop_bit_exact(cuda_device, golden, H, W):
+    """Pillow bicubic Resize(224) + CenterCrop(224): bit-exact against the oracle (itself pinned to PIL)."""
+    from oracle import resize
+
+    g = golden("resize.npz")
+    tag = f"{H}x{W}"
+    seed = int(g["seed_" + tag]) if "seed_" + tag in g.files else H * 3 + W
+    img = np.random.default_rng(seed).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    chw = np.ascontiguousarray(img.transpose(2, 0, 1))[None]
+    got = ops.resize_center_crop(torch.from_numpy(chw).to(cuda_device), wrap=False).cpu().numpy()[0]
+    assert np.array_equal(got, resize.resize_center_crop_u8(chw[0]))
+    if "pil_" + tag in g.files:
+        assert np.array_equal(got, g["pil_" + tag])
+    # student regimes: the wrap precedes the resize
+    got_w = ops.resize_center_crop(torch.from_numpy(chw).to(cuda_device), wrap=True).cpu().numpy()[0]
+    assert np.array_equal(got_w, resize.resize_center_crop_u8(prologue.to_pil_u8(chw[0])))
+    f = (torch.from_numpy(chw).float() / 255.0).to(cuda_device)
+    got_f = ops.resize_center_crop(f, wrap=True).cpu().numpy()[0]
+    assert np.array_equal(got_f, got)  # regime B round-trips to the original uint8
+    assert ops.resize_geometry(H, W)[:2] == resize.resized_size(H, W)
+
+
 def test_prologue_full_size_properties(cuda_device):
     """BASELINE-size batch (256 clips x 16 frames): size-independent integer properties."""
     gen = torch.Generator(device="cuda").manual_seed(3)
@@ -338,8 +361,15 @@ def test_student_config1_against_reference_golden(cuda_device, golden):
     embC, _, logC = ours((u8.float() / 255.0 - mean) / std)
     assert _cos_min(embC, torch.from_numpy(g["regC_emb"])) >= COS_MIN
     assert (logC.cpu() - torch.from_numpy(g["regC_logits"])).abs().max().item() <= LOGIT_TOL
+    # 640x360 frames: wrap -> Pillow bicubic resize -> centre crop -> normalise, against the reference file's output
+    gr = golden("resize.npz")
+    gen = torch.Generator().manual_seed(31)
+    big = torch.randint(0, 256, (1, 2, 3, 360, 640), dtype=torch.uint8, generator=gen)
+    embR, _, logR = ours(big)
+    assert _cos_min(embR, torch.from_numpy(gr["student_emb"])) >= COS_MIN
+    assert (logR.cpu() - torch.from_numpy(gr["student_logits"])).abs().max().item() <= LOGIT_TOL
     with pytest.raises(NotImplementedError):
-        ours(torch.zeros(1, 1, 3, 360, 640, dtype=torch.uint8))
+        ours(torch.zeros(1, 1, 3, 100, 640, dtype=torch.uint8))
 
 
 MODES = {

@@ -155,3 +155,28 @@ def test_losses_match_reference(golden):
     lg, tg = torch.from_numpy(g["logits"]), torch.from_numpy(g["targets"])
     assert np.isclose(float(olosses.classification_loss(lg, tg)), float(g["bce"]), atol=1e-6)
     assert np.isclose(float(olosses.classification_loss(lg, tg, positive_weight=3)), float(g["bce_pw"]), atol=1e-6)
+
+
+def test_resize_oracle_matches_pil(golden):
+    from oracle import resize
+
+    g = golden("resize.npz")
+    for tag, (H, W) in {"360x640": (360, 640), "240x320": (240, 320), "500x375": (500, 375)}.items():
+        img = np.random.default_rng(int(g["seed_" + tag])).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        got = resize.resize_center_crop_u8(np.ascontiguousarray(img.transpose(2, 0, 1)))
+        assert np.array_equal(got, g["pil_" + tag]), tag
+    assert resize.resized_size(360, 640) == (224, 398) and resize.resized_size(640, 360) == (398, 224)
+    # same-size frames are untouched (PIL's identity shortcut), and bicubic at scale 1 is an exact identity
+    x = np.random.default_rng(0).integers(0, 256, size=(3, 224, 224), dtype=np.uint8)
+    assert np.array_equal(resize.resize_center_crop_u8(x), x)
+    b, k = resize.precompute_coeffs(50, 50)
+    assert all(k[i, i - b[i, 0]] == 1 << 22 for i in range(50))
+
+
+def test_student_oracle_on_640x360_frames(golden):
+    g = golden("resize.npz")
+    m = _student()
+    gen = torch.Generator().manual_seed(31)
+    frames = torch.randint(0, 256, (1, 2, 3, 360, 640), dtype=torch.uint8, generator=gen)
+    emb, _, logits = m(frames)
+    assert np.allclose(emb.numpy(), g["student_emb"], atol=2e-5) and np.allclose(logits.numpy(), g["student_logits"], atol=2e-5)

@@ -47,7 +47,13 @@ class CLIPVisionFeatures(nn.Module):
         dev = self.visual.proj.device
         if dev.type != "cuda":
             raise _lib.VmcError("CLIPVisionFeatures runs on CUDA only (no CPU fallback)")
-        patches = ops.prologue(frames_u8.to(dev, non_blocking=True), wrap=False, dst="patch", patch=self.visual.patch_size)
+        frames_u8 = frames_u8.to(dev, non_blocking=True)
+        res = self.visual.input_resolution
+        if frames_u8.shape[-2] != res or frames_u8.shape[-1] != res:
+            # CLIPImageProcessor: bicubic resize of the shortest edge to 224 + centre crop (PIL resampler; torchvision's
+            # crop rounding, identical to HF's for the reference's 640x360 -> 398x224 geometry)
+            frames_u8 = ops.resize_center_crop(frames_u8, wrap=False, size=res)
+        patches = ops.prologue(frames_u8, wrap=False, dst="patch", patch=self.visual.patch_size)
         return self.visual.forward_patches(patches, frames_u8.shape[0])
 
     forward = get_image_features

@@ -577,6 +577,61 @@ cosine_loss_kernel(const float* __restrict__ s, const float* __restrict__ t, int
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Pillow bicubic resize + centre crop for non-224x224 frames (Resize(224, BICUBIC) -> CenterCrop(224)
+// of clip's _transform, reached from models/student_model.py:77-78).  Pillow's 8-bit resampler
+// (src/libImaging/Resample.c): 22-bit fixed-point coefficients, horizontal pass then vertical pass,
+// each accumulated from 2^21 and clipped to uint8.  Integer arithmetic: bit-exact.
+// The to_pil_image wrap of the student is applied to the source pixel on load (it precedes the resize).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_wrapped(const void* src, int src_kind, size_t idx) {
+  if (src_kind == VMC_SRC_F32_WRAP) return wrap_f32(reinterpret_cast<const float*>(src)[idx]);
+  const uint32_t u = reinterpret_cast<const uint8_t*>(src)[idx];
+  return src_kind == VMC_SRC_U8_WRAP ? ((0u - u) & 255u) : u;
+}
+__device__ __forceinline__ uint8_t clip8_fixed(int acc) {
+  const int v = acc >> 22;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// tmp[f][c][y][xo] = horizontal pass at resized column (left + xo)
+__global__ void __launch_bounds__(256)
+resize_h_kernel(const void* __restrict__ src, int src_kind, uint8_t* __restrict__ tmp, int planes, int H,
+                int W, int size, int left, const int* __restrict__ bounds, const int* __restrict__ coef,
+                int ksize) {
+  const size_t total = (size_t)planes * H * size;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(idx % size);
+    const size_t row = idx / size;  // plane * H + y
+    const int xr = left + xo;
+    const int xmin = bounds[2 * xr], n = bounds[2 * xr + 1];
+    const int* k = coef + (size_t)xr * ksize;
+    int acc = 1 << 21;
+    for (int i = 0; i < n; ++i) acc += (int)load_wrapped(src, src_kind, row * W + xmin + i) * k[i];
+    tmp[idx] = clip8_fixed(acc);
+  }
+}
+// out[f][c][yo][xo] = vertical pass at resized row (top + yo) over tmp [planes, H, size]
+__global__ void __launch_bounds__(256)
+resize_v_kernel(const uint8_t* __restrict__ tmp, uint8_t* __restrict__ out, int planes, int H, int size,
+                int top, const int* __restrict__ bounds, const int* __restrict__ coef, int ksize) {
+  const size_t total = (size_t)planes * size * size;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(idx % size);
+    const int yo = (int)((idx / size) % size);
+    const size_t plane = idx / ((size_t)size * size);
+    const int yr = top + yo;
+    const int ymin = bounds[2 * yr], n = bounds[2 * yr + 1];
+    const int* k = coef + (size_t)yr * ksize;
+    const uint8_t* col = tmp + (plane * H + ymin) * size + xo;
+    int acc = 1 << 21;
+    for (int i = 0; i < n; ++i) acc += (int)col[(size_t)i * size] * k[i];
+    out[idx] = clip8_fixed(acc);
+  }
+}
+
 }  // namespace
 int vmc_get_option(int option);
 namespace {
@@ -758,4 +813,131 @@ int vmc_cosine_distill_loss(const float* s, const float* t, int rows, int d, flo
   return VMC_OK;
 }
 
+
+// ---- Pillow coefficient tables (host, double precision exactly as Resample.c) ----
+}  // extern "C"
+#include <math.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+namespace {
+double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+struct ResizeTable {
+  int* bounds = nullptr;  // device [out, 2]
+  int* coef = nullptr;    // device [out, ksize]
+  int ksize = 0;
+};
+int build_table(int in_size, int out_size, ResizeTable* t) {
+  const double scale = (double)in_size / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  std::vector<int> bounds(2 * (size_t)out_size), kk((size_t)out_size * ksize, 0);
+  std::vector<double> w(ksize);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      w[x] = bicubic_filter((x + xmin - center + 0.5) * ss);
+      ww += w[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      const double v = ww != 0.0 ? w[x] / ww : w[x];
+      kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << 22)) : (int)(0.5 + v * (1 << 22));
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  VMC_CUDA(cudaMalloc(&t->bounds, bounds.size() * sizeof(int)));
+  VMC_CUDA(cudaMalloc(&t->coef, kk.size() * sizeof(int)));
+  VMC_CUDA(cudaMemcpy(t->bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+  VMC_CUDA(cudaMemcpy(t->coef, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+  t->ksize = ksize;
+  return VMC_OK;
+}
+// tables are owned by the library, one per (device, in, out), built on first use
+int get_table(int in_size, int out_size, ResizeTable* out) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int>, ResizeTable> cache;
+  int dev = 0;
+  VMC_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_tuple(dev, in_size, out_size);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    ResizeTable t;
+    VMC_TRY(build_table(in_size, out_size, &t));
+    it = cache.emplace(key, t).first;
+  }
+  *out = it->second;
+  return VMC_OK;
+}
+}  // namespace
+extern "C" {
+
+int vmc_resize_geometry(int H, int W, int size, int* new_h, int* new_w, int* top, int* left) {
+  VMC_CHECK_ARG(H > 0 && W > 0 && size > 0, VMC_ERR_SHAPE, "vmc_resize_geometry: bad geometry");
+  // torchvision Resize(int): short side -> size, long side -> int(size * long / short)
+  int nh, nw;
+  if (W <= H) {
+    nw = size;
+    nh = (int)((double)size * H / W);
+  } else {
+    nh = size;
+    nw = (int)((double)size * W / H);
+  }
+  // CenterCrop: int(round((dim - size) / 2.0)) with Python's round-half-to-even
+  auto crop = [&](int dim) { return (int)nearbyint((dim - size) / 2.0); };
+  if (new_h) *new_h = nh;
+  if (new_w) *new_w = nw;
+  if (top) *top = crop(nh);
+  if (left) *left = crop(nw);
+  return VMC_OK;
+}
+
+int vmc_resize_center_crop(const void* frames, int src_kind, uint8_t* out, uint8_t* tmp, int F, int H,
+                           int W, int size, void* stream) {
+  VMC_CHECK_ARG(frames && out && tmp, VMC_ERR_ARG, "vmc_resize_center_crop: null pointer");
+  VMC_CHECK_ARG(src_kind >= VMC_SRC_U8 && src_kind <= VMC_SRC_F32_WRAP, VMC_ERR_ARG,
+                "vmc_resize_center_crop: unknown src_kind %d", src_kind);
+  VMC_CHECK_ARG(F > 0 && H >= size && W >= size, VMC_ERR_SHAPE,
+                "vmc_resize_center_crop: frames must be at least %dx%d (CenterCrop padding is not implemented)",
+                size, size);
+  int nh, nw, top, left;
+  VMC_TRY(vmc_resize_geometry(H, W, size, &nh, &nw, &top, &left));
+  ResizeTable th, tv;
+  VMC_TRY(get_table(W, nw, &th));
+  VMC_TRY(get_table(H, nh, &tv));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int planes = F * 3;
+  {
+    const size_t total = (size_t)planes * H * size;
+    VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, (double)planes * H * (W + size));
+    resize_h_kernel<<<grid_for(total, 256), 256, 0, st>>>(frames, src_kind, tmp, planes, H, W, size, left,
+                                                          th.bounds, th.coef, th.ksize);
+  }
+  VMC_LAUNCH_CHECK();
+  {
+    const size_t total = (size_t)planes * size * size;
+    VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, (double)planes * size * (H + size));
+    resize_v_kernel<<<grid_for(total, 256), 256, 0, st>>>(tmp, out, planes, H, size, top, tv.bounds, tv.coef,
+                                                          tv.ksize);
+  }
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch(2);
+  return VMC_OK;
+}
 }  // extern "C"

@@ -94,6 +94,35 @@ def prologue(frames: torch.Tensor, *, wrap: bool, dst: str, patch: int = 0, norm
     return out
 
 
+def resize_geometry(H: int, W: int, size: int = 224):
+    """torchvision Resize(size) + CenterCrop(size) geometry: (new_h, new_w, top, left)."""
+    v = [C.c_int() for _ in range(4)]
+    _lib.check(_lib.lib().vmc_resize_geometry(H, W, size, *[C.byref(x) for x in v]), "vmc_resize_geometry")
+    return tuple(x.value for x in v)
+
+
+def resize_center_crop(frames: torch.Tensor, *, wrap: bool, size: int = 224) -> torch.Tensor:
+    """frames [F,3,H,W] uint8/float32 -> uint8 [F,3,size,size]: (optional student wrap) -> Pillow bicubic resize of the
+    short side to ``size`` -> centre crop, bit-exact with ``Resize(224, BICUBIC)`` + ``CenterCrop(224)`` on PIL images."""
+    _need_cuda(frames)
+    if frames.dim() != 4 or frames.shape[1] != 3:
+        raise ValueError("frames must be [F,3,H,W]")
+    frames = frames.contiguous()
+    F_, _, H, W = frames.shape
+    if frames.dtype == torch.uint8:
+        src_kind = _lib.SRC_U8_WRAP if wrap else _lib.SRC_U8
+    elif frames.dtype == torch.float32:
+        src_kind = _lib.SRC_F32_WRAP
+    else:
+        raise TypeError("frames must be uint8 or float32")
+    out = torch.empty((F_, 3, size, size), dtype=torch.uint8, device=frames.device)
+    tmp = torch.empty((F_, 3, H, size), dtype=torch.uint8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _lib.check(_lib.lib().vmc_resize_center_crop(_p(frames), src_kind, _p(out), _p(tmp), F_, H, W, size, _stream()),
+                   "vmc_resize_center_crop")
+    return out
+
+
 def frame_diff(bgr: torch.Tensor, *, dst: str | None = None, patch: int = 0, want_diff: bool = True):
     """bgr [clips, T+1, H, W, 3] uint8 -> (diff_u8 [clips,T,H,W] | None, student prologue output | None).
 

@@ -36,9 +36,10 @@ class ResidualMLP(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         shp = x.shape
         x2 = x.reshape(-1, shp[-1]).float().contiguous()
-        h = ops.gemm(ops.cast_bf16(x2), self.fc1.weight.to(torch.bfloat16), bias=self.fc1.bias.float(), act=ops.ACT_GELU_ERF)
-        y = ops.gemm(h, self.fc2.weight.to(torch.bfloat16), bias=self.fc2.bias.float(), alpha=float(self.alpha), resid=x2,
-                     out_dtype=torch.float32)
+        h = ops.gemm(ops.cast_bf16(x2, split=True), ops.split_weight(self.fc1.weight), bias=self.fc1.bias.float(),
+                     act=ops.ACT_GELU_ERF, out_dtype=torch.float32)
+        y = ops.gemm(ops.cast_bf16(h, split=True), ops.split_weight(self.fc2.weight), bias=self.fc2.bias.float(),
+                     alpha=float(self.alpha), resid=x2, out_dtype=torch.float32)
         return y.view(shp)
 
 
@@ -94,7 +95,9 @@ class _StudentBase(nn.Module):
               self.classification_head[2].weight, self.classification_head[2].bias]
         sig = tuple((p.data_ptr(), p._version) for p in ps)
         if self._head_cache is None or self._head_cache[0] != sig:
-            packed = [p.detach().to(torch.bfloat16).contiguous() if p.dim() == 2 else p.detach().float().contiguous() for p in ps]
+            # heads are 0.002 % of the FLOPs: split-bf16 operands ([hi|lo|hi] x [Whi|Whi|Wlo], see ops.split_weight)
+            # keep them at fp32-class accuracy so the logit error is the tower's bf16 error alone
+            packed = [ops.split_weight(p) if p.dim() == 2 else p.detach().float().contiguous() for p in ps]
             self._head_cache = (sig, packed)
         return self._head_cache[1]
 
@@ -103,13 +106,13 @@ class _StudentBase(nn.Module):
         """bf16 patch matrix of B*T frames -> the three outputs of the reference forward."""
         emb = self.visual_encoder.forward_patches(patches, B * T)  # [B*T, D] fp32
         w1, b1, w2, b2, wc1, bc1, wc2, bc2 = self._heads()
-        e16 = ops.cast_bf16(emb)
-        h = ops.gemm(e16, w1, bias=b1, act=ops.ACT_GELU_ERF)
-        distill = ops.gemm(h, w2, bias=b2, alpha=float(self.residual_mlp.alpha), resid=emb, out_dtype=torch.float32)
+        h = ops.gemm(ops.cast_bf16(emb, split=True), w1, bias=b1, act=ops.ACT_GELU_ERF, out_dtype=torch.float32)
+        distill = ops.gemm(ops.cast_bf16(h, split=True), w2, bias=b2, alpha=float(self.residual_mlp.alpha), resid=emb,
+                           out_dtype=torch.float32)
         D = emb.shape[1]
-        _, pooled16 = ops.mean_rows(emb.view(B, T, D), want32=False, want16=True)
-        hc = ops.gemm(pooled16, wc1, bias=bc1, act=ops.ACT_RELU)
-        logits = ops.gemm(hc, wc2, bias=bc2, out_dtype=torch.float32)
+        pooled, _ = ops.mean_rows(emb.view(B, T, D), want32=True, want16=False)
+        hc = ops.gemm(ops.cast_bf16(pooled, split=True), wc1, bias=bc1, act=ops.ACT_RELU, out_dtype=torch.float32)
+        logits = ops.gemm(ops.cast_bf16(hc, split=True), wc2, bias=bc2, out_dtype=torch.float32)
         return emb.view(B, T, D), distill.view(B, T, D), logits
 
     @torch.no_grad()
@@ -118,10 +121,8 @@ class _StudentBase(nn.Module):
             raise ValueError("expected videos of shape (B, T, 3, H, W)")
         B, T, C, H, W = videos.shape
         res = self.visual_encoder.input_resolution
-        if H != res or W != res:
-            raise NotImplementedError(
-                f"{H}x{W} input: the Pillow bicubic Resize + CenterCrop of the reference preprocess is not in this path "
-                f"yet (SURVEY.md section 8f rank 1); feed {res}x{res} frames")
+        if H < res or W < res:
+            raise NotImplementedError(f"{H}x{W} input: frames smaller than {res}x{res} need CenterCrop padding (not implemented)")
         dev = self.visual_encoder.proj.device
         if dev.type != "cuda":
             raise _lib.VmcError("the student runs on CUDA only (no CPU fallback)")
@@ -129,7 +130,12 @@ class _StudentBase(nn.Module):
         if frames.dtype != torch.uint8:
             frames = frames.float()  # student_model.py:74
         frames = frames.to(dev, non_blocking=True)
-        patches = ops.prologue(frames, wrap=True, dst="patch", patch=self.visual_encoder.patch_size)
+        if H != res or W != res:
+            # Resize(224, BICUBIC) -> CenterCrop(224) of the reference preprocess, after the to_pil_image wrap
+            u8 = ops.resize_center_crop(frames, wrap=True, size=res)
+            patches = ops.prologue(u8, wrap=False, dst="patch", patch=self.visual_encoder.patch_size)
+        else:
+            patches = ops.prologue(frames, wrap=True, dst="patch", patch=self.visual_encoder.patch_size)
         return self.encode_patches(patches, B, T)
 
 
