@@ -148,6 +148,17 @@ int vmc_mean_rows(const float* x, float* y32, void* y16, int B, int T, int d, vo
 /* cosine distillation loss of losses.py:27-40: mean over rows of 1 - clamp(cos(s,t)); out: 1 fp32 */
 int vmc_cosine_distill_loss(const float* s, const float* t, int rows, int d, float* out, void* stream);
 
+/* ---- per-clip fused heads (fp32; weights TRANSPOSED [K, N] fp32) ---------------------------------
+ * vmc_student_heads: models/student_model.py:33-35,90-96 for one clip per CTA: distill [B,T,D] =
+ *   emb + alpha * fc2(GELU_erf(fc1(emb))); logits [B,C] = W2 relu(W1 mean_t(emb) + b1) + b2 (RAW embeddings pooled).
+ * vmc_tfam_head: TFAM/models/AMO_CLIP.py:170 for one clip per CTA: logits [B,C] =
+ *   Linear(GELU_erf(Linear(LayerNorm(mean over ALL T rows of x [B,T,D])))). */
+int vmc_student_heads(const float* emb, const float* w_fc1_t, const float* b_fc1, const float* w_fc2_t,
+                      const float* b_fc2, float alpha, const float* w_c1_t, const float* b_c1, const float* w_c2_t,
+                      const float* b_c2, float* distill, float* logits, int B, int T, int D, int H, int C, void* stream);
+int vmc_tfam_head(const float* x, const float* ln_g, const float* ln_b, float eps, const float* w1_t, const float* b1,
+                  const float* w2_t, const float* b2, float* logits, int B, int T, int D, int H, int C, void* stream);
+
 /* ---- whole ViT tower -----------------------------------------------------------
  * Replaces self.visual_encoder(x) (models/student_model.py:84) and
  * clip_model.get_image_features(pixel_values) (extract_embeddings.py:94).

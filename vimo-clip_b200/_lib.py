@@ -70,6 +70,8 @@ _SIGNATURES = {
     "vmc_cast_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vmc_mean_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vmc_cosine_distill_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vmc_student_heads": (C.c_int, [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p]),
+    "vmc_tfam_head": (C.c_int, [C.c_void_p] * 3 + [C.c_float] + [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_void_p]),
     "vmc_vit_workspace_bytes": (C.c_longlong, [C.POINTER(VitModel), C.c_int]),
     "vmc_vit_forward": (C.c_int, [C.POINTER(VitModel), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
 }

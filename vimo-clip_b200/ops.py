@@ -292,3 +292,34 @@ def cosine_distill_loss(student: torch.Tensor, teacher: torch.Tensor) -> torch.T
     with torch.cuda.device(s.device):
         _lib.check(_lib.lib().vmc_cosine_distill_loss(_p(s), _p(t), s.shape[0], s.shape[1], _p(out), _stream()), "vmc_cosine_distill_loss")
     return out[0]
+
+
+def student_heads(emb: torch.Tensor, w, alpha: float, num_classes: int):
+    """emb fp32 [B,T,D]; w = (fc1_t, b1, fc2_t, b2, c1_t, bc1, c2_t, bc2) with transposed fp32 weights [K,N].
+    Returns (distill [B,T,D], logits [B,C]) from ONE fused kernel, one CTA per clip."""
+    _need_cuda(emb, *w)
+    if emb.dtype != torch.float32 or emb.dim() != 3 or not emb.is_contiguous():
+        raise ValueError("emb must be contiguous fp32 [B,T,D]")
+    B, T, D = emb.shape
+    H = w[4].shape[1]
+    distill = torch.empty_like(emb)
+    logits = torch.empty((B, num_classes), dtype=torch.float32, device=emb.device)
+    with torch.cuda.device(emb.device):
+        _lib.check(_lib.lib().vmc_student_heads(_p(emb), _p(w[0]), _p(w[1]), _p(w[2]), _p(w[3]), float(alpha), _p(w[4]), _p(w[5]),
+                                                _p(w[6]), _p(w[7]), _p(distill), _p(logits), B, T, D, H, num_classes, _stream()),
+                   "vmc_student_heads")
+    return distill, logits
+
+
+def tfam_head(x: torch.Tensor, ln_g, ln_b, eps: float, w1_t, b1, w2_t, b2) -> torch.Tensor:
+    """x fp32 [B,T,D] -> logits [B,C]: mean over ALL T rows -> LayerNorm -> Linear -> GELU(erf) -> Linear, fused per clip."""
+    _need_cuda(x, ln_g, ln_b, w1_t, b1, w2_t, b2)
+    if x.dtype != torch.float32 or x.dim() != 3 or not x.is_contiguous():
+        raise ValueError("x must be contiguous fp32 [B,T,D]")
+    B, T, D = x.shape
+    H, Cn = w1_t.shape[1], w2_t.shape[1]
+    logits = torch.empty((B, Cn), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_tfam_head(_p(x), _p(ln_g), _p(ln_b), float(eps), _p(w1_t), _p(b1), _p(w2_t), _p(b2), _p(logits),
+                                            B, T, D, H, Cn, _stream()), "vmc_tfam_head")
+    return logits

@@ -95,9 +95,8 @@ class _StudentBase(nn.Module):
               self.classification_head[2].weight, self.classification_head[2].bias]
         sig = tuple((p.data_ptr(), p._version) for p in ps)
         if self._head_cache is None or self._head_cache[0] != sig:
-            # heads are 0.002 % of the FLOPs: split-bf16 operands ([hi|lo|hi] x [Whi|Whi|Wlo], see ops.split_weight)
-            # keep them at fp32-class accuracy so the logit error is the tower's bf16 error alone
-            packed = [ops.split_weight(p) if p.dim() == 2 else p.detach().float().contiguous() for p in ps]
+            # one fused fp32 kernel per clip (vmc_student_heads): weights transposed to [K, N] fp32 once
+            packed = [p.detach().float().t().contiguous() if p.dim() == 2 else p.detach().float().contiguous() for p in ps]
             self._head_cache = (sig, packed)
         return self._head_cache[1]
 
@@ -105,14 +104,9 @@ class _StudentBase(nn.Module):
     def encode_patches(self, patches: torch.Tensor, B: int, T: int):
         """bf16 patch matrix of B*T frames -> the three outputs of the reference forward."""
         emb = self.visual_encoder.forward_patches(patches, B * T)  # [B*T, D] fp32
-        w1, b1, w2, b2, wc1, bc1, wc2, bc2 = self._heads()
-        h = ops.gemm(ops.cast_bf16(emb, split=True), w1, bias=b1, act=ops.ACT_GELU_ERF, out_dtype=torch.float32)
-        distill = ops.gemm(ops.cast_bf16(h, split=True), w2, bias=b2, alpha=float(self.residual_mlp.alpha), resid=emb,
-                           out_dtype=torch.float32)
         D = emb.shape[1]
-        pooled, _ = ops.mean_rows(emb.view(B, T, D), want32=True, want16=False)
-        hc = ops.gemm(ops.cast_bf16(pooled, split=True), wc1, bias=bc1, act=ops.ACT_RELU, out_dtype=torch.float32)
-        logits = ops.gemm(ops.cast_bf16(hc, split=True), wc2, bias=bc2, out_dtype=torch.float32)
+        num_classes = self.classification_head[2].weight.shape[0]
+        distill, logits = ops.student_heads(emb.view(B, T, D), self._heads(), float(self.residual_mlp.alpha), num_classes)
         return emb.view(B, T, D), distill.view(B, T, D), logits
 
     @torch.no_grad()

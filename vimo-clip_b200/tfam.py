@@ -112,8 +112,9 @@ class AMO_CLIP(nn.Module):
                 act=ops.ACT_GELU_ERF if ly.activation == "gelu" else ops.ACT_RELU,
             ))
         c = self.classifier
-        head = dict(ln=(f32(c[0].weight), f32(c[0].bias), c[0].eps), w1=bf(c[1].weight), b1=f32(c[1].bias),
-                    w2=bf(c[4].weight), b2=f32(c[4].bias),
+        tr = lambda t: t.detach().float().t().contiguous()  # noqa: E731  transposed fp32 for the fused head kernel
+        head = dict(ln=(f32(c[0].weight), f32(c[0].bias), c[0].eps), w1t=tr(c[1].weight), b1=f32(c[1].bias),
+                    w2t=tr(c[4].weight), b2=f32(c[4].bias),
                     wp=bf(self.projection_layer.weight), bp=f32(self.projection_layer.bias))
         self._cache = (sig, (layers, head))
         return self._cache[1]
@@ -192,7 +193,6 @@ class AMO_CLIP(nn.Module):
         x16 = ops.cast_bf16(x32, split=True)
         for w in layers:
             x32, x16 = self._layer(x32, x16, B, T, w, valid, cross16, Tm, cross_valid)
-        pooled, _ = ops.mean_rows(x32.view(B, T, d))
-        _, p16 = ops.layernorm(pooled, head["ln"][0], head["ln"][1], eps=head["ln"][2], want32=False, want16=True, split16=True)
-        hid = ops.gemm(p16, head["w1"], bias=head["b1"], act=ops.ACT_GELU_ERF, out_dtype=torch.float32)
-        return ops.gemm(ops.cast_bf16(hid, split=True), head["w2"], bias=head["b2"], out_dtype=torch.float32)
+        # temporal pooling (ALL rows) + LayerNorm + MLP classifier: one fused fp32 kernel, one CTA per clip
+        return ops.tfam_head(x32.view(B, T, d), head["ln"][0], head["ln"][1], head["ln"][2], head["w1t"], head["b1"],
+                             head["w2t"], head["b2"])
