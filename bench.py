@@ -187,6 +187,8 @@ def ours_main(args):
     clips = args.clips
     torch.manual_seed(0)
     pipe = vmc.ViMoCLIPPipeline("openai/clip-vit-base-patch16", "ViT-B/32", num_classes=NUM_CLASSES, device=dev, clips_per_step=args.chunk)
+    pipe.rgb.visual.frames_in_flight = args.frames_in_flight
+    pipe.student.visual_encoder.frames_in_flight = args.frames_in_flight
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     rgb_dev = torch.randint(0, 256, (clips, T_RGB, 3, RES, RES), dtype=torch.uint8, device=dev, generator=gen)
     mot_dev = torch.randint(0, 256, (clips, T_MOT, 3, RES, RES), dtype=torch.uint8, device=dev, generator=gen)
@@ -262,6 +264,8 @@ def ours_main(args):
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": gemm["tflops"], "peak": peaks["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": (gemm["tflops"] / peaks["bf16_sustained"]) if gemm["tflops"] else None, "traffic": None,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "traffic_ncu_example": {"kernel": "gemm2_bf16_tcgen05_kernel<256,1> qkv M=201728 N=2304 K=768 (profiles/r01_gemm2_qkv_ncu_summary.txt)",
+                                        "dram_bytes_per_launch": 1.194e9, "algorithmic_bytes_per_launch": 1.243e9},
                 "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
                 "share_of_step": gemm["ms"] / sum(c["ms"] for c in classes.values()),
                 "hbm_kernels": {k: {"gbs": classes[k]["gbs"], "frac_of_hbm_peak": (classes[k]["gbs"] / peaks["hbm"]) if classes[k]["gbs"] else None}
@@ -309,7 +313,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU per step")
-    ap.add_argument("--chunk", type=int, default=64, help="clips per tower call (frames in flight = chunk*16)")
+    ap.add_argument("--chunk", type=int, default=128, help="clips staged per H2D copy / tower call")
+    ap.add_argument("--frames-in-flight", type=int, default=2048, help="frames per vmc_vit_forward call (workspace size)")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -16,7 +16,7 @@ from .tfam import AMO_CLIP
 
 class ViMoCLIPPipeline(nn.Module):
     def __init__(self, rgb_model: str = "openai/clip-vit-base-patch16", student_model: str = "ViT-B/32", num_classes: int = 140,
-                 frame_diff: bool = False, device="cuda", clips_per_step: int = 256):
+                 frame_diff: bool = False, device="cuda", clips_per_step: int = 128):
         super().__init__()
         self.rgb = CLIPVisionFeatures(rgb_model).to(device)
         cls = FrameDiffStudentModel if frame_diff else FlowStudentModel

@@ -63,7 +63,7 @@ class _Block(_Holder):
 
 class VisionTower(nn.Module):
     def __init__(self, patch: int, width: int, layers: int, heads: int, output_dim: int, input_resolution: int = 224,
-                 frames_in_flight: int = 1024):
+                 frames_in_flight: int = 2048):
         super().__init__()
         if width != heads * 64:
             raise ValueError("head_dim must be 64 (all CLIP ViT towers)")
