@@ -272,7 +272,9 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], float mx, in
 }
 // p = 2^(s*sc - mxs) for one chunk, packed to bf16 and written over the dead S columns; returns the
 // chunk's (fp32) sum in two independent accumulators to keep the FADD chains short
-template <bool MASK>
+// VAR: 0 = production; 1, 2 = what-if timing variants (WRONG results; tools/kernel_bench.py only):
+//      1 replaces MUFU.EX2 by an FMA, 2 sums the unrounded values (drops the LOP per element)
+template <bool MASK, int VAR = 0>
 __device__ __forceinline__ void chunk_exp_store(const uint32_t (&r)[32], float sc, float mxs, int valid,
                                                 uint32_t taddr, float& s0, float& s1) {
   uint32_t pk[16];
@@ -280,8 +282,13 @@ __device__ __forceinline__ void chunk_exp_store(const uint32_t (&r)[32], float s
   for (int j = 0; j < 16; ++j) {
     float e0 = 0.f, e1 = 0.f;
     if (!MASK || 2 * j < valid) {  // warp-uniform: padding columns cost no MUFU work
-      e0 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f));
-      e1 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f));
+      if (VAR == 1) {
+        e0 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f), 0.001f, 1.0f);
+        e1 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f), 0.001f, 1.0f);
+      } else {
+        e0 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f));
+        e1 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f));
+      }
       if (MASK && 2 * j + 1 >= valid) e1 = 0.f;
     }
     // fp32 -> bf16 in the integer ALU (round half up: + 0x8000, keep the high half; differs from
@@ -293,8 +300,13 @@ __device__ __forceinline__ void chunk_exp_store(const uint32_t (&r)[32], float s
     const uint32_t b0 = __float_as_uint(e0) + 0x8000u;
     const uint32_t b1 = __float_as_uint(e1) + 0x8000u;
     pk[j] = __byte_perm(b0, b1, 0x7632);  // {b1.hi16, b0.hi16}
-    s0 += __uint_as_float(b0 & 0xffff0000u);
-    s1 += __uint_as_float(b1 & 0xffff0000u);
+    if (VAR == 2) {
+      s0 += e0;
+      s1 += e1;
+    } else {
+      s0 += __uint_as_float(b0 & 0xffff0000u);
+      s1 += __uint_as_float(b1 & 0xffff0000u);
+    }
   }
   tmem_st_32x32b_x16(taddr, pk);
 }
@@ -315,6 +327,7 @@ struct Attn3Args {
 //   O   [64, 128)            fp32 output accumulator, also over consumed S columns
 //   P_b [32 c, 32 c + 16)    bf16 pairs of chunk c >= 4, written in place over its own chunk
 // so the PV MMA of the first 128 keys is issued while the softmax is still working on keys >= 128.
+template <int VAR>
 __global__ void __launch_bounds__(320, 1)
 attention_vit3_kernel(const __grid_constant__ CUtensorMap tm, const Attn3Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -474,15 +487,15 @@ attention_vit3_kernel(const __grid_constant__ CUtensorMap tm, const Attn3Args a)
           if (c + 1 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 1) * 32), r1);
           {
             const uint32_t pcol = tb + uint32_t(c < 4 ? c * 16 : c * 32);
-            if (c < n_full) chunk_exp_store<false>(r0, sc, mxs, 32, pcol, s0, s1);
-            else chunk_exp_store<true>(r0, sc, mxs, tail, pcol, s0, s1);
+            if (c < n_full) chunk_exp_store<false, VAR>(r0, sc, mxs, 32, pcol, s0, s1);
+            else chunk_exp_store<true, VAR>(r0, sc, mxs, tail, pcol, s0, s1);
           }
           if (c + 1 < n_chunks) {
             tmem_ld_wait();
             if (c + 2 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 2) * 32), r0);
             const uint32_t pcol = tb + uint32_t(c + 1 < 4 ? (c + 1) * 16 : (c + 1) * 32);
-            if (c + 1 < n_full) chunk_exp_store<false>(r1, sc, mxs, 32, pcol, s0, s1);
-            else chunk_exp_store<true>(r1, sc, mxs, tail, pcol, s0, s1);
+            if (c + 1 < n_full) chunk_exp_store<false, VAR>(r1, sc, mxs, 32, pcol, s0, s1);
+            else chunk_exp_store<true, VAR>(r1, sc, mxs, tail, pcol, s0, s1);
           }
           if (c == 2) {
             // chunks 0..3 (keys 0..127) are stored: release part A of the PV MMA.  The loads of
@@ -883,7 +896,8 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
   VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit: null pointer");
   VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 272, VMC_ERR_SHAPE,
                 "vmc_attention_vit: need 0 < L <= 272 tokens (L=%d)", L);
-  VMC_CHECK_ARG(impl >= 1 && impl <= 4, VMC_ERR_ARG, "vmc_attention_vit: impl must be 1..4");
+  VMC_CHECK_ARG((impl >= 1 && impl <= 4) || impl == 31 || impl == 32, VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 1..4");
   const int d = heads * HD;
   if (impl >= 3 && (L <= 128 || L > 256)) impl = 2;  // the persistent kernels cover two query tiles
   if (impl >= 3) {
@@ -906,8 +920,14 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     {
       VmcProfScope prof(VMC_K_ATTN_VIT, st3, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
       if (impl == 3) {
-        VMC_CUDA(cudaFuncSetAttribute(attention_vit3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-        attention_vit3_kernel<<<grid3, 320, smem3, st3>>>(tm3, a3);
+        VMC_CUDA(cudaFuncSetAttribute(attention_vit3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+        attention_vit3_kernel<0><<<grid3, 320, smem3, st3>>>(tm3, a3);
+      } else if (impl == 31) {  // what-if timing variants, wrong results (tools/kernel_bench.py)
+        VMC_CUDA(cudaFuncSetAttribute(attention_vit3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+        attention_vit3_kernel<1><<<grid3, 320, smem3, st3>>>(tm3, a3);
+      } else if (impl == 32) {
+        VMC_CUDA(cudaFuncSetAttribute(attention_vit3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+        attention_vit3_kernel<2><<<grid3, 320, smem3, st3>>>(tm3, a3);
       } else {
         VMC_CUDA(cudaFuncSetAttribute(attention_vit4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
         attention_vit4_kernel<<<grid3, 640, smem3, st3>>>(tm3, a3);
