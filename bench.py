@@ -185,6 +185,7 @@ def ours_main(args):
         torch.cuda.synchronize()
 
     clips = args.clips
+    ops.set_option(_lib.OPT_LN_FUSE, args.ln_fuse)
     torch.manual_seed(0)
     pipe = vmc.ViMoCLIPPipeline("openai/clip-vit-base-patch16", "ViT-B/32", num_classes=NUM_CLASSES, device=dev, clips_per_step=args.chunk)
     pipe.rgb.visual.frames_in_flight = args.frames_in_flight
@@ -317,6 +318,7 @@ def main():
     ap.add_argument("--frames-in-flight", type=int, default=2048, help="frames per vmc_vit_forward call (workspace size)")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ln-fuse", type=int, default=0, help="VMC_OPT_LN_FUSE: 0 separate LayerNorm kernels (default), 1 fused into residual GEMM epilogues, 2 fuse only c_proj->ln_1")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_main(args)

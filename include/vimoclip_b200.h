@@ -33,7 +33,9 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
  * Both implementations of each op are kept so the tests can cross-check them. */
 enum { VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
-       VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* 2 = band (smem-staged) kernel, else direct kernel */ };
+       VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* 2 = band (smem-staged) kernel, else direct kernel */,
+       VMC_OPT_LN_FUSE = 3 /* ViT tower: 0 = separate LayerNorm kernels (default, faster), 1 = ln_1/ln_2 fused into the
+                              residual GEMM epilogues, 2 = only c_proj -> next ln_1 fused */ };
 int vmc_set_option(int option, long long value);
 /* kernels launched by this library since the last reset (bench.py "gpu_launches") */
 long long vmc_launch_count(void);
@@ -98,6 +100,15 @@ typedef struct vmc_gemm_epilogue {
   float alpha;
   int row_group;      /* 0: orow = rrow = m.  g > 0 (patch embed): f = m / g, orow = m + f + 1,
                          rrow = m - f*g + 1 (token rows of frame f skip the CLS row; resid = pos-emb) */
+  /* Optional fused LayerNorm of the output rows (fp32 out + bias + residual epilogue only, N <= 1024, N % 128 == 0):
+   * after a CTA pair has written all N columns of a row block it normalises those rows (read back from L2) and
+   * writes ln_out[m, :] = bf16(LayerNorm(out[m, :]) * ln_gamma + ln_beta): the A operand of the next GEMM, without
+   * the separate LayerNorm pass over HBM.  ln_out NULL = off. */
+  const float* ln_gamma;
+  const float* ln_beta;
+  void* ln_out;       /* bf16 [M, ln_ldo] */
+  long long ln_ldo;
+  float ln_eps;
 } vmc_gemm_epilogue;
 int vmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                   const vmc_gemm_epilogue* epi, void* stream);

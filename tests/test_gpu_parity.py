@@ -213,6 +213,42 @@ def test_gemm_patch_embed_rowgroup_and_padded_k(cuda_device, gemm_impl):
     assert (xv[:, 1:] - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K", [(40000, 768, 768), (38000, 1024, 512), (50001, 768, 3072)])
+def test_gemm_fused_layernorm_epilogue(cuda_device, M, N, K):
+    """Residual GEMM with the LayerNorm of its output rows fused into the epilogue (row-owner tile order)."""
+    gen = torch.Generator(device="cuda").manual_seed(M)
+    a = torch.randn(M, K, device=cuda_device, generator=gen).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=cuda_device, generator=gen) * K**-0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=cuda_device, generator=gen)
+    x = torch.randn(M, N, device=cuda_device, generator=gen) * 2 + 0.3
+    g_ = 1 + 0.1 * torch.randn(N, device=cuda_device, generator=gen)
+    b_ = 0.1 * torch.randn(N, device=cuda_device, generator=gen)
+    ref_x = x + (a.float() @ w.float().t() + bias)
+    ln_out = torch.empty(M, N, device=cuda_device, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias=bias, resid=x, out=x, ln=(g_, b_, 1e-5, ln_out))  # in place, like the tower
+    assert (x - ref_x).abs().max().item() < 2e-4 * max(1.0, ref_x.abs().max().item())
+    # the fused LayerNorm must equal the stand-alone kernel on the SAME x, bit for bit
+    _, ref16 = ops.layernorm(x, g_, b_, want32=False, want16=True)
+    assert torch.equal(ln_out.view(torch.int16), ref16.view(torch.int16))
+
+
+def test_vit_tower_fused_vs_separate_layernorm(cuda_device):
+    """The tower with LayerNorm fused into the GEMM epilogues == the tower with separate LayerNorm kernels."""
+    torch.manual_seed(0)
+    tower = vmc.VisionTower.from_name("ViT-B/16").to(cuda_device)
+    gen = torch.Generator().manual_seed(6)
+    u8 = torch.randint(0, 256, (80, 3, 224, 224), dtype=torch.uint8, generator=gen).to(cuda_device)  # 80*197 rows: fused path on
+    patches = ops.prologue(u8, wrap=False, dst="patch", patch=16)
+    separate = tower.forward_patches(patches, 80).clone()
+    for mode in (1, 2):
+        ops.set_option(vmc._lib.OPT_LN_FUSE, mode)
+        try:
+            fused = tower.forward_patches(patches, 80).clone()
+        finally:
+            ops.set_option(vmc._lib.OPT_LN_FUSE, 0)
+        assert torch.equal(fused, separate), mode
+
+
 def test_gemm_linearity_full_size(cuda_device, gemm_impl):
     """BASELINE-size GEMM (64 frames x 197 tokens, fc1): G(a1 + a2) == G(a1) + G(a2) on exactly representable inputs."""
     gen = torch.Generator(device="cuda").manual_seed(9)

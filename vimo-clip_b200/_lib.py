@@ -17,7 +17,7 @@ SRC_U8, SRC_U8_WRAP, SRC_F32_WRAP, SRC_F32_NORM = 0, 1, 2, 3
 DST_U8, DST_F32_NCHW, DST_BF16_PATCH = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
 ABI_VERSION = 1
-OPT_GEMM_IMPL, OPT_ATTN_IMPL, OPT_PROLOGUE_IMPL = 0, 1, 2
+OPT_GEMM_IMPL, OPT_ATTN_IMPL, OPT_PROLOGUE_IMPL, OPT_LN_FUSE = 0, 1, 2, 3
 
 
 class GemmEpilogue(C.Structure):
@@ -31,6 +31,11 @@ class GemmEpilogue(C.Structure):
         ("act", C.c_int),
         ("alpha", C.c_float),
         ("row_group", C.c_int),
+        ("ln_gamma", C.c_void_p),
+        ("ln_beta", C.c_void_p),
+        ("ln_out", C.c_void_p),
+        ("ln_ldo", C.c_longlong),
+        ("ln_eps", C.c_float),
     ]
 
 

@@ -236,6 +236,28 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int num_tiles = g.tiles_m * g.tiles_n;
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
+  // Tile order.  Default: tile t = pair + i * num_pairs with N fastest, so the pairs running together
+  // share one A block.  MODE 4 (fused LayerNorm) needs a pair to OWN whole rows: it walks all N tiles of
+  // row block (pair + j * num_pairs) back to back; after the last one the CTA holds complete rows of x.
+  constexpr bool kRowOwner = (MODE == 4);
+  int my_tiles;
+  if (kRowOwner) {
+    const int my_blocks = pair < g.tiles_m ? (g.tiles_m - pair + num_pairs - 1) / num_pairs : 0;
+    my_tiles = my_blocks * g.tiles_n;
+  } else {
+    my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
+  }
+  auto tile_of = [&](int i, int& m_blk, int& n_blk) {
+    if (kRowOwner) {
+      const int j = i / g.tiles_n;
+      n_blk = i - j * g.tiles_n;
+      m_blk = pair + j * num_pairs;
+    } else {
+      const int t = pair + i * num_pairs;
+      n_blk = t % g.tiles_n;
+      m_blk = t / g.tiles_n;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -264,9 +286,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
-        const int n_blk = t % g.tiles_n;
-        const int m_blk = t / g.tiles_n;
+      for (int i = 0; i < my_tiles; ++i) {
+        int m_blk, n_blk;
+        tile_of(i, m_blk, n_blk);
         const int m_row = m_blk * (2 * BM) + (int)rank * BM;
         const int n_row = n_blk * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -293,7 +315,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      for (int i = 0; i < my_tiles; ++i) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
@@ -333,9 +355,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const bool has_res = e.resid != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int n_blk = t % g.tiles_n;
-      const int m_blk = t / g.tiles_n;
+    for (int i = 0; i < my_tiles; ++i) {
+      int m_blk, n_blk;
+      tile_of(i, m_blk, n_blk);
       const int row0 = m_blk * (2 * BM) + (int)rank * BM + quarter * 32;
       const int n_base = n_blk * BN + half * HALF_N;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -343,7 +365,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const uint32_t t_acc =
           tmem_base + uint32_t(acc * BN + half * HALF_N) + (uint32_t(quarter * 32) << 16);
       if constexpr (MODE != 0) {
-        epilogue_fast<MODE, HALF_N>(e, g.M, g.N, row0, n_base, t_acc, stg, lane);
+        epilogue_fast<(MODE == 4 ? 3 : MODE), HALF_N>(e, g.M, g.N, row0, n_base, t_acc, stg, lane);
       } else {
         // ---- generic path: any activation / alpha / ragged N / patch-embed row remap ----
 #pragma unroll 1
@@ -442,6 +464,57 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+      if constexpr (MODE == 4) {
+        if (n_blk == g.tiles_n - 1) {
+          // Fused LayerNorm of the NEXT op's input.  The 8 epilogue warps of this CTA have just written
+          // all N columns of its 128 rows of x (fp32): wait for each other, then normalise the rows
+          // straight out of L2 (same arithmetic as layernorm_kernel: one warp per row, row in
+          // registers, two-pass fp32 statistics) and write the bf16 A operand of the next GEMM.
+          // The accumulator was already handed back, so the next row block's MMAs run underneath.
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int nv = g.N >> 2;  // float4 per row (N <= 1024, N % 128 == 0)
+          const int cta_row0 = m_blk * (2 * BM) + (int)rank * BM;
+          for (int rr = ew; rr < BM; rr += 8) {
+            const int m = cta_row0 + rr;
+            if (m >= g.M) break;
+            const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) + (long long)m * e.ldo);
+            float4 v[8];
+            float sum = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = lane + 32 * q;
+              if (j < nv) {
+                v[q] = __ldcg(xr + j);  // L2: written moments ago by the other epilogue warps of this CTA
+                sum += (v[q].x + v[q].y) + (v[q].z + v[q].w);
+              }
+            }
+            const float mean = warp_sum(sum) / (float)g.N;
+            float sq = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = lane + 32 * q;
+              if (j < nv) {
+                const float a0 = v[q].x - mean, a1 = v[q].y - mean, a2 = v[q].z - mean, a3 = v[q].w - mean;
+                sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+              }
+            }
+            const float rstd = rsqrtf(warp_sum(sq) / (float)g.N + e.ln_eps);
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(e.ln_out) + (long long)m * e.ln_ldo;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = lane + 32 * q;
+              if (j < nv) {
+                const float4 gm = __ldg(reinterpret_cast<const float4*>(e.ln_gamma) + j);
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(e.ln_beta) + j);
+                uint2 pk;
+                pk.x = pack_bf16x2((v[q].x - mean) * rstd * gm.x + bt.x, (v[q].y - mean) * rstd * gm.y + bt.y);
+                pk.y = pack_bf16x2((v[q].z - mean) * rstd * gm.z + bt.z, (v[q].w - mean) * rstd * gm.w + bt.w);
+                reinterpret_cast<uint2*>(orow)[j] = pk;
+              }
+            }
+          }
+        }
+      }
     }
   }
 
@@ -508,12 +581,21 @@ int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ld
     else if (epi->out_bf16 && !epi->resid && epi->act == VMC_ACT_QUICKGELU) mode = 2;
     else if (!epi->out_bf16 && epi->resid && epi->act == VMC_ACT_NONE) mode = 3;
   }
+  if (epi->ln_out != nullptr) {
+    VMC_CHECK_ARG(mode == 3 && big && N <= 1024 && (N % 128) == 0 && epi->ln_gamma && epi->ln_beta &&
+                      epi->ldo >= N && (epi->ln_ldo % 4) == 0,
+                  VMC_ERR_ARG,
+                  "vmc_gemm_bf16: the fused LayerNorm needs the fp32 bias+residual epilogue, N %% 128 == 0, N <= 1024 "
+                  "and enough tiles for 128x256 pair tiles");
+    mode = 4;
+  }
 #define VMC_G2(BN_, MODE_) return launch_gemm2<BN_, MODE_>(A, lda, W, ldw, M, N, K, epi, stream)
   if (big) {
     switch (mode) {
       case 1: VMC_G2(256, 1);
       case 2: VMC_G2(256, 2);
       case 3: VMC_G2(256, 3);
+      case 4: VMC_G2(256, 4);
       default: VMC_G2(256, 0);
     }
   }

@@ -4,13 +4,16 @@
 //
 // Data layout in HBM for F frames in flight, L = (image/patch)^2 + 1 tokens, d = width:
 //   x     fp32 [F*L, d]      residual stream (fp32 so 12-24 pre-LN blocks stay within tolerance)
-//   xn    bf16 [F*L, d]      LayerNorm output / attention output (A operand of the next GEMM)
+//   xn    bf16 [F*L, d]      ln_1 output / attention output (A operand of the next GEMM)
+//   xn2   bf16 [F*L, d]      ln_2 output
 //   big   bf16 [F*L, 4d]     qkv ([F*L, 3d]) and MLP hidden ([F*L, 4d]) share this buffer
 //   cls   bf16 [F, d]        ln_post(CLS rows)
 // Reference: models/student_model.py:84 (self.visual_encoder(x)), extract_embeddings.py:94
 // (clip_model.get_image_features(pixel_values)).
 #include "common.cuh"
 #include "vimoclip_b200.h"
+
+int vmc_get_option(int option);
 
 namespace {
 
@@ -19,6 +22,7 @@ inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a
 struct Workspace {
   float* x;
   void* xn;
+  void* xn2;
   void* big;
   void* cls;
   long long total;
@@ -35,6 +39,8 @@ Workspace carve(const vmc_vit_model* m, int F, void* base) {
   w.x = reinterpret_cast<float*>(p + off);
   off += align_up(rows * d * 4, 1024);
   w.xn = p + off;
+  off += align_up(rows * d * 2, 1024);
+  w.xn2 = p + off;  // ln_2 output: the out_proj GEMM reads xn (attention output) while its epilogue writes this
   off += align_up(rows * d * 2, 1024);
   w.big = p + off;
   off += align_up(rows * 4 * d * 2, 1024);
@@ -92,11 +98,24 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
   VMC_TRY(vmc_layernorm(w.x, d, m->ln_pre_g, m->ln_pre_b, 1e-5f, w.x, d, nullptr, 0, 0, rows, d,
                         m->cls_pos0, L, stream));
 
+  // Optional LayerNorm fusion (VMC_OPT_LN_FUSE = 1: both, 2: only c_proj -> next ln_1; default 0 = off):
+  // ln_2 rides in the epilogue of the out_proj GEMM and the NEXT layer's ln_1 in the epilogue of the c_proj
+  // GEMM (the CTA pair that owns a row block normalises it out of L2).  Bit-identical to the separate
+  // kernels, but MEASURED SLOWER on the 256-clip step (233 ms vs 215 ms): a pair must then own all N tiles
+  // of a row block, the 74 concurrently live A blocks (116 MB at K = 3072) no longer fit the L2 that the
+  // default tile order shares between pairs, and the epilogue's extra L2 traffic lands on the K = 768 GEMMs
+  // that are epilogue-bound already.  Kept as a selectable, tested variant.
+  const long long pair_tiles = (long long)((rows + 255) / 256) * ((d + 255) / 256);
+  const int ln_opt = vmc_get_option(VMC_OPT_LN_FUSE);
+  const bool fuse_ln = vmc_get_option(VMC_OPT_GEMM_IMPL) != 1 && (ln_opt == 1 || ln_opt == 2) &&
+                       d <= 1024 && (d % 128) == 0 && pair_tiles >= vmc_num_sms();
+  const bool fuse_ln2 = fuse_ln && ln_opt == 1;
   for (int i = 0; i < m->layers; ++i) {
     const vmc_vit_layer& ly = m->layer[i];
     // x = x + out_proj(attn(ln_1(x)))
-    VMC_TRY(vmc_layernorm(w.x, d, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr, 0, w.xn, d, 0, rows, d, nullptr,
-                          0, stream));
+    if (i == 0 || !fuse_ln)
+      VMC_TRY(vmc_layernorm(w.x, d, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr, 0, w.xn, d, 0, rows, d, nullptr,
+                            0, stream));
     {
       vmc_gemm_epilogue e = {};
       e.bias = ly.b_qkv;
@@ -116,11 +135,19 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
       e.ldo = d;
       e.out_bf16 = 0;
       e.alpha = 1.0f;
+      if (fuse_ln2) {  // ln_2: the attention output in xn has been consumed by this very GEMM
+        e.ln_gamma = ly.ln2_g;
+        e.ln_beta = ly.ln2_b;
+        e.ln_out = w.xn2;
+        e.ln_ldo = d;
+        e.ln_eps = 1e-5f;
+      }
       VMC_TRY(vmc_gemm_bf16(w.xn, d, ly.w_out, d, rows, d, d, &e, stream));
     }
     // x = x + c_proj(QuickGELU(c_fc(ln_2(x))))
-    VMC_TRY(vmc_layernorm(w.x, d, ly.ln2_g, ly.ln2_b, 1e-5f, nullptr, 0, w.xn, d, 0, rows, d, nullptr,
-                          0, stream));
+    if (!fuse_ln2)
+      VMC_TRY(vmc_layernorm(w.x, d, ly.ln2_g, ly.ln2_b, 1e-5f, nullptr, 0, w.xn2, d, 0, rows, d, nullptr,
+                            0, stream));
     {
       vmc_gemm_epilogue e = {};
       e.bias = ly.b_fc1;
@@ -129,7 +156,7 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
       e.out_bf16 = 1;
       e.act = VMC_ACT_QUICKGELU;
       e.alpha = 1.0f;
-      VMC_TRY(vmc_gemm_bf16(w.xn, d, ly.w_fc1, d, rows, 4 * d, d, &e, stream));
+      VMC_TRY(vmc_gemm_bf16(w.xn2, d, ly.w_fc1, d, rows, 4 * d, d, &e, stream));
     }
     {
       vmc_gemm_epilogue e = {};
@@ -140,6 +167,13 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
       e.ldo = d;
       e.out_bf16 = 0;
       e.alpha = 1.0f;
+      if (fuse_ln && i + 1 < m->layers) {  // next layer's ln_1
+        e.ln_gamma = m->layer[i + 1].ln1_g;
+        e.ln_beta = m->layer[i + 1].ln1_b;
+        e.ln_out = w.xn;
+        e.ln_ldo = d;
+        e.ln_eps = 1e-5f;
+      }
       VMC_TRY(vmc_gemm_bf16(w.big, 4 * d, ly.w_fc2, 4 * d, rows, d, 4 * d, &e, stream));
     }
   }

@@ -162,8 +162,9 @@ def frame_diff(bgr: torch.Tensor, *, dst: str | None = None, patch: int = 0, wan
 # ---------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, alpha: float = 1.0, resid=None,
          out: torch.Tensor | None = None, out_dtype=torch.bfloat16, n: int | None = None, k: int | None = None,
-         row_group: int = 0, out_rows: int | None = None) -> torch.Tensor:
-    """out = alpha * act(a @ w.T + bias) + resid.  a [M, lda] bf16, w [N, ldw] bf16 (nn.Linear layout)."""
+         row_group: int = 0, out_rows: int | None = None, ln=None) -> torch.Tensor:
+    """out = alpha * act(a @ w.T + bias) + resid.  a [M, lda] bf16, w [N, ldw] bf16 (nn.Linear layout).
+    ln = (gamma, beta, eps, ln_out bf16 [M, N]): fused LayerNorm of the output rows (see vmc_gemm_epilogue)."""
     _need_cuda(a, w, bias, resid, out)
     if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         raise TypeError("gemm operands must be bf16")
@@ -189,6 +190,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, al
     e.act = act
     e.alpha = alpha
     e.row_group = row_group
+    if ln is not None:
+        g_, b_, eps_, ln_out = ln
+        _need_cuda(g_, b_, ln_out)
+        e.ln_gamma, e.ln_beta, e.ln_out, e.ln_ldo, e.ln_eps = g_.data_ptr(), b_.data_ptr(), ln_out.data_ptr(), ln_out.stride(0), eps_
     with torch.cuda.device(a.device):
         _lib.check(_lib.lib().vmc_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, C.byref(e), _stream()), "vmc_gemm_bf16")
     return out
