@@ -101,10 +101,11 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
   // Optional LayerNorm fusion (VMC_OPT_LN_FUSE = 1: both, 2: only c_proj -> next ln_1; default 0 = off):
   // ln_2 rides in the epilogue of the out_proj GEMM and the NEXT layer's ln_1 in the epilogue of the c_proj
   // GEMM (the CTA pair that owns a row block normalises it out of L2).  Bit-identical to the separate
-  // kernels, but MEASURED SLOWER on the 256-clip step (233 ms vs 215 ms): a pair must then own all N tiles
-  // of a row block, the 74 concurrently live A blocks (116 MB at K = 3072) no longer fit the L2 that the
-  // default tile order shares between pairs, and the epilogue's extra L2 traffic lands on the K = 768 GEMMs
-  // that are epilogue-bound already.  Kept as a selectable, tested variant.
+  // kernels, but MEASURED SLOWER on the 256-clip step (233 ms vs 215 ms).  Split by experiment: the
+  // row-owner tile order alone costs +12 ms of GEMM time (the 74 concurrently live A blocks, 116 MB at
+  // K = 3072, no longer fit the L2 that the default order shares between pairs), and the in-epilogue
+  // LayerNorm passes cost +22 ms (8 warps per SM walking rows serially are latency-bound) against the
+  // 19 ms the stand-alone kernels take at 85-100 % of HBM peak.  Kept as a selectable, tested variant.
   const long long pair_tiles = (long long)((rows + 255) / 256) * ((d + 255) / 256);
   const int ln_opt = vmc_get_option(VMC_OPT_LN_FUSE);
   const bool fuse_ln = vmc_get_option(VMC_OPT_GEMM_IMPL) != 1 && (ln_opt == 1 || ln_opt == 2) &&
