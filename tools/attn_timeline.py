@@ -1,3 +1,4 @@
+"""Needs the library built with the stamps: make -C vimo-clip_b200/csrc clean all EXTRA_NVCCFLAGS=-DVMC_ATTN_TIMELINE."""
 """Phase timeline (clock64) of CTA 0 of attention_vit3_kernel; prints cycles relative to the first stamp."""
 import os, sys
 import torch
