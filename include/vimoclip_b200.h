@@ -33,7 +33,7 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
  * Both implementations of each op are kept so the tests can cross-check them. */
 enum { VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
-       VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* 2 = band (smem-staged) kernel, else direct kernel */,
+       VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged) */,
        VMC_OPT_LN_FUSE = 3 /* ViT tower: 0 = separate LayerNorm kernels (default, faster), 1 = ln_1/ln_2 fused into the
                               residual GEMM epilogues, 2 = only c_proj -> next ln_1 fused */ };
 int vmc_set_option(int option, long long value);

@@ -140,3 +140,22 @@ print("ok")
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0 and b"ok" in out, out.decode()
+
+
+def test_fast_normalise_constants():
+    """The gather prologue emits bf16(fma(u, K_c, B_c)) (csrc/elementwise.cu: c_fastK / c_fastB).  For all 768
+    (u, c) pairs that equals bf16(RN((u/255 - mean_c)/std_c)), the exact fp32 chain of the oracle."""
+    from oracle import prologue as oprol
+
+    src = open(os.path.join(ROOT, "vimo-clip_b200", "csrc", "elementwise.cu")).read()
+    ks = [int(v, 16) for v in re.search(r"c_fastK\[3\] = \{([^}]*)\}", src).group(1).replace("u", "").split(",")]
+    bs = [int(v, 16) for v in re.search(r"c_fastB\[3\] = \{([^}]*)\}", src).group(1).replace("u", "").split(",")]
+    u8 = np.arange(256, dtype=np.uint8).reshape(1, 1, 16, 16).repeat(3, axis=1)
+    exact = torch.from_numpy(oprol.normalise_u8(u8)).to(torch.bfloat16).view(torch.int16).numpy()
+    for c in range(3):
+        k = float(np.uint32(ks[c]).view(np.float32))
+        b = float(np.uint32(bs[c]).view(np.float32))
+        # u*K is exact in float64 (8 + 24 bits) and so is the sum: one rounding to fp32 == fma semantics
+        fused = (np.arange(256, dtype=np.float64) * k + b).astype(np.float32)
+        got = torch.from_numpy(fused).to(torch.bfloat16).view(torch.int16).numpy()
+        assert np.array_equal(got, exact[0, c].reshape(-1)), c

@@ -66,14 +66,16 @@ if "ln" in which:
     ms = timeit(lambda: ops.layernorm(x, g_, g_))
     print(f"layernorm rows={F_ * 197} d=768: {ms:.3f} ms  {x.numel() * 6 / ms / 1e6:.0f} GB/s")
     u8 = torch.randint(0, 256, (F_, 3, 224, 224), dtype=torch.uint8, device=dev, generator=gen)
-    for impl in (0, 2):
+    for impl in (0, 1, 2):
         ops.set_option(vmc._lib.OPT_PROLOGUE_IMPL, impl)
         for p in (16, 32):
             ms = timeit(lambda: ops.prologue(u8, wrap=True, dst="patch", patch=p))
             print(f"prologue impl={impl} p={p} F={F_}: {ms:.3f} ms  {u8.numel() * 3 / ms / 1e6:.0f} GB/s")
     bgr = torch.randint(0, 256, (F_ // 16, 17, 224, 224, 3), dtype=torch.uint8, device=dev, generator=gen)
-    for impl in (0, 2):
+    for impl in (0, 1, 2):
         ops.set_option(vmc._lib.OPT_PROLOGUE_IMPL, impl)
         ms = timeit(lambda: ops.frame_diff(bgr, dst="patch", patch=32, want_diff=False))
         nfr = (F_ // 16) * 16
-        print(f"frame_diff+prologue impl={impl} p=32 frames={nfr}: {ms:.3f} ms  {nfr * 150528 * (6 + 6) / ms / 1e6:.0f} GB/s")
+        # algorithmic bytes: every BGR frame once (17 per 16 outputs, 3 B/px) + 3 bf16 channels written (6 B/px)
+        print(f"frame_diff+prologue impl={impl} p=32 frames={nfr}: {ms:.3f} ms  "
+              f"{nfr * 50176 * (3 * 17 / 16 + 6) / ms / 1e6:.0f} GB/s")

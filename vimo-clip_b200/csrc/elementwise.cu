@@ -424,6 +424,184 @@ frame_diff_patch_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ d
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Patch-matrix prologue in GATHER form (default for p % 8 == 0): threads are laid out over the OUTPUT.
+// One block = one band (frame f, patch-row py); work item q = (patch px, 16-byte output chunk j) with j
+// fastest, so a warp writes 512 contiguous bytes of one patch row (4 full 128-byte lines) where the
+// direct kernel writes 32 half-sectors 1.5 KB apart.  The matching 8 source pixels are an 8-byte load
+// (32 bytes for float sources); neighbouring patches of the band pick up the other half of each source
+// sector from L1/L2, so DRAM traffic stays at the algorithmic 1 + 2 bytes per pixel.  All loads of a
+// thread are issued before the first pixel is converted.
+// ---------------------------------------------------------------------------------------
+// bf16 patch output only: bf16(RN_fp32((u/255 - mean_c)/std_c)) == bf16(fma(float(u), K_c, B_c)) with
+// K_c = RN(1/(255 std_c)), B_c = RN(-mean_c/std_c) for ALL 768 (u, c) pairs (checked exhaustively on the host
+// in exact arithmetic, tests/test_host_cpu.py::test_fast_normalise_constants, and on the GPU against the
+// exact chain of the direct kernel).  One FMA instead of two verified divisions: the exact chain costs
+// 16 instructions per pixel, which kept the patch prologue at ~60 % of HBM peak.
+__constant__ uint32_t c_fastK[3] = {0x3c6f2e3du, 0x3c75e324u, 0x3c68fb48u};
+__constant__ uint32_t c_fastB[3] = {0xbfe568dcu, 0xbfe044b8u, 0xbfbd77d8u};
+
+// per-byte (-x) mod 256 of four packed uint8 (regime A wrap), no cross-byte carries
+__device__ __forceinline__ uint32_t neg4_u8(uint32_t w) {
+  const uint32_t x = ~w;
+  return ((x & 0x7f7f7f7fu) + 0x01010101u) ^ (x & 0x80808080u);
+}
+// byte i of w as an exact float: PRMT builds the bit pattern of 2^23 + b, one FADD removes the offset
+template <int I>
+__device__ __forceinline__ float byte_to_float(uint32_t w) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7550 + I)) - 8388608.0f;
+}
+__device__ __forceinline__ uint4 normalise_pack8_fast(uint32_t w0, uint32_t w1, int c) {
+  const float K = __uint_as_float(c_fastK[c]), B = __uint_as_float(c_fastB[c]);
+  uint4 o;
+  o.x = pack_bf16x2(__fmaf_rn(byte_to_float<0>(w0), K, B), __fmaf_rn(byte_to_float<1>(w0), K, B));
+  o.y = pack_bf16x2(__fmaf_rn(byte_to_float<2>(w0), K, B), __fmaf_rn(byte_to_float<3>(w0), K, B));
+  o.z = pack_bf16x2(__fmaf_rn(byte_to_float<0>(w1), K, B), __fmaf_rn(byte_to_float<1>(w1), K, B));
+  o.w = pack_bf16x2(__fmaf_rn(byte_to_float<2>(w1), K, B), __fmaf_rn(byte_to_float<3>(w1), K, B));
+  return o;
+}
+
+template <int P, int ITERS, bool F32SRC>
+__global__ void __launch_bounds__(384)
+prologue_gather_kernel(const void* __restrict__ src, int src_kind, __nv_bfloat16* __restrict__ dst,
+                       int H, int W, int ld) {
+  constexpr int PP = P * P;
+  constexpr int CPR = 3 * PP / 8;  // 16-byte chunks per patch row
+  constexpr int CPC = PP / 8;      // chunks per channel
+  constexpr int CPL = P / 8;       // chunks per image line of a patch
+  const int gw = W / P, gh = H / P;
+  const int f = blockIdx.x / gh, py = blockIdx.x - f * gh;
+  const int items = gw * CPR;
+  const size_t plane = (size_t)H * W;
+  const size_t band0 = (size_t)f * 3 * plane + (size_t)py * P * W;
+  __nv_bfloat16* drow = dst + ((size_t)f * gh * gw + (size_t)py * gw) * ld;
+
+  uint2 raw[F32SRC ? 1 : ITERS];
+  float4 rawf[F32SRC ? ITERS : 1][2];
+  if constexpr (!F32SRC) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int q = it * blockDim.x + threadIdx.x;
+      if (q < items) {
+        const int px = q / CPR, j = q - px * CPR;
+        const int c = j / CPC, r = j - c * CPC;
+        const int iy = r / CPL, h = r - iy * CPL;
+        raw[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(src) + band0 +
+                                                       c * plane + (size_t)iy * W + px * P + h * 8));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int q = it * blockDim.x + threadIdx.x;
+      if (q < items) {
+        const int px = q / CPR, j = q - px * CPR;
+        const int c = j / CPC, r = j - c * CPC;
+        const int iy = r / CPL, h = r - iy * CPL;
+        const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + band0 +
+                                                          c * plane + (size_t)iy * W + px * P + h * 8);
+        rawf[it][0] = __ldg(s);
+        rawf[it][1] = __ldg(s + 1);
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = it * blockDim.x + threadIdx.x;
+    if (q >= items) break;
+    const int px = q / CPR, j = q - px * CPR;
+    const int c = j / CPC;
+    uint4 o;
+    if constexpr (F32SRC) {
+      const float4 lo = rawf[it][0], hi = rawf[it][1];
+      if (src_kind == VMC_SRC_F32_NORM) {  // already-normalised pixel_values: layout change + bf16 only
+        o = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y),
+                       pack_bf16x2(hi.z, hi.w));
+      } else {
+        const uint32_t w0 = wrap_f32(lo.x) | (wrap_f32(lo.y) << 8) | (wrap_f32(lo.z) << 16) | (wrap_f32(lo.w) << 24);
+        const uint32_t w1 = wrap_f32(hi.x) | (wrap_f32(hi.y) << 8) | (wrap_f32(hi.z) << 16) | (wrap_f32(hi.w) << 24);
+        o = normalise_pack8_fast(w0, w1, c);
+      }
+    } else {
+      uint32_t w0 = raw[it].x, w1 = raw[it].y;
+      if (src_kind == VMC_SRC_U8_WRAP) {  // regime A: (-x) mod 256
+        w0 = neg4_u8(w0);
+        w1 = neg4_u8(w1);
+      }
+      o = normalise_pack8_fast(w0, w1, c);
+    }
+    reinterpret_cast<uint4*>(drow + (size_t)px * ld)[j] = o;
+  }
+}
+
+// Frame difference -> student patch matrix, gather form: work item = (patch px, line iy, 8-pixel group h);
+// the grey |difference| of the 8 pixels is computed once from 2 x 24 BGR bytes and emitted for the three
+// identical channels (each a 16-byte chunk; a warp writes 512 contiguous bytes per channel).
+template <int P, int ITERS>
+__global__ void __launch_bounds__(128)
+frame_diff_gather_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ diff_u8,
+                         __nv_bfloat16* __restrict__ dst, int T, int H, int W, int ld) {
+  constexpr int PP = P * P;
+  constexpr int CPC = PP / 8;
+  constexpr int CPL = P / 8;
+  const int gw = W / P, gh = H / P;
+  const int fo = blockIdx.x / gh, py = blockIdx.x - fo * gh;  // output frame = clip * T + t
+  const int clip = fo / T, t = fo - clip * T;
+  const size_t frame_bytes = (size_t)H * W * 3;
+  const uint8_t* s0 = bgr + ((size_t)clip * (T + 1) + t) * frame_bytes + (size_t)py * P * W * 3;
+  const int items = gw * CPC;
+  __nv_bfloat16* drow = dst + ((size_t)fo * gh * gw + (size_t)py * gw) * ld;
+
+  uint2 a[ITERS][3], b[ITERS][3];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = it * blockDim.x + threadIdx.x;
+    if (q < items) {
+      const int px = q / CPC, r = q - px * CPC;
+      const int iy = r / CPL, h = r - iy * CPL;
+      const uint2* p0 = reinterpret_cast<const uint2*>(s0 + ((size_t)iy * W + px * P + h * 8) * 3);
+      const uint2* p1 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p0) + frame_bytes);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        a[it][i] = __ldg(p0 + i);
+        b[it][i] = __ldg(p1 + i);
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int q = it * blockDim.x + threadIdx.x;
+    if (q >= items) break;
+    const int px = q / CPC, r = q - px * CPC;
+    const int iy = r / CPL, h = r - iy * CPL;
+    const uint32_t w0[6] = {a[it][0].x, a[it][0].y, a[it][1].x, a[it][1].y, a[it][2].x, a[it][2].y};
+    const uint32_t w1[6] = {b[it][0].x, b[it][0].y, b[it][1].x, b[it][1].y, b[it][2].x, b[it][2].y};
+    uint32_t d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t c0[3], c1[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int byte = 3 * i + k;
+        c0[k] = (w0[byte >> 2] >> (8 * (byte & 3))) & 255u;
+        c1[k] = (w1[byte >> 2] >> (8 * (byte & 3))) & 255u;
+      }
+      const int g0 = (int)bgr_gray(c0[0], c0[1], c0[2]);
+      const int g1 = (int)bgr_gray(c1[0], c1[1], c1[2]);
+      d[i] = (uint32_t)(g1 > g0 ? g1 - g0 : g0 - g1);  // cv2.absdiff(curr, prev)
+    }
+    uint2 wd;
+    wd.x = d[0] | (d[1] << 8) | (d[2] << 16) | (d[3] << 24);
+    wd.y = d[4] | (d[5] << 8) | (d[6] << 16) | (d[7] << 24);
+    if (diff_u8 != nullptr) {
+      *reinterpret_cast<uint2*>(diff_u8 + ((size_t)fo * H + (size_t)py * P + iy) * W + px * P + h * 8) = wd;
+    }
+    uint4* orow = reinterpret_cast<uint4*>(drow + (size_t)px * ld);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) orow[c * CPC + r] = normalise_pack8_fast(neg4_u8(wd.x), neg4_u8(wd.y), c);  // regime A wrap
+  }
+}
+
 // bf16 "split" operand for near-fp32 GEMMs on the bf16 tensor cores: x = hi + lo with hi = bf16(x),
 // lo = bf16(x - hi).  Rows are written as [hi | lo | hi] (3*d columns) and multiplied against weights
 // packed as [Whi | Whi | Wlo], i.e. x W^T ~= hi Whi^T + lo Whi^T + hi Wlo^T in ONE K = 3d GEMM.
@@ -683,9 +861,28 @@ int vmc_prologue(const void* frames, int src_kind, void* dst, int dst_kind, int 
   }
   const size_t total = (size_t)F * 3 * H * (W / 16);
   VMC_CHECK_ARG(total < (1ull << 31), VMC_ERR_SHAPE, "vmc_prologue: too many frames in one call (F=%d)", F);
-  if (dst_kind == VMC_DST_BF16_PATCH && vmc_get_option(VMC_OPT_PROLOGUE_IMPL) == 2) {
+  const int impl = vmc_get_option(VMC_OPT_PROLOGUE_IMPL);
+  const bool f32_src = src_kind == VMC_SRC_F32_WRAP || src_kind == VMC_SRC_F32_NORM;
+  // gather kernel: 7 work items per thread, block = items / 7 (192 threads at p = 16, 384 at p = 32, W = 224)
+  const int g_items = dst_kind == VMC_DST_BF16_PATCH ? (W / patch) * (3 * patch * patch / 8) : 0;
+  const int g_block = ((g_items + 6) / 7 + 31) / 32 * 32;
+  if (dst_kind == VMC_DST_BF16_PATCH && impl != 1 && impl != 2 && (patch == 16 || patch == 32) && (W % 8) == 0 &&
+      g_block <= 384) {
     const double px = (double)F * 3 * H * W;
-    const double in_b = (src_kind == VMC_SRC_F32_WRAP || src_kind == VMC_SRC_F32_NORM) ? 4.0 : 1.0;
+    const int bands = F * (H / patch);
+    __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dst);
+    VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * ((f32_src ? 4.0 : 1.0) + 2.0));
+    if (patch == 16 && !f32_src)
+      prologue_gather_kernel<16, 7, false><<<bands, g_block, 0, st>>>(frames, src_kind, d16, H, W, ld_patch);
+    else if (patch == 16)
+      prologue_gather_kernel<16, 7, true><<<bands, g_block, 0, st>>>(frames, src_kind, d16, H, W, ld_patch);
+    else if (!f32_src)
+      prologue_gather_kernel<32, 7, false><<<bands, g_block, 0, st>>>(frames, src_kind, d16, H, W, ld_patch);
+    else
+      prologue_gather_kernel<32, 7, true><<<bands, g_block, 0, st>>>(frames, src_kind, d16, H, W, ld_patch);
+  } else if (dst_kind == VMC_DST_BF16_PATCH && impl == 2) {
+    const double px = (double)F * 3 * H * W;
+    const double in_b = f32_src ? 4.0 : 1.0;
     const int bands = F * 3 * (H / patch);
     const int grid = bands < vmc_num_sms() * 8 ? bands : vmc_num_sms() * 8;
     VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * (in_b + 2.0));
@@ -722,7 +919,20 @@ int vmc_frame_diff_prologue(const uint8_t* bgr, uint8_t* diff_u8, void* dst, int
   }
   const size_t total = (size_t)clips * T * H * (W / 16);
   VMC_CHECK_ARG(total < (1ull << 31), VMC_ERR_SHAPE, "vmc_frame_diff_prologue: too many frames in one call");
-  if (dst && dst_kind == VMC_DST_BF16_PATCH && vmc_get_option(VMC_OPT_PROLOGUE_IMPL) == 2) {
+  const int impl = vmc_get_option(VMC_OPT_PROLOGUE_IMPL);
+  const int g_items = (dst && dst_kind == VMC_DST_BF16_PATCH) ? (W / patch) * (patch * patch / 8) : 0;
+  const int g_block = ((g_items + 6) / 7 + 31) / 32 * 32;
+  if (dst && dst_kind == VMC_DST_BF16_PATCH && impl != 1 && impl != 2 && (patch == 16 || patch == 32) &&
+      (W % 8) == 0 && g_block <= 128) {
+    const double px = (double)clips * T * H * W;
+    const int bands = clips * T * (H / patch);
+    __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dst);
+    VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * (6.0 + (diff_u8 ? 1.0 : 0.0) + 6.0));
+    if (patch == 16)
+      frame_diff_gather_kernel<16, 7><<<bands, g_block, 0, st>>>(bgr, diff_u8, d16, T, H, W, ld_patch);
+    else
+      frame_diff_gather_kernel<32, 7><<<bands, g_block, 0, st>>>(bgr, diff_u8, d16, T, H, W, ld_patch);
+  } else if (dst && dst_kind == VMC_DST_BF16_PATCH && impl == 2) {
     const double px = (double)clips * T * H * W;
     const int bands = clips * T * (H / patch);
     const int grid = bands < vmc_num_sms() * 8 ? bands : vmc_num_sms() * 8;
