@@ -186,6 +186,7 @@ def ours_main(args):
 
     clips = args.clips
     ops.set_option(_lib.OPT_LN_FUSE, args.ln_fuse)
+    ops.set_option(_lib.OPT_ATTN_IMPL, args.attn_impl)
     torch.manual_seed(0)
     pipe = vmc.ViMoCLIPPipeline("openai/clip-vit-base-patch16", "ViT-B/32", num_classes=NUM_CLASSES, device=dev, clips_per_step=args.chunk)
     pipe.rgb.visual.frames_in_flight = args.frames_in_flight
@@ -319,6 +320,7 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ln-fuse", type=int, default=0, help="VMC_OPT_LN_FUSE: 0 separate LayerNorm kernels (default), 1 fused into residual GEMM epilogues, 2 fuse only c_proj->ln_1")
+    ap.add_argument("--attn-impl", type=int, default=0, help="VMC_OPT_ATTN_IMPL: 0 library default, 3 / 5 select a ViT attention kernel generation")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_main(args)

@@ -30,7 +30,7 @@ const char* vmc_last_error(void);
 int vmc_abi_version(void);
 int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel,
- * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
+ * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row sums from the tensor core (L <= 224), 3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
  * Both implementations of each op are kept so the tests can cross-check them. */
 enum { VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
        VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged) */,

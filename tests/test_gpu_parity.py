@@ -278,7 +278,7 @@ def test_layernorm(cuda_device, d):
     assert torch.equal(y16, y32.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("impl", [4, 3, 2, 1])
+@pytest.mark.parametrize("impl", [5, 4, 3, 2, 1])
 @pytest.mark.parametrize("L,heads,F_", [(50, 12, 5), (197, 12, 3), (257, 16, 2), (128, 2, 2), (16, 1, 1), (129, 3, 2), (272, 1, 1), (197, 12, 40), (256, 4, 75), (200, 1, 1)])
 def test_attention_vit(cuda_device, L, heads, F_, impl):
     gen = torch.Generator(device="cuda").manual_seed(L)
@@ -292,7 +292,7 @@ def test_attention_vit(cuda_device, L, heads, F_, impl):
     assert err < 2e-2, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("impl", [4, 3, 2])
+@pytest.mark.parametrize("impl", [5, 4, 3, 2])
 def test_attention_vit_peaky_and_shifted_scores(cuda_device, impl):
     """Large score spread and a large common offset: the single-pass softmax (stabiliser = max of the
     first 32 keys) must stay as accurate as the exact-max reference."""

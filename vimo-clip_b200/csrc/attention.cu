@@ -788,6 +788,364 @@ attention_vit4_kernel(const __grid_constant__ CUtensorMap tm, const Attn3Args a)
 }
 
 // ---------------------------------------------------------------------------------------
+// A1, fifth generation (129 <= L <= 256): the two query tiles run OUT OF PHASE and the softmax warps do
+// nothing but softmax.
+//
+// What the v3 timeline showed: both tiles march in lockstep through  S MMA -> softmax -> PV -> O drain ->
+// next S MMA, because one MMA thread serves them in a fixed order, and the ~3k-cycle tail (PV part B,
+// accumulator drain, next S MMA) of BOTH tiles sits idle on the MUFU pipe at the same time (XU 54 % busy).
+// TMEM (512 columns) cannot hold a third score tile, so the bubble is hidden by phase instead:
+//   * warp 13, the MMA issuer, is event driven: it serves whichever tile's barrier completes next
+//     (try_wait with a short suspend hint, no spinning), and starts tile 1 half a period after tile 0;
+//   * warps 8-11 are EPILOGUE warps (one per TMEM lane quarter, both tiles): they drain O, release the
+//     tile's TMEM and write the output rows, so a softmax warp goes straight from its last chunk to the
+//     next item's scores;
+//   * the softmax normaliser comes from the tensor core: the PV MMA runs with N = 80, columns 64..79 of
+//     its B operand being a constant all-ones tile reached through the descriptor's leading-dimension
+//     offset, so column 64 of the accumulator is the row sum of exactly the bf16 probabilities the MMA
+//     consumed.  This removes the rounded-sum bookkeeping (2 LOP + 2 FADD of 13 instructions per pair) and
+//     the softmax -> epilogue hand-over of the row sums.
+// TMEM plan of one query tile (base = 256 t, n_chunks = ceil(Lk16 / 32) in 5..8):
+//   S    [0, Lk16)              fp32 scores
+//   P_a  [16 c, 16 c + 16)      bf16 pairs of chunk c < 5 (keys 0..159), over S columns already consumed
+//   O    [80, 144) sum [144,160) fp32 accumulator of the N = 80 PV MMA, over consumed S columns
+//   P_b  [32 c, 32 c + 16)      chunk c >= 5, in place over its own scores
+// ---------------------------------------------------------------------------------------
+// VAR: 0 = production; what-if timing variants (WRONG results; tools/kernel_bench.py only):
+//      1 = softmax warps only signal (pipeline floor), 2 = TMEM load + store without the math, 3 = FMA instead of MUFU
+template <bool MASK, int VAR = 0>
+__device__ __forceinline__ void chunk_exp_store5(const uint32_t (&r)[32], float sc, float mxs, int valid,
+                                                 uint32_t taddr) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float e0 = 0.f, e1 = 0.f;
+    if (VAR == 2) {
+      e0 = __uint_as_float(r[2 * j]);
+      e1 = __uint_as_float(r[2 * j + 1]);
+    } else if (!MASK || 2 * j < valid) {  // warp-uniform: padding columns cost no MUFU work
+      if (VAR == 3) {
+        e0 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f), 0.001f, 1.0f);
+        e1 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f), 0.001f, 1.0f);
+      } else {
+        e0 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f));
+        e1 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f));
+      }
+      if (MASK && 2 * j + 1 >= valid) e1 = 0.f;
+    }
+    // fp32 -> bf16 in the integer ALU (round half up; the XU pipe is the busy one)
+    pk[j] = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);
+  }
+  tmem_st_32x32b_x16(taddr, pk);
+}
+
+struct Attn5Args {
+  int L, heads, d, lk16, n_items;
+  __nv_bfloat16* out;
+  long long* dbg;  // timeline of CTA 0 (DBG instantiation only; tools/attn_timeline.py)
+  int cq, ck, cv, chead;  // column of head h's Q / K / V slice = c{q,k,v} + h * chead
+};
+#define VMC_DBG5(k_, slot)                                                                     \
+  do {                                                                                         \
+    if (DBG && a.dbg != nullptr && blockIdx.x == 0 && (k_) < 16) a.dbg[((k_) * 32) + (slot)] = clock64(); \
+  } while (0)
+
+constexpr int A5_THREADS = 448;  // 8 softmax + 4 epilogue + TMA + MMA warps
+constexpr int A5_PA_CHUNKS = 5;  // chunks (32 keys) whose P is packed into [0, 80): part A of the PV MMA
+constexpr int A5_OCOL = 80;      // accumulator columns [80, 160): 64 of O + 16 copies of the row sum
+
+template <int VAR, bool DBG = false>
+__global__ void __launch_bounds__(A5_THREADS, 1)
+attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm1,
+                      const Attn5Args a) {
+  // Shared memory: two rings, released at different times.  The timeline of the first v5 (one Q/K/V stage
+  // per item, freed when the item's last PV MMA retires) showed the NEXT-NEXT item's load being issued
+  // ~6k cycles (its own latency under load) before tile 0 needed it: the kernel was bound by the latency
+  // of one 96 KB load per SM.  Q and K are dead as soon as both S MMAs of the item have retired, i.e. a
+  // whole softmax earlier, so they get their own ring; the second tiles are loaded with (Lk16 - 128)-row
+  // boxes instead of 128-row ones (rows >= L are zero-filled by TMA either way).
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const int r1 = a.lk16 - 128;                          // rows of the second Q / K / V box (16..96)
+  const uint32_t mat_bytes = (uint32_t)(128 + r1) * 128u;  // one of Q, K, V for one item
+  const uint32_t qk_base = base;                         // ring of 2 x [Q | K]
+  const uint32_t v_base = base + 4 * mat_bytes;          // ring of 2 x V
+  const uint32_t ones_base = base + 6 * mat_bytes;
+  const int nkk = a.lk16 / 16;  // 16-key steps of the PV MMA
+  const uint32_t ones_bytes = (uint32_t)nkk * 2048u;
+  const uint32_t bar_base = ones_base + ones_bytes;
+  auto qk_full = [&](int s) { return bar_base + 8u * s; };
+  auto qk_empty = [&](int s) { return bar_base + 16u + 8u * s; };
+  auto s_full = [&](int t) { return bar_base + 32u + 8u * t; };
+  auto pa_full = [&](int t) { return bar_base + 48u + 8u * t; };
+  auto pb_full = [&](int t) { return bar_base + 64u + 8u * t; };
+  auto o_full = [&](int t) { return bar_base + 80u + 8u * t; };
+  auto s_empty = [&](int t) { return bar_base + 96u + 8u * t; };
+  auto v_full = [&](int s) { return bar_base + 112u + 8u * s; };
+  auto v_empty = [&](int s) { return bar_base + 128u + 8u * s; };
+  const uint32_t tmem_ptr_addr = bar_base + 144u;
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int n_my = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
+
+  // the all-ones "second MN atom" of the PV B operand (bf16 1.0 everywhere; any layout reads ones)
+  {
+    uint4* ones = reinterpret_cast<uint4*>(smem_raw + (ones_base - raw_addr));
+    for (uint32_t i = tid; i < ones_bytes / 16; i += A5_THREADS)
+      ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tm1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(qk_full(i), 1);
+      mbar_init(qk_empty(i), 1);
+      mbar_init(v_full(i), 1);
+      mbar_init(v_empty(i), 1);
+      mbar_init(s_full(i), 1);
+      mbar_init(pa_full(i), 4);  // one arrive per softmax warp of the tile
+      mbar_init(pb_full(i), 4);
+      mbar_init(o_full(i), 1);
+      mbar_init(s_empty(i), 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_ptr_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+  const int n_chunks = (a.lk16 + 31) / 32;  // 5..7
+
+  if (warp == 12) {
+    // ===================== TMA producer: serves both rings, never blocks on one of them =====================
+    // (hot polling: a nanosleep between polls reacts in ~700 cycles and was measured neither faster nor slower)
+    if (lane == 0) {
+      int kq = 0, kv = 0;
+      while (kq < n_my || kv < n_my) {
+        if (kq < n_my && mbar_test_wait(qk_empty(kq & 1), (((uint32_t)kq >> 1) & 1u) ^ 1u)) {
+          const int item = blockIdx.x + kq * gridDim.x;
+          const int head = item % a.heads, frame = item / a.heads;
+          const int s = kq & 1;
+          const uint32_t q = qk_base + s * 2 * mat_bytes, kk_ = q + mat_bytes;
+          VMC_DBG5(kq, 24);
+          mbar_arrive_expect_tx(qk_full(s), 2 * mat_bytes);
+          tma_load_3d(q, &tm, qk_full(s), a.cq + head * a.chead, 0, frame);
+          tma_load_3d(q + TILE, &tm1, qk_full(s), a.cq + head * a.chead, 128, frame);
+          tma_load_3d(kk_, &tm, qk_full(s), a.ck + head * a.chead, 0, frame);
+          tma_load_3d(kk_ + TILE, &tm1, qk_full(s), a.ck + head * a.chead, 128, frame);
+          ++kq;
+        }
+        if (kv < n_my && mbar_test_wait(v_empty(kv & 1), (((uint32_t)kv >> 1) & 1u) ^ 1u)) {
+          const int item = blockIdx.x + kv * gridDim.x;
+          const int head = item % a.heads, frame = item / a.heads;
+          const int s = kv & 1;
+          const uint32_t v = v_base + s * mat_bytes;
+          VMC_DBG5(kv, 26);
+          mbar_arrive_expect_tx(v_full(s), mat_bytes);
+          tma_load_3d(v, &tm, v_full(s), a.cv + head * a.chead, 0, frame);
+          tma_load_3d(v + TILE, &tm1, v_full(s), a.cv + head * a.chead, 128, frame);
+          ++kv;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 13) {
+    // ===================== MMA issuer (event driven, non-blocking polls) =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, a.lk16, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 80, 0, 1);  // B = [V | ones], MN-major
+      const int nka = nkk < 2 * A5_PA_CHUNKS ? nkk : 2 * A5_PA_CHUNKS;
+      int kt[2] = {0, 0};   // next item (local index) of each tile
+      int ph[2] = {0, 0};   // 0: S to issue, 1: waiting for P_a, 2: waiting for P_b
+      int sdone[2] = {0, 0};  // tiles whose S MMAs of the item in Q/K ring slot s have been issued
+      int fin[2] = {0, 0};    // tiles that have issued the last PV MMA of the item in V ring slot s
+      while (kt[0] < n_my || kt[1] < n_my) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (kt[t] >= n_my) continue;
+          const int k = kt[t];
+          const int s = k & 1;
+          const uint32_t par = (uint32_t)k & 1u;
+          const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
+          const uint32_t vst = v_base + s * mat_bytes;
+          // V descriptor: atom 0 = the TMA tile (64 head dims x 16 keys), atom 1 (N = 64..79) = LBO further = ones
+          const uint64_t dv0 = (umma_desc_sw128(vst) & ~(uint64_t(0x3FFF) << 16)) |
+                               (uint64_t((ones_base - vst) >> 4) << 16);
+          const uint32_t tcol = tmem_base + uint32_t(t * 256);
+          if (ph[t] == 0) {
+            // start tile 1 half a period late so that its softmax covers tile 0's MMA / drain tail
+            if (t == 1 && k == 0 && kt[0] == 0 && ph[0] < 2) continue;
+            if (!mbar_test_wait(qk_full(s), ring_par)) continue;
+            if (t == 0) VMC_DBG5(k, 25);
+            if (!mbar_test_wait(s_empty(t), par ^ 1u)) continue;
+            tc_fence_after();
+            VMC_DBG5(k, 0 + t);
+            const uint32_t qst = qk_base + s * 2 * mat_bytes;
+            const uint64_t dq = umma_desc_sw128(qst + t * TILE);
+            const uint64_t dk = umma_desc_sw128(qst + mat_bytes);
+#pragma unroll
+            for (int kq = 0; kq < HD / 16; ++kq)
+              umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s, kq != 0);
+            umma_commit(s_full(t));
+            if (++sdone[s] == 2) {  // both tiles' score MMAs are in flight: Q and K die when they retire
+              sdone[s] = 0;
+              umma_commit(qk_empty(s));
+            }
+            ph[t] = 1;
+          } else if (ph[t] == 1) {
+            if (!mbar_test_wait(pa_full(t), par)) continue;
+            if (!mbar_test_wait(v_full(s), ring_par)) continue;
+            tc_fence_after();
+            VMC_DBG5(k, 2 + t);
+            for (int kk = 0; kk < nka; ++kk)
+              umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv0 + uint64_t(kk * 128), idesc_pv, kk != 0);
+            ph[t] = 2;
+          } else {
+            if (!mbar_test_wait(pb_full(t), par)) continue;
+            tc_fence_after();
+            VMC_DBG5(k, 4 + t);
+            for (int kk = nka; kk < nkk; ++kk)
+              umma_ts(tcol + A5_OCOL, tcol + uint32_t((kk >> 1) * 32 + (kk & 1) * 8), dv0 + uint64_t(kk * 128),
+                      idesc_pv, 1u);
+            umma_commit(o_full(t));
+            if (++fin[s] == 2) {  // both tiles are done with this slot's V
+              fin[s] = 0;
+              umma_commit(v_empty(s));
+            }
+            kt[t] = k + 1;
+            ph[t] = 0;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 8) {
+    // ===================== epilogue warps: drain O, release the tile, write the rows =====================
+    const int q = warp - 8;
+    for (int k = 0; k < n_my; ++k) {
+      const int item = blockIdx.x + k * gridDim.x;
+      const int head = item % a.heads;
+      const int frame = item / a.heads;
+      const uint32_t par = (uint32_t)k & 1u;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {  // tile 0 leads tile 1 by half a period, so this is the completion order
+        const int row = t * 128 + q * 32 + lane;
+        const bool warp_active = (t * 128 + q * 32) < a.L;  // warp-uniform
+        const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
+        mbar_wait(o_full(t), par);
+        tc_fence_after();
+        if (q == 0 && lane == 0) VMC_DBG5(k, 11 + 8 * t);
+        uint32_t o0[32], o1[32];
+        uint32_t rs = 0x3F800000u;
+        if (warp_active) {
+          tmem_ld_32x32b_x32(tb + A5_OCOL, o0);
+          tmem_ld_32x32b_x32(tb + A5_OCOL + 32u, o1);
+          rs = tmem_ld_32x32b_x1(tb + A5_OCOL + 64u);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(s_empty(t));
+        if (q == 0 && lane == 0) VMC_DBG5(k, 12 + 8 * t);
+        if (warp_active && row < a.L) {
+          const float inv = 1.0f / __uint_as_float(rs);
+          __nv_bfloat16* orow = a.out + ((size_t)frame * a.L + row) * a.d + (size_t)head * HD;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+            reinterpret_cast<uint4*>(orow)[i] = o;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
+            reinterpret_cast<uint4*>(orow + 32)[i] = o;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warps =====================
+    const int t = warp >> 2;
+    const int q = warp & 3;
+    const bool warp_active = (t * 128 + q * 32) < a.L;  // warp-uniform
+    const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
+    const float sc = 0.125f * 1.4426950408889634f;
+    const int n_full = a.L >> 5;           // chunks with 32 valid columns
+    const int tail = a.L - (n_full << 5);  // valid columns of the last, partial chunk (0: none)
+    auto pcol = [&](int c) { return tb + uint32_t(c < A5_PA_CHUNKS ? c * 16 : c * 32); };
+    for (int k = 0; k < n_my; ++k) {
+      const uint32_t par = (uint32_t)k & 1u;
+      mbar_wait(s_full(t), par);
+      tc_fence_after();
+      if (q == 0 && lane == 0) VMC_DBG5(k, 8 + 8 * t);
+      if (warp_active && VAR == 1) {
+        if (lane == 0) mbar_arrive_relaxed(pa_full(t));
+      } else if (warp_active) {
+        // single pass over the score row, 32-column chunks double-buffered in registers; stabiliser = max of
+        // the first 32 keys (<= row max, so the row sum is >= 1; argument clamped at +120), see v3
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tb, r0);
+        tmem_ld_wait();
+        const float mxs = chunk_max<false>(r0, -INFINITY, 32) * sc;
+        for (int c = 0; c < n_chunks; c += 2) {
+          if (c != 0) tmem_ld_wait();
+          if (c + 1 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 1) * 32), r1);
+          if (c < n_full) chunk_exp_store5<false, VAR>(r0, sc, mxs, 32, pcol(c));
+          else chunk_exp_store5<true, VAR>(r0, sc, mxs, tail, pcol(c));
+          if (c == A5_PA_CHUNKS - 1) {
+            // chunks 0..4 (keys 0..159) are stored: release part A of the PV MMA.  The load of chunk 5
+            // issued above reads columns >= 160, disjoint from P_a and the accumulator.
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(pa_full(t));
+            if (q == 0 && lane == 0) VMC_DBG5(k, 9 + 8 * t);
+          }
+          if (c + 1 < n_chunks) {
+            tmem_ld_wait();
+            if (c + 2 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 2) * 32), r0);
+            if (c + 1 < n_full) chunk_exp_store5<false, VAR>(r1, sc, mxs, 32, pcol(c + 1));
+            else chunk_exp_store5<true, VAR>(r1, sc, mxs, tail, pcol(c + 1));
+          }
+        }
+        tmem_st_wait();
+      } else {
+        if (lane == 0) mbar_arrive_relaxed(pa_full(t));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(pb_full(t));
+      if (q == 0 && lane == 0) VMC_DBG5(k, 10 + 8 * t);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // TFAM attention: fp32, boolean key-padding mask (1 = attend), online softmax over 64-key tiles.
 // grid = (ceil(Tq/16), heads, B); 4 warps, each owning 4 query rows.
 // ---------------------------------------------------------------------------------------
@@ -900,10 +1258,48 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
   VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit: null pointer");
   VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 272, VMC_ERR_SHAPE,
                 "vmc_attention_vit: need 0 < L <= 272 tokens (L=%d)", L);
-  VMC_CHECK_ARG((impl >= 1 && impl <= 4) || impl == 31 || impl == 32, VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 1..4");
+  VMC_CHECK_ARG((impl >= 1 && impl <= 5) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 55), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 1..5");
   const int d = heads * HD;
-  if (impl >= 3 && (L <= 128 || L > 256)) impl = 2;  // the persistent kernels cover two query tiles
+  if (impl >= 3 && (L <= 128 || L > 256)) impl = 2;
+  if ((impl == 5 || impl >= 51) && L > 224) impl = 3;  // v5 keeps two Q/K and two V slots + the ones tile in smem  // the persistent kernels cover two query tiles
+  if (impl == 5 || impl >= 51) {
+    Attn5Args a5;
+    a5.L = L;
+    a5.heads = heads;
+    a5.d = d;
+    a5.lk16 = ((L + 15) / 16) * 16;
+    a5.n_items = F * heads;
+    a5.out = reinterpret_cast<__nv_bfloat16*>(out);
+    a5.dbg = reinterpret_cast<long long*>((uintptr_t)(unsigned long long)vmc_get_option64(VMC_OPT_DEBUG_PTR));
+    // packed [q | k | v] column blocks.  (A per-head interleaved layout [q_h | k_h | v_h], which would make
+    // the three slices of an item adjacent in DRAM, was timed and makes no difference: 0.372 ms either way.)
+    a5.cq = 0; a5.ck = d; a5.cv = 2 * d; a5.chead = HD;
+    CUtensorMap tm5;
+    const uint64_t dims5[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)F};
+    const uint64_t strides5[2] = {(uint64_t)3 * d * 2, (uint64_t)L * 3 * d * 2};
+    const uint32_t box5[3] = {HD, 128, 1};
+    VMC_TRY(vmc_encode_tmap_bf16(&tm5, qkv, 3, dims5, strides5, box5));
+    CUtensorMap tm5b;  // second Q / K / V tile: rows 128 .. Lk16 - 1
+    const uint32_t box5b[3] = {HD, (uint32_t)(a5.lk16 - 128), 1};
+    VMC_TRY(vmc_encode_tmap_bf16(&tm5b, qkv, 3, dims5, strides5, box5b));
+    const uint32_t smem5 = 6u * (uint32_t)a5.lk16 * 128u + (uint32_t)(a5.lk16 / 16) * 2048u + 256 + 1024;
+    cudaStream_t st5 = reinterpret_cast<cudaStream_t>(stream);
+    const int grid5 = a5.n_items < vmc_num_sms() ? a5.n_items : vmc_num_sms();
+    auto kern5 = impl == 5 ? attention_vit5_kernel<0>
+                 : impl == 51 ? attention_vit5_kernel<1>
+                 : impl == 52 ? attention_vit5_kernel<2>
+                 : impl == 53 ? attention_vit5_kernel<3>
+                 : impl == 54 ? attention_vit5_kernel<1, true> : attention_vit5_kernel<0, true>;  // 54 / 55: timeline stamps
+    VMC_CUDA(cudaFuncSetAttribute(kern5, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
+    {
+      VmcProfScope prof(VMC_K_ATTN_VIT, st5, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
+      kern5<<<grid5, A5_THREADS, smem5, st5>>>(tm5, tm5b, a5);
+    }
+    VMC_LAUNCH_CHECK();
+    vmc_count_launch();
+    return VMC_OK;
+  }
   if (impl >= 3) {
     Attn3Args a3;
     a3.L = L;
@@ -1001,7 +1397,7 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
 
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream) {
   const int opt = vmc_get_option(VMC_OPT_ATTN_IMPL);
-  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt >= 1 && opt <= 4) ? opt : 3, stream);
+  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt >= 1 && opt <= 5) ? opt : 5, stream);
 }
 
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk,

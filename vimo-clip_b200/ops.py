@@ -217,7 +217,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
     return y32, y16
 
 
-def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int, impl: int = 3) -> torch.Tensor:
+def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int, impl: int = 5) -> torch.Tensor:
     """qkv bf16 [F*L, 3*heads*64] -> bf16 [F*L, heads*64]; softmax(q k^T / 8) v per (frame, head)."""
     _need_cuda(qkv)
     d = heads * 64
