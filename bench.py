@@ -319,7 +319,7 @@ def main():
     ap.add_argument("--frames-in-flight", type=int, default=2048, help="frames per vmc_vit_forward call (workspace size)")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ln-fuse", type=int, default=0, help="VMC_OPT_LN_FUSE: 0 separate LayerNorm kernels (default), 1 fused into residual GEMM epilogues, 2 fuse only c_proj->ln_1")
+    ap.add_argument("--ln-fuse", type=int, default=0, help="VMC_OPT_LN_FUSE: 0 separate LayerNorm kernels (default), 3 ln_1+ln_2 folded into the qkv / c_fc GEMMs, 5 only ln_1 folded, 1/2 fused into residual GEMM epilogues")
     ap.add_argument("--attn-impl", type=int, default=0, help="VMC_OPT_ATTN_IMPL: 0 library default, 3 / 5 select a ViT attention kernel generation")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VMC_ABI_VERSION 1
+#define VMC_ABI_VERSION 2
 
 /* ---- runtime ---------------------------------------------------------------- */
 const char* vmc_last_error(void);
@@ -34,8 +34,10 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * Both implementations of each op are kept so the tests can cross-check them. */
 enum { VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
        VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged) */,
-       VMC_OPT_LN_FUSE = 3 /* ViT tower: 0 = separate LayerNorm kernels (default, faster), 1 = ln_1/ln_2 fused into the
-                              residual GEMM epilogues, 2 = only c_proj -> next ln_1 fused */ };
+       VMC_OPT_LN_FUSE = 3 /* ViT tower: 0/4 = separate LayerNorm kernels (default); 5 = ln_1 FOLDED into the qkv GEMM (c_proj
+                              emits bf16 rows + row statistics, no ln_1 pass); 3 = ln_2 folded into c_fc as well (-1.7 % step
+                              time, but the LayerNorm work moves into the GEMM epilogues); 1 = ln_1/ln_2 fused into the
+                              residual GEMM epilogues (row-owner tile order, measured slower), 2 = only c_proj -> ln_1 fused */ };
 int vmc_set_option(int option, long long value);
 /* kernels launched by this library since the last reset (bench.py "gpu_launches") */
 long long vmc_launch_count(void);
@@ -108,8 +110,24 @@ typedef struct vmc_gemm_epilogue {
   const float* ln_beta;
   void* ln_out;       /* bf16 [M, ln_ldo] */
   long long ln_ldo;
-  float ln_eps;
+  float ln_eps;      /* also the epsilon of the folded LayerNorm below */
+  /* LayerNorm FOLDING (no LayerNorm pass at all; CTA-pair kernel only).  For y = LayerNorm(x) * gamma + beta,
+   *   y W^T + b = rstd * (x W'^T - mean * colsum) + b',   W' = gamma (.) W,  colsum[n] = sum_k W'[n,k],  b' = b + W beta,
+   * so the GEMM that consumes LayerNorm(x) runs on the RAW rows x (bf16) with W', and its epilogue applies the per-row
+   * mean / rstd.  Producer side (fp32 out + bias + residual epilogue, i.e. the GEMM that writes the residual stream):
+   * raw16_out receives the bf16 copy of the output rows and stats_out per-row partial (sum, sum of squares), one
+   * float2 plane of stats_ld rows per vmc_gemm_stats_parts(M, N) column slices.  Consumer side (bf16 out + bias
+   * [+ QuickGELU] epilogue): stats_in / stats_parts / colsum describe the rows of A; statistics are over K columns. */
+  void* raw16_out;       /* producer: bf16 [M, raw16_ld], or NULL */
+  long long raw16_ld;
+  float* stats_out;      /* producer: float2 [parts][stats_ld], or NULL */
+  const float* stats_in; /* consumer: float2 [stats_parts][stats_ld], or NULL */
+  int stats_parts;
+  long long stats_ld;
+  const float* colsum;   /* consumer: [N] fp32 */
 } vmc_gemm_epilogue;
+/* number of column slices (partials per row) a producer GEMM of this shape writes to stats_out */
+int vmc_gemm_stats_parts(int M, int N);
 int vmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                   const vmc_gemm_epilogue* epi, void* stream);
 
@@ -126,6 +144,11 @@ int vmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, in
 int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
                   float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows, int d,
                   const float* cls_row, int cls_every, void* stream);
+/* Same, and stats_out[row] = float2(sum, sum of squares) of the fp32 OUTPUT row (NULL = off): the row statistics a
+ * LayerNorm folded into the next GEMM needs (vmc_gemm_epilogue.stats_in with stats_parts = 1). */
+int vmc_layernorm_stats(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+                        float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows,
+                        int d, const float* cls_row, int cls_every, float* stats_out, void* stream);
 
 /* ---- A1: ViT self-attention (no mask), head_dim 64 ------------------------------
  * qkv bf16 [F*L, 3*d] (q | k | v, heads contiguous inside each), out bf16 [F*L, d].
@@ -182,6 +205,10 @@ typedef struct vmc_vit_layer {
   const void* w_out;  const float* b_out;   /* [d, d], [d] */
   const void* w_fc1;  const float* b_fc1;   /* [4d, d], [4d] */
   const void* w_fc2;  const float* b_fc2;   /* [d, 4d], [d] */
+  /* LayerNorm folding (VMC_OPT_LN_FUSE = 3 / 5): ln_1 folded into the qkv GEMM and
+   * ln_2 into c_fc.  w_*_f = bf16(gamma (.) W), b_*_f = b + W beta, cs_* [n] = sum_k float(w_*_f[n,k]).  NULL = absent. */
+  const void* w_qkv_f; const float* b_qkv_f; const float* cs_qkv;
+  const void* w_fc1_f; const float* b_fc1_f; const float* cs_fc1;
 } vmc_vit_layer;
 typedef struct vmc_vit_model {
   int image, patch, width, layers, heads, out_dim;

@@ -239,14 +239,25 @@ def test_vit_tower_fused_vs_separate_layernorm(cuda_device):
     gen = torch.Generator().manual_seed(6)
     u8 = torch.randint(0, 256, (80, 3, 224, 224), dtype=torch.uint8, generator=gen).to(cuda_device)  # 80*197 rows: fused path on
     patches = ops.prologue(u8, wrap=False, dst="patch", patch=16)
-    separate = tower.forward_patches(patches, 80).clone()
-    for mode in (1, 2):
+    ops.set_option(vmc._lib.OPT_LN_FUSE, 4)
+    try:
+        separate = tower.forward_patches(patches, 80).clone()
+        for mode in (1, 2):
+            ops.set_option(vmc._lib.OPT_LN_FUSE, mode)
+            fused = tower.forward_patches(patches, 80).clone()
+            assert torch.equal(fused, separate), mode
+    finally:
+        ops.set_option(vmc._lib.OPT_LN_FUSE, 0)
+    # LayerNorm FOLDED into the consuming GEMMs (different rounding points, same mathematics):
+    # 5 = ln_1 only, 3 = ln_1 and ln_2
+    for mode in (5, 3):
         ops.set_option(vmc._lib.OPT_LN_FUSE, mode)
         try:
-            fused = tower.forward_patches(patches, 80).clone()
+            folded = tower.forward_patches(patches, 80)
         finally:
             ops.set_option(vmc._lib.OPT_LN_FUSE, 0)
-        assert torch.equal(fused, separate), mode
+        cos = torch.nn.functional.cosine_similarity(folded.double(), separate.double(), dim=-1).min().item()
+        assert cos >= 0.99998, (mode, cos)
 
 
 def test_gemm_linearity_full_size(cuda_device, gemm_impl):
@@ -276,6 +287,49 @@ def test_layernorm(cuda_device, d):
     ref = torch.nn.functional.layer_norm(x, (d,), g_, b_, 1e-5)
     assert (y32 - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
     assert torch.equal(y16, y32.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,d,N,act", [(394, 768, 2304, 0), (50000, 768, 3072, 1), (40000, 1024, 3072, 0), (700, 512, 1536, 1)])
+def test_gemm_layernorm_fold(cuda_device, M, d, N, act):
+    """LayerNorm folded into the consuming GEMM: a producer GEMM (bias + fp32 residual) emits bf16 rows + partial row
+    statistics, the consumer runs on the raw rows with gamma-folded weights (include/vimoclip_b200.h).  Checked against
+    fp32 LayerNorm + matmul on the same bf16 operands."""
+    gen = torch.Generator(device="cuda").manual_seed(M + N)
+    a0 = (torch.randn(M, d, device=cuda_device, generator=gen)).to(torch.bfloat16)
+    w0 = (torch.randn(d, d, device=cuda_device, generator=gen) * d**-0.5).to(torch.bfloat16)
+    b0 = torch.randn(d, device=cuda_device, generator=gen)
+    x = torch.randn(M, d, device=cuda_device, generator=gen) * 2 + 0.5
+    x[:, 7] += 30.0  # an outlier channel and a non-zero mean, as in real residual streams
+    parts = ops.gemm_stats_parts(M, d)
+    raw16 = torch.empty(M, d, dtype=torch.bfloat16, device=cuda_device)
+    stats = torch.zeros(parts, M, 2, device=cuda_device)
+    xnew = x.clone()
+    ops.gemm(a0, w0, bias=b0, resid=xnew, out=xnew, emit_stats=(raw16, stats))
+    ref_x = a0.float() @ w0.float().t() + b0 + x
+    assert (xnew - ref_x).abs().max().item() < 2e-3
+    assert torch.equal(raw16, xnew.to(torch.bfloat16))
+    st = stats.sum(0)
+    assert torch.allclose(st[:, 0], xnew.sum(1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(st[:, 1], (xnew * xnew).sum(1), rtol=1e-5, atol=1e-2)
+    # consumer
+    gamma = torch.randn(d, device=cuda_device, generator=gen) * 0.3 + 1.0
+    beta = torch.randn(d, device=cuda_device, generator=gen) * 0.2
+    w1 = torch.randn(N, d, device=cuda_device, generator=gen) * d**-0.5
+    b1 = torch.randn(N, device=cuda_device, generator=gen)
+    wf = (w1 * gamma[None, :]).to(torch.bfloat16)
+    colsum = wf.float().sum(1)
+    bf = b1 + w1 @ beta
+    got = ops.gemm(raw16, wf, bias=bf, act=act, fold=(stats, colsum, 1e-5)).float()
+    y = torch.nn.functional.layer_norm(xnew, (d,), gamma, beta, 1e-5)
+    ref = y @ w1.t() + b1
+    if act:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    # reference path of the library: LayerNorm kernel -> bf16 -> plain GEMM
+    _, y16 = ops.layernorm(xnew, gamma, beta)
+    base = ops.gemm(y16, w1.to(torch.bfloat16), bias=b1, act=act).float()
+    err_fold = (got - ref).abs().max().item()
+    err_base = (base - ref).abs().max().item()
+    assert err_fold < max(2.0 * err_base, 3e-2), (err_fold, err_base)
 
 
 @pytest.mark.parametrize("impl", [5, 4, 3, 2, 1])

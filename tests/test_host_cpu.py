@@ -22,7 +22,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(vmc._lib.EXPORTED_SYMBOLS), declared ^ set(vmc._lib.EXPORTED_SYMBOLS)
-    assert vmc._lib.lib().vmc_abi_version() == 1
+    assert vmc._lib.lib().vmc_abi_version() == 2
 
 
 def test_no_cpu_fallback():

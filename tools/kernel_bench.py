@@ -50,6 +50,24 @@ if "gemm" in which:
                 out = torch.empty(M, N, device=dev, dtype=kw.pop("out_dtype"))
             ms = timeit(lambda: ops.gemm(a, w, bias=b, out=out, **kw))
             print(f"gemm {name:16s} M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+        # LayerNorm folding: producers emit bf16 rows + row statistics, consumers apply mean / rstd in the epilogue
+        parts = ops.gemm_stats_parts(M, d)
+        raw16 = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
+        stats = torch.zeros(parts, M, 2, device=dev)
+        for name, a, N, K in [("out+res+stats", x, d, d), ("fc2+res+stats", h, d, 4 * d)]:
+            w = (torch.randn(N, K, device=dev, generator=gen) * K**-0.5).to(torch.bfloat16)
+            b = torch.randn(N, device=dev, generator=gen)
+            ms = timeit(lambda: ops.gemm(a, w, bias=b, resid=res, out=res, emit_stats=(raw16, stats)))
+            print(f"gemm {name:16s} M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+        stats.normal_().abs_()
+        stats[..., 1] += 100.0
+        for name, N, act in [("qkv fold", 3 * d, ops.ACT_NONE), ("fc1+qgelu fold", 4 * d, ops.ACT_QUICKGELU)]:
+            w = (torch.randn(N, d, device=dev, generator=gen) * d**-0.5).to(torch.bfloat16)
+            b = torch.randn(N, device=dev, generator=gen)
+            cs = w.float().sum(1)
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            ms = timeit(lambda: ops.gemm(x, w, bias=b, act=act, out=out, fold=(stats, cs, 1e-5)))
+            print(f"gemm {name:16s} M={M} N={N} K={d}: {ms:.3f} ms  {2.0 * M * N * d / ms / 1e9:.0f} TFLOP/s", flush=True)
 if "attn" in which:
     for L, heads in [(197, 12), (50, 12), (257, 16)][: int(os.environ.get("KB_ATTN_SHAPES", "3"))]:
         d = heads * 64

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libvimoclip_b200.so")
 SRC_U8, SRC_U8_WRAP, SRC_F32_WRAP, SRC_F32_NORM = 0, 1, 2, 3
 DST_U8, DST_F32_NCHW, DST_BF16_PATCH = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 OPT_GEMM_IMPL, OPT_ATTN_IMPL, OPT_PROLOGUE_IMPL, OPT_LN_FUSE = 0, 1, 2, 3
 
 
@@ -36,12 +36,20 @@ class GemmEpilogue(C.Structure):
         ("ln_out", C.c_void_p),
         ("ln_ldo", C.c_longlong),
         ("ln_eps", C.c_float),
+        ("raw16_out", C.c_void_p),
+        ("raw16_ld", C.c_longlong),
+        ("stats_out", C.c_void_p),
+        ("stats_in", C.c_void_p),
+        ("stats_parts", C.c_int),
+        ("stats_ld", C.c_longlong),
+        ("colsum", C.c_void_p),
     ]
 
 
 class VitLayer(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_out", "b_out", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_out", "b_out", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+        "w_qkv_f", "b_qkv_f", "cs_qkv", "w_fc1_f", "b_fc1_f", "cs_fc1")]
 
 
 class VitModel(C.Structure):
@@ -69,6 +77,8 @@ _SIGNATURES = {
     "vmc_resize_center_crop": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vmc_gemm_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), C.c_void_p]),
     "vmc_layernorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "vmc_layernorm_stats": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "vmc_gemm_stats_parts": (C.c_int, [C.c_int, C.c_int]),
     "vmc_attention_vit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vmc_attention_vit_impl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vmc_attention_masked": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* y32, long long ld32,
                  __nv_bfloat16* y16, long long ld16, int y16_split, int rows, int d,
-                 const float* __restrict__ cls_row, int cls_every) {
+                 const float* __restrict__ cls_row, int cls_every, float2* __restrict__ stats_out) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -657,6 +657,7 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+  float so = 0.f, qo = 0.f;  // (sum, sum of squares) of the OUTPUT row, for a LayerNorm folded into the next GEMM
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = lane + 32 * i;
@@ -668,6 +669,8 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      so += (o.x + o.y) + (o.z + o.w);
+      qo += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
       if (y32 != nullptr) reinterpret_cast<float4*>(y32 + (size_t)row * ld32)[j] = o;
       if (y16 != nullptr) {
         if (y16_split) {
@@ -680,6 +683,11 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
         }
       }
     }
+  }
+  if (stats_out != nullptr) {
+    so = warp_sum(so);
+    qo = warp_sum(qo);
+    if (lane == 0) stats_out[row] = make_float2(so, qo);
   }
 }
 
@@ -955,7 +963,16 @@ int vmc_frame_diff_prologue(const uint8_t* bgr, uint8_t* diff_u8, void* dst, int
 int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
                   float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows,
                   int d, const float* cls_row, int cls_every, void* stream) {
+  return vmc_layernorm_stats(x, ldx, gamma, beta, eps, y32, ld32, y16, ld16, y16_split, rows, d, cls_row,
+                             cls_every, nullptr, stream);
+}
+
+int vmc_layernorm_stats(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
+                        float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows,
+                        int d, const float* cls_row, int cls_every, float* stats_out, void* stream) {
   VMC_CHECK_ARG(x && gamma && beta && (y32 || y16), VMC_ERR_ARG, "vmc_layernorm: null pointer");
+  VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(stats_out) & 7) == 0, VMC_ERR_ALIGN,
+                "vmc_layernorm_stats: stats_out must be 8-byte aligned");
   VMC_CHECK_ARG(rows > 0 && d > 0 && (d % 4) == 0 && d <= 4096, VMC_ERR_SHAPE,
                 "vmc_layernorm: need d %% 4 == 0 and d <= 4096 (rows=%d d=%d)", rows, d);
   VMC_CHECK_ARG((ldx % 4) == 0 && (!y32 || (ld32 % 4) == 0) && (!y16 || (ld16 % 4) == 0),
@@ -967,7 +984,8 @@ int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float
   __nv_bfloat16* y16b = reinterpret_cast<__nv_bfloat16*>(y16);
 #define LN_LAUNCH(NV)                                                                            \
   layernorm_kernel<NV><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, y32, ld32, y16b, ld16,    \
-                                             y16_split, rows, d, cls_row, cls_every)
+                                             y16_split, rows, d, cls_row, cls_every,         \
+                                             reinterpret_cast<float2*>(stats_out))
   VmcProfScope prof(VMC_K_LAYERNORM, st, 0.0,
                     (double)rows * d * (4.0 + (y32 ? 4.0 : 0.0) + (y16 ? 2.0 : 0.0)));
   if (d <= 512) LN_LAUNCH(4);

@@ -377,8 +377,9 @@ extern "C" int vmc_gemm_bf16(const void* A, long long lda, const void* W, long l
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (vmc_get_option(VMC_OPT_GEMM_IMPL) != 1)  // default: CTA-pair kernel (gemm2.cu)
     return vmc_gemm2_dispatch(A, lda, W, ldw, M, N, K, epi, st);
-  VMC_CHECK_ARG(epi->ln_out == nullptr, VMC_ERR_ARG,
-                "vmc_gemm_bf16: the fused LayerNorm epilogue exists only in the CTA-pair kernel");
+  VMC_CHECK_ARG(epi->ln_out == nullptr && epi->raw16_out == nullptr && epi->stats_out == nullptr &&
+                    epi->stats_in == nullptr,
+                VMC_ERR_ARG, "vmc_gemm_bf16: the fused / folded LayerNorm epilogues exist only in the CTA-pair kernel");
   // single-CTA kernel: 128x256 tiles when there are enough to fill the machine twice; 128x128 otherwise.
   const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
   if (N > 128 && tiles256 >= 2LL * vmc_num_sms())

@@ -133,8 +133,12 @@ __device__ __forceinline__ float quickgelu_fast(float x) {
 //   MODE 1: bf16 out = acc + bias            (qkv)
 //   MODE 2: bf16 out = QuickGELU(acc + bias) (mlp.c_fc)
 //   MODE 3: fp32 out = resid + acc + bias    (attn.out_proj, mlp.c_proj; out may alias resid)
-template <int MODE, int HALF_N>
-__device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M, int N, int row0,
+// LNF   (consumer of a folded LayerNorm, MODE 1 / 2): acc <- rstd[m] * acc - mean[m] * rstd[m] * colsum[n]
+//       before the bias; mean / rstd come from the producer's partial row sums (statistics over K columns).
+// STATS (producer, MODE 3): also write the bf16 copy of the output rows and this warp's partial
+//       (sum, sum of squares) of each row over its HALF_N columns.
+template <int MODE, int HALF_N, bool LNF = false, bool STATS = false>
+__device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M, int N, int K, int row0,
                                               int n_base, uint32_t t_acc, uint8_t* stg, int lane) {
   const int lr = lane >> 3, lc = lane & 7;
   const int m_first = row0 + lr;
@@ -150,19 +154,69 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
     rstride = 4 * e.ldr * 4;
   }
   const float* bptr = e.bias + n_base + lc * 4;
+  // folded LayerNorm: every thread derives mean / rstd of ONE row (row0 + lane) from the producer's partial sums;
+  // after the transpose a lane holds rows 4 i + lr, so the 8 (rstd, -mean * rstd) pairs it needs come by shuffle
+  float ln_rs[8], ln_sh[8];
+  if constexpr (LNF) {
+    const int m = row0 + lane;
+    float rstd = 1.f, shift = 0.f;
+    if (m < M) {
+      float s = 0.f, q = 0.f;
+      for (int p = 0; p < e.stats_parts; ++p) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(e.stats_in) + (long long)p * e.stats_ld + m);
+        s += v.x;
+        q += v.y;
+      }
+      const float mean = s / (float)K;
+      const float var = fmaxf(q / (float)K - mean * mean, 0.f);
+      rstd = rsqrtf(var + e.ln_eps);
+      shift = -mean * rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ln_rs[i] = __shfl_sync(0xffffffffu, rstd, i * 4 + lr);
+      ln_sh[i] = __shfl_sync(0xffffffffu, shift, i * 4 + lr);
+    }
+  }
+  float psum[8], psq[8];
+  char* r16ptr = nullptr;
+  long long r16stride = 0;
+  if constexpr (STATS) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) psum[i] = psq[i] = 0.f;
+    r16ptr = reinterpret_cast<char*>(e.raw16_out) + ((long long)m_first * e.raw16_ld + n_base + lc * 4) * 2;
+    r16stride = 4 * e.raw16_ld * 2;
+  }
+  float4 res_next[8];
+  if constexpr (MODE == 3) {
+    const char* rp = rptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nvalid && n_base < N) res_next[i] = *reinterpret_cast<const float4*>(rp);
+      rp += rstride;
+    }
+  }
 #pragma unroll 1
   for (int c = 0; c < HALF_N / 32; ++c) {
     if (n_base + c * 32 >= N) break;  // warp-uniform
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + c * 32));
+    float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (LNF) cs4 = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base + c * 32 + lc * 4));
     float4 res[8];
     if constexpr (MODE == 3) {
-      const char* rp = rptr + c * 128;
+      // the residual rows of the NEXT chunk are requested while this one is processed: the epilogue of the
+      // K = 768 residual GEMMs is bound by bytes in flight (8 warps x 4 KB per SM), not by HBM bandwidth
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i < nvalid) res[i] = *reinterpret_cast<const float4*>(rp);
-        rp += rstride;
+      for (int i = 0; i < 8; ++i) res[i] = res_next[i];
+      if (c + 1 < HALF_N / 32 && n_base + (c + 1) * 32 < N) {
+        const char* rp = rptr + (c + 1) * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < nvalid) res_next[i] = *reinterpret_cast<const float4*>(rp);
+          rp += rstride;
+        }
       }
     }
     tmem_ld_wait();
@@ -179,13 +233,21 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
     }
     __syncwarp();
     char* op = optr + c * 32 * ESZ;
+    char* r16p = STATS ? r16ptr + c * 64 : nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 v = w[i];
-      v.x += b4.x;
-      v.y += b4.y;
-      v.z += b4.z;
-      v.w += b4.w;
+      if constexpr (LNF) {  // rstd * acc - mean * rstd * colsum[n] + bias'[n]
+        v.x = fmaf(v.x, ln_rs[i], fmaf(ln_sh[i], cs4.x, b4.x));
+        v.y = fmaf(v.y, ln_rs[i], fmaf(ln_sh[i], cs4.y, b4.y));
+        v.z = fmaf(v.z, ln_rs[i], fmaf(ln_sh[i], cs4.z, b4.z));
+        v.w = fmaf(v.w, ln_rs[i], fmaf(ln_sh[i], cs4.w, b4.w));
+      } else {
+        v.x += b4.x;
+        v.y += b4.y;
+        v.z += b4.z;
+        v.w += b4.w;
+      }
       if constexpr (MODE == 2) {
         v.x = quickgelu_fast(v.x);
         v.y = quickgelu_fast(v.y);
@@ -198,6 +260,15 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
         v.z += res[i].z;
         v.w += res[i].w;
         if (i < nvalid) *reinterpret_cast<float4*>(op) = v;
+        if constexpr (STATS) {
+          psum[i] += (v.x + v.y) + (v.z + v.w);
+          psq[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+          uint2 o;
+          o.x = pack_bf16x2(v.x, v.y);
+          o.y = pack_bf16x2(v.z, v.w);
+          if (i < nvalid) *reinterpret_cast<uint2*>(r16p) = o;
+          r16p += r16stride;
+        }
       } else {
         uint2 o;
         o.x = pack_bf16x2(v.x, v.y);
@@ -205,6 +276,20 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
         if (i < nvalid) *reinterpret_cast<uint2*>(op) = o;
       }
       op += ostride;
+    }
+  }
+  if constexpr (STATS) {
+    // the 8 lanes lc = 0..7 of a row hold its HALF_N columns between them
+    float2* sp = reinterpret_cast<float2*>(e.stats_out) + (long long)(n_base / HALF_N) * e.stats_ld + m_first;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = psum[i], q = psq[i];
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lc == 0 && i < nvalid) sp[4 * i] = make_float2(s, q);
     }
   }
 }
@@ -364,8 +449,12 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       tc_fence_after();
       const uint32_t t_acc =
           tmem_base + uint32_t(acc * BN + half * HALF_N) + (uint32_t(quarter * 32) << 16);
-      if constexpr (MODE != 0) {
-        epilogue_fast<(MODE == 4 ? 3 : MODE), HALF_N>(e, g.M, g.N, row0, n_base, t_acc, stg, lane);
+      if constexpr (MODE == 5) {
+        epilogue_fast<3, HALF_N, false, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
+      } else if constexpr (MODE == 6 || MODE == 7) {
+        epilogue_fast<MODE - 5, HALF_N, true, false>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
+      } else if constexpr (MODE != 0) {
+        epilogue_fast<(MODE == 4 ? 3 : MODE), HALF_N>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else {
         // ---- generic path: any activation / alpha / ragged N / patch-embed row remap ----
 #pragma unroll 1
@@ -558,7 +647,8 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
   {
     const double out_b = (double)M * N * (epi->out_bf16 ? 2 : 4);
     VmcProfScope prof(VMC_K_GEMM, stream, 2.0 * M * N * K,
-                      2.0 * ((double)M * K + (double)N * K) + out_b + (epi->resid ? 4.0 * M * N : 0.0));
+                      2.0 * ((double)M * K + (double)N * K) + out_b + (epi->resid ? 4.0 * M * N : 0.0) +
+                          (epi->raw16_out ? 2.0 * M * N : 0.0));
     gemm2_bf16_tcgen05_kernel<BN, MODE><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, g);
   }
   VMC_LAUNCH_CHECK();
@@ -567,6 +657,14 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
 }
 
 }  // namespace
+
+// Column slices per row a producer GEMM (stats_out) of this shape writes: one per epilogue warp column half.
+extern "C" int vmc_gemm_stats_parts(int M, int N) {
+  if (M <= 0 || N <= 0) return -1;
+  const long long tiles256 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+  const bool big = N > 128 && tiles256 >= (long long)vmc_num_sms();
+  return (N + (big ? 127 : 63)) / (big ? 128 : 64);
+}
 
 // Called by vmc_gemm_bf16 (gemm.cu) after argument validation.
 int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ldw, int M, int N,
@@ -580,6 +678,25 @@ int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ld
     if (epi->out_bf16 && !epi->resid && epi->act == VMC_ACT_NONE) mode = 1;
     else if (epi->out_bf16 && !epi->resid && epi->act == VMC_ACT_QUICKGELU) mode = 2;
     else if (!epi->out_bf16 && epi->resid && epi->act == VMC_ACT_NONE) mode = 3;
+  }
+  if (epi->raw16_out != nullptr || epi->stats_out != nullptr) {
+    VMC_CHECK_ARG(mode == 3 && epi->raw16_out && epi->stats_out && epi->ln_out == nullptr && (N % (big ? 128 : 64)) == 0 &&
+                      (epi->raw16_ld % 4) == 0 && epi->raw16_ld >= N && epi->stats_ld >= M &&
+                      (reinterpret_cast<uintptr_t>(epi->raw16_out) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(epi->stats_out) & 7) == 0,
+                  VMC_ERR_ARG,
+                  "vmc_gemm_bf16: raw16_out / stats_out need the fp32 bias+residual epilogue, both pointers, N a multiple "
+                  "of the column slice (%d) and stats_ld >= M", big ? 128 : 64);
+    mode = 5;
+  }
+  if (epi->stats_in != nullptr) {
+    VMC_CHECK_ARG((mode == 1 || mode == 2) && epi->colsum && epi->stats_parts > 0 && epi->stats_ld >= M &&
+                      (reinterpret_cast<uintptr_t>(epi->colsum) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(epi->stats_in) & 7) == 0,
+                  VMC_ERR_ARG,
+                  "vmc_gemm_bf16: a folded LayerNorm (stats_in) needs the bf16 bias [+ QuickGELU] epilogue, colsum and "
+                  "stats_parts > 0");
+    mode += 5;
   }
   if (epi->ln_out != nullptr) {
     VMC_CHECK_ARG(mode == 3 && big && N <= 1024 && (N % 128) == 0 && epi->ln_gamma && epi->ln_beta &&
@@ -596,6 +713,9 @@ int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ld
       case 2: VMC_G2(256, 2);
       case 3: VMC_G2(256, 3);
       case 4: VMC_G2(256, 4);
+      case 5: VMC_G2(256, 5);
+      case 6: VMC_G2(256, 6);
+      case 7: VMC_G2(256, 7);
       default: VMC_G2(256, 0);
     }
   }
@@ -603,6 +723,9 @@ int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ld
     case 1: VMC_G2(128, 1);
     case 2: VMC_G2(128, 2);
     case 3: VMC_G2(128, 3);
+    case 5: VMC_G2(128, 5);
+    case 6: VMC_G2(128, 6);
+    case 7: VMC_G2(128, 7);
     default: VMC_G2(128, 0);
   }
 #undef VMC_G2

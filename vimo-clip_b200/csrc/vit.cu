@@ -25,6 +25,7 @@ struct Workspace {
   void* xn2;
   void* big;
   void* cls;
+  float* stats;  // float2 [8][rows]: partial row statistics for the folded LayerNorms
   long long total;
 };
 
@@ -46,6 +47,8 @@ Workspace carve(const vmc_vit_model* m, int F, void* base) {
   off += align_up(rows * 4 * d * 2, 1024);
   w.cls = p + off;
   off += align_up((long long)F * d * 2, 1024);
+  w.stats = reinterpret_cast<float*>(p + off);
+  off += align_up(rows * 8 * 8, 1024);
   w.total = off;
   return w;
 }
@@ -94,9 +97,98 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
     VMC_TRY(vmc_gemm_bf16(patches, m->ld_patch, m->w_patch, m->ld_patch, F * n, d, kpatch, &e,
                           stream));
   }
+  // LayerNorm FOLDING (VMC_OPT_LN_FUSE = 3 or 5): ln_1 / ln_2 never run as kernels.  The GEMMs
+  // that write the residual stream (ln_pre here, then out_proj and c_proj) also emit the bf16 copy of their rows (xb)
+  // and per-row partial (sum, sum of squares); the qkv / c_fc GEMMs run on xb with gamma folded into the weights and
+  // apply mean / rstd in their epilogue.  Removes 2 x layers LayerNorm passes (6 bytes per element each).
+  const int ln_opt = vmc_get_option(VMC_OPT_LN_FUSE);
+  // Measured per 1024 ViT-B/16 frames (tools/kernel_bench.py): the consumer epilogues cost +0.03 ms (qkv) and +0.07 ms
+  // (c_fc, already the heaviest epilogue: QuickGELU); the producer outputs are free behind the compute-bound c_proj but
+  // cost +0.09..0.14 ms in the HBM-bound out_proj, against 0.14 ms per stand-alone LayerNorm.  A/B inside one process on
+  // the 256-clip step (tools/ab_ln.py): separate kernels 215.7 ms, ln_1 folded (5) 213.3 ms, both folded (3) 212.0 ms.
+  // The 1.7 % is real (fewer HBM bytes under the power cap) but moves LayerNorm work into the GEMM epilogues (GEMM class
+  // 1126 -> 949 TFLOP/s), so the DEFAULT stays with separate LayerNorm kernels and the fold is opt-in.
+  bool fold = (ln_opt == 3 || ln_opt == 5) && vmc_get_option(VMC_OPT_GEMM_IMPL) != 1 && (d % 128) == 0;
+  const bool fold2 = ln_opt == 3;
+  for (int i = 0; i < m->layers && fold; ++i)
+    fold = m->layer[i].w_qkv_f && m->layer[i].b_qkv_f && m->layer[i].cs_qkv && m->layer[i].w_fc1_f &&
+           m->layer[i].b_fc1_f && m->layer[i].cs_fc1;
+  const int res_parts = vmc_gemm_stats_parts(rows, d);  // column slices written by the out_proj / c_proj GEMMs
+  fold = fold && res_parts > 0 && res_parts <= 8 && (d % (d / res_parts)) == 0;
   // ln_pre in place on the residual stream; CLS rows are sourced from class_embedding + pos[0].
-  VMC_TRY(vmc_layernorm(w.x, d, m->ln_pre_g, m->ln_pre_b, 1e-5f, w.x, d, nullptr, 0, 0, rows, d,
-                        m->cls_pos0, L, stream));
+  VMC_TRY(vmc_layernorm_stats(w.x, d, m->ln_pre_g, m->ln_pre_b, 1e-5f, w.x, d, fold ? w.xn2 : nullptr, d, 0, rows,
+                              d, m->cls_pos0, L, fold ? w.stats : nullptr, stream));
+  if (fold) {
+    int parts = 1;  // ln_pre wrote one plane; the residual GEMMs write res_parts
+    for (int i = 0; i < m->layers; ++i) {
+      const vmc_vit_layer& ly = m->layer[i];
+      {  // qkv = LN1(x) Wqkv^T + b, on the raw rows
+        vmc_gemm_epilogue e = {};
+        e.bias = ly.b_qkv_f;
+        e.out = w.big;
+        e.ldo = 3 * d;
+        e.out_bf16 = 1;
+        e.alpha = 1.0f;
+        e.stats_in = w.stats;
+        e.stats_parts = parts;
+        e.stats_ld = rows;
+        e.colsum = ly.cs_qkv;
+        e.ln_eps = 1e-5f;
+        VMC_TRY(vmc_gemm_bf16(w.xn2, d, ly.w_qkv_f, d, rows, 3 * d, d, &e, stream));
+      }
+      VMC_TRY(vmc_attention_vit(w.big, w.xn, F, L, m->heads, stream));
+      {  // x += out_proj(attn); with ln_2 folded it also emits xb + statistics
+        vmc_gemm_epilogue e = {};
+        e.bias = ly.b_out;
+        e.resid = w.x;
+        e.ldr = d;
+        e.out = w.x;
+        e.ldo = d;
+        e.alpha = 1.0f;
+        if (fold2) {
+          e.raw16_out = w.xn2;
+          e.raw16_ld = d;
+          e.stats_out = w.stats;
+          e.stats_ld = rows;
+        }
+        VMC_TRY(vmc_gemm_bf16(w.xn, d, ly.w_out, d, rows, d, d, &e, stream));
+      }
+      parts = res_parts;
+      if (!fold2)
+        VMC_TRY(vmc_layernorm(w.x, d, ly.ln2_g, ly.ln2_b, 1e-5f, nullptr, 0, w.xn2, d, 0, rows, d, nullptr, 0, stream));
+      {  // h = QuickGELU(LN2(x) Wfc1^T + b)
+        vmc_gemm_epilogue e = {};
+        e.bias = fold2 ? ly.b_fc1_f : ly.b_fc1;
+        e.out = w.big;
+        e.ldo = 4 * d;
+        e.out_bf16 = 1;
+        e.act = VMC_ACT_QUICKGELU;
+        e.alpha = 1.0f;
+        if (fold2) {
+          e.stats_in = w.stats;
+          e.stats_parts = parts;
+          e.stats_ld = rows;
+          e.colsum = ly.cs_fc1;
+          e.ln_eps = 1e-5f;
+        }
+        VMC_TRY(vmc_gemm_bf16(w.xn2, d, fold2 ? ly.w_fc1_f : ly.w_fc1, d, rows, 4 * d, d, &e, stream));
+      }
+      {  // x += c_proj(h); emits xb + statistics for the next layer's ln_1
+        vmc_gemm_epilogue e = {};
+        e.bias = ly.b_fc2;
+        e.resid = w.x;
+        e.ldr = d;
+        e.out = w.x;
+        e.ldo = d;
+        e.alpha = 1.0f;
+        e.raw16_out = w.xn2;
+        e.raw16_ld = d;
+        e.stats_out = w.stats;
+        e.stats_ld = rows;
+        VMC_TRY(vmc_gemm_bf16(w.big, 4 * d, ly.w_fc2, 4 * d, rows, d, 4 * d, &e, stream));
+      }
+    }
+  }
 
   // Optional LayerNorm fusion (VMC_OPT_LN_FUSE = 1: both, 2: only c_proj -> next ln_1; default 0 = off):
   // ln_2 rides in the epilogue of the out_proj GEMM and the NEXT layer's ln_1 in the epilogue of the c_proj
@@ -107,11 +199,10 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
   // LayerNorm passes cost +22 ms (8 warps per SM walking rows serially are latency-bound) against the
   // 19 ms the stand-alone kernels take at 85-100 % of HBM peak.  Kept as a selectable, tested variant.
   const long long pair_tiles = (long long)((rows + 255) / 256) * ((d + 255) / 256);
-  const int ln_opt = vmc_get_option(VMC_OPT_LN_FUSE);
   const bool fuse_ln = vmc_get_option(VMC_OPT_GEMM_IMPL) != 1 && (ln_opt == 1 || ln_opt == 2) &&
                        d <= 1024 && (d % 128) == 0 && pair_tiles >= vmc_num_sms();
   const bool fuse_ln2 = fuse_ln && ln_opt == 1;
-  for (int i = 0; i < m->layers; ++i) {
+  for (int i = 0; i < m->layers && !fold; ++i) {
     const vmc_vit_layer& ly = m->layer[i];
     // x = x + out_proj(attn(ln_1(x)))
     if (i == 0 || !fuse_ln)

@@ -162,9 +162,11 @@ def frame_diff(bgr: torch.Tensor, *, dst: str | None = None, patch: int = 0, wan
 # ---------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, alpha: float = 1.0, resid=None,
          out: torch.Tensor | None = None, out_dtype=torch.bfloat16, n: int | None = None, k: int | None = None,
-         row_group: int = 0, out_rows: int | None = None, ln=None) -> torch.Tensor:
+         row_group: int = 0, out_rows: int | None = None, ln=None, emit_stats=None, fold=None) -> torch.Tensor:
     """out = alpha * act(a @ w.T + bias) + resid.  a [M, lda] bf16, w [N, ldw] bf16 (nn.Linear layout).
-    ln = (gamma, beta, eps, ln_out bf16 [M, N]): fused LayerNorm of the output rows (see vmc_gemm_epilogue)."""
+    ln = (gamma, beta, eps, ln_out bf16 [M, N]): fused LayerNorm of the output rows (see vmc_gemm_epilogue).
+    emit_stats = (raw16 bf16 [M, N], stats fp32 [parts, M, 2]): producer side of a folded LayerNorm.
+    fold = (stats fp32 [parts, M, 2], colsum fp32 [N], eps): consumer side (a = raw rows, w = gamma-folded weights)."""
     _need_cuda(a, w, bias, resid, out)
     if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         raise TypeError("gemm operands must be bf16")
@@ -194,9 +196,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, al
         g_, b_, eps_, ln_out = ln
         _need_cuda(g_, b_, ln_out)
         e.ln_gamma, e.ln_beta, e.ln_out, e.ln_ldo, e.ln_eps = g_.data_ptr(), b_.data_ptr(), ln_out.data_ptr(), ln_out.stride(0), eps_
+    if emit_stats is not None:
+        raw16, stats = emit_stats
+        _need_cuda(raw16, stats)
+        e.raw16_out, e.raw16_ld, e.stats_out, e.stats_ld = raw16.data_ptr(), raw16.stride(0), stats.data_ptr(), stats.shape[1]
+    if fold is not None:
+        stats, colsum, eps_ = fold
+        _need_cuda(stats, colsum)
+        e.stats_in, e.stats_parts, e.stats_ld, e.colsum, e.ln_eps = stats.data_ptr(), stats.shape[0], stats.shape[1], colsum.data_ptr(), eps_
     with torch.cuda.device(a.device):
         _lib.check(_lib.lib().vmc_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, C.byref(e), _stream()), "vmc_gemm_bf16")
     return out
+
+
+def gemm_stats_parts(M: int, N: int) -> int:
+    """Column slices per row that ``gemm(..., emit_stats=...)`` writes for this shape."""
+    return int(_lib.lib().vmc_gemm_stats_parts(M, N))
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5, want32: bool = False,

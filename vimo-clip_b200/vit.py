@@ -133,6 +133,15 @@ class VisionTower(nn.Module):
             ly.w_out, ly.b_out = bf(blk.attn.out_proj.weight), f32(blk.attn.out_proj.bias)
             ly.w_fc1, ly.b_fc1 = bf(blk.mlp.c_fc.weight), f32(blk.mlp.c_fc.bias)
             ly.w_fc2, ly.b_fc2 = bf(blk.mlp.c_proj.weight), f32(blk.mlp.c_proj.bias)
+            # LayerNorm folding (include/vimoclip_b200.h, vmc_gemm_epilogue): LN(x) W^T + b = rstd (x W'^T - mean colsum) + b'
+            for ln, lin, names in ((blk.ln_1, (blk.attn.in_proj_weight, blk.attn.in_proj_bias), ("w_qkv_f", "b_qkv_f", "cs_qkv")),
+                                   (blk.ln_2, (blk.mlp.c_fc.weight, blk.mlp.c_fc.bias), ("w_fc1_f", "b_fc1_f", "cs_fc1"))):
+                w32 = lin[0].detach().float()
+                wf = (w32 * ln.weight.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+                keep.append(wf)
+                setattr(ly, names[0], wf.data_ptr())
+                setattr(ly, names[1], f32(lin[1].detach().float() + w32 @ ln.bias.detach().float()))
+                setattr(ly, names[2], f32(wf.float().sum(dim=1)))  # of the ROUNDED weights: the mean term cancels exactly
         m = _lib.VitModel()
         m.image, m.patch, m.width, m.layers, m.heads, m.out_dim = self.input_resolution, p, d, self.layers, self.heads, self.output_dim
         m.ld_patch = ld
