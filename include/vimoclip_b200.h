@@ -193,6 +193,37 @@ int vmc_student_heads(const float* emb, const float* w_fc1_t, const float* b_fc1
 int vmc_tfam_head(const float* x, const float* ln_g, const float* ln_b, float eps, const float* w1_t, const float* b1,
                   const float* w2_t, const float* b2, float* logits, int B, int T, int D, int H, int C, void* stream);
 
+/* ---- TFAM training step: backward kernels -------------------------------
+ * TFAM/train_and_eval.py:66-101 (`loss.backward()` through TFAM/models/AMO_CLIP.py:37-51,99-171).  Every nn.Linear
+ * backward is two more vmc_gemm_bf16 calls on split-bf16 operands (dX = dY W, dW = dY^T X) fed by
+ * vmc_transpose_split; the rest are fp32 kernels.  All gradients are fp32. */
+/* x fp32 [R, C] -> y bf16 [C, 3R] (ldy >= 3R, multiple of 8): split operand of x^T; form 0 = [hi | lo | hi]
+ * (A side of vmc_gemm_bf16), form 1 = [hi | hi | lo] (W side). */
+int vmc_transpose_split(const float* x, long long ldx, void* y, long long ldy, int R, int C, int form,
+                        void* stream);
+/* out[c] (+)= sum_r x[r,c] * (y ? y[r,c] : 1): bias / LayerNorm parameter gradients; deterministic order */
+int vmc_colsum(const float* x, long long ldx, const float* y, long long ldy, float* out, int R, int C,
+               int accumulate, void* stream);
+/* LayerNorm backward per row from the saved LayerNorm INPUT z: dz, and xhat (optional) for dgamma = colsum(dy*xhat) */
+int vmc_layernorm_bwd(const float* z, long long ldz, const float* gamma, float eps, const float* dy,
+                      long long lddy, float* dz, long long lddz, float* xhat, long long ldxh, int rows, int d,
+                      void* stream);
+/* mode 0: out = a*b (dropout mask), 1: ReLU backward (b = activation output or pre-activation), 2: GELU(erf)
+ * backward (b = pre-activation), 3: out = a+b, 4: out = a*scale */
+int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* out, long long n, void* stream);
+/* out[b,t,:] = g[b,:] * scale (backward of the temporal mean, AMO_CLIP.py:170) */
+int vmc_broadcast_rows(const float* g, float* out, int B, int T, int d, float scale, void* stream);
+/* vmc_attention_masked with dropout on the attention probabilities: prob_mask fp32 [B, heads, Tq, Tk] holds 0 or
+ * 1/(1-p) (NULL = no dropout), as nn.MultiheadAttention(dropout=p) does in training mode */
+int vmc_attention_masked_train(const float* q, long long ldq, const float* k, long long ldk, const float* v,
+                               long long ldv, const uint8_t* key_valid, const float* prob_mask, void* out,
+                               int out_f32, long long ldo, int B, int Tq, int Tk, int heads, void* stream);
+/* backward of the above: dq [B*Tq, .], dk, dv [B*Tk, .] written at column head*64 (Tq, Tk <= ~128) */
+int vmc_attention_masked_bwd(const float* q, long long ldq, const float* k, long long ldk, const float* v,
+                             long long ldv, const uint8_t* key_valid, const float* prob_mask, const float* dO,
+                             long long lddo, float* dq, long long lddq, float* dk, long long lddk, float* dv,
+                             long long lddv, int B, int Tq, int Tk, int heads, void* stream);
+
 /* ---- whole ViT tower -----------------------------------------------------------
  * Replaces self.visual_encoder(x) (models/student_model.py:84) and
  * clip_model.get_image_features(pixel_values) (extract_embeddings.py:94).

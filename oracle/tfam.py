@@ -100,8 +100,13 @@ class TfamOracle(nn.Module):
         pe[:, 1::2] = torch.cos(pos * div)
         return pe
 
-    @torch.no_grad()
     def forward(self, rgb_emb, motion_emb, mask_rgb=None, mask_flow=None):
+        """Inference under no_grad; in ``.train()`` mode autograd stays on (the reference module has no decorator at
+        all: TFAM/train_and_eval.py:80 backpropagates through it) -- the oracle of the training-step parity tests."""
+        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+            return self._forward(rgb_emb, motion_emb, mask_rgb, mask_flow)
+
+    def _forward(self, rgb_emb, motion_emb, mask_rgb=None, mask_flow=None):
         attn_rgb = ~mask_rgb if mask_rgb is not None else None  # :125
         attn_flow = ~mask_flow if mask_flow is not None else None  # :126
         if self.use_pe:  # :129-134 (the reference adds in place; value semantics are the same)

@@ -534,3 +534,113 @@ def test_full_pipeline_small(cuda_device):
     # end to end the bf16 embedding error (cos >= 0.9995) feeds the fusion block: looser, stated bound
     assert (logits.cpu() - lg_ref).abs().max().item() <= 5e-2
     assert math.isfinite(float(logits.abs().sum()))
+
+
+# ---------------------------------------------------------------------------------------------------
+# TFAM training step: TFAM/train_and_eval.py:66-101 through our forward + backward kernels
+# ---------------------------------------------------------------------------------------------------
+def _tfam_pair(cuda_device, dropout=0.0, mlp_dropout=0.0, seed=0):
+    o_tf = otfam.TfamOracle(dropout=dropout, mlp_dropout=mlp_dropout)
+    with torch.no_grad():
+        weights.randomise_tfam_(o_tf, seed)
+    ours = vmc.AMO_CLIP(dropout=dropout, mlp_dropout=mlp_dropout, device=cuda_device)
+    ours.load_state_dict(o_tf.state_dict(), strict=True)
+    return o_tf, ours.to(cuda_device)
+
+
+def test_backward_building_blocks(cuda_device):
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    M, K, N = 96, 512, 140
+    x = torch.randn(M, K, device=cuda_device, generator=gen, requires_grad=True)
+    w = (torch.randn(N, K, device=cuda_device, generator=gen) * K**-0.5).requires_grad_()
+    dy = torch.randn(M, N, device=cuda_device, generator=gen)
+    from vimoclip_b200.tfam_train import _lin_bwd
+
+    dx, dw, db = _lin_bwd(dy, x.detach(), w.detach())
+    (x @ w.t()).backward(dy)
+    for got, ref in ((dx, x.grad), (dw, w.grad), (db, dy.sum(0))):
+        assert (got - ref).norm().item() <= 2e-4 * ref.norm().item()
+    # LayerNorm backward
+    z = (torch.randn(M, K, device=cuda_device, generator=gen) * 2 + 0.3).requires_grad_()
+    g_ = (1 + 0.1 * torch.randn(K, device=cuda_device, generator=gen)).requires_grad_()
+    b_ = torch.zeros(K, device=cuda_device, requires_grad=True)
+    dyl = torch.randn(M, K, device=cuda_device, generator=gen)
+    torch.nn.functional.layer_norm(z, (K,), g_, b_, 1e-5).backward(dyl)
+    dz, dg, dbt = ops.layernorm_bwd(z.detach(), g_.detach(), 1e-5, dyl)
+    for got, ref in ((dz, z.grad), (dg, g_.grad), (dbt, b_.grad)):
+        assert (got - ref).norm().item() <= 1e-4 * ref.norm().item()
+    # masked attention backward with probability dropout
+    B, Tq, Tk, h = 3, 16, 15, 8
+    d = h * 64
+    q = torch.randn(B * Tq, d, device=cuda_device, generator=gen, requires_grad=True)
+    k = torch.randn(B * Tk, d, device=cuda_device, generator=gen, requires_grad=True)
+    v = torch.randn(B * Tk, d, device=cuda_device, generator=gen, requires_grad=True)
+    valid = torch.ones(B, Tk, dtype=torch.bool, device=cuda_device)
+    valid[1, 11:] = False
+    pm = ((torch.rand(B, h, Tq, Tk, device=cuda_device, generator=gen) >= 0.2).float() / 0.8).contiguous()
+    dO = torch.randn(B * Tq, d, device=cuda_device, generator=gen)
+    qh, kh, vh = (t.view(B, -1, h, 64).transpose(1, 2) for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    s = s.masked_fill(~valid[:, None, None, :], float("-inf"))
+    ref_o = ((torch.softmax(s, -1) * pm) @ vh).transpose(1, 2).reshape(B * Tq, d)
+    got_o = ops.attention_masked(q.detach(), k.detach(), v.detach(), valid, B, Tq, Tk, h, out_dtype=torch.float32, prob_mask=pm)
+    assert (got_o - ref_o).abs().max().item() < 1e-4
+    ref_o.backward(dO)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.attention_masked_bwd(q.detach(), k.detach(), v.detach(), valid, pm, dO, B, Tq, Tk, h, dq, dk, dv)
+    for got, ref in ((dq, q.grad), (dk, k.grad), (dv, v.grad)):
+        assert (got - ref).norm().item() <= 1e-4 * ref.norm().item()
+
+
+def test_tfam_training_step_gradients_match_reference_autograd(cuda_device):
+    """config 1 batch (B=2, T=16/15, ragged masks), dropout off: logits and EVERY parameter gradient of the
+    BCEWithLogits loss equal fp32 autograd of the reference restatement (oracle pinned to TFAM/models/AMO_CLIP.py)."""
+    o_tf, ours = _tfam_pair(cuda_device)
+    o_tf.train()
+    ours.train()
+    gen = torch.Generator().manual_seed(11)
+    rgb, mot = torch.randn(2, 16, 512, generator=gen), torch.randn(2, 15, 512, generator=gen)
+    m_rgb = torch.arange(16)[None, :] < torch.tensor([16, 12])[:, None]  # collate_fn_pad masks (True = real frame)
+    m_mot = torch.arange(15)[None, :] < torch.tensor([15, 11])[:, None]
+    labels = (torch.rand(2, 140, generator=gen) < 0.05).float()
+    crit = torch.nn.BCEWithLogitsLoss()
+    ref_logits = o_tf(rgb, mot, m_rgb, m_mot)
+    crit(ref_logits, labels).backward()
+    logits = ours(rgb.to(cuda_device), mot.to(cuda_device), m_rgb.to(cuda_device), m_mot.to(cuda_device))
+    assert logits.requires_grad
+    assert (logits.detach().cpu() - ref_logits.detach()).abs().max().item() <= 1e-2
+    crit(logits, labels.to(cuda_device)).backward()
+    ref_grads = dict(o_tf.named_parameters())
+    checked = 0
+    for name, p in ours.named_parameters():
+        if name.startswith("projection_layer"):
+            assert p.grad is None  # unused by the cross-attention configuration, as in the reference
+            continue
+        ref = ref_grads[name].grad
+        err = (p.grad.cpu() - ref).norm().item()
+        assert err <= 2e-3 * ref.norm().item() + 1e-9, (name, err, ref.norm().item())
+        checked += 1
+    assert checked == 4 * 18 + 6
+
+
+def test_tfam_training_loop_with_dropout_reduces_loss(cuda_device):
+    """AdamW(lr 1e-4, wd 0.1) as TFAM/train_and_eval.py:53-58 with the reference's dropout rates: the loss goes down."""
+    _, ours = _tfam_pair(cuda_device, dropout=0.1, mlp_dropout=0.3, seed=1)
+    ours.train()
+    gen = torch.Generator().manual_seed(5)
+    rgb = torch.randn(32, 16, 512, generator=gen).to(cuda_device)
+    mot = torch.randn(32, 15, 512, generator=gen).to(cuda_device)
+    labels = (torch.rand(32, 140, generator=gen) < 0.05).float().to(cuda_device)
+    opt = torch.optim.AdamW(ours.parameters(), lr=1e-4, weight_decay=0.1)
+    crit = torch.nn.BCEWithLogitsLoss()
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = crit(ours(rgb, mot), labels)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(l == l for l in losses)
+    assert sum(losses[-3:]) < 0.8 * sum(losses[:3]), losses
+    ours.eval()
+    assert not ours(rgb, mot).requires_grad

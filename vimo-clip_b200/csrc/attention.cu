@@ -1156,7 +1156,7 @@ __global__ void __launch_bounds__(128)
 attention_masked_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k,
                         long long ldk, const float* __restrict__ v, long long ldv,
                         const uint8_t* __restrict__ key_valid, void* __restrict__ out_v,
-                        int out_f32, long long ldo, int Tq, int Tk) {
+                        int out_f32, long long ldo, int Tq, int Tk, const float* __restrict__ pmask) {
   __shared__ float sq[QB][HD];
   __shared__ float sk[KB][HD + 1];
   __shared__ float sv[KB][HD];
@@ -1205,11 +1205,19 @@ attention_masked_kernel(const float* __restrict__ q, long long ldq, const float*
       const float p0 = (s0 == -INFINITY) ? 0.f : __expf(s0 - m_new);
       const float p1 = (s1 == -INFINITY) ? 0.f : __expf(s1 - m_new);
       l[i] = l[i] * corr + warp_sum(p0 + p1);
+      float pd0 = p0, pd1 = p1;
+      if (pmask != nullptr && q0 + r < Tq) {
+        // training: dropout on the attention probabilities (nn.MultiheadAttention(dropout=p)); the mask holds
+        // 0 or 1/(1-p) and touches only the PV product, the normaliser sums the un-dropped probabilities
+        const float* pmr = pmask + (((size_t)b * gridDim.y + h) * Tq + q0 + r) * Tk;
+        if (j0 < Tk) pd0 *= pmr[j0];
+        if (j1 < Tk) pd1 *= pmr[j1];
+      }
       float a0 = o0[i] * corr, a1 = o1[i] * corr;
 #pragma unroll 8
       for (int j = 0; j < 32; ++j) {
-        const float pj0 = __shfl_sync(0xffffffffu, p0, j);
-        const float pj1 = __shfl_sync(0xffffffffu, p1, j);
+        const float pj0 = __shfl_sync(0xffffffffu, pd0, j);
+        const float pj1 = __shfl_sync(0xffffffffu, pd1, j);
         a0 = fmaf(pj0, sv[j][lane], a0);
         a1 = fmaf(pj0, sv[j][lane + 32], a1);
         a0 = fmaf(pj1, sv[j + 32][lane], a0);
@@ -1404,6 +1412,14 @@ int vmc_attention_masked(const float* q, long long ldq, const float* k, long lon
                          const float* v, long long ldv, const uint8_t* key_valid, void* out,
                          int out_f32, long long ldo, int B, int Tq, int Tk, int heads,
                          void* stream) {
+  return vmc_attention_masked_train(q, ldq, k, ldk, v, ldv, key_valid, nullptr, out, out_f32, ldo, B, Tq, Tk, heads,
+                                    stream);
+}
+
+int vmc_attention_masked_train(const float* q, long long ldq, const float* k, long long ldk,
+                               const float* v, long long ldv, const uint8_t* key_valid, const float* prob_mask,
+                               void* out, int out_f32, long long ldo, int B, int Tq, int Tk, int heads,
+                               void* stream) {
   VMC_CHECK_ARG(q && k && v && out, VMC_ERR_ARG, "vmc_attention_masked: null pointer");
   VMC_CHECK_ARG(B > 0 && Tq > 0 && Tk > 0 && heads > 0 && B <= 65535 && heads <= 65535,
                 VMC_ERR_SHAPE, "vmc_attention_masked: bad shape B=%d Tq=%d Tk=%d heads=%d", B, Tq,
@@ -1414,7 +1430,7 @@ int vmc_attention_masked(const float* q, long long ldq, const float* k, long lon
     VmcProfScope prof(VMC_K_ATTN_SMALL, st, 4.0 * B * heads * (double)Tq * Tk * HD,
                       4.0 * B * heads * HD * (Tq + 2.0 * Tk) + 2.0 * B * Tq * heads * HD);
     attention_masked_kernel<<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, key_valid,
-                                                  out, out_f32, ldo, Tq, Tk);
+                                                  out, out_f32, ldo, Tq, Tk, prob_mask);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();

@@ -1,0 +1,352 @@
+// Backward-pass kernels of the TFAM block (the TFAM training step,
+// TFAM/train_and_eval.py:66-101 -> loss.backward() through TFAM/models/AMO_CLIP.py:37-51,170).
+//
+// The training step is GEMM-shaped like the forward: every nn.Linear backward is two more tcgen05 GEMMs
+// (dX = dY W, dW = dY^T X) on the split-bf16 operands, fed by the transposing cast below.  The remaining
+// pieces are small fp32 SIMT kernels: LayerNorm backward (row statistics recomputed from the saved input),
+// masked attention backward (one CTA per (clip, head), probabilities recomputed in shared memory), column
+// sums for the bias / LayerNorm parameter gradients and a few element-wise ops (ReLU / GELU backward,
+// dropout, add).  TFAM is 0.08 % of the path's FLOPs; these kernels are written for clarity, not peak.
+#include "common.cuh"
+#include "vimoclip_b200.h"
+
+namespace {
+
+using namespace vmc;
+
+constexpr int HD = 64;
+
+// fp32 [R, C] -> bf16 [C, 3R] "split" operand of the TRANSPOSE: hi = bf16(x), lo = bf16(x - hi);
+// form 0 (activation side) = [hi | lo | hi], form 1 (weight side) = [hi | hi | lo].
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                       long long ldy, int R, int C, int form) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? x[(size_t)r * ldx + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < R) {
+      const float v = tile[tx][i];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      __nv_bfloat16* row = y + (size_t)c * ldy;
+      row[r] = hi;
+      row[(size_t)R + r] = form == 0 ? lo : hi;
+      row[(size_t)2 * R + r] = form == 0 ? hi : lo;
+    }
+  }
+}
+
+// out[c] (+)= sum_r x[r, c] * (y ? y[r, c] : 1): deterministic (one block owns 32 columns, fixed order)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y, long long ldy,
+              float* __restrict__ out, int R, int C, int accumulate) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < C) {
+    for (int r = ty; r < R; r += 8) {
+      const float a = x[(size_t)r * ldx + c];
+      s += y ? a * y[(size_t)r * ldy + c] : a;
+    }
+  }
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+// LayerNorm backward, one warp per row.  z = the LayerNorm INPUT (saved by the forward), statistics
+// recomputed.  dz = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma;  xhat_out = xhat (for
+// dgamma = colsum(dy * xhat), dbeta = colsum(dy)).
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ z, long long ldz, const float* __restrict__ gamma, float eps,
+                     const float* __restrict__ dy, long long lddy, float* __restrict__ dz, long long lddz,
+                     float* __restrict__ xhat_out, long long ldxh, int rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* zr = z + (size_t)row * ldz;
+  const float* dyr = dy + (size_t)row * lddy;
+  float s = 0.f;
+  for (int j = lane; j < d; j += 32) s += zr[j];
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float a = zr[j] - mean;
+    q += a * a;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+  float m1 = 0.f, m2 = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float xh = (zr[j] - mean) * rstd;
+    const float g = dyr[j] * gamma[j];
+    m1 += g;
+    m2 += g * xh;
+  }
+  m1 = warp_sum(m1) / (float)d;
+  m2 = warp_sum(m2) / (float)d;
+  for (int j = lane; j < d; j += 32) {
+    const float xh = (zr[j] - mean) * rstd;
+    const float g = dyr[j] * gamma[j];
+    dz[(size_t)row * lddz + j] = rstd * (g - m1 - xh * m2);
+    if (xhat_out) xhat_out[(size_t)row * ldxh + j] = xh;
+  }
+}
+
+// element-wise helpers of the backward pass
+enum { ELT_MUL = 0, ELT_RELU_BWD = 1, ELT_GELU_BWD = 2, ELT_ADD = 3, ELT_SCALE = 4 };
+__global__ void __launch_bounds__(256)
+eltwise_kernel(int mode, const float* __restrict__ a, const float* __restrict__ b, float scale,
+               float* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float x = a[i];
+    float r;
+    switch (mode) {
+      case ELT_MUL: r = x * b[i]; break;
+      case ELT_RELU_BWD: r = b[i] > 0.f ? x : 0.f; break;
+      case ELT_GELU_BWD: {  // b = pre-activation; d/db [0.5 b (1 + erf(b / sqrt 2))]
+        const float u = b[i];
+        r = x * (0.5f * (1.0f + erff(u * 0.70710678118654752440f)) + u * 0.3989422804014327f * expf(-0.5f * u * u));
+        break;
+      }
+      case ELT_ADD: r = x + b[i]; break;
+      default: r = x * scale; break;
+    }
+    out[i] = r;
+  }
+}
+
+// mean over T backward: out[b, t, :] = g[b, :] * scale
+__global__ void __launch_bounds__(256)
+broadcast_rows_kernel(const float* __restrict__ g, float* __restrict__ out, int B, int T, int d, float scale) {
+  const size_t n = (size_t)B * T * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % d);
+    const size_t b = i / ((size_t)T * d);
+    out[i] = g[b * d + j] * scale;
+  }
+}
+
+// Masked attention backward for one (clip, head): probabilities recomputed in shared memory.
+//   A = P (.) m  (m = attention-probability dropout mask, already scaled by 1/(1-p); NULL = ones)
+//   O = A V;  dV = A^T dO;  dA = dO V^T;  dP = dA (.) m;  dS = P (.) (dP - rowsum(P (.) dP));
+//   dQ = scale dS K;  dK = scale dS^T Q
+__global__ void __launch_bounds__(256)
+attention_masked_bwd_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k, long long ldk,
+                            const float* __restrict__ v, long long ldv, const uint8_t* __restrict__ key_valid,
+                            const float* __restrict__ pmask, const float* __restrict__ dO, long long lddo,
+                            float* __restrict__ dq, long long lddq, float* __restrict__ dk, long long lddk,
+                            float* __restrict__ dv, long long lddv, int Tq, int Tk, int heads) {
+  extern __shared__ float sm[];
+  float* sq = sm;                      // [Tq][64]
+  float* sdo = sq + (size_t)Tq * HD;   // [Tq][64]
+  float* sk = sdo + (size_t)Tq * HD;   // [Tk][65]
+  float* sv = sk + (size_t)Tk * 65;    // [Tk][65]
+  float* sp = sv + (size_t)Tk * 65;    // [Tq][Tk + 1]
+  const int ldp = Tk + 1;
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const uint8_t* kvb = key_valid ? key_valid + (size_t)b * Tk : nullptr;
+  const float* pm = pmask ? pmask + ((size_t)b * heads + h) * Tq * Tk : nullptr;
+  for (int i = tid; i < Tq * HD; i += blockDim.x) {
+    const int r = i / HD, c = i % HD;
+    sq[i] = q[((size_t)b * Tq + r) * ldq + h * HD + c];
+    sdo[i] = dO[((size_t)b * Tq + r) * lddo + h * HD + c];
+  }
+  for (int i = tid; i < Tk * HD; i += blockDim.x) {
+    const int r = i / HD, c = i % HD;
+    sk[r * 65 + c] = k[((size_t)b * Tk + r) * ldk + h * HD + c];
+    sv[r * 65 + c] = v[((size_t)b * Tk + r) * ldv + h * HD + c];
+  }
+  __syncthreads();
+  // ---- P = softmax(scale q k^T + mask) ----
+  for (int i = warp; i < Tq; i += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < Tk; j += 32) {
+      float s = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < HD; ++c) s = fmaf(sq[i * HD + c], sk[j * 65 + c], s);
+      s *= 0.125f;
+      if (kvb && !kvb[j]) s = -INFINITY;
+      sp[i * ldp + j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float s = sp[i * ldp + j];
+      const float p = (s == -INFINITY) ? 0.f : __expf(s - mx);
+      sp[i * ldp + j] = p;
+      sum += p;
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    for (int j = lane; j < Tk; j += 32) sp[i * ldp + j] *= inv;
+  }
+  __syncthreads();
+  // ---- dV_j = sum_i A_ij dO_i ----
+  for (int j = warp; j < Tk; j += nw) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = 0; i < Tq; ++i) {
+      float a = sp[i * ldp + j];
+      if (pm) a *= pm[(size_t)i * Tk + j];
+      a0 = fmaf(a, sdo[i * HD + lane], a0);
+      a1 = fmaf(a, sdo[i * HD + lane + 32], a1);
+    }
+    float* o = dv + ((size_t)b * Tk + j) * lddv + h * HD;
+    o[lane] = a0;
+    o[lane + 32] = a1;
+  }
+  __syncthreads();
+  // ---- dS = P (.) (dP - rowsum(P (.) dP)), in place over P ----
+  for (int i = warp; i < Tq; i += nw) {
+    float acc = 0.f;
+    for (int j = lane; j < Tk; j += 32) {
+      float dp = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < HD; ++c) dp = fmaf(sdo[i * HD + c], sv[j * 65 + c], dp);
+      if (pm) dp *= pm[(size_t)i * Tk + j];
+      acc = fmaf(sp[i * ldp + j], dp, acc);
+    }
+    acc = warp_sum(acc);
+    for (int j = lane; j < Tk; j += 32) {  // dP recomputed: cheaper than a second Tq x Tk buffer
+      float dp = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < HD; ++c) dp = fmaf(sdo[i * HD + c], sv[j * 65 + c], dp);
+      if (pm) dp *= pm[(size_t)i * Tk + j];
+      sp[i * ldp + j] = sp[i * ldp + j] * (dp - acc);
+    }
+  }
+  __syncthreads();
+  // ---- dQ_i = scale sum_j dS_ij K_j ----
+  for (int i = warp; i < Tq; i += nw) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < Tk; ++j) {
+      const float s = sp[i * ldp + j];
+      a0 = fmaf(s, sk[j * 65 + lane], a0);
+      a1 = fmaf(s, sk[j * 65 + lane + 32], a1);
+    }
+    float* o = dq + ((size_t)b * Tq + i) * lddq + h * HD;
+    o[lane] = a0 * 0.125f;
+    o[lane + 32] = a1 * 0.125f;
+  }
+  // ---- dK_j = scale sum_i dS_ij Q_i ----
+  for (int j = warp; j < Tk; j += nw) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = 0; i < Tq; ++i) {
+      const float s = sp[i * ldp + j];
+      a0 = fmaf(s, sq[i * HD + lane], a0);
+      a1 = fmaf(s, sq[i * HD + lane + 32], a1);
+    }
+    float* o = dk + ((size_t)b * Tk + j) * lddk + h * HD;
+    o[lane] = a0 * 0.125f;
+    o[lane + 32] = a1 * 0.125f;
+  }
+}
+
+int grid_cap(size_t n) {
+  size_t g = (n + 255) / 256;
+  const size_t cap = (size_t)vmc_num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int vmc_transpose_split(const float* x, long long ldx, void* y, long long ldy, int R, int C, int form,
+                        void* stream) {
+  VMC_CHECK_ARG(x && y, VMC_ERR_ARG, "vmc_transpose_split: null pointer");
+  VMC_CHECK_ARG(R > 0 && C > 0 && ldx >= C && ldy >= 3LL * R && (form == 0 || form == 1), VMC_ERR_SHAPE,
+                "vmc_transpose_split: bad shape R=%d C=%d ldx=%lld ldy=%lld", R, C, ldx, ldy);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
+  transpose_split_kernel<<<grid, 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, R, C, form);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_colsum(const float* x, long long ldx, const float* y, long long ldy, float* out, int R, int C,
+               int accumulate, void* stream) {
+  VMC_CHECK_ARG(x && out, VMC_ERR_ARG, "vmc_colsum: null pointer");
+  VMC_CHECK_ARG(R > 0 && C > 0, VMC_ERR_SHAPE, "vmc_colsum: bad shape R=%d C=%d", R, C);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
+  colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(x, ldx, y, ldy, out, R, C, accumulate);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_layernorm_bwd(const float* z, long long ldz, const float* gamma, float eps, const float* dy,
+                      long long lddy, float* dz, long long lddz, float* xhat, long long ldxh, int rows, int d,
+                      void* stream) {
+  VMC_CHECK_ARG(z && gamma && dy && dz, VMC_ERR_ARG, "vmc_layernorm_bwd: null pointer");
+  VMC_CHECK_ARG(rows > 0 && d > 0, VMC_ERR_SHAPE, "vmc_layernorm_bwd: bad shape rows=%d d=%d", rows, d);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VmcProfScope prof(VMC_K_LAYERNORM, st, 0.0, (double)rows * d * 16.0);
+  layernorm_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(z, ldz, gamma, eps, dy, lddy, dz, lddz, xhat, ldxh, rows, d);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* out, long long n, void* stream) {
+  VMC_CHECK_ARG(a && out && n > 0 && mode >= ELT_MUL && mode <= ELT_SCALE, VMC_ERR_ARG, "vmc_eltwise: bad argument");
+  VMC_CHECK_ARG(b != nullptr || mode == ELT_SCALE, VMC_ERR_ARG, "vmc_eltwise: mode %d needs a second operand", mode);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
+  eltwise_kernel<<<grid_cap((size_t)n), 256, 0, st>>>(mode, a, b, scale, out, (size_t)n);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_broadcast_rows(const float* g, float* out, int B, int T, int d, float scale, void* stream) {
+  VMC_CHECK_ARG(g && out && B > 0 && T > 0 && d > 0, VMC_ERR_ARG, "vmc_broadcast_rows: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
+  broadcast_rows_kernel<<<grid_cap((size_t)B * T * d), 256, 0, st>>>(g, out, B, T, d, scale);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_attention_masked_bwd(const float* q, long long ldq, const float* k, long long ldk, const float* v,
+                             long long ldv, const uint8_t* key_valid, const float* prob_mask, const float* dO,
+                             long long lddo, float* dq, long long lddq, float* dk, long long lddk, float* dv,
+                             long long lddv, int B, int Tq, int Tk, int heads, void* stream) {
+  VMC_CHECK_ARG(q && k && v && dO && dq && dk && dv, VMC_ERR_ARG, "vmc_attention_masked_bwd: null pointer");
+  VMC_CHECK_ARG(B > 0 && heads > 0 && Tq > 0 && Tk > 0 && B <= 65535, VMC_ERR_SHAPE,
+                "vmc_attention_masked_bwd: bad shape B=%d Tq=%d Tk=%d heads=%d", B, Tq, Tk, heads);
+  const size_t smem = ((size_t)2 * Tq * HD + (size_t)2 * Tk * 65 + (size_t)Tq * (Tk + 1)) * sizeof(float);
+  VMC_CHECK_ARG(smem <= 227 * 1024, VMC_ERR_SHAPE,
+                "vmc_attention_masked_bwd: Tq=%d, Tk=%d need %zu B of shared memory (limit 227 KB: about 128 x 128)",
+                Tq, Tk, smem);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VMC_CUDA(cudaFuncSetAttribute(attention_masked_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  dim3 grid(heads, B);
+  {
+    VmcProfScope prof(VMC_K_ATTN_SMALL, st, 10.0 * B * heads * (double)Tq * Tk * HD, 0.0);
+    attention_masked_bwd_kernel<<<grid, 256, smem, st>>>(q, ldq, k, ldk, v, ldv, key_valid, prob_mask, dO, lddo, dq,
+                                                         lddq, dk, lddk, dv, lddv, Tq, Tk, heads);
+  }
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+}  // extern "C"

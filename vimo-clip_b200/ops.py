@@ -245,9 +245,12 @@ def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int, impl: int = 5)
 
 
 def attention_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_valid, B: int, Tq: int, Tk: int, heads: int,
-                     out_dtype=torch.bfloat16) -> torch.Tensor:
-    """q [B*Tq, *], k/v [B*Tk, *] fp32 views (row-major, heads*64 columns) -> bf16 or fp32 [B*Tq, heads*64]."""
-    _need_cuda(q, k, v, key_valid)
+                     out_dtype=torch.bfloat16, prob_mask=None) -> torch.Tensor:
+    """q [B*Tq, *], k/v [B*Tk, *] fp32 views (row-major, heads*64 columns) -> bf16 or fp32 [B*Tq, heads*64].
+    prob_mask fp32 [B, heads, Tq, Tk] (0 or 1/(1-p)): dropout on the attention probabilities (training)."""
+    _need_cuda(q, k, v, key_valid, prob_mask)
+    if prob_mask is not None and (prob_mask.dtype != torch.float32 or tuple(prob_mask.shape) != (B, heads, Tq, Tk) or not prob_mask.is_contiguous()):
+        raise ValueError("prob_mask must be contiguous fp32 [B, heads, Tq, Tk]")
     for t in (q, k, v):
         if t.dtype != torch.float32 or t.stride(1) != 1:
             raise ValueError("attention_masked inputs must be fp32 row-major")
@@ -259,8 +262,9 @@ def attention_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_vali
     out = torch.empty((B * Tq, heads * 64), dtype=out_dtype, device=q.device)
     with torch.cuda.device(q.device):
         _lib.check(
-            _lib.lib().vmc_attention_masked(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(key_valid), _p(out),
-                                            1 if out_dtype == torch.float32 else 0, out.stride(0), B, Tq, Tk, heads, _stream()),
+            _lib.lib().vmc_attention_masked_train(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(key_valid),
+                                                  _p(prob_mask), _p(out), 1 if out_dtype == torch.float32 else 0, out.stride(0),
+                                                  B, Tq, Tk, heads, _stream()),
             "vmc_attention_masked",
         )
     return out
@@ -272,7 +276,11 @@ def cast_bf16(x: torch.Tensor, split: bool = False) -> torch.Tensor:
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("cast_bf16 input must be fp32 [rows, d] row-major")
     rows, d = x.shape
-    y = torch.empty((rows, 3 * d if split else d), dtype=torch.bfloat16, device=x.device)
+    cols = 3 * d if split else d
+    if cols % 8:  # GEMM operands need a row stride that is a multiple of 8 elements: zero-padded tail, pass k=3*d
+        y = torch.zeros((rows, (cols + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)
+    else:
+        y = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().vmc_cast_bf16(_p(x), x.stride(0), _p(y), y.stride(0), rows, d, 1 if split else 0, _stream()), "vmc_cast_bf16")
     return y
@@ -343,3 +351,85 @@ def tfam_head(x: torch.Tensor, ln_g, ln_b, eps: float, w1_t, b1, w2_t, b2) -> to
         _lib.check(_lib.lib().vmc_tfam_head(_p(x), _p(ln_g), _p(ln_b), float(eps), _p(w1_t), _p(b1), _p(w2_t), _p(b2), _p(logits),
                                             B, T, D, H, Cn, _stream()), "vmc_tfam_head")
     return logits
+
+
+# ---- backward-pass ops of the TFAM training step (csrc/backward.cu) ----
+ELT_MUL, ELT_RELU_BWD, ELT_GELU_BWD, ELT_ADD, ELT_SCALE = 0, 1, 2, 3, 4
+
+
+def _f32_2d(*ts):
+    for t in ts:
+        if t is not None and (t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1):
+            raise ValueError("expected fp32 row-major 2-D tensors")
+
+
+def transpose_split(x: torch.Tensor, form: int) -> torch.Tensor:
+    """x fp32 [R, C] -> bf16 [C, ceil8(3R)]: split operand of x^T (form 0 = [hi|lo|hi], 1 = [hi|hi|lo]); use ``k=3*R``."""
+    _need_cuda(x)
+    _f32_2d(x)
+    R, Cn = x.shape
+    ld = (3 * R + 7) // 8 * 8
+    y = torch.zeros((Cn, ld), dtype=torch.bfloat16, device=x.device) if ld != 3 * R else torch.empty((Cn, ld), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_transpose_split(_p(x), x.stride(0), _p(y), y.stride(0), R, Cn, form, _stream()), "vmc_transpose_split")
+    return y
+
+
+def colsum(x: torch.Tensor, y: torch.Tensor | None = None, out: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:
+    """out[c] (+)= sum_r x[r,c] * (y[r,c] if y is given else 1)."""
+    _need_cuda(x, y, out)
+    _f32_2d(x, y)
+    R, Cn = x.shape
+    if out is None:
+        out = torch.empty(Cn, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_colsum(_p(x), x.stride(0), _p(y), 0 if y is None else y.stride(0), _p(out), R, Cn, 1 if accumulate else 0,
+                                         _stream()), "vmc_colsum")
+    return out
+
+
+def layernorm_bwd(z: torch.Tensor, gamma: torch.Tensor, eps: float, dy: torch.Tensor):
+    """-> (dz, dgamma, dbeta) for y = LayerNorm(z) * gamma + beta; z is the saved LayerNorm input."""
+    _need_cuda(z, gamma, dy)
+    _f32_2d(z, dy)
+    rows, d = z.shape
+    dz = torch.empty_like(z)
+    xhat = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().vmc_layernorm_bwd(_p(z), z.stride(0), _p(gamma), float(eps), _p(dy), dy.stride(0), _p(dz), dz.stride(0),
+                                                _p(xhat), xhat.stride(0), rows, d, _stream()), "vmc_layernorm_bwd")
+    return dz, colsum(dy, xhat), colsum(dy)
+
+
+def eltwise(mode: int, a: torch.Tensor, b: torch.Tensor | None = None, scale: float = 1.0) -> torch.Tensor:
+    _need_cuda(a, b)
+    if a.dtype != torch.float32 or not a.is_contiguous() or (b is not None and (b.dtype != torch.float32 or not b.is_contiguous() or b.numel() != a.numel())):
+        raise ValueError("eltwise operands must be contiguous fp32 of equal size")
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().vmc_eltwise(mode, _p(a), _p(b), float(scale), _p(out), a.numel(), _stream()), "vmc_eltwise")
+    return out
+
+
+def broadcast_rows(g: torch.Tensor, T: int, scale: float) -> torch.Tensor:
+    """g fp32 [B, d] -> [B*T, d] with out[b*T + t] = g[b] * scale (backward of the temporal mean)."""
+    _need_cuda(g)
+    _f32_2d(g)
+    B, d = g.shape
+    out = torch.empty((B * T, d), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().vmc_broadcast_rows(_p(g.contiguous()), _p(out), B, T, d, float(scale), _stream()), "vmc_broadcast_rows")
+    return out
+
+
+def attention_masked_bwd(q, k, v, key_valid, prob_mask, dO, B: int, Tq: int, Tk: int, heads: int, dq, dk, dv) -> None:
+    """Backward of ``attention_masked``: writes dq [B*Tq, .], dk / dv [B*Tk, .] (fp32 row-major views, heads*64 columns)."""
+    _need_cuda(q, k, v, key_valid, prob_mask, dO, dq, dk, dv)
+    _f32_2d(q, k, v, dO, dq, dk, dv)
+    with torch.cuda.device(q.device):
+        _lib.check(
+            _lib.lib().vmc_attention_masked_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(key_valid), _p(prob_mask),
+                                                _p(dO), dO.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0),
+                                                B, Tq, Tk, heads, _stream()),
+            "vmc_attention_masked_bwd",
+        )

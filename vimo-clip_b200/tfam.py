@@ -149,14 +149,26 @@ class AMO_CLIP(nn.Module):
             return None
         return mask.to(device=dev, dtype=torch.bool).contiguous()
 
-    @torch.no_grad()
     def forward(self, rgb_emb, motion_emb, mask_rgb=None, mask_flow=None):
-        """rgb_emb [B,T_r,d], motion_emb [B,T_m,d], masks bool [B,T] (True = real frame) -> logits [B,C]."""
+        """rgb_emb [B,T_r,d], motion_emb [B,T_m,d], masks bool [B,T] (True = real frame) -> logits [B,C].
+
+        ``.eval()``: inference kernels, no autograd.  ``.train()``: the training step of
+        ``TFAM/train_and_eval.py:66-101`` -- logits carry a backward through our kernels (``tfam_train.py``)."""
         dev = self.classifier[0].weight.device
         if dev.type != "cuda":
             raise _lib.VmcError("AMO_CLIP runs on CUDA only (no CPU fallback); call .to('cuda') first")
-        if self.training:
-            raise _lib.VmcError("this drop-in implements the inference forward; call .eval() (training is SURVEY.md 8f rank 2)")
+        if self.training and torch.is_grad_enabled():
+            if not self.use_cross_attention or self.use_only_rgb or self.use_only_flow or self.use_pe:
+                raise _lib.VmcError("training is implemented for the default cross-attention configuration "
+                                    "(TFAM/cfg_AK/config_default.yaml); the ablation modes run in .eval() only")
+            from .tfam_train import tfam_train_forward
+
+            return tfam_train_forward(self, rgb_emb.to(dev).float(), motion_emb.to(dev).float(), self._valid(mask_rgb, dev),
+                                      self._valid(mask_flow, dev))
+        with torch.no_grad():
+            return self._forward_eval(rgb_emb, motion_emb, mask_rgb, mask_flow, dev)
+
+    def _forward_eval(self, rgb_emb, motion_emb, mask_rgb, mask_flow, dev):
         layers, head = self._packed()
         d = self.d_model
         if self.use_pe:  # AMO_CLIP.py:129-134: added IN PLACE to the caller's tensors
