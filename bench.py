@@ -263,11 +263,20 @@ def ours_main(args):
                           "gbs": (by_c[i] / (ms_c[i] * 1e6) if ms_c[i] > 0 else None)} for i in range(n)}
     peaks = load_peaks()
     gemm = classes["gemm_tcgen05"]
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": gemm["tflops"], "peak": peaks["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": (gemm["tflops"] / peaks["bf16_sustained"]) if gemm["tflops"] else None, "traffic": None,
+    # DRAM traffic per launch of the GEMM class: dram__bytes_read + dram__bytes_write summed over the launches of one step
+    # in the committed ncu launch list (same command line), divided by the launch count -- ncu cannot run inside the bench
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_step_launches_dram.json")
+    if os.path.exists(tpath) and clips == 256 and args.frames_in_flight == 2048 and args.ln_fuse == 0:
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["gemm_class"]["dram_bytes_per_launch"]
+        traffic_src = "profiles/r01_step_launches_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the %d GEMM launches of one step)" % tj["gemm_class"]["launches"]
+    roofline = {"bound": "tensor", "kernel": "gemm2_bf16_tcgen05_kernel", "achieved": gemm["tflops"], "peak": peaks["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": (gemm["tflops"] / peaks["bf16_sustained"]) if gemm["tflops"] else None, "traffic": traffic,
+                "traffic_unit": "bytes per launch (DRAM, ncu)", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": (gemm["gbs"] * gemm["ms"] * 1e6 / max(1, gemm["launches"])) if gemm["gbs"] else None,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "traffic_ncu_example": {"kernel": "gemm2_bf16_tcgen05_kernel<256,1> qkv M=201728 N=2304 K=768 (profiles/r01_gemm2_qkv_ncu_summary.txt)",
-                                        "dram_bytes_per_launch": 1.194e9, "algorithmic_bytes_per_launch": 1.243e9},
                 "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
                 "share_of_step": gemm["ms"] / sum(c["ms"] for c in classes.values()),
                 "hbm_kernels": {k: {"gbs": classes[k]["gbs"], "frac_of_hbm_peak": (classes[k]["gbs"] / peaks["hbm"]) if classes[k]["gbs"] else None}
@@ -317,7 +326,7 @@ def main():
     ap.add_argument("--clips", type=int, default=256, help="clips per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="clips staged per H2D copy / tower call")
     ap.add_argument("--frames-in-flight", type=int, default=2048, help="frames per vmc_vit_forward call (workspace size)")
-    ap.add_argument("--ref-clips", type=int, default=2, help="clips per CPU-baseline step (bounded sample)")
+    ap.add_argument("--ref-clips", type=int, default=16, help="clips per CPU-baseline step (bounded sample: ~10 s per pass on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ln-fuse", type=int, default=0, help="VMC_OPT_LN_FUSE: 0 separate LayerNorm kernels (default), 3 ln_1+ln_2 folded into the qkv / c_fc GEMMs, 5 only ln_1 folded, 1/2 fused into residual GEMM epilogues")
     ap.add_argument("--attn-impl", type=int, default=0, help="VMC_OPT_ATTN_IMPL: 0 library default, 3 / 5 select a ViT attention kernel generation")
