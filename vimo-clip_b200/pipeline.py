@@ -27,23 +27,27 @@ class ViMoCLIPPipeline(nn.Module):
         self._copy_stream = None
 
     def _stage(self, rgb_u8, motion_u8, c0):
-        """Queue the host->device copy of one clip chunk on the copy stream; returns (rgb, motion, event)."""
+        """Queue the host->device copies of one clip chunk on the copy stream: RGB first, then motion, each with its own
+        event, so the RGB tower starts as soon as ITS frames have arrived while the motion frames are still in flight.
+        Returns (rgb, rgb_event, motion, motion_event)."""
         r = rgb_u8[c0:c0 + self.clips_per_step]
         m = motion_u8[c0:c0 + self.clips_per_step]
         if r.is_cuda and m.is_cuda:
-            return r, m, None
+            return r, None, m, None
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         compute = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self._copy_stream):
             r = r.to(self.device, non_blocking=True)
+            ev_r = torch.cuda.Event()
+            ev_r.record(self._copy_stream)
             m = m.to(self.device, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self._copy_stream)
+            ev_m = torch.cuda.Event()
+            ev_m.record(self._copy_stream)
         # the buffers are produced on the copy stream and consumed on the compute stream
         r.record_stream(compute)
         m.record_stream(compute)
-        return r, m, ev
+        return r, ev_r, m, ev_m
 
     @torch.no_grad()
     def forward(self, rgb_u8: torch.Tensor, motion_u8: torch.Tensor, mask_rgb=None, mask_flow=None):
@@ -58,13 +62,16 @@ class ViMoCLIPPipeline(nn.Module):
         starts = list(range(0, N, self.clips_per_step))
         staged = self._stage(rgb_u8, motion_u8, starts[0])
         for k, c0 in enumerate(starts):
-            r, m, ev = staged
+            r, ev_r, m, ev_m = staged
             if k + 1 < len(starts):
                 staged = self._stage(rgb_u8, motion_u8, starts[k + 1])
-            if ev is not None:
-                torch.cuda.current_stream(self.device).wait_event(ev)
+            compute = torch.cuda.current_stream(self.device)
+            if ev_r is not None:
+                compute.wait_event(ev_r)
             n = r.shape[0]
             e_rgb.append(self.rgb.get_image_features_u8(r.reshape(n * T, *r.shape[2:])).view(n, T, -1))
+            if ev_m is not None:
+                compute.wait_event(ev_m)
             e_mot.append(self.student(m)[0])
         er = e_rgb[0] if len(e_rgb) == 1 else torch.cat(e_rgb)
         em = e_mot[0] if len(e_mot) == 1 else torch.cat(e_mot)
