@@ -539,11 +539,11 @@ def test_full_pipeline_small(cuda_device):
 # ---------------------------------------------------------------------------------------------------
 # TFAM training step: TFAM/train_and_eval.py:66-101 through our forward + backward kernels
 # ---------------------------------------------------------------------------------------------------
-def _tfam_pair(cuda_device, dropout=0.0, mlp_dropout=0.0, seed=0):
-    o_tf = otfam.TfamOracle(dropout=dropout, mlp_dropout=mlp_dropout)
+def _tfam_pair(cuda_device, dropout=0.0, mlp_dropout=0.0, seed=0, **mode):
+    o_tf = otfam.TfamOracle(dropout=dropout, mlp_dropout=mlp_dropout, **mode)
     with torch.no_grad():
         weights.randomise_tfam_(o_tf, seed)
-    ours = vmc.AMO_CLIP(dropout=dropout, mlp_dropout=mlp_dropout, device=cuda_device)
+    ours = vmc.AMO_CLIP(dropout=dropout, mlp_dropout=mlp_dropout, device=cuda_device, **mode)
     ours.load_state_dict(o_tf.state_dict(), strict=True)
     return o_tf, ours.to(cuda_device)
 
@@ -592,10 +592,12 @@ def test_backward_building_blocks(cuda_device):
         assert (got - ref).norm().item() <= 1e-4 * ref.norm().item()
 
 
-def test_tfam_training_step_gradients_match_reference_autograd(cuda_device):
-    """config 1 batch (B=2, T=16/15, ragged masks), dropout off: logits and EVERY parameter gradient of the
-    BCEWithLogits loss equal fp32 autograd of the reference restatement (oracle pinned to TFAM/models/AMO_CLIP.py)."""
-    o_tf, ours = _tfam_pair(cuda_device)
+@pytest.mark.parametrize("tag", list(MODES))
+def test_tfam_training_step_gradients_match_reference_autograd(cuda_device, tag):
+    """config 1 batch (B=2, T=16/15, ragged masks), dropout off, every fusion mode of the ablation grid: logits and EVERY
+    parameter gradient of the BCEWithLogits loss equal fp32 autograd of the reference restatement (oracle pinned to
+    TFAM/models/AMO_CLIP.py); parameters the mode does not use get no gradient on either side."""
+    o_tf, ours = _tfam_pair(cuda_device, **MODES[tag])
     o_tf.train()
     ours.train()
     gen = torch.Generator().manual_seed(11)
@@ -604,23 +606,24 @@ def test_tfam_training_step_gradients_match_reference_autograd(cuda_device):
     m_mot = torch.arange(15)[None, :] < torch.tensor([15, 11])[:, None]
     labels = (torch.rand(2, 140, generator=gen) < 0.05).float()
     crit = torch.nn.BCEWithLogitsLoss()
-    ref_logits = o_tf(rgb, mot, m_rgb, m_mot)
+    ref_logits = o_tf(rgb.clone(), mot.clone(), m_rgb, m_mot)
     crit(ref_logits, labels).backward()
-    logits = ours(rgb.to(cuda_device), mot.to(cuda_device), m_rgb.to(cuda_device), m_mot.to(cuda_device))
+    logits = ours(rgb.clone().to(cuda_device), mot.clone().to(cuda_device), m_rgb.to(cuda_device), m_mot.to(cuda_device))
     assert logits.requires_grad
     assert (logits.detach().cpu() - ref_logits.detach()).abs().max().item() <= 1e-2
     crit(logits, labels.to(cuda_device)).backward()
     ref_grads = dict(o_tf.named_parameters())
     checked = 0
     for name, p in ours.named_parameters():
-        if name.startswith("projection_layer"):
-            assert p.grad is None  # unused by the cross-attention configuration, as in the reference
-            continue
         ref = ref_grads[name].grad
+        if ref is None:
+            assert p.grad is None, name  # unused by this fusion mode, as in the reference
+            continue
         err = (p.grad.cpu() - ref).norm().item()
-        assert err <= 2e-3 * ref.norm().item() + 1e-9, (name, err, ref.norm().item())
+        # 5e-3: pre-activations within ~1e-6 of the ReLU kink flip their gate between the two fp32 summation orders
+        assert err <= 5e-3 * ref.norm().item() + 1e-9, (name, err, ref.norm().item())
         checked += 1
-    assert checked == 4 * 18 + 6
+    assert checked == {"cross": 78, "cross_pe": 78, "rgb_only": 54, "flow_only": 54, "concat_t": 54, "concat_e": 56}[tag]
 
 
 def test_tfam_training_loop_with_dropout_reduces_loss(cuda_device):

@@ -158,15 +158,31 @@ class AMO_CLIP(nn.Module):
         if dev.type != "cuda":
             raise _lib.VmcError("AMO_CLIP runs on CUDA only (no CPU fallback); call .to('cuda') first")
         if self.training and torch.is_grad_enabled():
-            if not self.use_cross_attention or self.use_only_rgb or self.use_only_flow or self.use_pe:
-                raise _lib.VmcError("training is implemented for the default cross-attention configuration "
-                                    "(TFAM/cfg_AK/config_default.yaml); the ablation modes run in .eval() only")
-            from .tfam_train import tfam_train_forward
-
-            return tfam_train_forward(self, rgb_emb.to(dev).float(), motion_emb.to(dev).float(), self._valid(mask_rgb, dev),
-                                      self._valid(mask_flow, dev))
+            return self._forward_train(rgb_emb, motion_emb, mask_rgb, mask_flow, dev)
         with torch.no_grad():
             return self._forward_eval(rgb_emb, motion_emb, mask_rgb, mask_flow, dev)
+
+    def _forward_train(self, rgb_emb, motion_emb, mask_rgb, mask_flow, dev):
+        """Mode selection of AMO_CLIP.py:129-167 (host-side tensor plumbing), then the training Function."""
+        from .tfam_train import tfam_train_forward
+
+        if self.use_pe:  # in place on the caller's tensors, as the reference does
+            rgb_emb += self.positional_encoding(rgb_emb.size(1), rgb_emb.device).unsqueeze(0)
+            motion_emb += self.positional_encoding(motion_emb.size(1), motion_emb.device).unsqueeze(0)
+        rgb, mot = rgb_emb.to(dev).float(), motion_emb.to(dev).float()
+        v_rgb, v_mot = self._valid(mask_rgb, dev), self._valid(mask_flow, dev)
+        if self.use_only_rgb:
+            return tfam_train_forward(self, rgb, None, v_rgb, None)
+        if self.use_only_flow:
+            return tfam_train_forward(self, mot, None, v_mot, None)
+        if self.use_cross_attention:
+            return tfam_train_forward(self, rgb, mot, v_rgb, v_mot)
+        rgb, v_rgb = rgb[:, :-1, :], v_rgb[:, :-1]  # AMO_CLIP.py:153-154
+        if self.concat_dim == 1:
+            return tfam_train_forward(self, torch.cat([rgb, mot], dim=1), None, torch.cat([v_rgb, v_mot], dim=1).contiguous(), None)
+        if self.concat_dim == -1:
+            return tfam_train_forward(self, torch.cat([rgb, mot], dim=-1), None, v_mot, None, proj=True)
+        raise ValueError("concat_dim must be 1 or -1")
 
     def _forward_eval(self, rgb_emb, motion_emb, mask_rgb, mask_flow, dev):
         layers, head = self._packed()

@@ -7,7 +7,7 @@ call sequence: in training mode ``AMO_CLIP.forward`` returns logits attached to 
 ``loss.backward()``, ``torch.optim.AdamW`` and ``torch.nn.parallel.DistributedDataParallel`` (whose bucketed
 NCCL all-reduce hooks fire on the parameters' AccumulateGrad nodes) work unchanged.
 
-Arithmetic (default cross-attention configuration, ``AMO_CLIP.py:146-150,170``):
+Arithmetic (all fusion modes of ``AMO_CLIP.py:136-167``; the default is cross-attention, ``:146-150,170``):
   * every ``nn.Linear`` forward is one tcgen05 GEMM on split-bf16 operands; its backward is two more
     (``dX = dY W`` and ``dW = dY^T X``) fed by ``ops.transpose_split``; bias gradients are column sums;
   * LayerNorm, masked attention (with dropout on the probabilities), ReLU / GELU, dropout and the temporal
@@ -29,10 +29,12 @@ _PER_LAYER = ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.o
 _HEAD = ("classifier.0.weight", "classifier.0.bias", "classifier.1.weight", "classifier.1.bias", "classifier.4.weight", "classifier.4.bias")
 
 
-def trainable_parameters(model):
-    """The parameters the cross-attention configuration uses, in the order TfamTrainFunction takes them."""
+def trainable_parameters(model, proj: bool = False):
+    """The parameters in the order TfamTrainFunction takes them (projection_layer only in the embedding-concat mode)."""
     named = dict(model.named_parameters())
     names = [f"layers.{i}.{n}" for i in range(len(model.layers)) for n in _PER_LAYER] + list(_HEAD)
+    if proj:
+        names += ["projection_layer.weight", "projection_layer.bias"]
     return names, [named[n] for n in names]
 
 
@@ -63,17 +65,25 @@ def _drop(x, mask):
 
 class TfamTrainFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cfg, rgb, mot, v_rgb, v_mot, *params):
+    def forward(ctx, cfg, x_in, mot, v_rgb, v_mot, *params):
+        """x_in [B,T,d] (or [B,T,2d] when cfg["proj"]: the embedding-concat mode projects it first); mot = cross-attention
+        source [B,Tm,d] or None (rgb-only / flow-only / concat modes: AttentionLayer.forward skips the cross block)."""
         d, h, p_drop, p_mlp, eps_list = cfg["d"], cfg["heads"], cfg["dropout"], cfg["mlp_dropout"], cfg["eps"]
         n_layers = cfg["layers"]
-        dev = rgb.device
-        B, T, _ = rgb.shape
-        Tm = mot.shape[1]
+        cross = mot is not None
+        dev = x_in.device
+        B, T, _ = x_in.shape
+        Tm = mot.shape[1] if cross else 0
         M, Mm = B * T, B * Tm
-        x = rgb.reshape(M, d).contiguous()
-        m32 = mot.reshape(Mm, d).contiguous()
-        saved = []
         k = len(_PER_LAYER)
+        x = x_in.reshape(M, x_in.shape[2]).contiguous()
+        proj_in = None
+        if cfg["proj"]:  # AMO_CLIP.py:163-165: x = projection_layer(cat([rgb[:, :-1], motion], -1))
+            wp, bp = params[n_layers * k + len(_HEAD):]
+            proj_in = x
+            x = _lin_fwd(x, wp, bp)
+        m32 = mot.reshape(Mm, d).contiguous() if cross else None
+        saved = []
         for li in range(n_layers):
             (w_sin, b_sin, w_so, b_so, w_cin, b_cin, w_co, b_co, w1, b1, w2, b2, gs, bs, gc, bc, gf, bf_) = params[li * k:(li + 1) * k]
             e_s, e_c, e_f = eps_list[li]
@@ -84,14 +94,17 @@ class TfamTrainFunction(torch.autograd.Function):
             dm1 = _dropout_mask((M, d), p_drop, dev)
             z1 = ops.eltwise(ops.ELT_ADD, x, _drop(_lin_fwd(a1, w_so, b_so), dm1))
             x1, _ = ops.layernorm(z1, gs, bs, eps=e_s, want32=True, want16=False)
-            # cross-attention block (AMO_CLIP.py:43-45)
-            q2 = _lin_fwd(x1, w_cin[:d], b_cin[:d])
-            kv = _lin_fwd(m32, w_cin[d:], b_cin[d:])
-            pm2 = _dropout_mask((B, h, T, Tm), p_drop, dev)
-            a2 = ops.attention_masked(q2, kv[:, :d], kv[:, d:], v_mot, B, T, Tm, h, out_dtype=torch.float32, prob_mask=pm2)
-            dm2 = _dropout_mask((M, d), p_drop, dev)
-            z2 = ops.eltwise(ops.ELT_ADD, x1, _drop(_lin_fwd(a2, w_co, b_co), dm2))
-            x2, _ = ops.layernorm(z2, gc, bc, eps=e_c, want32=True, want16=False)
+            # cross-attention block (AMO_CLIP.py:43-45), skipped when there is no cross source
+            q2 = kv = pm2 = a2 = dm2 = z2 = None
+            x2 = x1
+            if cross:
+                q2 = _lin_fwd(x1, w_cin[:d], b_cin[:d])
+                kv = _lin_fwd(m32, w_cin[d:], b_cin[d:])
+                pm2 = _dropout_mask((B, h, T, Tm), p_drop, dev)
+                a2 = ops.attention_masked(q2, kv[:, :d], kv[:, d:], v_mot, B, T, Tm, h, out_dtype=torch.float32, prob_mask=pm2)
+                dm2 = _dropout_mask((M, d), p_drop, dev)
+                z2 = ops.eltwise(ops.ELT_ADD, x1, _drop(_lin_fwd(a2, w_co, b_co), dm2))
+                x2, _ = ops.layernorm(z2, gc, bc, eps=e_c, want32=True, want16=False)
             # feed-forward block (AMO_CLIP.py:48-49)
             h_pre = _lin_fwd(x2, w1, b1)
             h_act = _lin_fwd(x2, w1, b1, act=cfg["act"][li])
@@ -103,7 +116,7 @@ class TfamTrainFunction(torch.autograd.Function):
             saved.append(dict(x=x, qkv=qkv, a1=a1, z1=z1, x1=x1, q2=q2, kv=kv, a2=a2, z2=z2, x2=x2, h_pre=h_pre, h_d=h_d, z3=z3,
                               pm1=pm1, dm1=dm1, pm2=pm2, dm2=dm2, dmh=dmh, dm3=dm3))
             x = x3
-        g0, b0, wc1, bc1, wc2, bc2 = params[n_layers * k:]
+        g0, b0, wc1, bc1, wc2, bc2 = params[n_layers * k:n_layers * k + len(_HEAD)]
         pooled, _ = ops.mean_rows(x.view(B, T, d), want32=True)  # ALL rows, padded ones included (AMO_CLIP.py:170)
         n32, _ = ops.layernorm(pooled, g0, b0, eps=cfg["head_eps"], want32=True, want16=False)
         u_pre = _lin_fwd(n32, wc1, bc1)
@@ -113,7 +126,7 @@ class TfamTrainFunction(torch.autograd.Function):
         logits = _lin_fwd(u_d, wc2, bc2)
         ctx.cfg, ctx.saved, ctx.head = cfg, saved, dict(pooled=pooled, n32=n32, u_pre=u_pre, u_d=u_d, dmu=dmu)
         ctx.m32, ctx.v_rgb, ctx.v_mot, ctx.shape = m32, v_rgb, v_mot, (B, T, Tm)
-        ctx.params = params
+        ctx.params, ctx.proj_in, ctx.cross = params, proj_in, cross
         return logits
 
     @staticmethod
@@ -125,14 +138,15 @@ class TfamTrainFunction(torch.autograd.Function):
         k = len(_PER_LAYER)
         grads = [None] * len(params)
         hd = ctx.head
-        g0, b0, wc1, bc1, wc2, bc2 = params[n_layers * k:]
+        g0, b0, wc1, bc1, wc2, bc2 = params[n_layers * k:n_layers * k + len(_HEAD)]
+        cross = ctx.cross
         dlogits = dlogits.float().contiguous()
         du_d, gw2, gb2 = _lin_bwd(dlogits, hd["u_d"], wc2)
         du = _drop(du_d, hd["dmu"])
         du_pre = ops.eltwise(ops.ELT_GELU_BWD, du, hd["u_pre"])
         dn, gw1, gb1 = _lin_bwd(du_pre, hd["n32"], wc1)
         dpooled, gg0, gb0 = ops.layernorm_bwd(hd["pooled"], g0, cfg["head_eps"], dn)
-        grads[n_layers * k:] = [gg0, gb0, gw1, gb1, gw2, gb2]
+        grads[n_layers * k:n_layers * k + len(_HEAD)] = [gg0, gb0, gw1, gb1, gw2, gb2]
         dx = ops.broadcast_rows(dpooled, T, 1.0 / T)  # gradient w.r.t. the last layer's output rows
         for li in reversed(range(n_layers)):
             (w_sin, b_sin, w_so, b_so, w_cin, b_cin, w_co, b_co, w1, b1, w2, b2, gs, bs, gc, bc, gf, bf_) = params[li * k:(li + 1) * k]
@@ -146,16 +160,20 @@ class TfamTrainFunction(torch.autograd.Function):
             dx2_b, g_w1, g_b1 = _lin_bwd(dh_pre, s["x2"], w1)
             dx2 = ops.eltwise(ops.ELT_ADD, dz3, dx2_b)
             # ---- cross-attention block ----
-            dz2, g_gc, g_bc = ops.layernorm_bwd(s["z2"], gc, e_c, dx2)
-            da2, g_wco, g_bco = _lin_bwd(_drop(dz2, s["dm2"]), s["a2"], w_co)
-            dq2 = torch.empty((M, d), dtype=torch.float32, device=dx.device)
-            dkv = torch.empty((Mm, 2 * d), dtype=torch.float32, device=dx.device)
-            ops.attention_masked_bwd(s["q2"], s["kv"][:, :d], s["kv"][:, d:], ctx.v_mot, s["pm2"], da2, B, T, Tm, h,
-                                     dq2, dkv[:, :d], dkv[:, d:])
-            g_wcin = torch.empty_like(w_cin, dtype=torch.float32)
-            dx1_b, _, g_bq = _lin_bwd(dq2, s["x1"], w_cin[:d], dw_out=g_wcin[:d])
-            _, _, g_bkv = _lin_bwd(dkv, ctx.m32, w_cin[d:], need_dx=False, dw_out=g_wcin[d:])
-            dx1 = ops.eltwise(ops.ELT_ADD, dz2, dx1_b)
+            g_wcin = g_bcin = g_wco = g_bco = g_gc = g_bc = None  # unused parameters get no gradient, as in the reference
+            dx1 = dx2
+            if cross:
+                dz2, g_gc, g_bc = ops.layernorm_bwd(s["z2"], gc, e_c, dx2)
+                da2, g_wco, g_bco = _lin_bwd(_drop(dz2, s["dm2"]), s["a2"], w_co)
+                dq2 = torch.empty((M, d), dtype=torch.float32, device=dx.device)
+                dkv = torch.empty((Mm, 2 * d), dtype=torch.float32, device=dx.device)
+                ops.attention_masked_bwd(s["q2"], s["kv"][:, :d], s["kv"][:, d:], ctx.v_mot, s["pm2"], da2, B, T, Tm, h,
+                                         dq2, dkv[:, :d], dkv[:, d:])
+                g_wcin = torch.empty_like(w_cin, dtype=torch.float32)
+                dx1_b, _, g_bq = _lin_bwd(dq2, s["x1"], w_cin[:d], dw_out=g_wcin[:d])
+                _, _, g_bkv = _lin_bwd(dkv, ctx.m32, w_cin[d:], need_dx=False, dw_out=g_wcin[d:])
+                g_bcin = torch.cat([g_bq, g_bkv])
+                dx1 = ops.eltwise(ops.ELT_ADD, dz2, dx1_b)
             # ---- self-attention block ----
             dz1, g_gs, g_bs = ops.layernorm_bwd(s["z1"], gs, e_s, dx1)
             da1, g_wso, g_bso = _lin_bwd(_drop(dz1, s["dm1"]), s["a1"], w_so)
@@ -163,23 +181,31 @@ class TfamTrainFunction(torch.autograd.Function):
             qkv = s["qkv"]
             ops.attention_masked_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx.v_rgb, s["pm1"], da1, B, T, T, h,
                                      dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:])
-            dx_b, g_wsin, g_bsin = _lin_bwd(dqkv, s["x"], w_sin, need_dx=li > 0)
-            if li > 0:
+            need_dx = li > 0 or cfg["proj"]
+            dx_b, g_wsin, g_bsin = _lin_bwd(dqkv, s["x"], w_sin, need_dx=need_dx)
+            if need_dx:
                 dx = ops.eltwise(ops.ELT_ADD, dz1, dx_b)
-            grads[li * k:(li + 1) * k] = [g_wsin, g_bsin, g_wso, g_bso, g_wcin, torch.cat([g_bq, g_bkv]), g_wco, g_bco,
+            grads[li * k:(li + 1) * k] = [g_wsin, g_bsin, g_wso, g_bso, g_wcin, g_bcin, g_wco, g_bco,
                                           g_w1, g_b1, g_w2, g_b2, g_gs, g_bs, g_gc, g_bc, g_gf, g_bf]
+        if cfg["proj"]:
+            wp = params[n_layers * k + len(_HEAD)]
+            _, g_wp, g_bp = _lin_bwd(dx, ctx.proj_in, wp, need_dx=False)
+            grads[n_layers * k + len(_HEAD):] = [g_wp, g_bp]
         ctx.saved = None
         return (None, None, None, None, None, *grads)
 
 
-def tfam_train_forward(model, rgb, mot, v_rgb, v_mot):
-    """Training-mode forward of the cross-attention ``AMO_CLIP`` (called by ``AMO_CLIP.forward`` when ``self.training``)."""
-    _, params = trainable_parameters(model)
+def tfam_train_forward(model, x_in, cross_src, v_x, v_cross, proj: bool = False):
+    """Training-mode forward of ``AMO_CLIP`` (called by ``AMO_CLIP.forward`` when ``self.training``): ``x_in`` is the
+    sequence the layers run on (already selected / concatenated per fusion mode), ``cross_src`` the cross-attention
+    source or None."""
+    _, params = trainable_parameters(model, proj)
     cfg = dict(
+        proj=proj,
         d=model.d_model, heads=model.nhead, layers=len(model.layers),
         dropout=float(model.layers[0].dropout.p), mlp_dropout=float(model.classifier[3].p),
         eps=[(ly.norm_self.eps, ly.norm_cross.eps, ly.norm_ffn.eps) for ly in model.layers],
         act=[ops.ACT_GELU_ERF if ly.activation == "gelu" else ops.ACT_RELU for ly in model.layers],
         head_eps=model.classifier[0].eps,
     )
-    return TfamTrainFunction.apply(cfg, rgb, mot, v_rgb, v_mot, *params)
+    return TfamTrainFunction.apply(cfg, x_in, cross_src, v_x, v_cross, *params)
