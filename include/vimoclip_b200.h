@@ -201,6 +201,10 @@ int vmc_tfam_head(const float* x, const float* ln_g, const float* ln_b, float ep
  * (A side of vmc_gemm_bf16), form 1 = [hi | hi | lo] (W side). */
 int vmc_transpose_split(const float* x, long long ldx, void* y, long long ldy, int R, int C, int form,
                         void* stream);
+/* plain transposing cast x [R, C] (fp32, or bf16 when src_bf16) -> y bf16 [C, R] (ldy >= R, multiple of 8): operands of the bf16
+ * dW GEMMs of the student's backward (train.py:95-107); vmc_cast_f32: bf16 [rows, d] -> fp32 */
+int vmc_transpose_cast(const void* x, int src_bf16, long long ldx, void* y, long long ldy, int R, int C, void* stream);
+int vmc_cast_f32(const void* x, long long ldx, float* y, long long ldy, int rows, int d, void* stream);
 /* out[c] (+)= sum_r x[r,c] * (y ? y[r,c] : 1): bias / LayerNorm parameter gradients; deterministic order */
 int vmc_colsum(const float* x, long long ldx, const float* y, long long ldy, float* out, int R, int C,
                int accumulate, void* stream);
@@ -209,7 +213,8 @@ int vmc_layernorm_bwd(const float* z, long long ldz, const float* gamma, float e
                       long long lddy, float* dz, long long lddz, float* xhat, long long ldxh, int rows, int d,
                       void* stream);
 /* mode 0: out = a*b (dropout mask), 1: ReLU backward (b = activation output or pre-activation), 2: GELU(erf)
- * backward (b = pre-activation), 3: out = a+b, 4: out = a*scale */
+ * backward (b = pre-activation), 3: out = a+b, 4: out = a*scale, 5: QuickGELU forward a*sigmoid(1.702a), 6: QuickGELU
+ * backward (b = pre-activation), 7: out = scale*a + b */
 int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* out, long long n, void* stream);
 /* out[b,t,:] = g[b,:] * scale (backward of the temporal mean, AMO_CLIP.py:170) */
 int vmc_broadcast_rows(const float* g, float* out, int B, int T, int d, float scale, void* stream);

@@ -39,9 +39,14 @@ class StudentOracle(nn.Module):
         self.residual_mlp = ResidualMLP(d, alpha=alpha)
         self.classification_head = nn.Sequential(nn.Linear(d, d // 2), nn.ReLU(), nn.Linear(d // 2, num_classes))
 
-    @torch.no_grad()
     def forward(self, videos: torch.Tensor):
-        """videos [B,T,3,224,224] uint8 or float -> (emb [B,T,D], emb_distill [B,T,D], logits [B,C])."""
+        """videos [B,T,3,224,224] uint8 or float -> (emb [B,T,D], emb_distill [B,T,D], logits [B,C]).
+        Inference under no_grad; in ``.train()`` mode autograd stays on (train.py:95-107 backpropagates through the
+        reference module) -- the oracle of the student training-step parity test."""
+        with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+            return self._forward(videos)
+
+    def _forward(self, videos: torch.Tensor):
         B, T, C, H, W = videos.shape
         frames = videos.reshape(B * T, C, H, W)  # student_model.py:74 (.float() happens in preprocess_frames)
         x = torch.from_numpy(prologue.preprocess_frames(frames.cpu().numpy()))  # :77-78

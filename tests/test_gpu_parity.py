@@ -647,3 +647,68 @@ def test_tfam_training_loop_with_dropout_reduces_loss(cuda_device):
     assert sum(losses[-3:]) < 0.8 * sum(losses[:3]), losses
     ours.eval()
     assert not ours(rgb, mot).requires_grad
+
+
+# ---------------------------------------------------------------------------------------------------
+# Student training step: train.py:86-107 through our forward + backward kernels
+# ---------------------------------------------------------------------------------------------------
+def test_student_training_step_gradients_match_reference_autograd(cuda_device):
+    """2 clips x 3 frames through the ViT-B/32 student in .train() mode: the loss of train.py:98-101 (cosine distillation
+    against teacher embeddings + BCE with positive weight) backpropagated through our kernels gives every parameter
+    gradient of the tower and the heads to bf16 accuracy against fp32 autograd of the reference restatement."""
+    oracle = ostudent.StudentOracle("ViT-B/32", seed=0)
+    with torch.no_grad():
+        weights.randomise_heads_(oracle, 0)
+    ours = vmc.FlowStudentModel("ViT-B/32", device=cuda_device, num_classes=140, alpha=0.1)
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    oracle.train()
+    ours.train()
+    gen = torch.Generator().manual_seed(21)
+    frames = torch.randint(0, 256, (2, 3, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    teacher = torch.randn(2, 3, 512, generator=gen)
+    labels = (torch.rand(2, 140, generator=gen) < 0.05).float()
+
+    def loss_of(model, dev):
+        emb, dis, logits = model(frames)
+        l = olosses.distillation_loss(dis, teacher.to(dev), mode="cosine") + olosses.classification_loss(logits, labels.to(dev), 10.0)
+        return l + 0.01 * emb.pow(2).mean()  # the raw embeddings get a gradient of their own too
+
+    loss_ref = loss_of(oracle, "cpu")
+    loss_ref.backward()
+    loss = loss_of(ours, cuda_device)
+    assert abs(loss.item() - loss_ref.item()) <= 2e-2 * abs(loss_ref.item())
+    loss.backward()
+    ref = dict(oracle.named_parameters())
+    worst = 0.0
+    n = 0
+    for name, p in ours.named_parameters():
+        r = ref[name].grad
+        assert p.grad is not None and r is not None, name
+        err = (p.grad.cpu() - r).norm().item() / (r.norm().item() + 1e-12)
+        worst = max(worst, err)
+        assert err <= 6e-2, (name, err, r.norm().item())
+        n += 1
+    assert n == 5 + 12 * 12 + 3 + 8
+    print(f"student training step: worst relative gradient error {worst:.3e} over {n} tensors")
+
+
+def test_student_training_loop_reduces_loss(cuda_device):
+    """Adam(lr 1e-5) on ALL parameters as train.py:66: the distillation + classification loss goes down."""
+    torch.manual_seed(3)
+    ours = vmc.FrameDiffStudentModel("ViT-B/32", device=cuda_device, num_classes=140).train()
+    gen = torch.Generator().manual_seed(8)
+    frames = torch.randint(0, 256, (4, 4, 3, 224, 224), dtype=torch.uint8, generator=gen).to(cuda_device)
+    teacher = torch.randn(4, 4, 512, generator=gen).to(cuda_device)
+    labels = (torch.rand(4, 140, generator=gen) < 0.05).float().to(cuda_device)
+    opt = torch.optim.Adam(ours.parameters(), lr=1e-5)
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        emb, dis, logits = ours(frames)
+        loss = vmc.losses.distillation_loss(dis, teacher, mode="cosine") + vmc.losses.classification_loss(logits, labels)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    ours.eval()
+    assert not ours(frames)[0].requires_grad

@@ -43,6 +43,35 @@ transpose_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16
   }
 }
 
+// plain transposing cast: x [R, C] (fp32 or bf16) -> y bf16 [C, R] (ldy >= R); the operands of the bf16 dW GEMMs
+// of the student's backward (dW = dY^T X: both operands are transposes of row-major activations)
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_cast_kernel(const T* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? static_cast<float>(x[(size_t)r * ldx + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < R) y[(size_t)c * ldy + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ y, long long ldy, int rows, int d) {
+  const size_t total = (size_t)rows * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / d;
+    const int c = (int)(i - r * d);
+    y[r * ldy + c] = __bfloat162float(x[r * ldx + c]);
+  }
+}
+
 // out[c] (+)= sum_r x[r, c] * (y ? y[r, c] : 1): deterministic (one block owns 32 columns, fixed order)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y, long long ldy,
@@ -106,7 +135,8 @@ layernorm_bwd_kernel(const float* __restrict__ z, long long ldz, const float* __
 }
 
 // element-wise helpers of the backward pass
-enum { ELT_MUL = 0, ELT_RELU_BWD = 1, ELT_GELU_BWD = 2, ELT_ADD = 3, ELT_SCALE = 4 };
+enum { ELT_MUL = 0, ELT_RELU_BWD = 1, ELT_GELU_BWD = 2, ELT_ADD = 3, ELT_SCALE = 4, ELT_QGELU_FWD = 5, ELT_QGELU_BWD = 6,
+       ELT_AXPY = 7 };
 __global__ void __launch_bounds__(256)
 eltwise_kernel(int mode, const float* __restrict__ a, const float* __restrict__ b, float scale,
                float* __restrict__ out, size_t n) {
@@ -122,6 +152,14 @@ eltwise_kernel(int mode, const float* __restrict__ a, const float* __restrict__ 
         break;
       }
       case ELT_ADD: r = x + b[i]; break;
+      case ELT_QGELU_FWD: r = x / (1.0f + __expf(-1.702f * x)); break;  // x * sigmoid(1.702 x), CLIP's QuickGELU
+      case ELT_QGELU_BWD: {  // b = pre-activation: d/db [b sigmoid(1.702 b)] = s (1 + 1.702 b (1 - s))
+        const float u = b[i];
+        const float sg = 1.0f / (1.0f + __expf(-1.702f * u));
+        r = x * sg * (1.0f + 1.702f * u * (1.0f - sg));
+        break;
+      }
+      case ELT_AXPY: r = fmaf(scale, x, b[i]); break;  // scale * a + b
       default: r = x * scale; break;
     }
     out[i] = r;
@@ -279,6 +317,34 @@ int vmc_transpose_split(const float* x, long long ldx, void* y, long long ldy, i
   return VMC_OK;
 }
 
+int vmc_transpose_cast(const void* x, int src_bf16, long long ldx, void* y, long long ldy, int R, int C, void* stream) {
+  VMC_CHECK_ARG(x && y, VMC_ERR_ARG, "vmc_transpose_cast: null pointer");
+  VMC_CHECK_ARG(R > 0 && C > 0 && ldx >= C && ldy >= R, VMC_ERR_SHAPE, "vmc_transpose_cast: bad shape R=%d C=%d ldx=%lld ldy=%lld",
+                R, C, ldx, ldy);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
+  if (src_bf16)
+    transpose_cast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                                                               reinterpret_cast<__nv_bfloat16*>(y), ldy, R, C);
+  else
+    transpose_cast_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), ldx,
+                                                       reinterpret_cast<__nv_bfloat16*>(y), ldy, R, C);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_cast_f32(const void* x, long long ldx, float* y, long long ldy, int rows, int d, void* stream) {
+  VMC_CHECK_ARG(x && y && rows > 0 && d > 0 && ldx >= d && ldy >= d, VMC_ERR_ARG, "vmc_cast_f32: bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
+  cast_f32_kernel<<<grid_cap((size_t)rows * d), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, y, ldy, rows, d);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
 int vmc_colsum(const float* x, long long ldx, const float* y, long long ldy, float* out, int R, int C,
                int accumulate, void* stream) {
   VMC_CHECK_ARG(x && out, VMC_ERR_ARG, "vmc_colsum: null pointer");
@@ -305,8 +371,9 @@ int vmc_layernorm_bwd(const float* z, long long ldz, const float* gamma, float e
 }
 
 int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* out, long long n, void* stream) {
-  VMC_CHECK_ARG(a && out && n > 0 && mode >= ELT_MUL && mode <= ELT_SCALE, VMC_ERR_ARG, "vmc_eltwise: bad argument");
-  VMC_CHECK_ARG(b != nullptr || mode == ELT_SCALE, VMC_ERR_ARG, "vmc_eltwise: mode %d needs a second operand", mode);
+  VMC_CHECK_ARG(a && out && n > 0 && mode >= ELT_MUL && mode <= ELT_AXPY, VMC_ERR_ARG, "vmc_eltwise: bad argument");
+  VMC_CHECK_ARG(b != nullptr || mode == ELT_SCALE || mode == ELT_QGELU_FWD, VMC_ERR_ARG,
+                "vmc_eltwise: mode %d needs a second operand", mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
   eltwise_kernel<<<grid_cap((size_t)n), 256, 0, st>>>(mode, a, b, scale, out, (size_t)n);

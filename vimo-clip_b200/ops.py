@@ -354,7 +354,7 @@ def tfam_head(x: torch.Tensor, ln_g, ln_b, eps: float, w1_t, b1, w2_t, b2) -> to
 
 
 # ---- backward-pass ops of the TFAM training step (csrc/backward.cu) ----
-ELT_MUL, ELT_RELU_BWD, ELT_GELU_BWD, ELT_ADD, ELT_SCALE = 0, 1, 2, 3, 4
+ELT_MUL, ELT_RELU_BWD, ELT_GELU_BWD, ELT_ADD, ELT_SCALE, ELT_QGELU_FWD, ELT_QGELU_BWD, ELT_AXPY = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 def _f32_2d(*ts):
@@ -372,6 +372,31 @@ def transpose_split(x: torch.Tensor, form: int) -> torch.Tensor:
     y = torch.zeros((Cn, ld), dtype=torch.bfloat16, device=x.device) if ld != 3 * R else torch.empty((Cn, ld), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().vmc_transpose_split(_p(x), x.stride(0), _p(y), y.stride(0), R, Cn, form, _stream()), "vmc_transpose_split")
+    return y
+
+
+def transpose_cast(x: torch.Tensor) -> torch.Tensor:
+    """x [R, C] fp32 or bf16 (row-major) -> bf16 [C, ceil8(R)] = x^T (zero-padded tail): pass ``k=R`` to ``gemm``."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.stride(1) != 1 or x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("transpose_cast input must be a row-major fp32 / bf16 matrix")
+    R, Cn = x.shape
+    ld = (R + 7) // 8 * 8
+    y = torch.zeros((Cn, ld), dtype=torch.bfloat16, device=x.device) if ld != R else torch.empty((Cn, ld), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_transpose_cast(_p(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _p(y), y.stride(0), R, Cn, _stream()),
+                   "vmc_transpose_cast")
+    return y
+
+
+def cast_f32(x: torch.Tensor) -> torch.Tensor:
+    """bf16 [rows, d] (row-major view) -> contiguous fp32."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.stride(1) != 1 or x.dtype != torch.bfloat16:
+        raise ValueError("cast_f32 input must be a row-major bf16 matrix")
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_cast_f32(_p(x), x.stride(0), _p(y), y.stride(0), x.shape[0], x.shape[1], _stream()), "vmc_cast_f32")
     return y
 
 

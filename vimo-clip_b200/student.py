@@ -109,8 +109,19 @@ class _StudentBase(nn.Module):
         distill, logits = ops.student_heads(emb.view(B, T, D), self._heads(), float(self.residual_mlp.alpha), num_classes)
         return emb.view(B, T, D), distill.view(B, T, D), logits
 
-    @torch.no_grad()
     def forward(self, videos: torch.Tensor):
+        """``.eval()``: inference kernels under no_grad.  ``.train()`` (train.py:86-107): the three outputs carry a backward
+        through our kernels for every parameter of the tower and the heads (``student_train.py``)."""
+        train = self.training and torch.is_grad_enabled()
+        with torch.no_grad():
+            patches, B, T = self._patches(videos)
+            if not train:
+                return self.encode_patches(patches, B, T)
+        from .student_train import student_train_forward
+
+        return student_train_forward(self, patches, B, T)
+
+    def _patches(self, videos: torch.Tensor):
         if videos.dim() != 5 or videos.shape[2] != 3:
             raise ValueError("expected videos of shape (B, T, 3, H, W)")
         B, T, C, H, W = videos.shape
@@ -130,7 +141,7 @@ class _StudentBase(nn.Module):
             patches = ops.prologue(u8, wrap=False, dst="patch", patch=self.visual_encoder.patch_size)
         else:
             patches = ops.prologue(frames, wrap=True, dst="patch", patch=self.visual_encoder.patch_size)
-        return self.encode_patches(patches, B, T)
+        return patches, B, T
 
 
 class FlowStudentModel(_StudentBase):
