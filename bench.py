@@ -136,7 +136,8 @@ def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    clips = args.ref_clips
+    # bounded sample: ~0.55 s of CPU work per clip on 16 threads; keep the whole --steps/--warmup run within ~2.5 minutes
+    clips = max(1, min(args.ref_clips, int(270 / max(1, args.steps + max(args.warmup, 1)))))
     fps, ms, cores, threads = cpu_reference_run(args.steps, max(args.warmup, 1), clips)
     line = {
         "impl": "reference", "metric": "frames/sec (CLIP ViT+MoCLIP+TFAM)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
