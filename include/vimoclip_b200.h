@@ -223,11 +223,13 @@ int vmc_broadcast_rows(const float* g, float* out, int B, int T, int d, float sc
 int vmc_attention_masked_train(const float* q, long long ldq, const float* k, long long ldk, const float* v,
                                long long ldv, const uint8_t* key_valid, const float* prob_mask, void* out,
                                int out_f32, long long ldo, int B, int Tq, int Tk, int heads, void* stream);
-/* backward of the above: dq [B*Tq, .], dk, dv [B*Tk, .] written at column head*64 (Tq, Tk <= ~128) */
+/* backward of the above: dq [B*Tq, .], dk, dv [B*Tk, .] written at column head*64.  workspace NULL: one CTA per (clip,
+ * head) with the probabilities in shared memory (Tq, Tk <= ~128); workspace = 2*B*heads*Tq floats: tiled two-pass kernels
+ * (log-sum-exp + dQ, then dK / dV) for any Tq, Tk. */
 int vmc_attention_masked_bwd(const float* q, long long ldq, const float* k, long long ldk, const float* v,
                              long long ldv, const uint8_t* key_valid, const float* prob_mask, const float* dO,
                              long long lddo, float* dq, long long lddq, float* dk, long long lddk, float* dv,
-                             long long lddv, int B, int Tq, int Tk, int heads, void* stream);
+                             long long lddv, int B, int Tq, int Tk, int heads, float* workspace, void* stream);
 
 /* ---- whole ViT tower -----------------------------------------------------------
  * Replaces self.visual_encoder(x) (models/student_model.py:84) and

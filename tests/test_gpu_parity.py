@@ -652,20 +652,22 @@ def test_tfam_training_loop_with_dropout_reduces_loss(cuda_device):
 # ---------------------------------------------------------------------------------------------------
 # Student training step: train.py:86-107 through our forward + backward kernels
 # ---------------------------------------------------------------------------------------------------
-def test_student_training_step_gradients_match_reference_autograd(cuda_device):
-    """2 clips x 3 frames through the ViT-B/32 student in .train() mode: the loss of train.py:98-101 (cosine distillation
+@pytest.mark.parametrize("name,T", [("ViT-B/32", 3), ("ViT-B/16", 1)])
+def test_student_training_step_gradients_match_reference_autograd(cuda_device, name, T):
+    """2 clips x T frames through the student in .train() mode (ViT-B/32: the reference's training tower, 50 tokens;
+    ViT-B/16: 197 tokens, tiled attention backward): the loss of train.py:98-101 (cosine distillation
     against teacher embeddings + BCE with positive weight) backpropagated through our kernels gives every parameter
     gradient of the tower and the heads to bf16 accuracy against fp32 autograd of the reference restatement."""
-    oracle = ostudent.StudentOracle("ViT-B/32", seed=0)
+    oracle = ostudent.StudentOracle(name, seed=0)
     with torch.no_grad():
         weights.randomise_heads_(oracle, 0)
-    ours = vmc.FlowStudentModel("ViT-B/32", device=cuda_device, num_classes=140, alpha=0.1)
+    ours = vmc.FlowStudentModel(name, device=cuda_device, num_classes=140, alpha=0.1)
     ours.load_state_dict(oracle.state_dict(), strict=True)
     oracle.train()
     ours.train()
     gen = torch.Generator().manual_seed(21)
-    frames = torch.randint(0, 256, (2, 3, 3, 224, 224), dtype=torch.uint8, generator=gen)
-    teacher = torch.randn(2, 3, 512, generator=gen)
+    frames = torch.randint(0, 256, (2, T, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    teacher = torch.randn(2, T, 512, generator=gen)
     labels = (torch.rand(2, 140, generator=gen) < 0.05).float()
 
     def loss_of(model, dev):

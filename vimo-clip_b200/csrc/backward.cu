@@ -293,6 +293,203 @@ attention_masked_bwd_kernel(const float* __restrict__ q, long long ldq, const fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tiled masked-attention backward for any Tq / Tk (the kernel above keeps the whole Tq x Tk probability matrix in
+// shared memory: ~128 x 128).  Flash-attention style, fp32 SIMT, 32 x 32 tiles:
+//   pass A (one block per 32 queries): stream the key tiles twice -- (1) online log-sum-exp and
+//           D_i = sum_j P_ij m_ij (dO_i . v_j); (2) dS_ij = P_ij (m_ij dO_i . v_j - D_i), dQ_i += dS_ij k_j / 8.
+//           lse and D go to global memory for pass B.
+//   pass B (one block per 32 keys): stream the query tiles: P_ij = exp(s_ij - lse_i), dV_j += P_ij m_ij dO_i,
+//           dK_j += dS_ij q_i / 8.
+// Thread roles per tile: warp w computes the 8 x 32 block of scores of query rows 8 w .. 8 w + 7 (lane = key), then
+// thread t accumulates 16 of the 64 head dims of row t / 4.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TB = 32;
+
+__device__ __forceinline__ float dot64(const float* __restrict__ a, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll 16
+  for (int c = 0; c < HD; ++c) s = fmaf(a[c], b[c], s);
+  return s;
+}
+
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k, long long ldk,
+                   const float* __restrict__ v, long long ldv, const uint8_t* __restrict__ key_valid,
+                   const float* __restrict__ pmask, const float* __restrict__ dO, long long lddo,
+                   float* __restrict__ dq, long long lddq, float* __restrict__ lse_out, float* __restrict__ d_out,
+                   int Tq, int Tk, int heads) {
+  __shared__ float sq[TB][HD], sdo[TB][HD], sk[TB][HD + 1], sv[TB][HD + 1], sds[TB][TB + 1];
+  __shared__ float s_lse[TB], s_d[TB];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint8_t* kvb = key_valid ? key_valid + (size_t)b * Tk : nullptr;
+  const float* pm = pmask ? pmask + ((size_t)b * heads + h) * Tq * Tk : nullptr;
+  for (int i = tid; i < TB * HD; i += 128) {
+    const int r = i / HD, c = i % HD;
+    const bool ok = q0 + r < Tq;
+    sq[r][c] = ok ? q[((size_t)b * Tq + q0 + r) * ldq + h * HD + c] : 0.f;
+    sdo[r][c] = ok ? dO[((size_t)b * Tq + q0 + r) * lddo + h * HD + c] : 0.f;
+  }
+  float m_run[8], l_run[8], d_run[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { m_run[i] = -INFINITY; l_run[i] = 0.f; d_run[i] = 0.f; }
+  auto load_kv = [&](int k0) {
+    __syncthreads();
+    for (int i = tid; i < TB * HD; i += 128) {
+      const int r = i / HD, c = i % HD;
+      const bool ok = k0 + r < Tk;
+      sk[r][c] = ok ? k[((size_t)b * Tk + k0 + r) * ldk + h * HD + c] : 0.f;
+      sv[r][c] = ok ? v[((size_t)b * Tk + k0 + r) * ldv + h * HD + c] : 0.f;
+    }
+    __syncthreads();
+  };
+  // ---- pass 1: log-sum-exp and D, online over the key tiles ----
+  for (int k0 = 0; k0 < Tk; k0 += TB) {
+    load_kv(k0);
+    const int j = k0 + lane;
+    const bool jv = j < Tk && !(kvb && !kvb[j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      const float s = jv ? dot64(sq[r], sk[lane]) * 0.125f : -INFINITY;
+      float dp = dot64(sdo[r], sv[lane]);
+      if (pm && q0 + r < Tq && j < Tk) dp *= pm[(size_t)(q0 + r) * Tk + j];
+      const float m_new = fmaxf(m_run[i], warp_max(s));
+      const float corr = (m_new == -INFINITY) ? 1.f : __expf(m_run[i] - m_new);
+      const float p = (s == -INFINITY) ? 0.f : __expf(s - m_new);
+      l_run[i] = l_run[i] * corr + warp_sum(p);
+      d_run[i] = d_run[i] * corr + warp_sum(p * dp);
+      m_run[i] = m_new;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      s_lse[r] = m_run[i] + __logf(l_run[i]);
+      s_d[r] = d_run[i] / l_run[i];
+      if (q0 + r < Tq) {
+        lse_out[((size_t)b * heads + h) * Tq + q0 + r] = s_lse[r];
+        d_out[((size_t)b * heads + h) * Tq + q0 + r] = s_d[r];
+      }
+    }
+  }
+  // ---- pass 2: dQ ----
+  const int orow = tid >> 2, oc = (tid & 3) * 16;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  for (int k0 = 0; k0 < Tk; k0 += TB) {
+    load_kv(k0);  // (also orders the s_lse / s_d writes before their first use)
+    const int j = k0 + lane;
+    const bool jv = j < Tk && !(kvb && !kvb[j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      float ds = 0.f;
+      if (jv) {
+        const float p = __expf(dot64(sq[r], sk[lane]) * 0.125f - s_lse[r]);
+        float dp = dot64(sdo[r], sv[lane]);
+        if (pm && q0 + r < Tq) dp *= pm[(size_t)(q0 + r) * Tk + j];
+        ds = p * (dp - s_d[r]);
+      }
+      sds[r][lane] = ds;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < TB; ++jj) {
+      const float ds = sds[orow][jj];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = fmaf(ds, sk[jj][oc + c], acc[c]);
+    }
+  }
+  if (q0 + orow < Tq) {
+    float* o = dq + ((size_t)b * Tq + q0 + orow) * lddq + h * HD + oc;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = acc[c] * 0.125f;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k, long long ldk,
+                    const float* __restrict__ v, long long ldv, const uint8_t* __restrict__ key_valid,
+                    const float* __restrict__ pmask, const float* __restrict__ dO, long long lddo,
+                    const float* __restrict__ lse, const float* __restrict__ dvec, float* __restrict__ dk,
+                    long long lddk, float* __restrict__ dv, long long lddv, int Tq, int Tk, int heads) {
+  __shared__ float sq[TB][HD + 1], sdo[TB][HD + 1], sk[TB][HD], sv[TB][HD], sp[TB][TB + 1], sds[TB][TB + 1];
+  __shared__ float s_lse[TB], s_d[TB];
+  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * TB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint8_t* kvb = key_valid ? key_valid + (size_t)b * Tk : nullptr;
+  const float* pm = pmask ? pmask + ((size_t)b * heads + h) * Tq * Tk : nullptr;
+  for (int i = tid; i < TB * HD; i += 128) {
+    const int r = i / HD, c = i % HD;
+    const bool ok = k0 + r < Tk;
+    sk[r][c] = ok ? k[((size_t)b * Tk + k0 + r) * ldk + h * HD + c] : 0.f;
+    sv[r][c] = ok ? v[((size_t)b * Tk + k0 + r) * ldv + h * HD + c] : 0.f;
+  }
+  const int orow = tid >> 2, oc = (tid & 3) * 16;  // this thread accumulates key row orow, head dims oc .. oc + 15
+  float akk[16], avv[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { akk[c] = 0.f; avv[c] = 0.f; }
+  for (int q0 = 0; q0 < Tq; q0 += TB) {
+    __syncthreads();
+    for (int i = tid; i < TB * HD; i += 128) {
+      const int r = i / HD, c = i % HD;
+      const bool ok = q0 + r < Tq;
+      sq[r][c] = ok ? q[((size_t)b * Tq + q0 + r) * ldq + h * HD + c] : 0.f;
+      sdo[r][c] = ok ? dO[((size_t)b * Tq + q0 + r) * lddo + h * HD + c] : 0.f;
+    }
+    if (tid < TB) {
+      const bool ok = q0 + tid < Tq;
+      s_lse[tid] = ok ? lse[((size_t)b * heads + h) * Tq + q0 + tid] : 0.f;
+      s_d[tid] = ok ? dvec[((size_t)b * heads + h) * Tq + q0 + tid] : 0.f;
+    }
+    __syncthreads();
+    // warp w: keys 8 w .. 8 w + 7 of the tile, lane = query row
+    const int i = q0 + lane;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int r = warp * 8 + jj, j = k0 + r;
+      float pmv = 0.f, ds = 0.f;
+      if (i < Tq && j < Tk && !(kvb && !kvb[j])) {
+        float s = 0.f, dp = 0.f;
+#pragma unroll 16
+        for (int c = 0; c < HD; ++c) {
+          s = fmaf(sq[lane][c], sk[r][c], s);
+          dp = fmaf(sdo[lane][c], sv[r][c], dp);
+        }
+        const float p = __expf(s * 0.125f - s_lse[lane]);
+        const float mk = pm ? pm[(size_t)i * Tk + j] : 1.f;
+        pmv = p * mk;
+        ds = p * (dp * mk - s_d[lane]);
+      }
+      sp[r][lane] = pmv;
+      sds[r][lane] = ds;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int ii = 0; ii < TB; ++ii) {
+      const float pv = sp[orow][ii], ds = sds[orow][ii];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        avv[c] = fmaf(pv, sdo[ii][oc + c], avv[c]);
+        akk[c] = fmaf(ds, sq[ii][oc + c], akk[c]);
+      }
+    }
+  }
+  if (k0 + orow < Tk) {
+    float* ok_ = dk + ((size_t)b * Tk + k0 + orow) * lddk + h * HD + oc;
+    float* ov_ = dv + ((size_t)b * Tk + k0 + orow) * lddv + h * HD + oc;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      ok_[c] = akk[c] * 0.125f;
+      ov_[c] = avv[c];
+    }
+  }
+}
+
 int grid_cap(size_t n) {
   size_t g = (n + 255) / 256;
   const size_t cap = (size_t)vmc_num_sms() * 16;
@@ -395,15 +592,28 @@ int vmc_broadcast_rows(const float* g, float* out, int B, int T, int d, float sc
 int vmc_attention_masked_bwd(const float* q, long long ldq, const float* k, long long ldk, const float* v,
                              long long ldv, const uint8_t* key_valid, const float* prob_mask, const float* dO,
                              long long lddo, float* dq, long long lddq, float* dk, long long lddk, float* dv,
-                             long long lddv, int B, int Tq, int Tk, int heads, void* stream) {
+                             long long lddv, int B, int Tq, int Tk, int heads, float* workspace, void* stream) {
   VMC_CHECK_ARG(q && k && v && dO && dq && dk && dv, VMC_ERR_ARG, "vmc_attention_masked_bwd: null pointer");
   VMC_CHECK_ARG(B > 0 && heads > 0 && Tq > 0 && Tk > 0 && B <= 65535, VMC_ERR_SHAPE,
                 "vmc_attention_masked_bwd: bad shape B=%d Tq=%d Tk=%d heads=%d", B, Tq, Tk, heads);
   const size_t smem = ((size_t)2 * Tq * HD + (size_t)2 * Tk * 65 + (size_t)Tq * (Tk + 1)) * sizeof(float);
-  VMC_CHECK_ARG(smem <= 227 * 1024, VMC_ERR_SHAPE,
-                "vmc_attention_masked_bwd: Tq=%d, Tk=%d need %zu B of shared memory (limit 227 KB: about 128 x 128)",
-                Tq, Tk, smem);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (smem > 200 * 1024 || workspace != nullptr) {
+    // tiled path: any Tq / Tk; workspace = 2 * B * heads * Tq floats (log-sum-exp and D per query row)
+    VMC_CHECK_ARG(workspace != nullptr, VMC_ERR_WORKSPACE,
+                  "vmc_attention_masked_bwd: Tq=%d, Tk=%d need the tiled path: pass a workspace of 2*B*heads*Tq floats", Tq, Tk);
+    VMC_CHECK_ARG(heads <= 65535, VMC_ERR_SHAPE, "vmc_attention_masked_bwd: too many heads");
+    float* lse = workspace;
+    float* dvec = workspace + (size_t)B * heads * Tq;
+    VmcProfScope prof(VMC_K_ATTN_SMALL, st, 14.0 * B * heads * (double)Tq * Tk * HD, 0.0);
+    attn_bwd_dq_kernel<<<dim3((Tq + TB - 1) / TB, heads, B), 128, 0, st>>>(q, ldq, k, ldk, v, ldv, key_valid, prob_mask, dO,
+                                                                            lddo, dq, lddq, lse, dvec, Tq, Tk, heads);
+    attn_bwd_dkv_kernel<<<dim3((Tk + TB - 1) / TB, heads, B), 128, 0, st>>>(q, ldq, k, ldk, v, ldv, key_valid, prob_mask, dO,
+                                                                             lddo, lse, dvec, dk, lddk, dv, lddv, Tq, Tk, heads);
+    VMC_LAUNCH_CHECK();
+    vmc_count_launch(2);
+    return VMC_OK;
+  }
   VMC_CUDA(cudaFuncSetAttribute(attention_masked_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid(heads, B);
   {

@@ -447,14 +447,17 @@ def broadcast_rows(g: torch.Tensor, T: int, scale: float) -> torch.Tensor:
     return out
 
 
-def attention_masked_bwd(q, k, v, key_valid, prob_mask, dO, B: int, Tq: int, Tk: int, heads: int, dq, dk, dv) -> None:
-    """Backward of ``attention_masked``: writes dq [B*Tq, .], dk / dv [B*Tk, .] (fp32 row-major views, heads*64 columns)."""
+def attention_masked_bwd(q, k, v, key_valid, prob_mask, dO, B: int, Tq: int, Tk: int, heads: int, dq, dk, dv, tiled=None) -> None:
+    """Backward of ``attention_masked``: writes dq [B*Tq, .], dk / dv [B*Tk, .] (fp32 row-major views, heads*64 columns).
+    ``tiled``: None = the shared-memory kernel when Tq x Tk fits (~128 x 128), else the tiled two-pass kernels; True forces them."""
     _need_cuda(q, k, v, key_valid, prob_mask, dO, dq, dk, dv)
     _f32_2d(q, k, v, dO, dq, dk, dv)
+    need = (2 * Tq * 64 + 2 * Tk * 65 + Tq * (Tk + 1)) * 4
+    ws = torch.empty(2 * B * heads * Tq, dtype=torch.float32, device=q.device) if (tiled or need > 200 * 1024) else None
     with torch.cuda.device(q.device):
         _lib.check(
             _lib.lib().vmc_attention_masked_bwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(key_valid), _p(prob_mask),
                                                 _p(dO), dO.stride(0), _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0),
-                                                B, Tq, Tk, heads, _stream()),
+                                                B, Tq, Tk, heads, _p(ws), _stream()),
             "vmc_attention_masked_bwd",
         )

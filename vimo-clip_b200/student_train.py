@@ -11,8 +11,9 @@ Forward = the inference kernels, orchestrated here layer by layer so the activat
   * every Linear / the patch-embedding conv: ``dX = dY W`` and ``dW = dY^T X`` as bf16 tcgen05 GEMMs (fp32 accumulation);
     the transposed operands come from ``ops.transpose_cast``; bias gradients are deterministic column sums;
   * LayerNorm backward from the saved LayerNorm inputs; QuickGELU backward element-wise;
-  * attention backward: one CTA per (frame, head) with the probabilities recomputed in shared memory
-    (``vmc_attention_masked_bwd``: L <= ~128 tokens, i.e. ViT-B/32 -- the reference's training default, ``train.py:63``);
+  * attention backward (``vmc_attention_masked_bwd``): one CTA per (frame, head) with the probabilities recomputed in shared
+    memory for ViT-B/32 (50 tokens, the reference's training default, ``train.py:63``), tiled flash-style kernels for
+    longer sequences (ViT-B/16: 197 tokens);
   * heads (ResidualMLP, temporal mean, classification head) in split-bf16 GEMMs like the TFAM step.
 Operands are bf16 (activations and gradients rounded once per GEMM), accumulators fp32: gradients agree with fp32 autograd of
 the reference to bf16 accuracy (a few 1e-3 .. 1e-2 relative per tensor; tests/test_gpu_parity.py).
@@ -21,7 +22,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib, ops
+from . import ops
 from .tfam_train import _lin_bwd, _lin_fwd
 
 _PER_BLOCK = ("ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",
@@ -186,10 +187,6 @@ class StudentTrainFunction(torch.autograd.Function):
 def student_train_forward(model, patches: torch.Tensor, B: int, T: int):
     """Training-mode ``encode_patches`` of the student (called by ``_StudentBase.forward`` when ``self.training``)."""
     tower = model.visual_encoder
-    L = tower.tokens
-    if L > 128:
-        raise _lib.VmcError(f"student training is implemented for towers with <= 128 tokens (ViT-B/32, the reference's training "
-                            f"default, train.py:63); this tower has {L}")
     _, params = trainable_parameters(model)
     cfg = dict(patch=tower.patch_size, d=tower.width, heads=tower.heads, layers=tower.layers, res=tower.input_resolution,
                F=B * T, B=B, T=T, alpha=float(model.residual_mlp.alpha))
