@@ -714,3 +714,32 @@ def test_student_training_loop_reduces_loss(cuda_device):
     assert all(l == l for l in losses) and losses[-1] < losses[0], losses
     ours.eval()
     assert not ours(frames)[0].requires_grad
+
+
+def test_clip_image_processor_dropin_matches_hf(cuda_device):
+    """extract_embeddings.py:89-94: PIL frames -> processor -> .to(device) -> get_image_features(**inputs).  The GPU
+    processor (Pillow-exact bicubic resize + centre crop + P1 normalise) against the installed HF CLIPImageProcessor."""
+    from PIL import Image
+    from transformers import CLIPImageProcessor as HFProcessor
+
+    from torchvision.transforms import CenterCrop, Compose, InterpolationMode, Normalize, Resize, ToTensor
+
+    pil_path = Compose([Resize(224, interpolation=InterpolationMode.BICUBIC), CenterCrop(224), ToTensor(),
+                        Normalize(clip_shim.CLIP_MEAN, clip_shim.CLIP_STD)])  # the PIL arithmetic of the pinned 4.53.2 slow path
+    gen = np.random.default_rng(12)
+    for (H, W) in ((224, 224), (360, 640)):
+        imgs = [Image.fromarray(gen.integers(0, 256, (H, W, 3), dtype=np.uint8)) for _ in range(3)]
+        inputs = vmc.CLIPImageProcessor()(images=imgs, return_tensors="pt").to(cuda_device)
+        got = inputs["pixel_values"].cpu()
+        ref_pil = torch.stack([pil_path(im) for im in imgs])
+        assert got.shape == ref_pil.shape
+        assert torch.equal(got, ref_pil), (H, W)  # bit-exact against the PIL path
+        ref = HFProcessor()(images=imgs, return_tensors="pt")["pixel_values"]
+        diff = (got - ref).abs()
+        if (H, W) == (224, 224):  # no resampling: only the <= 1 ulp rescale/normalise difference (SURVEY.md App. B.6)
+            assert diff.max().item() <= 5e-7
+        else:  # the installed transformers 5.5 resizes with torchvision's tensor bicubic: off by one uint8 level in places
+            assert diff.max().item() <= 1.05 / 255 / 0.26 and (diff > 1e-6).float().mean().item() < 0.1
+    feats = vmc.CLIPVisionFeatures("openai/clip-vit-base-patch32").to(cuda_device)
+    out = feats.get_image_features(**inputs)
+    assert out.shape == (3, 512) and torch.isfinite(out).all()

@@ -6,13 +6,14 @@ reference):
 * ``FlowStudentModel`` / ``FrameDiffStudentModel``  (models/student_model*.py)
 * ``AMO_CLIP``                                      (TFAM/models/AMO_CLIP.py)
 * ``CLIPVisionFeatures.get_image_features``         (HF ``CLIPModel`` as used by extract_embeddings.py)
+* ``CLIPImageProcessor``                            (HF processor call of extract_embeddings.py:91-93, on the GPU)
 * ``distillation_loss`` / ``classification_loss``   (losses.py)
 
 All arithmetic of the path runs in hand-written sm_100a CUDA kernels reached through the C-ABI of
 ``include/vimoclip_b200.h`` (``libvimoclip_b200.so``).  There is no CPU fallback.
 """
 from . import _lib, indexing, ops  # noqa: F401
-from .clip_hf import CLIPVisionFeatures  # noqa: F401
+from .clip_hf import CLIPImageProcessor, CLIPVisionFeatures  # noqa: F401
 from .losses import classification_loss, distillation_loss  # noqa: F401
 from .pipeline import ViMoCLIPPipeline  # noqa: F401
 from .student import FlowStudentModel, FrameDiffStudentModel, ResidualMLP  # noqa: F401

@@ -57,3 +57,54 @@ class CLIPVisionFeatures(nn.Module):
         return self.visual.forward_patches(patches, frames_u8.shape[0])
 
     forward = get_image_features
+
+
+class _ProcessorOutput(dict):
+    """What ``CLIPImageProcessor.__call__`` returns as far as ``extract_embeddings.py:91-94`` uses it:
+    ``inputs = processor(images=..., return_tensors="pt"); inputs = inputs.to(device); model.get_image_features(**inputs)``.
+    The frames stay uint8 until ``.to(device)``; resize / crop / rescale / normalise then run on the GPU."""
+
+    def __init__(self, frames_u8: torch.Tensor, size: int):
+        super().__init__()
+        self._u8, self._size = frames_u8, size
+
+    def to(self, device):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.VmcError("the image processor runs on CUDA only (no CPU fallback)")
+        u8 = self._u8.to(dev, non_blocking=True)
+        if u8.shape[-2] != self._size or u8.shape[-1] != self._size:
+            u8 = ops.resize_center_crop(u8, wrap=False, size=self._size)
+        self["pixel_values"] = ops.prologue(u8, wrap=False, dst="f32")
+        return self
+
+    @property
+    def pixel_values(self):
+        return self["pixel_values"]
+
+
+class CLIPImageProcessor:
+    """Drop-in for HF ``CLIPImageProcessor`` on the call surface of ``extract_embeddings.py:18,89-93`` (defaults: bicubic
+    resize of the shortest edge to 224, centre crop 224, rescale 1/255, CLIP mean / std): a list of PIL images or
+    HxWx3 uint8 arrays of one size -> ``pixel_values`` fp32 [T,3,224,224], computed by the Pillow-exact resize kernel and
+    the P1 prologue on the GPU ((u8/255 - mean)/std with true fp32 divisions; within 1 ulp of the HF slow path)."""
+
+    def __init__(self, size: int = 224):
+        self.size = size
+
+    @classmethod
+    def from_pretrained(cls, *_args, **_kw):
+        return cls()
+
+    def __call__(self, images, return_tensors: str = "pt"):
+        import numpy as np
+
+        if return_tensors != "pt":
+            raise ValueError("only return_tensors='pt' is supported")
+        if not isinstance(images, (list, tuple)):
+            images = [images]
+        arrs = [np.asarray(im.convert("RGB") if hasattr(im, "convert") else im) for im in images]
+        if any(a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3 for a in arrs) or len({a.shape for a in arrs}) != 1:
+            raise ValueError("expected RGB uint8 images (PIL or HxWx3 arrays) of one common size")
+        frames = torch.from_numpy(np.stack(arrs)).permute(0, 3, 1, 2).contiguous()
+        return _ProcessorOutput(frames, self.size)
