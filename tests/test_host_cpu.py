@@ -159,3 +159,56 @@ def test_fast_normalise_constants():
         fused = (np.arange(256, dtype=np.float64) * k + b).astype(np.float32)
         got = torch.from_numpy(fused).to(torch.bfloat16).view(torch.int16).numpy()
         assert np.array_equal(got, exact[0, c].reshape(-1)), c
+
+
+def test_embedding_store_layout_and_roundtrip(tmp_path):
+    """The on-disk contract between the stages (extract_embeddings.py:50-55,106-119; TFAM/data/dataset.py:25-73) on the
+    sidecar format: same hierarchy, attributes and h5py-style access."""
+    from vimoclip_b200.store import EmbeddingStore, write_video
+
+    path = tmp_path / "ak_val_clip_embeddings.vmc"
+    rng = np.random.default_rng(0)
+    embs = {f"vid{i}": rng.standard_normal((5 + i, 512)).astype(np.float32) for i in range(3)}
+    with EmbeddingStore(path, "w") as hf:
+        hf.attrs["num_classes"] = 140
+        hf.attrs["dataset_name"] = "AnimalKingdom"
+        hf.attrs["clip_model"] = "ViT-B/16"
+        for vid, e in embs.items():
+            lab = np.zeros(140, dtype=np.float32)
+            lab[[3, 77]] = 1.0
+            g = write_video(hf, vid, torch.from_numpy(e), lab, total_frames=e.shape[0], original_frames=10 * e.shape[0])
+            assert g["embeddings"].shape == e.shape
+        hf.create_dataset("video_ids", data=np.array(list(embs), dtype=object))
+        with pytest.raises(ValueError):
+            hf.create_group("vid0")  # h5py raises on duplicates too
+    with EmbeddingStore(path, "r") as f:
+        assert sorted(f.keys()) == ["vid0", "vid1", "vid2", "video_ids"]
+        assert f.attrs["num_classes"] == 140 and f.attrs["clip_model"] == "ViT-B/16"
+        assert list(f["video_ids"][:]) == list(embs)
+        for vid, e in embs.items():
+            assert f[vid]["embeddings"].shape[0] == e.shape[0]  # the max_frames filter of TFAM/data/dataset.py:30
+            assert np.array_equal(f[vid]["embeddings"][:], e) and f[vid]["embeddings"].dtype == np.float32
+            assert f[vid]["labels"][:].sum() == 2.0
+            assert f[vid].attrs["total_frames"] == e.shape[0] and f[vid].attrs["original_frames"] == 10 * e.shape[0]
+        with pytest.raises(OSError):
+            f.create_group("nope")
+        with pytest.raises(KeyError):
+            f["missing"]
+    # resume (inference_frame_diff.py: skip videos already present) and MammalNet-style nesting + extendable datasets
+    with EmbeddingStore(path, "a") as f:
+        assert "vid1" in f and "vid9" not in f
+        g = f.create_group("trimmed_videos/clipA")
+        ds = g.create_dataset("embeddings", shape=(0, 512), maxshape=(None, 512), dtype=np.float32, compression="gzip", chunks=(2048, 512))
+        off = 0
+        for chunk in (rng.standard_normal((4, 512)).astype(np.float32), rng.standard_normal((3, 512)).astype(np.float32)):
+            ds.resize(off + chunk.shape[0], axis=0)  # extract_embeddings_mammalNet.py:137-141
+            ds[off:off + chunk.shape[0]] = chunk
+            off += chunk.shape[0]
+        last = chunk
+    with EmbeddingStore(path, "r") as f:
+        assert "trimmed_videos" in f and list(f["trimmed_videos"].keys()) == ["clipA"]
+        e = f["trimmed_videos"]["clipA"]["embeddings"]
+        assert e.shape == (7, 512) and np.array_equal(e[4:], last)
+        assert f["trimmed_videos/clipA"]["embeddings"].shape == (7, 512)
+        with pytest.raises(ImportError):
+            f.to_hdf5(str(tmp_path / "x.h5"))  # h5py is absent here; on a machine that has it this writes the reference layout
