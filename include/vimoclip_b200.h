@@ -205,9 +205,12 @@ int vmc_transpose_split(const float* x, long long ldx, void* y, long long ldy, i
  * dW GEMMs of the student's backward (train.py:95-107); vmc_cast_f32: bf16 [rows, d] -> fp32 */
 int vmc_transpose_cast(const void* x, int src_bf16, long long ldx, void* y, long long ldy, int R, int C, void* stream);
 int vmc_cast_f32(const void* x, long long ldx, float* y, long long ldy, int rows, int d, void* stream);
-/* out[c] (+)= sum_r x[r,c] * (y ? y[r,c] : 1): bias / LayerNorm parameter gradients; deterministic order */
+/* out[c] (+)= sum_r x[r,c] * (y ? y[r,c] : 1): bias / LayerNorm parameter gradients; deterministic order.
+ * workspace: vmc_colsum_slices(R, C) * C floats (row slices summed in parallel, then added in index order), or NULL for
+ * the single-stage kernel (one block per 32 columns: slow for tall matrices). */
+int vmc_colsum_slices(int R, int C);
 int vmc_colsum(const float* x, long long ldx, const float* y, long long ldy, float* out, int R, int C,
-               int accumulate, void* stream);
+               int accumulate, float* workspace, void* stream);
 /* LayerNorm backward per row from the saved LayerNorm INPUT z: dz, and xhat (optional) for dgamma = colsum(dy*xhat) */
 int vmc_layernorm_bwd(const float* z, long long ldz, const float* gamma, float eps, const float* dy,
                       long long lddy, float* dz, long long lddz, float* xhat, long long ldxh, int rows, int d,
@@ -216,6 +219,12 @@ int vmc_layernorm_bwd(const float* z, long long ldz, const float* gamma, float e
  * backward (b = pre-activation), 3: out = a+b, 4: out = a*scale, 5: QuickGELU forward a*sigmoid(1.702a), 6: QuickGELU
  * backward (b = pre-activation), 7: out = scale*a + b */
 int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* out, long long n, void* stream);
+/* y = bf16(QuickGELU(x)) over n contiguous fp32 elements (n % 4 == 0): the c_fc activation of the student's training forward */
+int vmc_qgelu_cast(const float* x, void* y, long long n, void* stream);
+/* ViT self-attention backward for towers of at most 64 tokens (ViT-B/32), straight from the packed bf16 qkv buffer
+ * [F*L, 3*heads*64]: dqkv fp32 [F*L, 3*heads*64] from dO fp32 [F*L, heads*64] (row stride lddo) */
+int vmc_attention_vit_bwd_short(const void* qkv, const float* dO, long long lddo, float* dqkv, int F, int L, int heads,
+                                void* stream);
 /* out[b,t,:] = g[b,:] * scale (backward of the temporal mean, AMO_CLIP.py:170) */
 int vmc_broadcast_rows(const float* g, float* out, int B, int T, int d, float scale, void* stream);
 /* vmc_attention_masked with dropout on the attention probabilities: prob_mask fp32 [B, heads, Tq, Tk] holds 0 or

@@ -72,3 +72,60 @@ def test_report_torch_eager_context(cuda_device):
     lours, _ = timed(lambda: pipe.student(m1), reps=10)
     print(f"latency, ONE clip of {Tm} frames through the ViT-B/32 student: torch eager fp32 {l32 * 1e3:.2f} ms, eager bf16 {l16 * 1e3:.2f} ms, "
           f"this repository {lours * 1e3:.2f} ms")
+
+
+@pytest.mark.gpu
+def test_report_training_step_context(cuda_device):
+    """Student training step (train.py:86-107) on 32 clips x 16 frames (the reference trains on sequences of hundreds of
+    frames, models/student_model.py:104): stock PyTorch eager autograd of the reference modules
+    (fp32 and bf16 autocast) next to this repository's forward + backward kernels, same weights and inputs."""
+    from oracle import losses as olosses
+
+    clips, T = 32, 16
+    gen = torch.Generator().manual_seed(7)
+    frames = torch.randint(0, 256, (clips, T, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    teacher = torch.randn(clips, T, 512, generator=gen).to(cuda_device)
+    labels = (torch.rand(clips, 140, generator=gen) < 0.05).float().to(cuda_device)
+    oracle = ostudent.StudentOracle("ViT-B/32", seed=0)
+    weights.randomise_heads_(oracle, 0)
+    oracle = oracle.to(cuda_device).train()
+    ours = vmc.FlowStudentModel("ViT-B/32", device=cuda_device, num_classes=140)
+    ours.load_state_dict(oracle.state_dict(), strict=True)
+    ours.train()
+    x = torch.from_numpy(prologue.preprocess_frames(frames.reshape(-1, 3, 224, 224).numpy())).to(cuda_device)
+    frames_d = frames.to(cuda_device)
+
+    def eager_step(dtype):
+        for p in oracle.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+            emb = oracle.visual_encoder(x).float().view(clips, T, -1)
+            dis = oracle.residual_mlp(emb)
+            logits = oracle.classification_head(emb.mean(dim=1))
+        loss = olosses.distillation_loss(dis, teacher, mode="cosine") + olosses.classification_loss(logits, labels)
+        loss.backward()
+        return loss
+
+    def our_step():
+        for p in ours.parameters():
+            p.grad = None
+        emb, dis, logits = ours(frames_d)
+        loss = vmc.losses.distillation_loss(dis, teacher, mode="cosine") + vmc.losses.classification_loss(logits, labels)
+        loss.backward()
+        return loss
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps, out
+
+    t32, l32 = timed(lambda: eager_step(torch.float32))
+    t16, _ = timed(lambda: eager_step(torch.bfloat16))
+    tours, lours = timed(our_step)
+    print(f"\nstudent training step, {clips} clips x {T} frames (ViT-B/32, forward + backward, no optimiser): torch eager fp32 {t32 * 1e3:.1f} ms, "
+          f"eager bf16 autocast {t16 * 1e3:.1f} ms, this repository {tours * 1e3:.1f} ms; loss {l32.item():.5f} vs {lours.item():.5f}")
+    assert abs(l32.item() - lours.item()) <= 2e-2 * abs(l32.item())

@@ -560,6 +560,13 @@ def test_backward_building_blocks(cuda_device):
     (x @ w.t()).backward(dy)
     for got, ref in ((dx, x.grad), (dw, w.grad), (db, dy.sum(0))):
         assert (got - ref).norm().item() <= 2e-4 * ref.norm().item()
+    # column sums: single-stage (short) and two-stage (tall) paths, with and without the element-wise product
+    for R, Cn in ((96, 140), (5000, 768), (30000, 100)):
+        xs = torch.randn(R, Cn, device=cuda_device, generator=gen)
+        ys = torch.randn(R, Cn, device=cuda_device, generator=gen)
+        assert torch.allclose(ops.colsum(xs), xs.double().sum(0).float(), rtol=1e-4, atol=1e-3)
+        assert torch.allclose(ops.colsum(xs, ys), (xs.double() * ys.double()).sum(0).float(), rtol=1e-4, atol=1e-3)
+        assert torch.equal(ops.colsum(xs, ys), ops.colsum(xs, ys))  # deterministic
     # LayerNorm backward
     z = (torch.randn(M, K, device=cuda_device, generator=gen) * 2 + 0.3).requires_grad_()
     g_ = (1 + 0.1 * torch.randn(K, device=cuda_device, generator=gen)).requires_grad_()
@@ -743,3 +750,43 @@ def test_clip_image_processor_dropin_matches_hf(cuda_device):
     feats = vmc.CLIPVisionFeatures("openai/clip-vit-base-patch32").to(cuda_device)
     out = feats.get_image_features(**inputs)
     assert out.shape == (3, 512) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("B,Tq,Tk,h,drop", [(2, 150, 197, 4, True), (1, 197, 197, 12, False), (3, 33, 300, 2, True),
+                                            (2, 100, 90, 3, True), (2, 64, 64, 2, True), (3, 16, 15, 8, True)])
+@pytest.mark.parametrize("path", ["auto", "tiled"])
+def test_attention_backward_all_paths(cuda_device, B, Tq, Tk, h, drop, path):
+    """Masked attention backward against torch autograd: the register-tiled short-sequence kernel (<= 64 x 64), the
+    shared-memory kernel (<= ~128 x 128) and the tiled flash-style kernels (any length; forced with ``tiled``)."""
+    gen = torch.Generator(device="cuda").manual_seed(Tq + Tk)
+    d = h * 64
+    q = torch.randn(B * Tq, d, device=cuda_device, generator=gen, requires_grad=True)
+    k = torch.randn(B * Tk, d, device=cuda_device, generator=gen, requires_grad=True)
+    v = torch.randn(B * Tk, d, device=cuda_device, generator=gen, requires_grad=True)
+    valid = torch.ones(B, Tk, dtype=torch.bool, device=cuda_device)
+    valid[0, Tk - Tk // 4:] = False
+    pm = ((torch.rand(B, h, Tq, Tk, device=cuda_device, generator=gen) >= 0.1).float() / 0.9).contiguous() if drop else None
+    dO = torch.randn(B * Tq, d, device=cuda_device, generator=gen)
+    qh, kh, vh = (t.view(B, -1, h, 64).transpose(1, 2) for t in (q, k, v))
+    s = (qh @ kh.transpose(-1, -2) / 8.0).masked_fill(~valid[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, -1)
+    ((p * pm if drop else p) @ vh).transpose(1, 2).reshape(B * Tq, d).backward(dO)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.attention_masked_bwd(q.detach(), k.detach(), v.detach(), valid, pm, dO, B, Tq, Tk, h, dq, dk, dv,
+                             tiled=True if path == "tiled" else None)
+    for got, ref in ((dq, q.grad), (dk, k.grad), (dv, v.grad)):
+        assert (got - ref).norm().item() <= 1e-4 * ref.norm().item()
+
+
+def test_attention_vit_backward_from_bf16_qkv(cuda_device):
+    """ViT self-attention backward straight from the packed bf16 qkv buffer (ViT-B/32: 50 tokens) == fp32 path on the cast."""
+    gen = torch.Generator(device="cuda").manual_seed(50)
+    F_, L, h = 5, 50, 12
+    d = h * 64
+    qkv = torch.randn(F_ * L, 3 * d, device=cuda_device, generator=gen).to(torch.bfloat16)
+    dO = torch.randn(F_ * L, d, device=cuda_device, generator=gen)
+    got = ops.attention_vit_bwd(qkv, dO, F_, L, h)
+    q32 = qkv.float().requires_grad_()
+    qh, kh, vh = (q32[:, i * d:(i + 1) * d].view(F_, L, h, 64).transpose(1, 2) for i in range(3))
+    (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, -1) @ vh).transpose(1, 2).reshape(F_ * L, d).backward(dO)
+    assert (got - q32.grad).norm().item() <= 1e-4 * q32.grad.norm().item()

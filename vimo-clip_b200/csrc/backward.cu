@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "vimoclip_b200.h"
 
+int vmc_get_option(int option);
+
 namespace {
 
 using namespace vmc;
@@ -96,6 +98,51 @@ colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restric
   }
 }
 
+// two-stage variant for tall matrices: grid (C / 32, slices); block (x, s) sums rows [s * rows_per, (s + 1) * rows_per) into
+// part[s][c]; colsum_finish_kernel adds the slices in index order, so the result is still deterministic
+__global__ void __launch_bounds__(256)
+colsum_slice_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ y, long long ldy,
+                    float* __restrict__ part, int R, int C, int rows_per) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per;
+  const int r1 = min(R, r0 + rows_per);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains: loads of four rows in flight per thread
+  if (c < C) {
+    int r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      const float a0 = x[(size_t)r * ldx + c], a1 = x[(size_t)(r + 8) * ldx + c];
+      const float a2 = x[(size_t)(r + 16) * ldx + c], a3 = x[(size_t)(r + 24) * ldx + c];
+      if (y) {
+        s0 = fmaf(a0, y[(size_t)r * ldy + c], s0);
+        s1 = fmaf(a1, y[(size_t)(r + 8) * ldy + c], s1);
+        s2 = fmaf(a2, y[(size_t)(r + 16) * ldy + c], s2);
+        s3 = fmaf(a3, y[(size_t)(r + 24) * ldy + c], s3);
+      } else {
+        s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+      }
+    }
+    for (; r < r1; r += 8) s0 += y ? x[(size_t)r * ldx + c] * y[(size_t)r * ldy + c] : x[(size_t)r * ldx + c];
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    part[(size_t)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ part, float* __restrict__ out, int slices, int C, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int s = 0; s < slices; ++s) t += part[(size_t)s * C + c];
+  out[c] = accumulate ? out[c] + t : t;
+}
+
 // LayerNorm backward, one warp per row.  z = the LayerNorm INPUT (saved by the forward), statistics
 // recomputed.  dz = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma;  xhat_out = xhat (for
 // dgamma = colsum(dy * xhat), dbeta = colsum(dy)).
@@ -163,6 +210,18 @@ eltwise_kernel(int mode, const float* __restrict__ a, const float* __restrict__ 
       default: r = x * scale; break;
     }
     out[i] = r;
+  }
+}
+
+// h16 = bf16(QuickGELU(h_pre)): the activation of the training forward without an fp32 intermediate
+__global__ void __launch_bounds__(256)
+qgelu_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 o;
+    o.x = pack_bf16x2(v.x / (1.0f + __expf(-1.702f * v.x)), v.y / (1.0f + __expf(-1.702f * v.y)));
+    o.y = pack_bf16x2(v.z / (1.0f + __expf(-1.702f * v.z)), v.w / (1.0f + __expf(-1.702f * v.w)));
+    reinterpret_cast<uint2*>(y)[i] = o;
   }
 }
 
@@ -290,6 +349,168 @@ attention_masked_bwd_kernel(const float* __restrict__ q, long long ldq, const fl
     float* o = dk + ((size_t)b * Tk + j) * lddk + h * HD;
     o[lane] = a0 * 0.125f;
     o[lane + 32] = a1 * 0.125f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Masked attention backward for SHORT sequences (Tq, Tk <= 64: the 50-token ViT-B/32 student, 16-frame TFAM clips).
+// The kernel above spends two shared-memory loads per FMA (ncu launch list of a student training step: 1.3 ms per layer,
+// 27 % of the step).  Here the five products of the backward are small register-tiled GEMMs: 256 threads as a 16 x 16
+// grid, each thread owns a 4 x 4 block of the output (rows ty + 16 a, columns tx + 16 b or head dims 4 tx .. 4 tx + 3),
+// operands are read as float4 -- 8 LDS.128 per 64 FMAs in the K-contiguous products.
+//   S = Q K^T / 8 -> P = softmax(S + mask);   dP = (dO V^T) (.) m;   dS = P (.) (dP - rowsum(P (.) dP))
+//   dV = (P (.) m)^T dO;   dQ = dS K / 8;   dK = dS^T Q / 8
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SB_LD = 68;   // row stride of the [T][64] operands: 16-byte aligned, conflict-free for quarter-warp LDS.128
+constexpr int SB_LDP = 68;  // row stride of the [Tq][Tk] matrices (Tk <= 64)
+
+// C[i][j] = sum_c A[i][c] B[j][c] over 64 columns; rows i = ty + 16 a, j = tx + 16 b
+__device__ __forceinline__ void nt_tile(const float* __restrict__ A, const float* __restrict__ B, int ty, int tx,
+                                        float (&acc)[4][4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < HD; c += 4) {
+    float4 av[4], bv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(A + (ty + 16 * a) * SB_LD + c);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bv[b] = *reinterpret_cast<const float4*>(B + (tx + 16 * b) * SB_LD + c);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        acc[a][b] = fmaf(av[a].x, bv[b].x, fmaf(av[a].y, bv[b].y, fmaf(av[a].z, bv[b].z, fmaf(av[a].w, bv[b].w, acc[a][b]))));
+  }
+}
+// C[r][d] = sum_t A(t, r) B[t][d], r = ty + 16 a, d = 4 tx .. 4 tx + 3; TRANS: A(t, r) = A[t][r] else A[r][t]
+template <bool TRANS>
+__device__ __forceinline__ void tn_tile(const float* __restrict__ A, const float* __restrict__ B, int T, int ty, int tx,
+                                        float4 (&acc)[4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < T; ++t) {
+    const float4 bv = *reinterpret_cast<const float4*>(B + t * SB_LD + 4 * tx);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float av = TRANS ? A[t * SB_LDP + ty + 16 * a] : A[(ty + 16 * a) * SB_LDP + t];
+      acc[a].x = fmaf(av, bv.x, acc[a].x);
+      acc[a].y = fmaf(av, bv.y, acc[a].y);
+      acc[a].z = fmaf(av, bv.z, acc[a].z);
+      acc[a].w = fmaf(av, bv.w, acc[a].w);
+    }
+  }
+}
+
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+
+template <typename TQ>  // float (TFAM) or __nv_bfloat16 (the ViT's packed qkv buffer, read without a cast pass)
+__global__ void __launch_bounds__(256)
+attention_bwd_short_kernel(const TQ* __restrict__ q, long long ldq, const TQ* __restrict__ k, long long ldk,
+                           const TQ* __restrict__ v, long long ldv, const uint8_t* __restrict__ key_valid,
+                           const float* __restrict__ pmask, const float* __restrict__ dO, long long lddo,
+                           float* __restrict__ dq, long long lddq, float* __restrict__ dk, long long lddk,
+                           float* __restrict__ dv, long long lddv, int Tq, int Tk, int heads) {
+  extern __shared__ __align__(16) float sm[];
+  float* sq = sm;                  // [64][SB_LD]  (rows >= Tq zero)
+  float* sdo = sq + 64 * SB_LD;
+  float* sk = sdo + 64 * SB_LD;    // rows >= Tk zero
+  float* sv = sk + 64 * SB_LD;
+  float* sp = sv + 64 * SB_LD;     // [64][SB_LDP]  P, then A = P (.) m
+  float* sds = sp + 64 * SB_LDP;   // dP (.) m, then dS
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ty = tid >> 4, tx = tid & 15;
+  const uint8_t* kvb = key_valid ? key_valid + (size_t)b * Tk : nullptr;
+  const float* pm = pmask ? pmask + ((size_t)b * heads + h) * Tq * Tk : nullptr;
+  for (int i = tid; i < 64 * 16; i += 256) {  // float4 granules
+    const int r = i >> 4, c = (i & 15) * 4;
+    float4 zq = make_float4(0.f, 0.f, 0.f, 0.f), zo = zq, zk = zq, zv = zq;
+    if (r < Tq) {
+      zq = load4(q + ((size_t)b * Tq + r) * ldq + h * HD + c);
+      zo = load4(dO + ((size_t)b * Tq + r) * lddo + h * HD + c);
+    }
+    if (r < Tk) {
+      zk = load4(k + ((size_t)b * Tk + r) * ldk + h * HD + c);
+      zv = load4(v + ((size_t)b * Tk + r) * ldv + h * HD + c);
+    }
+    *reinterpret_cast<float4*>(sq + r * SB_LD + c) = zq;
+    *reinterpret_cast<float4*>(sdo + r * SB_LD + c) = zo;
+    *reinterpret_cast<float4*>(sk + r * SB_LD + c) = zk;
+    *reinterpret_cast<float4*>(sv + r * SB_LD + c) = zv;
+  }
+  __syncthreads();
+  float acc[4][4];
+  nt_tile(sq, sk, ty, tx, acc);  // scores
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int j = tx + 16 * bb;
+      const bool ok = j < Tk && !(kvb && !kvb[j]);
+      sp[(ty + 16 * a) * SB_LDP + j] = ok ? acc[a][bb] * 0.125f : -INFINITY;
+    }
+  nt_tile(sdo, sv, ty, tx, acc);  // dP
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      const int i = ty + 16 * a, j = tx + 16 * bb;
+      float dp = acc[a][bb];
+      if (pm && i < Tq && j < Tk) dp *= pm[(size_t)i * Tk + j];
+      sds[i * SB_LDP + j] = dp;
+    }
+  __syncthreads();
+  // row pass: softmax, D_i, dS; A = P (.) m for dV
+  for (int i = warp; i < 64; i += 8) {
+    const float s0 = sp[i * SB_LDP + lane], s1 = sp[i * SB_LDP + lane + 32];
+    const float mx = warp_max(fmaxf(s0, s1));
+    float p0 = (s0 == -INFINITY) ? 0.f : __expf(s0 - mx), p1 = (s1 == -INFINITY) ? 0.f : __expf(s1 - mx);
+    const float inv = 1.0f / warp_sum(p0 + p1);
+    p0 *= inv;
+    p1 *= inv;
+    const float d0 = sds[i * SB_LDP + lane], d1 = sds[i * SB_LDP + lane + 32];
+    const float D = warp_sum(p0 * d0 + p1 * d1);
+    sds[i * SB_LDP + lane] = (i < Tq) ? p0 * (d0 - D) : 0.f;
+    sds[i * SB_LDP + lane + 32] = (i < Tq) ? p1 * (d1 - D) : 0.f;
+    float a0 = p0, a1 = p1;
+    if (pm && i < Tq) {
+      if (lane < Tk) a0 *= pm[(size_t)i * Tk + lane];
+      if (lane + 32 < Tk) a1 *= pm[(size_t)i * Tk + lane + 32];
+    }
+    sp[i * SB_LDP + lane] = (i < Tq) ? a0 : 0.f;
+    sp[i * SB_LDP + lane + 32] = (i < Tq) ? a1 : 0.f;
+  }
+  __syncthreads();
+  float4 o[4];
+  tn_tile<true>(sp, sdo, Tq, ty, tx, o);  // dV[j][d] = sum_i A[i][j] dO[i][d]
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int j = ty + 16 * a;
+    if (j < Tk) *reinterpret_cast<float4*>(dv + ((size_t)b * Tk + j) * lddv + h * HD + 4 * tx) = o[a];
+  }
+  tn_tile<true>(sds, sq, Tq, ty, tx, o);  // dK[j][d] = sum_i dS[i][j] Q[i][d] / 8
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int j = ty + 16 * a;
+    if (j < Tk)
+      *reinterpret_cast<float4*>(dk + ((size_t)b * Tk + j) * lddk + h * HD + 4 * tx) =
+          make_float4(o[a].x * 0.125f, o[a].y * 0.125f, o[a].z * 0.125f, o[a].w * 0.125f);
+  }
+  tn_tile<false>(sds, sk, Tk, ty, tx, o);  // dQ[i][d] = sum_j dS[i][j] K[j][d] / 8
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = ty + 16 * a;
+    if (i < Tq)
+      *reinterpret_cast<float4*>(dq + ((size_t)b * Tq + i) * lddq + h * HD + 4 * tx) =
+          make_float4(o[a].x * 0.125f, o[a].y * 0.125f, o[a].z * 0.125f, o[a].w * 0.125f);
   }
 }
 
@@ -542,12 +763,31 @@ int vmc_cast_f32(const void* x, long long ldx, float* y, long long ldy, int rows
   return VMC_OK;
 }
 
+int vmc_colsum_slices(int R, int C) {
+  if (R <= 0 || C <= 0) return -1;
+  if (R < 2048) return 1;  // single-stage kernel
+  const int col_blocks = (C + 31) / 32;
+  int slices = (4 * vmc_num_sms() + col_blocks - 1) / col_blocks;  // ~4 blocks per SM in total
+  const int max_slices = (R + 255) / 256;
+  slices = slices < 1 ? 1 : (slices > max_slices ? max_slices : slices);
+  return slices > 64 ? 64 : slices;
+}
+
 int vmc_colsum(const float* x, long long ldx, const float* y, long long ldy, float* out, int R, int C,
-               int accumulate, void* stream) {
+               int accumulate, float* workspace, void* stream) {
   VMC_CHECK_ARG(x && out, VMC_ERR_ARG, "vmc_colsum: null pointer");
   VMC_CHECK_ARG(R > 0 && C > 0, VMC_ERR_SHAPE, "vmc_colsum: bad shape R=%d C=%d", R, C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, (double)R * C * (y ? 8.0 : 4.0));
+  const int slices = vmc_colsum_slices(R, C);
+  if (workspace != nullptr && slices > 1) {  // workspace: slices * C floats
+    const int rows_per = ((R + slices - 1) / slices + 7) / 8 * 8;
+    colsum_slice_kernel<<<dim3((C + 31) / 32, slices), 256, 0, st>>>(x, ldx, y, ldy, workspace, R, C, rows_per);
+    colsum_finish_kernel<<<(C + 255) / 256, 256, 0, st>>>(workspace, out, slices, C, accumulate);
+    VMC_LAUNCH_CHECK();
+    vmc_count_launch(2);
+    return VMC_OK;
+  }
   colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(x, ldx, y, ldy, out, R, C, accumulate);
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
@@ -579,11 +819,45 @@ int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* ou
   return VMC_OK;
 }
 
+int vmc_qgelu_cast(const float* x, void* y, long long n, void* stream) {
+  VMC_CHECK_ARG(x && y && n > 0 && (n % 4) == 0, VMC_ERR_ARG, "vmc_qgelu_cast: n must be a positive multiple of 4");
+  VMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(y) & 7)) == 0, VMC_ERR_ALIGN,
+                "vmc_qgelu_cast: misaligned pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VmcProfScope prof(VMC_K_OTHER, st, 0.0, 6.0 * n);
+  qgelu_cast_kernel<<<grid_cap((size_t)n / 4), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), (size_t)n / 4);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
 int vmc_broadcast_rows(const float* g, float* out, int B, int T, int d, float scale, void* stream) {
   VMC_CHECK_ARG(g && out && B > 0 && T > 0 && d > 0, VMC_ERR_ARG, "vmc_broadcast_rows: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);
   broadcast_rows_kernel<<<grid_cap((size_t)B * T * d), 256, 0, st>>>(g, out, B, T, d, scale);
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_attention_vit_bwd_short(const void* qkv, const float* dO, long long lddo, float* dqkv, int F, int L, int heads,
+                                void* stream) {
+  VMC_CHECK_ARG(qkv && dO && dqkv, VMC_ERR_ARG, "vmc_attention_vit_bwd_short: null pointer");
+  VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 64 && F <= 65535 && (lddo % 4) == 0, VMC_ERR_SHAPE,
+                "vmc_attention_vit_bwd_short: need 0 < L <= 64 tokens (L=%d); longer towers go through vmc_attention_masked_bwd", L);
+  const int d = heads * HD;
+  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t smem_s = (size_t)(4 * 64 * SB_LD + 2 * 64 * SB_LDP) * sizeof(float);
+  VMC_CUDA(cudaFuncSetAttribute(attention_bwd_short_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_s));
+  {
+    VmcProfScope prof(VMC_K_ATTN_SMALL, st, 10.0 * F * heads * (double)L * L * HD, 0.0);
+    attention_bwd_short_kernel<__nv_bfloat16><<<dim3(heads, F), 256, smem_s, st>>>(
+        p, 3LL * d, p + d, 3LL * d, p + 2 * d, 3LL * d, nullptr, nullptr, dO, lddo, dqkv, 3LL * d, dqkv + d, 3LL * d,
+        dqkv + 2 * d, 3LL * d, L, L, heads);
+  }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
   return VMC_OK;
@@ -598,6 +872,23 @@ int vmc_attention_masked_bwd(const float* q, long long ldq, const float* k, long
                 "vmc_attention_masked_bwd: bad shape B=%d Tq=%d Tk=%d heads=%d", B, Tq, Tk, heads);
   const size_t smem = ((size_t)2 * Tq * HD + (size_t)2 * Tk * 65 + (size_t)Tq * (Tk + 1)) * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool aligned16 = ((ldq | ldk | ldv | lddo | lddq | lddk | lddv) % 4) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                           reinterpret_cast<uintptr_t>(dO) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
+                           reinterpret_cast<uintptr_t>(dv)) & 15) == 0;
+  if (workspace == nullptr && Tq <= 64 && Tk <= 64 && aligned16 && vmc_get_option(4) != 1) {
+    // short sequences: register-tiled kernel (VMC option 4 = 1 selects the first-generation kernel for cross-checks)
+    const size_t smem_s = (size_t)(4 * 64 * SB_LD + 2 * 64 * SB_LDP) * sizeof(float);
+    VMC_CUDA(cudaFuncSetAttribute(attention_bwd_short_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    {
+      VmcProfScope prof(VMC_K_ATTN_SMALL, st, 10.0 * B * heads * (double)Tq * Tk * HD, 0.0);
+      attention_bwd_short_kernel<float><<<dim3(heads, B), 256, smem_s, st>>>(q, ldq, k, ldk, v, ldv, key_valid, prob_mask, dO,
+                                                                             lddo, dq, lddq, dk, lddk, dv, lddv, Tq, Tk, heads);
+    }
+    VMC_LAUNCH_CHECK();
+    vmc_count_launch();
+    return VMC_OK;
+  }
   if (smem > 200 * 1024 || workspace != nullptr) {
     // tiled path: any Tq / Tk; workspace = 2 * B * heads * Tq floats (log-sum-exp and D per query row)
     VMC_CHECK_ARG(workspace != nullptr, VMC_ERR_WORKSPACE,

@@ -407,9 +407,11 @@ def colsum(x: torch.Tensor, y: torch.Tensor | None = None, out: torch.Tensor | N
     R, Cn = x.shape
     if out is None:
         out = torch.empty(Cn, dtype=torch.float32, device=x.device)
+    slices = int(_lib.lib().vmc_colsum_slices(R, Cn))
+    ws = torch.empty(slices * Cn, dtype=torch.float32, device=x.device) if slices > 1 else None
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().vmc_colsum(_p(x), x.stride(0), _p(y), 0 if y is None else y.stride(0), _p(out), R, Cn, 1 if accumulate else 0,
-                                         _stream()), "vmc_colsum")
+                                         _p(ws), _stream()), "vmc_colsum")
     return out
 
 
@@ -461,3 +463,30 @@ def attention_masked_bwd(q, k, v, key_valid, prob_mask, dO, B: int, Tq: int, Tk:
                                                 B, Tq, Tk, heads, _p(ws), _stream()),
             "vmc_attention_masked_bwd",
         )
+
+
+def qgelu_cast(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (contiguous, numel % 4 == 0) -> bf16 QuickGELU(x) = x * sigmoid(1.702 x)."""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.numel() % 4:
+        raise ValueError("qgelu_cast input must be contiguous fp32 with numel % 4 == 0")
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_qgelu_cast(_p(x), _p(y), x.numel(), _stream()), "vmc_qgelu_cast")
+    return y
+
+
+def attention_vit_bwd(qkv: torch.Tensor, dO: torch.Tensor, F_: int, L: int, heads: int) -> torch.Tensor:
+    """Backward of ``attention_vit``: qkv bf16 [F*L, 3d] (saved by the forward), dO fp32 [F*L, d] -> dqkv fp32 [F*L, 3d]."""
+    _need_cuda(qkv, dO)
+    d = heads * 64
+    dqkv = torch.empty((F_ * L, 3 * d), dtype=torch.float32, device=qkv.device)
+    if L <= 64:
+        with torch.cuda.device(qkv.device):
+            _lib.check(_lib.lib().vmc_attention_vit_bwd_short(_p(qkv), _p(dO), dO.stride(0), _p(dqkv), F_, L, heads, _stream()),
+                       "vmc_attention_vit_bwd_short")
+    else:
+        q32 = cast_f32(qkv)
+        attention_masked_bwd(q32[:, :d], q32[:, d:2 * d], q32[:, 2 * d:], None, None, dO, F_, L, L, heads,
+                             dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:])
+    return dqkv

@@ -92,7 +92,7 @@ class StudentTrainFunction(torch.autograd.Function):
             x_mid = _gemm16(a, _bf(wo), bias=bo.detach().float(), resid=x, out_dtype=torch.float32)
             _, xn2 = ops.layernorm(x_mid, g2.detach().float(), b2_.detach().float())
             h_pre = _gemm16(xn2, _bf(w1), bias=bb1.detach().float(), out_dtype=torch.float32)
-            h16 = ops.cast_bf16(ops.eltwise(ops.ELT_QGELU_FWD, h_pre))
+            h16 = ops.qgelu_cast(h_pre)
             x_next = _gemm16(h16, _bf(w2), bias=bb2.detach().float(), resid=x_mid, out_dtype=torch.float32)
             saved.append(dict(x=x, xn=xn, qkv=qkv, a=a, x_mid=x_mid, xn2=xn2, h_pre=h_pre, h16=h16))
             x = x_next
@@ -162,10 +162,7 @@ class StudentTrainFunction(torch.autograd.Function):
             dx_mid = ops.eltwise(ops.ELT_ADD, dx, dz2)
             # x_mid = x + out_proj(attn(ln_1(x)))
             da, g_wo, g_bo = _lin_bwd16(dx_mid, s["a"], wo)
-            qkv32 = ops.cast_f32(s["qkv"])
-            dqkv = torch.empty((M, 3 * d), dtype=torch.float32, device=dev)
-            ops.attention_masked_bwd(qkv32[:, :d], qkv32[:, d:2 * d], qkv32[:, 2 * d:], None, None, da, F_, L, L, heads,
-                                     dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:])
+            dqkv = ops.attention_vit_bwd(s["qkv"], da, F_, L, heads)
             dxn, g_wqkv, g_bqkv = _lin_bwd16(dqkv, s["xn"], wqkv)
             dz1, g_g1, g_bt1 = ops.layernorm_bwd(s["x"], g1.detach().float(), 1e-5, dxn)
             dx = ops.eltwise(ops.ELT_ADD, dx_mid, dz1)
