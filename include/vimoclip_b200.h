@@ -130,6 +130,12 @@ typedef struct vmc_gemm_epilogue {
 int vmc_gemm_stats_parts(int M, int N);
 int vmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                   const vmc_gemm_epilogue* epi, void* stream);
+/* Same product with operands given TRANSPOSED in memory: a_transposed: A points to A^T [K, M] row-major (lda >= M);
+ * w_transposed: W points to W^T [K, N] row-major (ldw >= N).  They become MN-major UMMA operands (TMA boxes of
+ * 64 x 64, no transposing pass): the backward GEMMs dW = dY^T X (both transposed) and dX = dY W (W transposed) read
+ * the row-major activations / weights as they are (train.py:95-107, TFAM/train_and_eval.py:80-84). */
+int vmc_gemm_bf16_ex(const void* A, long long lda, int a_transposed, const void* W, long long ldw, int w_transposed,
+                     int M, int N, int K, const vmc_gemm_epilogue* epi, void* stream);
 
 /* ---- E1: LayerNorm (fp32 statistics, eps inside sqrt) ---------------------------
  * y = (x - mean) / sqrt(var + eps) * gamma + beta per row of width d (d % 4 == 0, d <= 4096).

@@ -790,3 +790,26 @@ def test_attention_vit_backward_from_bf16_qkv(cuda_device):
     qh, kh, vh = (q32[:, i * d:(i + 1) * d].view(F_, L, h, 64).transpose(1, 2) for i in range(3))
     (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, -1) @ vh).transpose(1, 2).reshape(F_ * L, d).backward(dO)
     assert (got - q32.grad).norm().item() <= 1e-4 * q32.grad.norm().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 2304, 6400), (140, 256, 96), (3072, 768, 25600), (500, 333 // 8 * 8 + 8, 1000), (40000, 768, 768)])
+@pytest.mark.parametrize("a_t,w_t", [(True, True), (False, True), (True, False)])
+def test_gemm_transposed_operands(cuda_device, M, N, K, a_t, w_t):
+    """MN-major UMMA operands: A and / or W given transposed in memory ([K, M] / [K, N] row-major), as the backward GEMMs
+    dW = dY^T X and dX = dY W read them -- no transposing pass."""
+    gen = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=cuda_device, generator=gen)).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=cuda_device, generator=gen) * K**-0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device=cuda_device, generator=gen)
+    ref = a.float() @ w.float().t() + bias
+    def transposed(x):  # [R, C] -> view [C, R] of a buffer whose row stride is a multiple of 8 elements (TMA: 16-byte strides)
+        R, Cn = x.shape
+        buf = torch.zeros(Cn, (R + 7) // 8 * 8, dtype=x.dtype, device=x.device)
+        buf[:, :R] = x.t()
+        return buf[:, :R]
+
+    a_arg = transposed(a) if a_t else a
+    w_arg = transposed(w) if w_t else w
+    got = ops.gemm(a_arg, w_arg, bias=bias, out_dtype=torch.float32, a_t=a_t, w_t=w_t)
+    assert got.shape == (M, N)
+    assert (got - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())

@@ -350,17 +350,25 @@ int launch_gemm(const void* A, long long lda, const void* W, long long ldw, int 
 }  // namespace
 
 int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ldw, int M, int N,
-                       int K, const vmc_gemm_epilogue* epi, cudaStream_t stream);
+                       int K, const vmc_gemm_epilogue* epi, cudaStream_t stream, int a_mn, int b_mn);
 int vmc_get_option(int option);
 
 extern "C" int vmc_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M,
                              int N, int K, const vmc_gemm_epilogue* epi, void* stream) {
+  return vmc_gemm_bf16_ex(A, lda, 0, W, ldw, 0, M, N, K, epi, stream);
+}
+
+extern "C" int vmc_gemm_bf16_ex(const void* A, long long lda, int a_transposed, const void* W, long long ldw,
+                                int w_transposed, int M, int N, int K, const vmc_gemm_epilogue* epi, void* stream) {
   VMC_CHECK_ARG(A && W && epi && epi->out, VMC_ERR_ARG, "vmc_gemm_bf16: null pointer");
   VMC_CHECK_ARG(M > 0 && N > 0 && K > 0, VMC_ERR_SHAPE, "vmc_gemm_bf16: bad shape M=%d N=%d K=%d",
                 M, N, K);
-  VMC_CHECK_ARG(lda >= K && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0, VMC_ERR_ALIGN,
-                "vmc_gemm_bf16: lda/ldw must be >= K and multiples of 8 elements (lda=%lld ldw=%lld K=%d)",
+  VMC_CHECK_ARG(lda >= (a_transposed ? M : K) && ldw >= (w_transposed ? N : K) && (lda % 8) == 0 && (ldw % 8) == 0,
+                VMC_ERR_ALIGN,
+                "vmc_gemm_bf16: lda/ldw must cover the operand's row length and be multiples of 8 elements (lda=%lld ldw=%lld K=%d)",
                 lda, ldw, K);
+  VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, VMC_ERR_ALIGN,
+                "vmc_gemm_bf16: operands must be 16-byte aligned");
   const int oalign = epi->out_bf16 ? 8 : 4;
   VMC_CHECK_ARG(epi->ldo >= N && (epi->ldo % oalign) == 0 &&
                     (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0,
@@ -376,7 +384,9 @@ extern "C" int vmc_gemm_bf16(const void* A, long long lda, const void* W, long l
                 "vmc_gemm_bf16: unknown activation %d", epi->act);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (vmc_get_option(VMC_OPT_GEMM_IMPL) != 1)  // default: CTA-pair kernel (gemm2.cu)
-    return vmc_gemm2_dispatch(A, lda, W, ldw, M, N, K, epi, st);
+    return vmc_gemm2_dispatch(A, lda, W, ldw, M, N, K, epi, st, a_transposed ? 1 : 0, w_transposed ? 1 : 0);
+  VMC_CHECK_ARG(!a_transposed && !w_transposed, VMC_ERR_ARG,
+                "vmc_gemm_bf16_ex: transposed (MN-major) operands exist only in the CTA-pair kernel");
   VMC_CHECK_ARG(epi->ln_out == nullptr && epi->raw16_out == nullptr && epi->stats_out == nullptr &&
                     epi->stats_in == nullptr,
                 VMC_ERR_ARG, "vmc_gemm_bf16: the fused / folded LayerNorm epilogues exist only in the CTA-pair kernel");

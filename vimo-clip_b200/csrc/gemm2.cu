@@ -32,8 +32,17 @@ constexpr int NUM_THREADS = 320;
 struct Gemm2Args {
   int M, N, K;
   int tiles_m, tiles_n;  // pair tiles
+  int a_mn, b_mn;        // operand given TRANSPOSED in memory ([K, M] / [K, N] row-major): MN-major UMMA operand
   vmc_gemm_epilogue epi;
 };
+
+// MN-major SW128 operand: TMA boxes of 64 (MN, contiguous) x 64 (K) elements land as 64 rows of 128 bytes = the canonical
+// layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) with SBO = 1024 B between 8-row K groups and LBO = 8192 B between the
+// 64-element MN atoms (one box each).  A 16-deep K step advances the start address by two K groups (2048 B).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFF) >> 4) | (uint64_t(8192 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
 
 template <int BN>
 struct Cfg2 {
@@ -382,8 +391,18 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           const uint32_t sb = sa + C::A_BYTES;
           const uint32_t full_leader = mapa_rank(full_bar(stage), 0);
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * C::STAGE_BYTES);
-          tma_load_2d_cg2(sa, &tmA, full_leader, kb * BK, m_row);
-          tma_load_2d_cg2(sb, &tmB, full_leader, kb * BK, n_row);
+          if (g.a_mn) {
+            tma_load_2d_cg2(sa, &tmA, full_leader, m_row, kb * BK);
+            tma_load_2d_cg2(sa + 8192, &tmA, full_leader, m_row + 64, kb * BK);
+          } else {
+            tma_load_2d_cg2(sa, &tmA, full_leader, kb * BK, m_row);
+          }
+          if (g.b_mn) {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_cg2(sb + j * 8192, &tmB, full_leader, n_row + 64 * j, kb * BK);
+          } else {
+            tma_load_2d_cg2(sb, &tmB, full_leader, kb * BK, n_row);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -395,7 +414,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, BN, g.a_mn, g.b_mn);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -409,12 +428,12 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           tc_fence_after();
           const uint32_t sa = base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sb);
+          const uint64_t da = g.a_mn ? umma_desc_sw128_mn(sa) : umma_desc_sw128(sa);
+          const uint64_t db = g.b_mn ? umma_desc_sw128_mn(sb) : umma_desc_sw128(sb);
+          const uint64_t sta = g.a_mn ? 128 : 2, stb = g.b_mn ? 128 : 2;  // start-address step per UMMA_K (16-byte units)
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_ss_cg2(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+            umma_ss_cg2(d_tmem, da + sta * k, db + stb * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_mc2(empty_bar(stage));
           if (++stage == STAGES) {
             stage = 0;
@@ -617,16 +636,26 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
 template <int BN, int MODE>
 int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
-                 const vmc_gemm_epilogue* epi, cudaStream_t stream) {
+                 const vmc_gemm_epilogue* epi, cudaStream_t stream, int a_mn = 0, int b_mn = 0) {
   using C = Cfg2<BN>;
   CUtensorMap tmA, tmB;
-  {
+  if (a_mn) {  // A given as A^T [K, M] row-major
+    const uint64_t dims[2] = {(uint64_t)M, (uint64_t)K};
+    const uint64_t strides[1] = {(uint64_t)lda * 2};
+    const uint32_t box[2] = {64, BK};
+    VMC_TRY(vmc_encode_tmap_bf16(&tmA, A, 2, dims, strides, box));
+  } else {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t strides[1] = {(uint64_t)lda * 2};
     const uint32_t box[2] = {BK, BM};
     VMC_TRY(vmc_encode_tmap_bf16(&tmA, A, 2, dims, strides, box));
   }
-  {
+  if (b_mn) {  // W given as W^T [K, N] row-major
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
+    const uint64_t strides[1] = {(uint64_t)ldw * 2};
+    const uint32_t box[2] = {64, BK};
+    VMC_TRY(vmc_encode_tmap_bf16(&tmB, W, 2, dims, strides, box));
+  } else {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t strides[1] = {(uint64_t)ldw * 2};
     const uint32_t box[2] = {BK, BN / 2};
@@ -636,6 +665,8 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
   g.M = M;
   g.N = N;
   g.K = K;
+  g.a_mn = a_mn;
+  g.b_mn = b_mn;
   g.tiles_m = (M + 2 * BM - 1) / (2 * BM);
   g.tiles_n = (N + BN - 1) / BN;
   g.epi = *epi;
@@ -668,7 +699,7 @@ extern "C" int vmc_gemm_stats_parts(int M, int N) {
 
 // Called by vmc_gemm_bf16 (gemm.cu) after argument validation.
 int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ldw, int M, int N,
-                       int K, const vmc_gemm_epilogue* epi, cudaStream_t stream) {
+                       int K, const vmc_gemm_epilogue* epi, cudaStream_t stream, int a_mn, int b_mn) {
   const long long tiles256 = (long long)((M + 255) / 256) * ((N + 255) / 256);
   const bool big = N > 128 && tiles256 >= (long long)vmc_num_sms();
   // specialised epilogues (see epilogue_fast): the four GEMMs of every ViT block
@@ -706,7 +737,7 @@ int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ld
                   "and enough tiles for 128x256 pair tiles");
     mode = 4;
   }
-#define VMC_G2(BN_, MODE_) return launch_gemm2<BN_, MODE_>(A, lda, W, ldw, M, N, K, epi, stream)
+#define VMC_G2(BN_, MODE_) return launch_gemm2<BN_, MODE_>(A, lda, W, ldw, M, N, K, epi, stream, a_mn, b_mn)
   if (big) {
     switch (mode) {
       case 1: VMC_G2(256, 1);

@@ -162,19 +162,22 @@ def frame_diff(bgr: torch.Tensor, *, dst: str | None = None, patch: int = 0, wan
 # ---------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, alpha: float = 1.0, resid=None,
          out: torch.Tensor | None = None, out_dtype=torch.bfloat16, n: int | None = None, k: int | None = None,
-         row_group: int = 0, out_rows: int | None = None, ln=None, emit_stats=None, fold=None) -> torch.Tensor:
+         row_group: int = 0, out_rows: int | None = None, ln=None, emit_stats=None, fold=None, a_t: bool = False,
+         w_t: bool = False) -> torch.Tensor:
     """out = alpha * act(a @ w.T + bias) + resid.  a [M, lda] bf16, w [N, ldw] bf16 (nn.Linear layout).
     ln = (gamma, beta, eps, ln_out bf16 [M, N]): fused LayerNorm of the output rows (see vmc_gemm_epilogue).
     emit_stats = (raw16 bf16 [M, N], stats fp32 [parts, M, 2]): producer side of a folded LayerNorm.
-    fold = (stats fp32 [parts, M, 2], colsum fp32 [N], eps): consumer side (a = raw rows, w = gamma-folded weights)."""
+    fold = (stats fp32 [parts, M, 2], colsum fp32 [N], eps): consumer side (a = raw rows, w = gamma-folded weights).
+    a_t / w_t: the operand is given transposed in memory (a = A^T [K, M], w = W^T [K, N], row-major): MN-major UMMA
+    operands, no transposing pass (the dW = dY^T X and dX = dY W GEMMs of the backward)."""
     _need_cuda(a, w, bias, resid, out)
     if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         raise TypeError("gemm operands must be bf16")
     if a.stride(-1) != 1 or w.stride(-1) != 1:
         raise ValueError("gemm operands must be row-major")
-    M = a.shape[0]
-    K = a.shape[1] if k is None else k
-    N = w.shape[0] if n is None else n
+    M = a.shape[1] if a_t else a.shape[0]
+    K = (a.shape[0] if a_t else a.shape[1]) if k is None else k
+    N = (w.shape[1] if w_t else w.shape[0]) if n is None else n
     if out is None:
         rows = M if out_rows is None else out_rows
         out = torch.empty((rows, N), dtype=out_dtype, device=a.device)
@@ -205,7 +208,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, al
         _need_cuda(stats, colsum)
         e.stats_in, e.stats_parts, e.stats_ld, e.colsum, e.ln_eps = stats.data_ptr(), stats.shape[0], stats.shape[1], colsum.data_ptr(), eps_
     with torch.cuda.device(a.device):
-        _lib.check(_lib.lib().vmc_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), M, N, K, C.byref(e), _stream()), "vmc_gemm_bf16")
+        _lib.check(_lib.lib().vmc_gemm_bf16_ex(_p(a), a.stride(0), 1 if a_t else 0, _p(w), w.stride(0), 1 if w_t else 0, M, N, K,
+                                               C.byref(e), _stream()), "vmc_gemm_bf16")
     return out
 
 

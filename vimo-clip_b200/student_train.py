@@ -9,7 +9,8 @@ sequence: in training mode the forward returns the three outputs attached to aut
 Forward = the inference kernels, orchestrated here layer by layer so the activations the backward needs stay in HBM
 (x, ln_1(x), qkv, attention output, x after out_proj, ln_2, the c_fc pre-activation, QuickGELU(.)).  Backward:
   * every Linear / the patch-embedding conv: ``dX = dY W`` and ``dW = dY^T X`` as bf16 tcgen05 GEMMs (fp32 accumulation);
-    the transposed operands come from ``ops.transpose_cast``; bias gradients are deterministic column sums;
+    the row-major activations / weights are read as MN-major UMMA operands (``vmc_gemm_bf16_ex``: no transposing pass);
+    bias gradients are deterministic column sums;
   * LayerNorm backward from the saved LayerNorm inputs; QuickGELU backward element-wise;
   * attention backward (``vmc_attention_masked_bwd``): one CTA per (frame, head) with the probabilities recomputed in shared
     memory for ViT-B/32 (50 tokens, the reference's training default, ``train.py:63``), tiled flash-style kernels for
@@ -54,11 +55,12 @@ def _lin_bwd16(dy32, x16, w32, need_dx=True):
     """bf16 Linear backward: y = x W^T + b with x16 [M,K] bf16 (saved), W [N,K] fp32 parameter, dy fp32 [M,N].
     Returns (dx fp32 | None, dW fp32 [N,K], db fp32 [N])."""
     M, N = dy32.shape
-    dy16 = ops.cast_bf16(dy32)
+    dy16 = ops.cast_bf16(dy32)[:, :N]  # (row stride padded to a multiple of 8 when N is not one)
     dx = None
-    if need_dx:  # dx[M,K] = dy[M,N] W[N,K]: the GEMM's "weight" operand is W^T [K, N]
-        dx = _gemm16(dy16, ops.transpose_cast(w32.detach().float()), k=N, out_dtype=torch.float32)
-    dw = _gemm16(ops.transpose_cast(dy16), ops.transpose_cast(x16), k=M, out_dtype=torch.float32)
+    if need_dx:  # dx[M,K] = dy[M,N] W[N,K]: W [N,K] row-major IS the transposed "weight" operand (MN-major B)
+        dx = _gemm16(dy16, _bf(w32), w_t=True, out_dtype=torch.float32)
+    # dW[N,K] = dy^T x: both operands are the row-major activations, read as MN-major UMMA operands (no transposing pass)
+    dw = _gemm16(dy16, x16, a_t=True, w_t=True, out_dtype=torch.float32)
     return dx, dw, ops.colsum(dy32)
 
 
@@ -146,7 +148,7 @@ class StudentTrainFunction(torch.autograd.Function):
         # ---- proj and ln_post (CLS rows only) ----
         de16 = ops.cast_bf16(de)
         d_cls = _gemm16(de16, _bf(proj), k=D, out_dtype=torch.float32)  # [F, d] = de [F, D] proj^T: W operand = proj [d, D]
-        g_proj = _gemm16(ops.transpose_cast(m["cls16"]), ops.transpose_cast(de16), k=F_, out_dtype=torch.float32)  # [d, D]
+        g_proj = _gemm16(m["cls16"], de16, a_t=True, w_t=True, out_dtype=torch.float32)  # [d, D] = cls^T de
         dz_cls, g_gpost, g_bpost = ops.layernorm_bwd(m["z_cls"], gpost.detach().float(), 1e-5, d_cls)
         dx = zeros(M, d)
         dx.view(F_, L, d)[:, 0, :] = dz_cls
@@ -172,7 +174,7 @@ class StudentTrainFunction(torch.autograd.Function):
         g_pos = ops.colsum(dz0.view(F_, L * d)).view(L, d)  # sum over frames
         g_cls = g_pos[0].clone()
         dz_tok = dz0.view(F_, L, d)[:, 1:, :].reshape(F_ * n, d).contiguous()  # token rows (strided copy: plumbing)
-        g_conv = _gemm16(ops.transpose_cast(dz_tok), ops.transpose_cast(m["patches"][:, :kp]), k=F_ * n, out_dtype=torch.float32)
+        g_conv = _gemm16(ops.cast_bf16(dz_tok), m["patches"][:, :kp], a_t=True, w_t=True, out_dtype=torch.float32)  # dz_tok^T patches
         grads = [g_conv.view_as(conv_w), g_cls, g_pos, g_gpre, g_bpre]
         for gb in grads_blocks:
             grads += gb
