@@ -188,6 +188,7 @@ def ours_main(args):
     clips = args.clips
     ops.set_option(_lib.OPT_LN_FUSE, args.ln_fuse)
     ops.set_option(_lib.OPT_ATTN_IMPL, args.attn_impl)
+    ops.set_option(_lib.OPT_LAST_BLOCK_CLS, 1 if args.last_block_cls else 0)
     torch.manual_seed(0)
     pipe = vmc.ViMoCLIPPipeline("openai/clip-vit-base-patch16", "ViT-B/32", num_classes=NUM_CLASSES, device=dev, clips_per_step=args.chunk)
     pipe.rgb.visual.frames_in_flight = args.frames_in_flight
@@ -330,6 +331,9 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=16, help="clips per CPU-baseline step (bounded sample: ~10 s per pass on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ln-fuse", type=int, default=0, help="VMC_OPT_LN_FUSE: 0 separate LayerNorm kernels (default), 3 ln_1+ln_2 folded into the qkv / c_fc GEMMs, 5 only ln_1 folded, 1/2 fused into residual GEMM epilogues")
+    ap.add_argument("--last-block-cls", action="store_true",
+                    help="opt-in exact shortcut: the last transformer block computes only the CLS row of its output (NOT the default: "
+                         "the headline run does the reference's full per-token work)")
     ap.add_argument("--attn-impl", type=int, default=0, help="VMC_OPT_ATTN_IMPL: 0 library default, 3 / 5 select a ViT attention kernel generation")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -32,7 +32,10 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel,
  * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row sums from the tensor core (L <= 224), 3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
  * Both implementations of each op are kept so the tests can cross-check them. */
-enum { VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
+enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* 1 = first-generation shared-memory attention backward (cross-checks) */,
+       VMC_OPT_LAST_BLOCK_CLS = 5 /* ViT tower, opt-in: 1 = in the LAST block compute only what the output reads (the CLS row):
+                                     K / V of all tokens, but query, out_proj, ln_2 and the MLP on the F CLS rows only */,
+       VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
        VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged) */,
        VMC_OPT_LN_FUSE = 3 /* ViT tower: 0/4 = separate LayerNorm kernels (default); 5 = ln_1 FOLDED into the qkv GEMM (c_proj
                               emits bf16 rows + row statistics, no ln_1 pass); 3 = ln_2 folded into c_fc as well (-1.7 % step
@@ -162,6 +165,8 @@ int vmc_layernorm_stats(const float* x, long long ldx, const float* gamma, const
  * Replaces nn.MultiheadAttention inside OpenAI ResidualAttentionBlock / HF CLIPAttention.
  */
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream);
+/* CLS-query attention of the last block (VMC_OPT_LAST_BLOCK_CLS): q_cls bf16 [F, d], kv bf16 [F*L, 2d] = [k | v] -> out bf16 [F, d] */
+int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L, int heads, void* stream);
 /* same, selecting the implementation: 3 = persistent, pipelined kernel with 8 softmax warps (default for
  * 128 < L <= 256; other L fall back to 2), 4 = the same pipeline with 16 softmax warps (measured slower), 2 = one CTA per (frame, head) with P kept in TMEM as the A operand of the PV MMA,
  * 1 = P staged through shared memory (first version; kept as a cross-check in the tests) */

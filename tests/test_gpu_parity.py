@@ -813,3 +813,23 @@ def test_gemm_transposed_operands(cuda_device, M, N, K, a_t, w_t):
     got = ops.gemm(a_arg, w_arg, bias=bias, out_dtype=torch.float32, a_t=a_t, w_t=w_t)
     assert got.shape == (M, N)
     assert (got - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("name,nframes", [("ViT-B/32", 5), ("ViT-B/16", 3), ("ViT-L/14", 2)])
+def test_vit_tower_last_block_cls_only(cuda_device, name, nframes):
+    """Opt-in VMC_OPT_LAST_BLOCK_CLS: the last block computes only the CLS row of its attention / MLP output (all the tower
+    output reads).  Same embeddings as the full computation."""
+    torch.manual_seed(1)
+    tower = vmc.VisionTower.from_name(name).to(cuda_device)
+    gen = torch.Generator().manual_seed(9)
+    u8 = torch.randint(0, 256, (nframes, 3, 224, 224), dtype=torch.uint8, generator=gen).to(cuda_device)
+    patches = ops.prologue(u8, wrap=False, dst="patch", patch=tower.patch_size)
+    full = tower.forward_patches(patches, nframes).clone()
+    ops.set_option(vmc._lib.OPT_LAST_BLOCK_CLS, 1)
+    try:
+        short = tower.forward_patches(patches, nframes).clone()
+    finally:
+        ops.set_option(vmc._lib.OPT_LAST_BLOCK_CLS, 0)
+    cos = torch.nn.functional.cosine_similarity(full.double(), short.double(), dim=-1).min().item()
+    assert cos >= 0.99999, cos  # the CLS path keeps the probabilities in fp32 where the tcgen05 path rounds them to bf16
+    assert (full - short).abs().max().item() <= 5e-3 * full.abs().max().item()

@@ -1248,6 +1248,57 @@ attention_masked_kernel(const float* __restrict__ q, long long ldq, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// CLS-query attention for the LAST transformer block (opt-in, VMC_OPT_LAST_BLOCK_CLS): the tower's output is
+// ln_post(x[:, 0]) @ proj, so in the last block only the CLS row of the attention / MLP output is ever read.  One
+// CTA per (frame, head): q = the CLS query [64], K / V = all L tokens (bf16, packed [F*L, 2d] = [k | v]).
+// Memory-bound (K and V are read once); scores by one warp per key (coalesced 128-byte rows, shuffle reduction).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attention_cls_kernel(const __nv_bfloat16* __restrict__ qcls, const __nv_bfloat16* __restrict__ kv,
+                     __nv_bfloat16* __restrict__ out, int L, int heads) {
+  extern __shared__ float s_sc[];  // [L] scores -> probabilities
+  __shared__ float s_red[4];
+  __shared__ float s_o[2][HD];
+  const int f = blockIdx.y, h = blockIdx.x;
+  const int d = heads * HD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat162 q2 = reinterpret_cast<const __nv_bfloat162*>(qcls + (size_t)f * d + h * HD)[lane];
+  const float qx = __low2float(q2), qy = __high2float(q2);
+  const __nv_bfloat16* kbase = kv + (size_t)f * L * 2 * d + h * HD;
+  const __nv_bfloat16* vbase = kbase + d;
+  for (int j = warp; j < L; j += 4) {
+    const __nv_bfloat162 k2 = reinterpret_cast<const __nv_bfloat162*>(kbase + (size_t)j * 2 * d)[lane];
+    const float s = warp_sum(qx * __low2float(k2) + qy * __high2float(k2));
+    if (lane == 0) s_sc[j] = s * 0.125f;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < L; j += 128) mx = fmaxf(mx, s_sc[j]);
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j < L; j += 128) {
+    const float p = __expf(s_sc[j] - mx);
+    s_sc[j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.0f / ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3]));
+  // O[dim] = sum_j p_j v_j[dim]: 64 dims x 2 key halves
+  const int dim = tid & 63, half = tid >> 6;
+  float acc = 0.f;
+  for (int j = half; j < L; j += 2) acc = fmaf(s_sc[j], __bfloat162float(vbase[(size_t)j * 2 * d + dim]), acc);
+  s_o[half][dim] = acc;
+  __syncthreads();
+  if (tid < HD) out[(size_t)f * d + h * HD + tid] = __float2bfloat16_rn((s_o[0][tid] + s_o[1][tid]) * inv);
+}
+
 uint32_t pow2_at_least(uint32_t v) {
   uint32_t p = 32;
   while (p < v) p <<= 1;
@@ -1397,6 +1448,21 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VmcProfScope prof(VMC_K_ATTN_VIT, st, fl, 8.0 * F * L * d);
     attention_vit_kernel<false><<<grid, 128, smem, st>>>(tm, a);
+  }
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
+int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L, int heads, void* stream) {
+  VMC_CHECK_ARG(q_cls && kv && out, VMC_ERR_ARG, "vmc_attention_cls: null pointer");
+  VMC_CHECK_ARG(F > 0 && F <= 65535 && heads > 0 && L > 0 && L <= 8192, VMC_ERR_SHAPE, "vmc_attention_cls: bad shape F=%d L=%d", F, L);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    VmcProfScope prof(VMC_K_ATTN_VIT, st, 4.0 * F * heads * (double)L * HD, 4.0 * F * (double)L * heads * HD);
+    attention_cls_kernel<<<dim3(heads, F), 128, (size_t)L * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(q_cls), reinterpret_cast<const __nv_bfloat16*>(kv),
+        reinterpret_cast<__nv_bfloat16*>(out), L, heads);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();

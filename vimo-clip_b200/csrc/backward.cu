@@ -876,8 +876,8 @@ int vmc_attention_masked_bwd(const float* q, long long ldq, const float* k, long
                          ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                            reinterpret_cast<uintptr_t>(dO) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(dk) |
                            reinterpret_cast<uintptr_t>(dv)) & 15) == 0;
-  if (workspace == nullptr && Tq <= 64 && Tk <= 64 && aligned16 && vmc_get_option(4) != 1) {
-    // short sequences: register-tiled kernel (VMC option 4 = 1 selects the first-generation kernel for cross-checks)
+  if (workspace == nullptr && Tq <= 64 && Tk <= 64 && aligned16 && vmc_get_option(VMC_OPT_ATTN_BWD_IMPL) != 1) {
+    // short sequences: register-tiled kernel (VMC_OPT_ATTN_BWD_IMPL = 1 selects the first-generation kernel for cross-checks)
     const size_t smem_s = (size_t)(4 * 64 * SB_LD + 2 * 64 * SB_LDP) * sizeof(float);
     VMC_CUDA(cudaFuncSetAttribute(attention_bwd_short_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
     {

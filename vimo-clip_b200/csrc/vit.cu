@@ -202,8 +202,76 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
   const bool fuse_ln = vmc_get_option(VMC_OPT_GEMM_IMPL) != 1 && (ln_opt == 1 || ln_opt == 2) &&
                        d <= 1024 && (d % 128) == 0 && pair_tiles >= vmc_num_sms();
   const bool fuse_ln2 = fuse_ln && ln_opt == 1;
+  // Opt-in (VMC_OPT_LAST_BLOCK_CLS = 1): the tower returns ln_post(x[:, 0]) @ proj, so the LAST block's attention / MLP
+  // output is only ever read at the CLS row.  K and V still come from all tokens; the query, out_proj, ln_2, c_fc and
+  // c_proj run on the F CLS rows only (20 of the block's 24 L d^2 GEMM FLOPs and its attention disappear; the embeddings
+  // are the same numbers).  Off by default: the bench measures the reference's full per-token work.
+  const bool cls_only = vmc_get_option(VMC_OPT_LAST_BLOCK_CLS) == 1 && !fold && !fuse_ln;
+  float* xcls = nullptr;  // [F, d] fp32: the CLS rows after the last block
   for (int i = 0; i < m->layers && !fold; ++i) {
     const vmc_vit_layer& ly = m->layer[i];
+    if (cls_only && i == m->layers - 1) {
+      // scratch carved from xn2 (only F rows of it are needed from here on)
+      char* sp = reinterpret_cast<char*>(w.xn2);
+      void* q_cls = sp;                                                   // bf16 [F, d]
+      void* a_cls = sp + (size_t)F * d * 2;                               // bf16 [F, d]
+      void* n_cls = sp + (size_t)F * d * 4;                               // bf16 [F, d]
+      xcls = reinterpret_cast<float*>(sp + (size_t)F * d * 6);            // fp32 [F, d]
+      void* h_cls = sp + (size_t)F * d * 10;                              // bf16 [F, 4d]  (18 F d bytes <= 2 F L d)
+      const char* wq = reinterpret_cast<const char*>(ly.w_qkv);
+      VMC_TRY(vmc_layernorm(w.x, d, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr, 0, w.xn, d, 0, rows, d, nullptr, 0, stream));
+      {  // k, v of every token
+        vmc_gemm_epilogue e = {};
+        e.bias = ly.b_qkv + d;
+        e.out = w.big;
+        e.ldo = 2 * d;
+        e.out_bf16 = 1;
+        e.alpha = 1.0f;
+        VMC_TRY(vmc_gemm_bf16(w.xn, d, wq + (size_t)d * d * 2, d, rows, 2 * d, d, &e, stream));
+      }
+      {  // q of the CLS rows (row stride L * d)
+        vmc_gemm_epilogue e = {};
+        e.bias = ly.b_qkv;
+        e.out = q_cls;
+        e.ldo = d;
+        e.out_bf16 = 1;
+        e.alpha = 1.0f;
+        VMC_TRY(vmc_gemm_bf16(w.xn, (long long)L * d, wq, d, F, d, d, &e, stream));
+      }
+      VMC_TRY(vmc_attention_cls(q_cls, w.big, a_cls, F, L, m->heads, stream));
+      {
+        vmc_gemm_epilogue e = {};
+        e.bias = ly.b_out;
+        e.resid = w.x;
+        e.ldr = (long long)L * d;
+        e.out = xcls;
+        e.ldo = d;
+        e.alpha = 1.0f;
+        VMC_TRY(vmc_gemm_bf16(a_cls, d, ly.w_out, d, F, d, d, &e, stream));
+      }
+      VMC_TRY(vmc_layernorm(xcls, d, ly.ln2_g, ly.ln2_b, 1e-5f, nullptr, 0, n_cls, d, 0, F, d, nullptr, 0, stream));
+      {
+        vmc_gemm_epilogue e = {};
+        e.bias = ly.b_fc1;
+        e.out = h_cls;
+        e.ldo = 4 * d;
+        e.out_bf16 = 1;
+        e.act = VMC_ACT_QUICKGELU;
+        e.alpha = 1.0f;
+        VMC_TRY(vmc_gemm_bf16(n_cls, d, ly.w_fc1, d, F, 4 * d, d, &e, stream));
+      }
+      {
+        vmc_gemm_epilogue e = {};
+        e.bias = ly.b_fc2;
+        e.resid = xcls;
+        e.ldr = d;
+        e.out = xcls;
+        e.ldo = d;
+        e.alpha = 1.0f;
+        VMC_TRY(vmc_gemm_bf16(h_cls, 4 * d, ly.w_fc2, 4 * d, F, d, 4 * d, &e, stream));
+      }
+      break;
+    }
     // x = x + out_proj(attn(ln_1(x)))
     if (i == 0 || !fuse_ln)
       VMC_TRY(vmc_layernorm(w.x, d, ly.ln1_g, ly.ln1_b, 1e-5f, nullptr, 0, w.xn, d, 0, rows, d, nullptr,
@@ -270,8 +338,8 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
     }
   }
   // ln_post on the CLS rows (row stride L*d), then @ proj (no bias), fp32 out.
-  VMC_TRY(vmc_layernorm(w.x, (long long)L * d, m->ln_post_g, m->ln_post_b, 1e-5f, nullptr, 0, w.cls,
-                        d, 0, F, d, nullptr, 0, stream));
+  VMC_TRY(vmc_layernorm(xcls ? xcls : w.x, xcls ? (long long)d : (long long)L * d, m->ln_post_g, m->ln_post_b, 1e-5f,
+                        nullptr, 0, w.cls, d, 0, F, d, nullptr, 0, stream));
   {
     vmc_gemm_epilogue e = {};
     e.out = out;
