@@ -1146,6 +1146,448 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------
+// Attention v6 (224 < L <= 257; ViT-L/14: 257 tokens = CLS + 256 patches).  Two 128-row query tiles with the whole
+// score row in TMEM cover at most 256 keys (2 x 256 of the 512 TMEM columns), so v5 stops at 256 tokens and 257
+// would need a third, one-row query tile.  v6 runs the v5 pipeline on the PATCH tokens only (queries and keys
+// 1 .. L-1: the TMA boxes simply start at token 1) and handles the CLS token on the CUDA cores, in two extra warps
+// that work out of the same Q / K / V tiles in shared memory while the tensor core is busy:
+//   * warp 14, "CLS key": s_cls[r] = q_r . k_cls for the <= 256 patch queries (swizzled LDS.128 of the Q rows).  The
+//     softmax thread of row r turns it into p_cls = 2^(s_cls sc - m_r) with the row's own stabiliser; the epilogue
+//     adds p_cls v_cls to the accumulator and p_cls to the tensor-core row sum before normalising;
+//   * warp 15, "CLS query": the whole attention row of q_cls in fp32 (scores over the K tile + k_cls, softmax,
+//     P V over the V tile + v_cls) -> output row 0.
+// Q / K are released by three arrivals (score MMAs retired + both CLS warps), V by two.  The all-ones tile of the
+// N = 80 PV MMA (row sums from the tensor core) is ONE 2 KB block here: each 16-key step gets its own descriptor
+// whose leading-dimension offset points back at it (v5 keeps one copy per step: 32 KB at 256 keys).
+// ---------------------------------------------------------------------------------------
+struct Attn6Args {
+  int L, heads, d, lk16, n_items;  // lk16 = 16-multiple >= L - 1 (patch keys)
+  __nv_bfloat16* out;
+  const __nv_bfloat16* qkv;
+};
+constexpr int A6_THREADS = 512;  // 8 softmax + 4 epilogue + TMA + MMA + 2 CLS warps
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// one 64-element bf16 row (128 bytes, global) -> 64 floats in registers; every lane reads the same row (broadcast)
+__device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&w)[64]) {
+  const uint4* p4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 v = __ldg(p4 + c);
+    w[8 * c + 0] = bf_lo(v.x); w[8 * c + 1] = bf_hi(v.x);
+    w[8 * c + 2] = bf_lo(v.y); w[8 * c + 3] = bf_hi(v.y);
+    w[8 * c + 4] = bf_lo(v.z); w[8 * c + 5] = bf_hi(v.z);
+    w[8 * c + 6] = bf_lo(v.w); w[8 * c + 7] = bf_hi(v.w);
+  }
+}
+// dot product of row r of a 128B-swizzled [rows x 64] bf16 tile (contiguous 128-row tiles, base 1024-B aligned) with w
+__device__ __forceinline__ float swz_row_dot64(uint32_t tile_base, int r, const float (&w)[64]) {
+  const uint32_t ra = tile_base + (uint32_t)r * 128u;
+  const uint32_t x = (uint32_t)(r & 7);
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 v = lds128(ra + ((uint32_t(c) ^ x) << 4));
+    a0 = fmaf(bf_lo(v.x), w[8 * c + 0], a0); a1 = fmaf(bf_hi(v.x), w[8 * c + 1], a1);
+    a0 = fmaf(bf_lo(v.y), w[8 * c + 2], a0); a1 = fmaf(bf_hi(v.y), w[8 * c + 3], a1);
+    a0 = fmaf(bf_lo(v.z), w[8 * c + 4], a0); a1 = fmaf(bf_hi(v.z), w[8 * c + 5], a1);
+    a0 = fmaf(bf_lo(v.w), w[8 * c + 6], a0); a1 = fmaf(bf_hi(v.w), w[8 * c + 7], a1);
+  }
+  return a0 + a1;
+}
+
+__global__ void __launch_bounds__(A6_THREADS, 1)
+attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm1,
+                      const Attn6Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const int Lp = a.L - 1;                                  // patch tokens = MMA queries and keys
+  const int r1 = a.lk16 - 128;                             // rows of the second Q / K / V box
+  const uint32_t mat_bytes = (uint32_t)(128 + r1) * 128u;  // one of Q, K, V for one item
+  const uint32_t qk_base = base;                           // ring of 2 x [Q | K]
+  const uint32_t v_base = base + 4 * mat_bytes;            // ring of 2 x V
+  const uint32_t ones_base = base + 6 * mat_bytes;         // 2 KB of bf16 1.0
+  const uint32_t scls_base = ones_base + 2048u;            // fp32 [2][256]: q_r . k_cls of the patch queries
+  const uint32_t pcls_base = scls_base + 2048u;            // fp32 [2][256]: p_cls of the patch queries
+  const uint32_t pbuf_base = pcls_base + 2048u;            // fp32 [256]: probabilities of the CLS query row
+  const uint32_t bar_base = pbuf_base + 1024u;
+  const int nkk = a.lk16 / 16;  // 16-key steps of the PV MMA
+  auto qk_full = [&](int s) { return bar_base + 8u * s; };
+  auto qk_empty = [&](int s) { return bar_base + 16u + 8u * s; };
+  auto s_full = [&](int t) { return bar_base + 32u + 8u * t; };
+  auto pa_full = [&](int t) { return bar_base + 48u + 8u * t; };
+  auto pb_full = [&](int t) { return bar_base + 64u + 8u * t; };
+  auto o_full = [&](int t) { return bar_base + 80u + 8u * t; };
+  auto s_empty = [&](int t) { return bar_base + 96u + 8u * t; };
+  auto v_full = [&](int s) { return bar_base + 112u + 8u * s; };
+  auto v_empty = [&](int s) { return bar_base + 128u + 8u * s; };
+  auto c_full = [&](int s) { return bar_base + 144u + 8u * s; };
+  auto c_empty = [&](int s) { return bar_base + 160u + 8u * s; };
+  const uint32_t tmem_ptr_addr = bar_base + 176u;
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
+  float* scls = reinterpret_cast<float*>(smem_raw + (scls_base - raw_addr));
+  float* pcls = reinterpret_cast<float*>(smem_raw + (pcls_base - raw_addr));
+  float* pbuf = reinterpret_cast<float*>(smem_raw + (pbuf_base - raw_addr));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int n_my = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
+
+  {
+    uint4* ones = reinterpret_cast<uint4*>(smem_raw + (ones_base - raw_addr));
+    for (uint32_t i = tid; i < 2048u / 16; i += A6_THREADS)
+      ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tm1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(qk_full(i), 1);
+      mbar_init(qk_empty(i), 3);  // score MMAs retired + CLS-key warp + CLS-query warp
+      mbar_init(v_full(i), 1);
+      mbar_init(v_empty(i), 2);   // PV MMAs retired + CLS-query warp
+      mbar_init(s_full(i), 1);
+      mbar_init(pa_full(i), 4);
+      mbar_init(pb_full(i), 4);
+      mbar_init(o_full(i), 1);
+      mbar_init(s_empty(i), 4);
+      mbar_init(c_full(i), 1);
+      mbar_init(c_empty(i), 8);  // one arrive per softmax warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_ptr_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+  const int n_chunks = (a.lk16 + 31) / 32;  // 5..8
+
+  if (warp == 12) {
+    // ===================== TMA producer (patch tokens: rows 1 .. of the frame) =====================
+    if (lane == 0) {
+      int kq = 0, kv = 0;
+      while (kq < n_my || kv < n_my) {
+        if (kq < n_my && mbar_test_wait(qk_empty(kq & 1), (((uint32_t)kq >> 1) & 1u) ^ 1u)) {
+          const int item = blockIdx.x + kq * gridDim.x;
+          const int head = item % a.heads, frame = item / a.heads;
+          const int s = kq & 1;
+          const uint32_t q = qk_base + s * 2 * mat_bytes, kk_ = q + mat_bytes;
+          mbar_arrive_expect_tx(qk_full(s), 2 * mat_bytes);
+          tma_load_3d(q, &tm, qk_full(s), head * HD, 1, frame);
+          tma_load_3d(q + TILE, &tm1, qk_full(s), head * HD, 129, frame);
+          tma_load_3d(kk_, &tm, qk_full(s), a.d + head * HD, 1, frame);
+          tma_load_3d(kk_ + TILE, &tm1, qk_full(s), a.d + head * HD, 129, frame);
+          ++kq;
+        }
+        if (kv < n_my && mbar_test_wait(v_empty(kv & 1), (((uint32_t)kv >> 1) & 1u) ^ 1u)) {
+          const int item = blockIdx.x + kv * gridDim.x;
+          const int head = item % a.heads, frame = item / a.heads;
+          const int s = kv & 1;
+          const uint32_t v = v_base + s * mat_bytes;
+          mbar_arrive_expect_tx(v_full(s), mat_bytes);
+          tma_load_3d(v, &tm, v_full(s), 2 * a.d + head * HD, 1, frame);
+          tma_load_3d(v + TILE, &tm1, v_full(s), 2 * a.d + head * HD, 129, frame);
+          ++kv;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 13) {
+    // ===================== MMA issuer (event driven, as v5) =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, a.lk16, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 80, 0, 1);  // B = [V | ones], MN-major
+      const int nka = nkk < 2 * A5_PA_CHUNKS ? nkk : 2 * A5_PA_CHUNKS;
+      int kt[2] = {0, 0};
+      int ph[2] = {0, 0};
+      int sdone[2] = {0, 0};
+      int fin[2] = {0, 0};
+      while (kt[0] < n_my || kt[1] < n_my) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (kt[t] >= n_my) continue;
+          const int k = kt[t];
+          const int s = k & 1;
+          const uint32_t par = (uint32_t)k & 1u;
+          const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
+          const uint32_t vst = v_base + s * mat_bytes;
+          // V descriptor of 16-key step kk: atom 0 = the TMA tile rows [16 kk, 16 kk + 16) (64 head dims), atom 1
+          // (N = 64..79) = LBO further = the ones block
+          auto dv = [&](int kk) {
+            const uint32_t va = vst + (uint32_t)kk * 2048u;
+            return (umma_desc_sw128(va) & ~(uint64_t(0x3FFF) << 16)) | (uint64_t((ones_base - va) >> 4) << 16);
+          };
+          const uint32_t tcol = tmem_base + uint32_t(t * 256);
+          if (ph[t] == 0) {
+            if (t == 1 && k == 0 && kt[0] == 0 && ph[0] < 2) continue;
+            if (!mbar_test_wait(qk_full(s), ring_par)) continue;
+            if (!mbar_test_wait(s_empty(t), par ^ 1u)) continue;
+            tc_fence_after();
+            const uint32_t qst = qk_base + s * 2 * mat_bytes;
+            const uint64_t dq = umma_desc_sw128(qst + t * TILE);
+            const uint64_t dk = umma_desc_sw128(qst + mat_bytes);
+#pragma unroll
+            for (int kq = 0; kq < HD / 16; ++kq)
+              umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s, kq != 0);
+            umma_commit(s_full(t));
+            if (++sdone[s] == 2) {
+              sdone[s] = 0;
+              umma_commit(qk_empty(s));
+            }
+            ph[t] = 1;
+          } else if (ph[t] == 1) {
+            if (!mbar_test_wait(pa_full(t), par)) continue;
+            if (!mbar_test_wait(v_full(s), ring_par)) continue;
+            tc_fence_after();
+            for (int kk = 0; kk < nka; ++kk)
+              umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv(kk), idesc_pv, kk != 0);
+            ph[t] = 2;
+          } else {
+            if (!mbar_test_wait(pb_full(t), par)) continue;
+            tc_fence_after();
+            for (int kk = nka; kk < nkk; ++kk)
+              umma_ts(tcol + A5_OCOL, tcol + uint32_t((kk >> 1) * 32 + (kk & 1) * 8), dv(kk), idesc_pv, 1u);
+            umma_commit(o_full(t));
+            if (++fin[s] == 2) {
+              fin[s] = 0;
+              umma_commit(v_empty(s));
+            }
+            kt[t] = k + 1;
+            ph[t] = 0;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 14) {
+    // ===================== CLS key: s_cls[r] = q_r . k_cls for the patch queries =====================
+    for (int k = 0; k < n_my; ++k) {
+      const int item = blockIdx.x + k * gridDim.x;
+      const int head = item % a.heads, frame = item / a.heads;
+      const int s = k & 1;
+      float w[64];
+      load_row64(a.qkv + (size_t)frame * a.L * 3 * a.d + a.d + head * HD, w);  // k of token 0
+      mbar_wait(qk_full(s), ((uint32_t)k >> 1) & 1u);
+      mbar_wait(c_empty(s), (((uint32_t)k >> 1) & 1u) ^ 1u);  // slot s of s_cls: read by all softmax warps of item k - 2
+      const uint32_t qst = qk_base + s * 2 * mat_bytes;
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+        const int r = lane + 32 * i;
+        if (r < a.lk16) scls[s * 256 + r] = swz_row_dot64(qst, r, w);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(c_full(s));
+        mbar_arrive(qk_empty(s));
+      }
+    }
+  } else if (warp == 15) {
+    // ===================== CLS query: the attention row of token 0, fp32 on the CUDA cores =====================
+    for (int k = 0; k < n_my; ++k) {
+      const int item = blockIdx.x + k * gridDim.x;
+      const int head = item % a.heads, frame = item / a.heads;
+      const int s = k & 1;
+      const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
+      const __nv_bfloat16* row0 = a.qkv + (size_t)frame * a.L * 3 * a.d + head * HD;
+      float w[64];
+      load_row64(row0, w);  // q of token 0
+      const uint32_t kc2 = __ldg(reinterpret_cast<const uint32_t*>(row0 + a.d) + lane);
+      const uint32_t vc2 = __ldg(reinterpret_cast<const uint32_t*>(row0 + 2 * a.d) + lane);
+      // q_cls . k_cls: lane l holds dims 2l, 2l+1 of both rows
+      const uint32_t qc2 = __ldg(reinterpret_cast<const uint32_t*>(row0) + lane);
+      const float sc0 = warp_sum(fmaf(bf_lo(qc2), bf_lo(kc2), bf_hi(qc2) * bf_hi(kc2))) * 0.125f;
+      mbar_wait(qk_full(s), ring_par);
+      const uint32_t kst = qk_base + s * 2 * mat_bytes + mat_bytes;
+      float sj[8];
+      float mx = sc0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = lane + 32 * i;
+        sj[i] = j < Lp ? swz_row_dot64(kst, j, w) * 0.125f : -INFINITY;
+        mx = fmaxf(mx, sj[i]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qk_empty(s));
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float p = __expf(sj[i] - mx);  // exp(-inf) = 0 for the padding keys
+        pbuf[lane + 32 * i] = p;
+        sum += p;
+      }
+      const float pc = __expf(sc0 - mx);
+      sum = warp_sum(sum) + pc;
+      __syncwarp();
+      mbar_wait(v_full(s), ring_par);
+      // O[2 lane, 2 lane + 1] = sum_j p_j V[j][..]: a warp reads one swizzled 128-byte V row per key (conflict free)
+      const uint32_t vst = v_base + s * mat_bytes;
+      const uint32_t c16 = (uint32_t)lane >> 2, o4 = ((uint32_t)lane & 3u) << 2;
+      float o0 = pc * bf_lo(vc2), o1 = pc * bf_hi(vc2);
+      float e0 = 0.f, e1 = 0.f;
+      for (int j = 0; j < a.lk16; j += 4) {
+        const float4 p4 = *reinterpret_cast<const float4*>(pbuf + j);
+        uint32_t v0, v1, v2, v3;
+        const uint32_t ra = vst + (uint32_t)j * 128u + o4;
+        const uint32_t x = (uint32_t)(j & 7);  // j is a multiple of 4: rows j..j+3 have (row & 7) = x .. x + 3
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v0) : "r"(ra + ((c16 ^ x) << 4)));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v1) : "r"(ra + 128u + ((c16 ^ (x + 1)) << 4)));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v2) : "r"(ra + 256u + ((c16 ^ (x + 2)) << 4)));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v3) : "r"(ra + 384u + ((c16 ^ (x + 3)) << 4)));
+        o0 = fmaf(p4.x, bf_lo(v0), o0); o1 = fmaf(p4.x, bf_hi(v0), o1);
+        e0 = fmaf(p4.y, bf_lo(v1), e0); e1 = fmaf(p4.y, bf_hi(v1), e1);
+        o0 = fmaf(p4.z, bf_lo(v2), o0); o1 = fmaf(p4.z, bf_hi(v2), o1);
+        e0 = fmaf(p4.w, bf_lo(v3), e0); e1 = fmaf(p4.w, bf_hi(v3), e1);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_empty(s));
+      const float inv = 1.0f / sum;
+      reinterpret_cast<uint32_t*>(a.out + (size_t)frame * a.L * a.d + (size_t)head * HD)[lane] =
+          pack_bf16x2((o0 + e0) * inv, (o1 + e1) * inv);
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue warps: drain O, add the CLS key, write the rows =====================
+    const int q = warp - 8;
+    for (int k = 0; k < n_my; ++k) {
+      const int item = blockIdx.x + k * gridDim.x;
+      const int head = item % a.heads;
+      const int frame = item / a.heads;
+      const uint32_t par = (uint32_t)k & 1u;
+      // v of token 0: the same 128 bytes for every row of the item (L2 hit for the first reader, L1 after that)
+      const uint4* vc4 = reinterpret_cast<const uint4*>(a.qkv + (size_t)frame * a.L * 3 * a.d + 2 * a.d + head * HD);
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int row = t * 128 + q * 32 + lane;           // patch index; token row + 1
+        const bool warp_active = (t * 128 + q * 32) < Lp;  // warp-uniform
+        const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
+        mbar_wait(o_full(t), par);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        uint32_t rs = 0x3F800000u;
+        if (warp_active) {
+          tmem_ld_32x32b_x32(tb + A5_OCOL, o0);
+          tmem_ld_32x32b_x32(tb + A5_OCOL + 32u, o1);
+          rs = tmem_ld_32x32b_x1(tb + A5_OCOL + 64u);
+          tmem_ld_wait();
+        }
+        const float pc = pcls[(k & 1) * 256 + row];
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(s_empty(t));
+        if (warp_active && row < Lp) {
+          const float inv = 1.0f / (__uint_as_float(rs) + pc);
+          __nv_bfloat16* orow = a.out + ((size_t)frame * a.L + row + 1) * a.d + (size_t)head * HD;
+          uint32_t vc[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = __ldg(vc4 + c);
+            vc[4 * c] = v.x; vc[4 * c + 1] = v.y; vc[4 * c + 2] = v.z; vc[4 * c + 3] = v.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(fmaf(pc, bf_lo(vc[4 * i + 0]), __uint_as_float(o0[8 * i + 0])) * inv,
+                              fmaf(pc, bf_hi(vc[4 * i + 0]), __uint_as_float(o0[8 * i + 1])) * inv);
+            o.y = pack_bf16x2(fmaf(pc, bf_lo(vc[4 * i + 1]), __uint_as_float(o0[8 * i + 2])) * inv,
+                              fmaf(pc, bf_hi(vc[4 * i + 1]), __uint_as_float(o0[8 * i + 3])) * inv);
+            o.z = pack_bf16x2(fmaf(pc, bf_lo(vc[4 * i + 2]), __uint_as_float(o0[8 * i + 4])) * inv,
+                              fmaf(pc, bf_hi(vc[4 * i + 2]), __uint_as_float(o0[8 * i + 5])) * inv);
+            o.w = pack_bf16x2(fmaf(pc, bf_lo(vc[4 * i + 3]), __uint_as_float(o0[8 * i + 6])) * inv,
+                              fmaf(pc, bf_hi(vc[4 * i + 3]), __uint_as_float(o0[8 * i + 7])) * inv);
+            reinterpret_cast<uint4*>(orow)[i] = o;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(fmaf(pc, bf_lo(vc[16 + 4 * i + 0]), __uint_as_float(o1[8 * i + 0])) * inv,
+                              fmaf(pc, bf_hi(vc[16 + 4 * i + 0]), __uint_as_float(o1[8 * i + 1])) * inv);
+            o.y = pack_bf16x2(fmaf(pc, bf_lo(vc[16 + 4 * i + 1]), __uint_as_float(o1[8 * i + 2])) * inv,
+                              fmaf(pc, bf_hi(vc[16 + 4 * i + 1]), __uint_as_float(o1[8 * i + 3])) * inv);
+            o.z = pack_bf16x2(fmaf(pc, bf_lo(vc[16 + 4 * i + 2]), __uint_as_float(o1[8 * i + 4])) * inv,
+                              fmaf(pc, bf_hi(vc[16 + 4 * i + 2]), __uint_as_float(o1[8 * i + 5])) * inv);
+            o.w = pack_bf16x2(fmaf(pc, bf_lo(vc[16 + 4 * i + 3]), __uint_as_float(o1[8 * i + 6])) * inv,
+                              fmaf(pc, bf_hi(vc[16 + 4 * i + 3]), __uint_as_float(o1[8 * i + 7])) * inv);
+            reinterpret_cast<uint4*>(orow + 32)[i] = o;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warps (as v5, plus the CLS key's probability) =====================
+    const int t = warp >> 2;
+    const int q = warp & 3;
+    const bool warp_active = (t * 128 + q * 32) < Lp;  // warp-uniform
+    const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
+    const float sc = 0.125f * 1.4426950408889634f;
+    const int n_full = Lp >> 5;
+    const int tail = Lp - (n_full << 5);
+    const int row = t * 128 + q * 32 + lane;
+    auto pcol = [&](int c) { return tb + uint32_t(c < A5_PA_CHUNKS ? c * 16 : c * 32); };
+    for (int k = 0; k < n_my; ++k) {
+      const uint32_t par = (uint32_t)k & 1u;
+      mbar_wait(s_full(t), par);
+      tc_fence_after();
+      float mxs = 0.f;
+      if (warp_active) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tb, r0);
+        tmem_ld_wait();
+        mxs = chunk_max<false>(r0, -INFINITY, 32) * sc;
+        for (int c = 0; c < n_chunks; c += 2) {
+          if (c != 0) tmem_ld_wait();
+          if (c + 1 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 1) * 32), r1);
+          if (c < n_full) chunk_exp_store5<false, 0>(r0, sc, mxs, 32, pcol(c));
+          else chunk_exp_store5<true, 0>(r0, sc, mxs, tail, pcol(c));
+          if (c == A5_PA_CHUNKS - 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(pa_full(t));
+          }
+          if (c + 1 < n_chunks) {
+            tmem_ld_wait();
+            if (c + 2 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 2) * 32), r0);
+            if (c + 1 < n_full) chunk_exp_store5<false, 0>(r1, sc, mxs, 32, pcol(c + 1));
+            else chunk_exp_store5<true, 0>(r1, sc, mxs, tail, pcol(c + 1));
+          }
+        }
+        tmem_st_wait();
+      } else {
+        if (lane == 0) mbar_arrive_relaxed(pa_full(t));
+      }
+      // the CLS key, scored by warp 14: same stabiliser as the row's other keys; consumed by the epilogue warps
+      mbar_wait(c_full(k & 1), ((uint32_t)k >> 1) & 1u);
+      pcls[(k & 1) * 256 + row] = ex2_approx(fminf(fmaf(scls[(k & 1) * 256 + row], sc, -mxs), 120.f));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c_empty(k & 1));
+      if (lane == 0) mbar_arrive(pb_full(t));  // release: publishes p_cls (via the MMA commit) to the epilogue warps
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // TFAM attention: fp32, boolean key-padding mask (1 = attend), online softmax over 64-key tiles.
 // grid = (ceil(Tq/16), heads, B); 4 warps, each owning 4 query rows.
 // ---------------------------------------------------------------------------------------
@@ -1317,9 +1759,40 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
   VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit: null pointer");
   VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 272, VMC_ERR_SHAPE,
                 "vmc_attention_vit: need 0 < L <= 272 tokens (L=%d)", L);
-  VMC_CHECK_ARG((impl >= 1 && impl <= 5) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 55), VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 1..5");
+  VMC_CHECK_ARG((impl >= 1 && impl <= 6) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 55), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 1..6");
   const int d = heads * HD;
+  // v6 = the v5 pipeline on the patch tokens + the CLS token on the CUDA cores: default above v5's 224 tokens (ViT-L/14: 257)
+  if (impl == 5 && L > 224 && L <= 257) impl = 6;
+  if (impl == 6 && (L < 145 || L > 257)) impl = 5;
+  if (impl == 6) {
+    Attn6Args a6;
+    a6.L = L;
+    a6.heads = heads;
+    a6.d = d;
+    a6.lk16 = ((L - 1 + 15) / 16) * 16;
+    a6.n_items = F * heads;
+    a6.out = reinterpret_cast<__nv_bfloat16*>(out);
+    a6.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    CUtensorMap tm6, tm6b;
+    const uint64_t dims6[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)F};
+    const uint64_t strides6[2] = {(uint64_t)3 * d * 2, (uint64_t)L * 3 * d * 2};
+    const uint32_t box6[3] = {HD, 128, 1};
+    const uint32_t box6b[3] = {HD, (uint32_t)(a6.lk16 - 128), 1};
+    VMC_TRY(vmc_encode_tmap_bf16(&tm6, qkv, 3, dims6, strides6, box6));
+    VMC_TRY(vmc_encode_tmap_bf16(&tm6b, qkv, 3, dims6, strides6, box6b));
+    const uint32_t smem6 = 6u * (uint32_t)a6.lk16 * 128u + 2048u + 5u * 1024u + 256u + 1024u;
+    cudaStream_t st6 = reinterpret_cast<cudaStream_t>(stream);
+    const int grid6 = a6.n_items < vmc_num_sms() ? a6.n_items : vmc_num_sms();
+    VMC_CUDA(cudaFuncSetAttribute(attention_vit6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6));
+    {
+      VmcProfScope prof(VMC_K_ATTN_VIT, st6, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
+      attention_vit6_kernel<<<grid6, A6_THREADS, smem6, st6>>>(tm6, tm6b, a6);
+    }
+    VMC_LAUNCH_CHECK();
+    vmc_count_launch();
+    return VMC_OK;
+  }
   if (impl >= 3 && (L <= 128 || L > 256)) impl = 2;
   if ((impl == 5 || impl >= 51) && L > 224) impl = 3;  // v5 keeps two Q/K and two V slots + the ones tile in smem  // the persistent kernels cover two query tiles
   if (impl == 5 || impl >= 51) {
