@@ -69,6 +69,11 @@ def test_prologue_patchify_bf16(cuda_device, prologue_impl, patch):
     assert got.shape == (3 * (224 // patch) ** 2, ops.patch_ld(patch))
     assert torch.equal(got[:, :k].view(torch.int16), ref.view(torch.int16))
     assert torch.count_nonzero(got[:, k:]) == 0
+    # no-wrap uint8 (HF processor path, extract_embeddings.py:89-93)
+    gotN = ops.prologue(u8.to(cuda_device), wrap=False, dst="patch", patch=patch).cpu()
+    refN = torch.from_numpy(prologue.patchify(prologue.normalise_u8(u8.numpy()), patch)).to(torch.bfloat16)
+    assert torch.equal(gotN[:, :k].view(torch.int16), refN.view(torch.int16))
+    assert torch.count_nonzero(gotN[:, k:]) == 0
     # float wrap regimes through the patch path
     fB = (u8.float() / 255.0).to(cuda_device)
     gotB = ops.prologue(fB, wrap=True, dst="patch", patch=patch).cpu()

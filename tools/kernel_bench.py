@@ -86,7 +86,7 @@ if "ln" in which:
     u8 = torch.randint(0, 256, (F_, 3, 224, 224), dtype=torch.uint8, device=dev, generator=gen)
     for impl in (0, 1, 2):
         ops.set_option(vmc._lib.OPT_PROLOGUE_IMPL, impl)
-        for p in (16, 32):
+        for p in (16, 32, 14):
             ms = timeit(lambda: ops.prologue(u8, wrap=True, dst="patch", patch=p))
             print(f"prologue impl={impl} p={p} F={F_}: {ms:.3f} ms  {u8.numel() * 3 / ms / 1e6:.0f} GB/s")
     bgr = torch.randint(0, 256, (F_ // 16, 17, 224, 224, 3), dtype=torch.uint8, device=dev, generator=gen)

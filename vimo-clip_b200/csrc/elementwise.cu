@@ -534,6 +534,176 @@ prologue_gather_kernel(const void* __restrict__ src, int src_kind, __nv_bfloat16
   }
 }
 
+// Gather form for patch sizes whose lines are not 8-pixel multiples (ViT-L/14: p = 14, patch row 588 elements, ld = 592):
+// same output-ordered work split as prologue_gather_kernel (one block per band, work item = (patch, 16-byte output
+// chunk), a warp writes 512 contiguous bytes), but a chunk's 8 source pixels straddle image lines / channels, so they
+// are fetched as single elements (L1 hits: the band's lines are read completely by this block) with the position
+// advanced incrementally.  The pad columns [3 p^2, ld) are written here (zeros): no separate memset pass.
+template <bool F32SRC, int ITERS>
+__global__ void __launch_bounds__(256)
+prologue_gather_any_kernel(const void* __restrict__ src, int src_kind, __nv_bfloat16* __restrict__ dst,
+                           int H, int W, int P, int ld) {
+  const int PP = P * P;
+  const int CPR = ld / 8;  // 16-byte chunks per patch row, padding included
+  const int gw = W / P, gh = H / P;
+  const int f = blockIdx.x / gh, py = blockIdx.x - f * gh;
+  const int items = gw * CPR;
+  const size_t plane = (size_t)H * W;
+  const size_t band0 = (size_t)f * 3 * plane + (size_t)py * P * W;
+  __nv_bfloat16* drow = dst + ((size_t)f * gh * gw + (size_t)py * gw) * ld;
+  const float K0 = __uint_as_float(c_fastK[0]), K1 = __uint_as_float(c_fastK[1]), K2 = __uint_as_float(c_fastK[2]);
+  const float B0 = __uint_as_float(c_fastB[0]), B1 = __uint_as_float(c_fastB[1]), B2 = __uint_as_float(c_fastB[2]);
+  for (int q0 = 0; q0 < items; q0 += ITERS * (int)blockDim.x) {
+    float x[ITERS][8];       // raw source values (bytes as exact floats)
+    uint32_t ccode[ITERS];   // 2 bits per element: channel, 3 = padding
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int q = q0 + it * (int)blockDim.x + (int)threadIdx.x;
+      ccode[it] = 0xFFFFu;
+      if (q < items) {
+        const int px = q / CPR, j = q - px * CPR;
+        const int e = 8 * j;
+        int c = e / PP;
+        const int r = e - c * PP;
+        int iy = r / P, ix = r - iy * P;
+        size_t off = band0 + (size_t)c * plane + (size_t)iy * W + (size_t)px * P + ix;
+        uint32_t code = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = c < 3;
+          if constexpr (F32SRC) x[it][i] = ok ? __ldg(reinterpret_cast<const float*>(src) + off) : 0.f;
+          else x[it][i] = ok ? (float)__ldg(reinterpret_cast<const uint8_t*>(src) + off) : 0.f;
+          code |= (uint32_t)(ok ? c : 3) << (2 * i);
+          ++ix;
+          ++off;
+          if (ix == P) {
+            ix = 0;
+            ++iy;
+            off += (size_t)(W - P);
+            if (iy == P) {
+              iy = 0;
+              ++c;
+              off += plane - (size_t)P * W;
+            }
+          }
+        }
+        ccode[it] = code;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int q = q0 + it * (int)blockDim.x + (int)threadIdx.x;
+      if (q >= items) break;
+      const int px = q / CPR, j = q - px * CPR;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t c = (ccode[it] >> (2 * i)) & 3u;
+        float u = x[it][i];
+        if (F32SRC && src_kind == VMC_SRC_F32_NORM) {
+          v[i] = c == 3u ? 0.f : u;
+        } else {
+          if constexpr (F32SRC) u = (float)wrap_f32(u);
+          else if (src_kind == VMC_SRC_U8_WRAP) u = (float)((256u - (uint32_t)u) & 255u);
+          const float K = c == 0u ? K0 : (c == 1u ? K1 : K2), B = c == 0u ? B0 : (c == 1u ? B1 : B2);
+          v[i] = c == 3u ? 0.f : __fmaf_rn(u, K, B);
+        }
+      }
+      reinterpret_cast<uint4*>(drow + (size_t)px * ld)[j] =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+  }
+}
+
+// ViT-L/14 (p = 14), uint8 sources: the element-wise gather above is bound by L1 wavefronts (a warp's byte loads touch
+// ~19 image lines), and a block that loads its band, synchronises, computes, synchronises and stores keeps too few
+// bytes in flight (3.3 TB/s).  This kernel is persistent and moves whole bands with 1-D bulk async copies (TMA) on
+// both sides, double buffered:
+//   1. load: the P lines of a channel are one contiguous run of P * W bytes -> three cp.async.bulk per band into
+//      stage k & 1, completion on an mbarrier, issued one band ahead;
+//   2. compute: work item = (patch, line l = c * P + iy): P pixels of ONE channel -> P/2 aligned pixel pairs
+//      (LDS.U16; P even, so a pair never straddles a line), the single-FMA normalise with one (K, B) pair per item,
+//      P/2 32-bit stores into the staged patch rows (row stride + 16 B: 2-way instead of 8-way bank conflicts);
+//   3. store: one cp.async.bulk per patch row (ld bf16, pad columns [3 p^2, ld) = zeros written once), read out of
+//      the other output stage while the next band is computed (cp.async.bulk.wait_group.read).
+template <int P>
+__global__ void __launch_bounds__(256)
+prologue_band_gather_u8_kernel(const uint8_t* __restrict__ src, int src_kind, __nv_bfloat16* __restrict__ dst,
+                               int H, int W, int ld, int n_bands) {
+  extern __shared__ __align__(128) uint8_t s_raw[];  // [2 x (3 P W) pixel bytes | 2 x gw staged rows | 2 mbarriers]
+  const int gw = W / P, gh = H / P;
+  const size_t plane = (size_t)H * W;
+  const uint32_t in_bytes = 3u * P * (uint32_t)W;
+  const uint32_t rs = (uint32_t)ld * 2u + 16u;
+  const uint32_t out_bytes = (uint32_t)gw * rs;
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(s_raw);
+  const uint32_t so = sb + 2u * in_bytes;
+  const uint32_t bar = so + 2u * out_bytes;
+  const int tid = threadIdx.x;
+  const int n_my = (n_bands - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue_load = [&](int k) {  // thread 0
+    const int b = blockIdx.x + k * gridDim.x;
+    const int f = b / gh, py = b - f * gh;
+    const uint8_t* band = src + (size_t)f * 3 * plane + (size_t)py * P * W;
+    const uint32_t st = sb + (uint32_t)(k & 1) * in_bytes, mb = bar + 8u * (k & 1);
+    mbar_arrive_expect_tx(mb, in_bytes);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       st + (uint32_t)c * P * W),
+                   "l"(band + (size_t)c * plane), "r"((uint32_t)(P * W)), "r"(mb)
+                   : "memory");
+  };
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar + 8, 1);
+    fence_mbar_init();
+  }
+  // zero both output stages once: the pad columns stay zero, everything else is overwritten per band
+  for (uint32_t i = tid; i < 2u * out_bytes / 16u; i += blockDim.x)
+    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(so + 16u * i), "r"(0u) : "memory");
+  __syncthreads();
+  if (tid == 0 && n_my > 0) issue_load(0);
+  const bool wrap = src_kind == VMC_SRC_U8_WRAP;
+  const int items = gw * 3 * P;
+  for (int k = 0; k < n_my; ++k) {
+    const int s = k & 1;
+    // output stage s was handed to the bulk stores of band k - 2: wait until they have READ it
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();  // ... and every thread is done reading input stage s ^ 1 (band k - 1)
+    if (tid == 0 && k + 1 < n_my) issue_load(k + 1);
+    mbar_wait(bar + 8u * s, ((uint32_t)k >> 1) & 1u);
+    const uint32_t ib = sb + (uint32_t)s * in_bytes, ob = so + (uint32_t)s * out_bytes;
+    for (int q = tid; q < items; q += blockDim.x) {
+      const int l = q / gw, px = q - l * gw;  // patches fastest
+      const int c = l / P;
+      const float K = __uint_as_float(c_fastK[c]), B = __uint_as_float(c_fastB[c]);
+      const uint32_t ia = ib + (uint32_t)(l * W + px * P);
+      const uint32_t oa = ob + (uint32_t)px * rs + (uint32_t)(l * P) * 2u;
+#pragma unroll
+      for (int i = 0; i < P / 2; ++i) {
+        uint32_t w;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w) : "r"(ia + 2u * i));
+        if (wrap) w = neg4_u8(w) & 0xFFFFu;
+        const uint32_t o = pack_bf16x2(__fmaf_rn(byte_to_float<0>(w), K, B), __fmaf_rn(byte_to_float<1>(w), K, B));
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(oa + 4u * i), "r"(o) : "memory");
+      }
+    }
+    fence_proxy_async_smem();  // the staged rows are read by the async proxy
+    __syncthreads();
+    if (tid == 0) {
+      const int b = blockIdx.x + k * gridDim.x;  // band b = (frame, patch row): its gw patch rows are rows b * gw ..
+      __nv_bfloat16* drow = dst + (size_t)b * gw * ld;
+      for (int px = 0; px < gw; ++px)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(drow + (size_t)px * ld),
+                     "r"(ob + (uint32_t)px * rs), "r"((uint32_t)ld * 2u)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // Frame difference -> student patch matrix, gather form: work item = (patch px, line iy, 8-pixel group h);
 // the grey |difference| of the 8 pixels is computed once from 2 x 24 BGR bytes and emitted for the three
 // identical channels (each a 16-byte chunk; a warp writes 512 contiguous bytes per channel).
@@ -863,14 +1033,38 @@ int vmc_prologue(const void* frames, int src_kind, void* dst, int dst_kind, int 
                     (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
                 VMC_ERR_ALIGN, "vmc_prologue: pointers must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dst_kind == VMC_DST_BF16_PATCH && ld_patch != 3 * patch * patch) {
-    const size_t n = (size_t)F * (H / patch) * (W / patch);
-    VMC_CUDA(cudaMemsetAsync(dst, 0, n * ld_patch * 2, st));
-  }
   const size_t total = (size_t)F * 3 * H * (W / 16);
   VMC_CHECK_ARG(total < (1ull << 31), VMC_ERR_SHAPE, "vmc_prologue: too many frames in one call (F=%d)", F);
   const int impl = vmc_get_option(VMC_OPT_PROLOGUE_IMPL);
   const bool f32_src = src_kind == VMC_SRC_F32_WRAP || src_kind == VMC_SRC_F32_NORM;
+  // patch sizes other than 16 / 32 (ViT-L/14): element-wise gather kernel, writes the pad columns itself
+  const bool gather_any = dst_kind == VMC_DST_BF16_PATCH && impl != 1 && impl != 2 && patch != 16 && patch != 32 &&
+                          (ld_patch % 8) == 0 && ld_patch >= 3 * patch * patch;
+  if (dst_kind == VMC_DST_BF16_PATCH && ld_patch != 3 * patch * patch && !gather_any) {
+    const size_t n = (size_t)F * (H / patch) * (W / patch);
+    VMC_CUDA(cudaMemsetAsync(dst, 0, n * ld_patch * 2, st));
+  }
+  if (gather_any) {
+    const double px = (double)F * 3 * H * W;
+    const int bands = F * (H / patch);
+    __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dst);
+    {
+      VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * ((f32_src ? 4.0 : 1.0) + 2.0));
+      const size_t smem14 = 2 * ((size_t)3 * 14 * W + (size_t)(W / 14) * (ld_patch * 2 + 16)) + 16;
+      if (!f32_src && patch == 14 && (W % 16) == 0 && (((size_t)H * W) % 16) == 0 && smem14 <= 100 * 1024) {
+        auto k14 = prologue_band_gather_u8_kernel<14>;
+        VMC_CUDA(cudaFuncSetAttribute(k14, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem14));
+        const int per_sm = (int)((220 * 1024) / (smem14 + 1024));
+        const int grid14 = bands < vmc_num_sms() * per_sm ? bands : vmc_num_sms() * per_sm;
+        k14<<<grid14, 256, smem14, st>>>(reinterpret_cast<const uint8_t*>(frames), src_kind, d16, H, W, ld_patch, bands);
+      }
+      else if (f32_src) prologue_gather_any_kernel<true, 5><<<bands, 256, 0, st>>>(frames, src_kind, d16, H, W, patch, ld_patch);
+      else prologue_gather_any_kernel<false, 5><<<bands, 256, 0, st>>>(frames, src_kind, d16, H, W, patch, ld_patch);
+    }
+    VMC_LAUNCH_CHECK();
+    vmc_count_launch();
+    return VMC_OK;
+  }
   // gather kernel: 7 work items per thread, block = items / 7 (192 threads at p = 16, 384 at p = 32, W = 224)
   const int g_items = dst_kind == VMC_DST_BF16_PATCH ? (W / patch) * (3 * patch * patch / 8) : 0;
   const int g_block = ((g_items + 6) / 7 + 31) / 32 * 32;
