@@ -29,6 +29,7 @@ def timeit(fn, iters=iters, warm=3):
 gen = torch.Generator(device="cuda").manual_seed(0)
 import vimoclip_b200 as vmc  # noqa: E402
 ops.set_option(vmc._lib.OPT_GEMM_IMPL, int(os.environ.get("KB_GEMM_IMPL", "0")))
+ops.set_option(vmc._lib.OPT_ATTN_PREFETCH, int(os.environ.get("KB_ATTN_PREFETCH", "0")))
 if "gemm" in which:
     for L, d in [(197, 768), (50, 768)]:
         M = F_ * L

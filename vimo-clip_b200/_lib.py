@@ -18,6 +18,7 @@ DST_U8, DST_F32_NCHW, DST_BF16_PATCH = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
 ABI_VERSION = 2
 OPT_GEMM_IMPL, OPT_ATTN_IMPL, OPT_PROLOGUE_IMPL, OPT_LN_FUSE, OPT_ATTN_BWD_IMPL, OPT_LAST_BLOCK_CLS = 0, 1, 2, 3, 4, 5
+OPT_ATTN_PREFETCH = 6
 
 
 class GemmEpilogue(C.Structure):

@@ -1588,6 +1588,281 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------
+// Attention v7 (L <= 64; ViT-B/32: 50 tokens): the v5 pipeline with TWO (frame, head) items packed into each 128-row
+// query tile.  v2 gives a 50-token item a whole CTA and a whole 128-row tile (39 % of the rows and of the softmax threads
+// busy, one serial load -> MMA -> softmax -> MMA -> store chain per CTA).  Here rows 0..63 of a tile are item A and rows
+// 64..127 item B; the K and V tiles are stacked the same way, S = [Q_A; Q_B] [K_A; K_B]^T is one 128 x 128 UMMA whose
+// off-diagonal blocks are discarded: a softmax thread exponentiates the 64 columns of its own item and writes ZERO
+// probabilities for the other item's keys, so O = P [V_A; V_B] (N = 80: 64 dims + the all-ones row-sum columns) is
+// block diagonal too.  One CTA iteration = 4 items (two tiles in flight); everything else -- Q/K and V rings released
+// separately, event-driven MMA issuer, epilogue warps, single-pass softmax with the first-chunk stabiliser -- is v5.
+// TMEM plan of a tile (base 256 t): S [0,128); P chunk c at [16 c, 16 c + 16); O [80,144) + row sum [144,160), written
+// only after every S column has been consumed (one PV phase).
+// ---------------------------------------------------------------------------------------
+struct Attn7Args {
+  int L, heads, d, n_items;
+  int pf;  // L2 prefetch distance in CTA iterations (0 = off)
+  __nv_bfloat16* out;
+};
+
+__global__ void __launch_bounds__(A5_THREADS, 1)
+attention_vit7_kernel(const __grid_constant__ CUtensorMap tm, const Attn7Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t qk_base = base;                // ring of 2 x [Q t0 | Q t1 | K t0 | K t1], 16 KB tiles
+  const uint32_t v_base = base + 8 * TILE;      // ring of 2 x [V t0 | V t1]
+  const uint32_t ones_base = base + 12 * TILE;  // 2 KB of bf16 1.0
+  const uint32_t bar_base = ones_base + 2048u;
+  auto qk_full = [&](int s) { return bar_base + 8u * s; };
+  auto qk_empty = [&](int s) { return bar_base + 16u + 8u * s; };
+  auto s_full = [&](int t) { return bar_base + 32u + 8u * t; };
+  auto p_full = [&](int t) { return bar_base + 48u + 8u * t; };
+  auto o_full = [&](int t) { return bar_base + 64u + 8u * t; };
+  auto s_empty = [&](int t) { return bar_base + 80u + 8u * t; };
+  auto v_full = [&](int s) { return bar_base + 96u + 8u * s; };
+  auto v_empty = [&](int s) { return bar_base + 112u + 8u * s; };
+  const uint32_t tmem_ptr_addr = bar_base + 128u;
+  volatile uint32_t* tmem_ptr_generic =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int n_groups = (a.n_items + 3) / 4;  // 4 items per CTA iteration
+  const int n_my = (n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  {
+    uint4* ones = reinterpret_cast<uint4*>(smem_raw + (ones_base - raw_addr));
+    for (uint32_t i = tid; i < 2048u / 16; i += A5_THREADS)
+      ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    // rows of a half tile that no TMA box ever writes (a group's missing items) must not hold NaN patterns: K / V
+    // garbage would reach valid rows through 0 * NaN.  Zero the rings once.
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw + (base - raw_addr));
+    for (uint32_t i = tid; i < 12u * TILE / 16; i += A5_THREADS) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&tm);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(qk_full(i), 1);
+      mbar_init(qk_empty(i), 1);
+      mbar_init(v_full(i), 1);
+      mbar_init(v_empty(i), 1);
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i), 4);
+      mbar_init(o_full(i), 1);
+      mbar_init(s_empty(i), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_ptr_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_generic;
+
+  if (warp == 12) {
+    // ===================== TMA producer: 64-row boxes (rows >= L zero-filled), item j of the group -> half tile j =====
+    if (lane == 0) {
+      int kq = 0, kv = 0;
+      while (kq < n_my || kv < n_my) {
+        if (kq < n_my && mbar_test_wait(qk_empty(kq & 1), (((uint32_t)kq >> 1) & 1u) ^ 1u)) {
+          const int g = blockIdx.x + kq * gridDim.x;
+          const int s = kq & 1;
+          const uint32_t q = qk_base + s * 4 * TILE, kk_ = q + 2 * TILE;
+          const int n_it = a.n_items - 4 * g < 4 ? a.n_items - 4 * g : 4;
+          mbar_arrive_expect_tx(qk_full(s), (uint32_t)n_it * TILE);
+          for (int j = 0; j < n_it; ++j) {
+            const int item = 4 * g + j;
+            const int head = item % a.heads, frame = item / a.heads;
+            tma_load_3d(q + j * (TILE / 2), &tm, qk_full(s), head * HD, 0, frame);
+            tma_load_3d(kk_ + j * (TILE / 2), &tm, qk_full(s), a.d + head * HD, 0, frame);
+          }
+          if (a.pf > 0 && kq + a.pf < n_my) {
+            // experiment (VMC_OPT_ATTN_PREFETCH): pull the boxes of a later iteration into L2 now.  Measured slightly
+            // SLOWER at every distance: the kernel is bound by the per-tile S -> softmax -> PV -> drain chain (ncu: every warp
+            // parked on an mbarrier, tensor pipe 17 %, DRAM 41 %), not by the load latency.
+            const int gp = blockIdx.x + (kq + a.pf) * gridDim.x;
+            const int n_p = a.n_items - 4 * gp < 4 ? a.n_items - 4 * gp : 4;
+            for (int j = 0; j < n_p; ++j) {
+              const int item = 4 * gp + j;
+              const int head = item % a.heads, frame = item / a.heads;
+              tma_prefetch_3d(&tm, head * HD, 0, frame);
+              tma_prefetch_3d(&tm, a.d + head * HD, 0, frame);
+              tma_prefetch_3d(&tm, 2 * a.d + head * HD, 0, frame);
+            }
+          }
+          ++kq;
+        }
+        if (kv < n_my && mbar_test_wait(v_empty(kv & 1), (((uint32_t)kv >> 1) & 1u) ^ 1u)) {
+          const int g = blockIdx.x + kv * gridDim.x;
+          const int s = kv & 1;
+          const uint32_t v = v_base + s * 2 * TILE;
+          const int n_it = a.n_items - 4 * g < 4 ? a.n_items - 4 * g : 4;
+          mbar_arrive_expect_tx(v_full(s), (uint32_t)n_it * (TILE / 2));
+          for (int j = 0; j < n_it; ++j) {
+            const int item = 4 * g + j;
+            const int head = item % a.heads, frame = item / a.heads;
+            tma_load_3d(v + j * (TILE / 2), &tm, v_full(s), 2 * a.d + head * HD, 0, frame);
+          }
+          ++kv;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 13) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 80, 0, 1);  // B = [V | ones], MN-major
+      int kt[2] = {0, 0};
+      int ph[2] = {0, 0};  // 0: S to issue, 1: waiting for P
+      int sdone[2] = {0, 0};
+      int fin[2] = {0, 0};
+      while (kt[0] < n_my || kt[1] < n_my) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (kt[t] >= n_my) continue;
+          const int k = kt[t];
+          const int s = k & 1;
+          const uint32_t par = (uint32_t)k & 1u;
+          const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
+          const uint32_t tcol = tmem_base + uint32_t(t * 256);
+          if (ph[t] == 0) {
+            if (t == 1 && k == 0 && kt[0] == 0 && ph[0] < 1) continue;  // tile 1 starts after tile 0's scores are issued
+            if (!mbar_test_wait(qk_full(s), ring_par)) continue;
+            if (!mbar_test_wait(s_empty(t), par ^ 1u)) continue;
+            tc_fence_after();
+            const uint32_t qst = qk_base + s * 4 * TILE;
+            const uint64_t dq = umma_desc_sw128(qst + t * TILE);
+            const uint64_t dk = umma_desc_sw128(qst + 2 * TILE + t * TILE);
+#pragma unroll
+            for (int kq = 0; kq < HD / 16; ++kq)
+              umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s, kq != 0);
+            umma_commit(s_full(t));
+            if (++sdone[s] == 2) {
+              sdone[s] = 0;
+              umma_commit(qk_empty(s));
+            }
+            ph[t] = 1;
+          } else {
+            if (!mbar_test_wait(p_full(t), par)) continue;
+            if (!mbar_test_wait(v_full(s), ring_par)) continue;
+            tc_fence_after();
+            const uint32_t vst = v_base + s * 2 * TILE + t * TILE;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint32_t va = vst + (uint32_t)kk * 2048u;
+              const uint64_t dv = (umma_desc_sw128(va) & ~(uint64_t(0x3FFF) << 16)) | (uint64_t((ones_base - va) >> 4) << 16);
+              umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv, idesc_pv, kk != 0);
+            }
+            umma_commit(o_full(t));
+            if (++fin[s] == 2) {
+              fin[s] = 0;
+              umma_commit(v_empty(s));
+            }
+            kt[t] = k + 1;
+            ph[t] = 0;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 8) {
+    // ===================== epilogue warps =====================
+    const int q = warp - 8;
+    for (int k = 0; k < n_my; ++k) {
+      const int g = blockIdx.x + k * gridDim.x;
+      const uint32_t par = (uint32_t)k & 1u;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int item = 4 * g + 2 * t + (q >> 1);  // warp-uniform: lane quarters 0, 1 = item A, 2, 3 = item B of the tile
+        const int tok = (q & 1) * 32 + lane;
+        const int head = item % a.heads, frame = item / a.heads;
+        const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
+        mbar_wait(o_full(t), par);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32b_x32(tb + A5_OCOL, o0);
+        tmem_ld_32x32b_x32(tb + A5_OCOL + 32u, o1);
+        const uint32_t rs = tmem_ld_32x32b_x1(tb + A5_OCOL + 64u);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(s_empty(t));
+        if (item < a.n_items && tok < a.L) {
+          const float inv = 1.0f / __uint_as_float(rs);
+          __nv_bfloat16* orow = a.out + ((size_t)frame * a.L + tok) * a.d + (size_t)head * HD;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+            reinterpret_cast<uint4*>(orow)[i] = o;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
+            reinterpret_cast<uint4*>(orow + 32)[i] = o;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warps: own item's 64 key columns, zeros for the other item's =====================
+    const int t = warp >> 2;
+    const int q = warp & 3;
+    const int blk = q >> 1;  // 0: item A (rows 0..63, keys 0..63), 1: item B
+    const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
+    const float sc = 0.125f * 1.4426950408889634f;
+    const int v0 = a.L < 32 ? a.L : 32;  // valid keys of the item's first / second 32-key chunk
+    const int v1 = a.L - 32 > 0 ? a.L - 32 : 0;
+    for (int k = 0; k < n_my; ++k) {
+      const uint32_t par = (uint32_t)k & 1u;
+      mbar_wait(s_full(t), par);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(tb + uint32_t(blk * 64), r0);
+      tmem_ld_32x32b_x32(tb + uint32_t(blk * 64 + 32), r1);
+      tmem_ld_wait();
+      // (P overlays S columns [0, 64), but a thread only ever touches its own TMEM lane: its scores are in registers now)
+      const float mxs = chunk_max<true>(r0, -INFINITY, v0) * sc;
+      if (v0 == 32) chunk_exp_store5<false, 0>(r0, sc, mxs, 32, tb + uint32_t((2 * blk) * 16));
+      else chunk_exp_store5<true, 0>(r0, sc, mxs, v0, tb + uint32_t((2 * blk) * 16));
+      chunk_exp_store5<true, 0>(r1, sc, mxs, v1, tb + uint32_t((2 * blk + 1) * 16));
+      {
+        uint32_t z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        tmem_st_32x32b_x16(tb + uint32_t((2 * (blk ^ 1)) * 16), z);
+        tmem_st_32x32b_x16(tb + uint32_t((2 * (blk ^ 1) + 1) * 16), z);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(p_full(t));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // TFAM attention: fp32, boolean key-padding mask (1 = attend), online softmax over 64-key tiles.
 // grid = (ceil(Tq/16), heads, B); 4 warps, each owning 4 query rows.
 // ---------------------------------------------------------------------------------------
@@ -1759,9 +2034,41 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
   VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit: null pointer");
   VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 272, VMC_ERR_SHAPE,
                 "vmc_attention_vit: need 0 < L <= 272 tokens (L=%d)", L);
-  VMC_CHECK_ARG((impl >= 1 && impl <= 6) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 55), VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 1..6");
+  VMC_CHECK_ARG((impl >= 1 && impl <= 7) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 55), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 1..7");
   const int d = heads * HD;
+  // v7 = two items packed per query tile in the v5 pipeline: default for short sequences (ViT-B/32: 50 tokens)
+  if (impl == 5 && L <= 64) impl = 7;
+  if (impl == 7 && L > 64) impl = 5;
+  if (impl == 7) {
+    Attn7Args a7;
+    a7.L = L;
+    a7.heads = heads;
+    a7.d = d;
+    a7.n_items = F * heads;
+    {
+      const int pf = vmc_get_option(VMC_OPT_ATTN_PREFETCH);
+      a7.pf = pf > 0 ? pf : 0;  // measured: 0.086 ms (off) vs 0.090-0.093 ms (distance 1..4) per 1024 ViT-B/32 frames -- off by default
+    }
+    a7.out = reinterpret_cast<__nv_bfloat16*>(out);
+    CUtensorMap tm7;
+    const uint64_t dims7[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)F};
+    const uint64_t strides7[2] = {(uint64_t)3 * d * 2, (uint64_t)L * 3 * d * 2};
+    const uint32_t box7[3] = {HD, 64, 1};
+    VMC_TRY(vmc_encode_tmap_bf16(&tm7, qkv, 3, dims7, strides7, box7));
+    const uint32_t smem7 = 12u * TILE + 2048u + 256u + 1024u;
+    cudaStream_t st7 = reinterpret_cast<cudaStream_t>(stream);
+    const int groups7 = (a7.n_items + 3) / 4;
+    const int grid7 = groups7 < vmc_num_sms() ? groups7 : vmc_num_sms();
+    VMC_CUDA(cudaFuncSetAttribute(attention_vit7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem7));
+    {
+      VmcProfScope prof(VMC_K_ATTN_VIT, st7, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
+      attention_vit7_kernel<<<grid7, A5_THREADS, smem7, st7>>>(tm7, a7);
+    }
+    VMC_LAUNCH_CHECK();
+    vmc_count_launch();
+    return VMC_OK;
+  }
   // v6 = the v5 pipeline on the patch tokens + the CLS token on the CUDA cores: default above v5's 224 tokens (ViT-L/14: 257)
   if (impl == 5 && L > 224 && L <= 257) impl = 6;
   if (impl == 6 && (L < 145 || L > 257)) impl = 5;
