@@ -373,6 +373,23 @@ def test_attention_vit_peaky_and_shifted_scores(cuda_device, impl, L):
     assert err < 3e-2, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("impl,L,heads,F_", [(7, 50, 12, 700), (5, 197, 12, 300), (6, 257, 16, 260), (6, 230, 4, 500)])
+def test_attention_vit_persistent_kernels_deterministic_at_scale(cuda_device, impl, L, heads, F_):
+    """Many items per CTA (ring slots, TMEM tiles and hand-over buffers reused dozens of times): the persistent kernels
+    must give bit-identical results run to run (a race shows up as run-to-run noise) and agree with the first-generation
+    per-item kernel (impl 2) on the same input."""
+    gen = torch.Generator(device="cuda").manual_seed(impl * 1000 + L)
+    d = heads * 64
+    qkv = (torch.randn(F_ * L, 3 * d, device=cuda_device, generator=gen) * 1.2).to(torch.bfloat16)
+    first = ops.attention_vit(qkv, F_, L, heads, impl=impl)
+    for _ in range(3):
+        again = ops.attention_vit(qkv, F_, L, heads, impl=impl)
+        assert torch.equal(first.view(torch.int16), again.view(torch.int16))
+    base = ops.attention_vit(qkv, F_, L, heads, impl=2)
+    # two bf16-rounded outputs: allow one bf16 ulp (2^-8 relative) of the value on top of the absolute bar
+    assert bool(((first.float() - base.float()).abs() <= 1e-2 + 2.0 ** -7 * base.float().abs()).all())
+
+
 @pytest.mark.parametrize("B,Tq,Tk", [(2, 16, 15), (3, 40, 100), (1, 5, 70)])
 def test_attention_masked(cuda_device, B, Tq, Tk):
     gen = torch.Generator(device="cuda").manual_seed(Tk)

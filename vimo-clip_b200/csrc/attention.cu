@@ -1172,6 +1172,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 // one 64-element bf16 row (128 bytes, global) -> 64 floats in registers; every lane reads the same row (broadcast)
@@ -1381,6 +1384,10 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       const int s = k & 1;
       float w[64];
       load_row64(a.qkv + (size_t)frame * a.L * 3 * a.d + a.d + head * HD, w);  // k of token 0
+      if (lane == 0 && k + 1 < n_my) {  // next item's row into L1: the load above is otherwise an exposed L2 round trip per item
+        const int nit = item + gridDim.x;
+        prefetch_l1(a.qkv + (size_t)(nit / a.heads) * a.L * 3 * a.d + a.d + (nit % a.heads) * HD);
+      }
       mbar_wait(qk_full(s), ((uint32_t)k >> 1) & 1u);
       mbar_wait(c_empty(s), (((uint32_t)k >> 1) & 1u) ^ 1u);  // slot s of s_cls: read by all softmax warps of item k - 2
       const uint32_t qst = qk_base + s * 2 * mat_bytes;
@@ -1406,7 +1413,11 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       float w[64];
       load_row64(row0, w);  // q of token 0
       const uint32_t kc2 = __ldg(reinterpret_cast<const uint32_t*>(row0 + a.d) + lane);
-      const uint32_t vc2 = __ldg(reinterpret_cast<const uint32_t*>(row0 + 2 * a.d) + lane);
+      const uint4 vc8 = __ldg(reinterpret_cast<const uint4*>(row0 + 2 * a.d) + (lane & 7));  // v_cls dims 8 (lane & 7) ..
+      if (lane < 3 && k + 1 < n_my) {  // next item's q / k / v rows of token 0 into L1
+        const int nit = item + gridDim.x;
+        prefetch_l1(a.qkv + (size_t)(nit / a.heads) * a.L * 3 * a.d + lane * a.d + (nit % a.heads) * HD);
+      }
       // q_cls . k_cls: lane l holds dims 2l, 2l+1 of both rows
       const uint32_t qc2 = __ldg(reinterpret_cast<const uint32_t*>(row0) + lane);
       const float sc0 = warp_sum(fmaf(bf_lo(qc2), bf_lo(kc2), bf_hi(qc2) * bf_hi(kc2))) * 0.125f;
@@ -1434,30 +1445,41 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       sum = warp_sum(sum) + pc;
       __syncwarp();
       mbar_wait(v_full(s), ring_par);
-      // O[2 lane, 2 lane + 1] = sum_j p_j V[j][..]: a warp reads one swizzled 128-byte V row per key (conflict free)
+      // O = sum_j p_j V[j]: lane = (key group g = lane >> 3, dim chunk c = lane & 7); per step the warp reads four swizzled
+      // 128-byte V rows with one LDS.128 per lane (4 wavefronts: optimal), 8 FMAs per lane; the four key groups are
+      // reduced with two shuffle rounds at the end.
       const uint32_t vst = v_base + s * mat_bytes;
-      const uint32_t c16 = (uint32_t)lane >> 2, o4 = ((uint32_t)lane & 3u) << 2;
-      float o0 = pc * bf_lo(vc2), o1 = pc * bf_hi(vc2);
-      float e0 = 0.f, e1 = 0.f;
-      for (int j = 0; j < a.lk16; j += 4) {
-        const float4 p4 = *reinterpret_cast<const float4*>(pbuf + j);
-        uint32_t v0, v1, v2, v3;
-        const uint32_t ra = vst + (uint32_t)j * 128u + o4;
-        const uint32_t x = (uint32_t)(j & 7);  // j is a multiple of 4: rows j..j+3 have (row & 7) = x .. x + 3
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v0) : "r"(ra + ((c16 ^ x) << 4)));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v1) : "r"(ra + 128u + ((c16 ^ (x + 1)) << 4)));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v2) : "r"(ra + 256u + ((c16 ^ (x + 2)) << 4)));
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v3) : "r"(ra + 384u + ((c16 ^ (x + 3)) << 4)));
-        o0 = fmaf(p4.x, bf_lo(v0), o0); o1 = fmaf(p4.x, bf_hi(v0), o1);
-        e0 = fmaf(p4.y, bf_lo(v1), e0); e1 = fmaf(p4.y, bf_hi(v1), e1);
-        o0 = fmaf(p4.z, bf_lo(v2), o0); o1 = fmaf(p4.z, bf_hi(v2), o1);
-        e0 = fmaf(p4.w, bf_lo(v3), e0); e1 = fmaf(p4.w, bf_hi(v3), e1);
+      const int g = lane >> 3;
+      const uint32_t c = (uint32_t)lane & 7u;
+      float acc[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) acc[m] = 0.f;
+#pragma unroll 2
+      for (int j0 = 0; j0 < a.lk16; j0 += 4) {
+        const int j = j0 + g;
+        const float pj = pbuf[j];
+        const uint4 v = lds128(vst + (uint32_t)j * 128u + ((c ^ (uint32_t)(j & 7)) << 4));
+        acc[0] = fmaf(pj, bf_lo(v.x), acc[0]); acc[1] = fmaf(pj, bf_hi(v.x), acc[1]);
+        acc[2] = fmaf(pj, bf_lo(v.y), acc[2]); acc[3] = fmaf(pj, bf_hi(v.y), acc[3]);
+        acc[4] = fmaf(pj, bf_lo(v.z), acc[4]); acc[5] = fmaf(pj, bf_hi(v.z), acc[5]);
+        acc[6] = fmaf(pj, bf_lo(v.w), acc[6]); acc[7] = fmaf(pj, bf_hi(v.w), acc[7]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(v_empty(s));
-      const float inv = 1.0f / sum;
-      reinterpret_cast<uint32_t*>(a.out + (size_t)frame * a.L * a.d + (size_t)head * HD)[lane] =
-          pack_bf16x2((o0 + e0) * inv, (o1 + e1) * inv);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 8);
+        acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 16);
+      }
+      if (lane < 8) {
+        const float inv = 1.0f / sum;
+        uint4 o;
+        o.x = pack_bf16x2(fmaf(pc, bf_lo(vc8.x), acc[0]) * inv, fmaf(pc, bf_hi(vc8.x), acc[1]) * inv);
+        o.y = pack_bf16x2(fmaf(pc, bf_lo(vc8.y), acc[2]) * inv, fmaf(pc, bf_hi(vc8.y), acc[3]) * inv);
+        o.z = pack_bf16x2(fmaf(pc, bf_lo(vc8.z), acc[4]) * inv, fmaf(pc, bf_hi(vc8.z), acc[5]) * inv);
+        o.w = pack_bf16x2(fmaf(pc, bf_lo(vc8.w), acc[6]) * inv, fmaf(pc, bf_hi(vc8.w), acc[7]) * inv);
+        reinterpret_cast<uint4*>(a.out + (size_t)frame * a.L * a.d + (size_t)head * HD)[lane] = o;
+      }
     }
   } else if (warp >= 8) {
     // ===================== epilogue warps: drain O, add the CLS key, write the rows =====================
