@@ -1164,47 +1164,60 @@ struct Attn6Args {
   int L, heads, d, lk16, n_items;  // lk16 = 16-multiple >= L - 1 (patch keys)
   __nv_bfloat16* out;
   const __nv_bfloat16* qkv;
+  int var;  // what-if timing variants (WRONG results; tools/kernel_bench.py impl 61..): bit 0 warp 14 idle, 1 warp 15 no scores,
+            // 2 warp 15 no P V, 3 epilogue without the CLS key, 4 softmax without the CLS key
 };
 constexpr int A6_THREADS = 512;  // 8 softmax + 4 epilogue + TMA + MMA + 2 CLS warps
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-// one 64-element bf16 row (128 bytes, global) -> 64 floats in registers; every lane reads the same row (broadcast)
-__device__ __forceinline__ void load_row64(const __nv_bfloat16* p, float (&w)[64]) {
-  const uint4* p4 = reinterpret_cast<const uint4*>(p);
+// A 64-element bf16 row in global memory as the B operand of four mma.m16n8k16 k-steps (every column of B = the row, so
+// every column of C is the same dot product): lane l holds k = 2 (l % 4), +1 (b0) and k + 8, +9 (b1) of each 16-deep step.
+__device__ __forceinline__ void load_bfrag64(const __nv_bfloat16* row, int lane, uint32_t (&b)[8]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 v = __ldg(p4 + c);
-    w[8 * c + 0] = bf_lo(v.x); w[8 * c + 1] = bf_hi(v.x);
-    w[8 * c + 2] = bf_lo(v.y); w[8 * c + 3] = bf_hi(v.y);
-    w[8 * c + 4] = bf_lo(v.z); w[8 * c + 5] = bf_hi(v.z);
-    w[8 * c + 6] = bf_lo(v.w); w[8 * c + 7] = bf_hi(v.w);
+  for (int ks = 0; ks < 4; ++ks) {
+    b[2 * ks] = __ldg(w + 8 * ks + (lane & 3));
+    b[2 * ks + 1] = __ldg(w + 8 * ks + 4 + (lane & 3));
   }
 }
-// dot product of row r of a 128B-swizzled [rows x 64] bf16 tile (contiguous 128-row tiles, base 1024-B aligned) with w
-__device__ __forceinline__ float swz_row_dot64(uint32_t tile_base, int r, const float (&w)[64]) {
-  const uint32_t ra = tile_base + (uint32_t)r * 128u;
-  const uint32_t x = (uint32_t)(r & 7);
-  float a0 = 0.f, a1 = 0.f;
+// dst[r] = tile row r . vector for the first 16 * n_blocks rows of a 128B-swizzled [rows x 64] bf16 tile (contiguous 128-row
+// tiles, base 1024-byte aligned), on the warp-level tensor path: per 16-row block four ldmatrix.x4 (the swizzled 16-byte
+// chunk of row r is chunk ^ (r & 7): the lanes supply the row addresses) + four mma.sync.m16n8k16 with fp32 accumulation --
+// 8 instructions per 16 rows instead of ~2200 CUDA-core instructions.  bf16 x bf16 products are exact in fp32.
+__device__ __forceinline__ void tile_rows_dot_mma(uint32_t tile_base, int n_blocks, const uint32_t (&b)[8], float* dst, int lane) {
+  const uint32_t m = (uint32_t)lane >> 3, r = (uint32_t)lane & 7u;
+  const uint32_t rowoff = ((m & 1u) * 8u + r) * 128u;
+  uint32_t coff[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 v = lds128(ra + ((uint32_t(c) ^ x) << 4));
-    a0 = fmaf(bf_lo(v.x), w[8 * c + 0], a0); a1 = fmaf(bf_hi(v.x), w[8 * c + 1], a1);
-    a0 = fmaf(bf_lo(v.y), w[8 * c + 2], a0); a1 = fmaf(bf_hi(v.y), w[8 * c + 3], a1);
-    a0 = fmaf(bf_lo(v.z), w[8 * c + 4], a0); a1 = fmaf(bf_hi(v.z), w[8 * c + 5], a1);
-    a0 = fmaf(bf_lo(v.w), w[8 * c + 6], a0); a1 = fmaf(bf_hi(v.w), w[8 * c + 7], a1);
+  for (int ks = 0; ks < 4; ++ks) coff[ks] = ((uint32_t(2 * ks) + (m >> 1)) ^ r) << 4;
+#pragma unroll 2
+  for (int rb = 0; rb < n_blocks; ++rb) {
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    const uint32_t ra = tile_base + (uint32_t)rb * 2048u + rowoff;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                   : "r"(ra + coff[ks]));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b[2 * ks]), "r"(b[2 * ks + 1]));
+    }
+    if ((lane & 3) == 0) {  // column 0 of C: rows lane / 4 (c0) and lane / 4 + 8 (c2)
+      dst[rb * 16 + (lane >> 2)] = c0;
+      dst[rb * 16 + 8 + (lane >> 2)] = c2;
+    }
+    (void)c1;
+    (void)c3;
   }
-  return a0 + a1;
 }
 
+template <int VAR>  // 0 = production; see Attn6Args::var (what-if timing variants, wrong results)
 __global__ void __launch_bounds__(A6_THREADS, 1)
 attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm1,
                       const Attn6Args a) {
@@ -1220,7 +1233,8 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
   const uint32_t scls_base = ones_base + 2048u;            // fp32 [2][256]: q_r . k_cls of the patch queries
   const uint32_t pcls_base = scls_base + 2048u;            // fp32 [2][256]: p_cls of the patch queries
   const uint32_t pbuf_base = pcls_base + 2048u;            // fp32 [256]: probabilities of the CLS query row
-  const uint32_t bar_base = pbuf_base + 1024u;
+  const uint32_t pb16_base = pbuf_base + 1024u;            // bf16 [256]: the same, rounded, as the A operand of the P V mma
+  const uint32_t bar_base = pb16_base + 512u;
   const int nkk = a.lk16 / 16;  // 16-key steps of the PV MMA
   auto qk_full = [&](int s) { return bar_base + 8u * s; };
   auto qk_empty = [&](int s) { return bar_base + 16u + 8u * s; };
@@ -1239,6 +1253,7 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
   float* scls = reinterpret_cast<float*>(smem_raw + (scls_base - raw_addr));
   float* pcls = reinterpret_cast<float*>(smem_raw + (pcls_base - raw_addr));
   float* pbuf = reinterpret_cast<float*>(smem_raw + (pbuf_base - raw_addr));
+  __nv_bfloat16* pb16 = reinterpret_cast<__nv_bfloat16*>(smem_raw + (pb16_base - raw_addr));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -1382,20 +1397,15 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       const int item = blockIdx.x + k * gridDim.x;
       const int head = item % a.heads, frame = item / a.heads;
       const int s = k & 1;
-      float w[64];
-      load_row64(a.qkv + (size_t)frame * a.L * 3 * a.d + a.d + head * HD, w);  // k of token 0
+      uint32_t bk[8];
+      load_bfrag64(a.qkv + (size_t)frame * a.L * 3 * a.d + a.d + head * HD, lane, bk);  // k of token 0 as the B operand
       if (lane == 0 && k + 1 < n_my) {  // next item's row into L1: the load above is otherwise an exposed L2 round trip per item
         const int nit = item + gridDim.x;
         prefetch_l1(a.qkv + (size_t)(nit / a.heads) * a.L * 3 * a.d + a.d + (nit % a.heads) * HD);
       }
       mbar_wait(qk_full(s), ((uint32_t)k >> 1) & 1u);
       mbar_wait(c_empty(s), (((uint32_t)k >> 1) & 1u) ^ 1u);  // slot s of s_cls: read by all softmax warps of item k - 2
-      const uint32_t qst = qk_base + s * 2 * mat_bytes;
-#pragma unroll 1
-      for (int i = 0; i < 8; ++i) {
-        const int r = lane + 32 * i;
-        if (r < a.lk16) scls[s * 256 + r] = swz_row_dot64(qst, r, w);
-      }
+      if (!(VAR & 1)) tile_rows_dot_mma(qk_base + s * 2 * mat_bytes, a.lk16 / 16, bk, scls + s * 256, lane);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(c_full(s));
@@ -1403,17 +1413,22 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       }
     }
   } else if (warp == 15) {
-    // ===================== CLS query: the attention row of token 0, fp32 on the CUDA cores =====================
+    // ===================== CLS query: the attention row of token 0 =====================
+    // (A software-pipelined order -- scores(k), release Q / K, P V(k - 1), softmax(k) -- was measured SLOWER, 0.51 vs 0.41 ms:
+    // it delays the V release instead.  What the what-if variants showed is that the ~1100 CUDA-core instructions of the score
+    // phase cost 0.1 ms; they now run on the warp-level tensor path, see tile_rows_dot_mma.)
     for (int k = 0; k < n_my; ++k) {
       const int item = blockIdx.x + k * gridDim.x;
       const int head = item % a.heads, frame = item / a.heads;
       const int s = k & 1;
       const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
       const __nv_bfloat16* row0 = a.qkv + (size_t)frame * a.L * 3 * a.d + head * HD;
-      float w[64];
-      load_row64(row0, w);  // q of token 0
+      uint32_t bq[8];
+      load_bfrag64(row0, lane, bq);  // q of token 0 as the B operand
       const uint32_t kc2 = __ldg(reinterpret_cast<const uint32_t*>(row0 + a.d) + lane);
-      const uint4 vc8 = __ldg(reinterpret_cast<const uint4*>(row0 + 2 * a.d) + (lane & 7));  // v_cls dims 8 (lane & 7) ..
+      uint32_t vcw[8];  // v_cls dims 8 nb + 2 (lane & 3), +1: the accumulator layout of lanes 0..3
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) vcw[nb] = __ldg(reinterpret_cast<const uint32_t*>(row0 + 2 * a.d) + 4 * nb + (lane & 3));
       if (lane < 3 && k + 1 < n_my) {  // next item's q / k / v rows of token 0 into L1
         const int nit = item + gridDim.x;
         prefetch_l1(a.qkv + (size_t)(nit / a.heads) * a.L * 3 * a.d + lane * a.d + (nit % a.heads) * HD);
@@ -1422,64 +1437,75 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       const uint32_t qc2 = __ldg(reinterpret_cast<const uint32_t*>(row0) + lane);
       const float sc0 = warp_sum(fmaf(bf_lo(qc2), bf_lo(kc2), bf_hi(qc2) * bf_hi(kc2))) * 0.125f;
       mbar_wait(qk_full(s), ring_par);
-      const uint32_t kst = qk_base + s * 2 * mat_bytes + mat_bytes;
+      if (!(VAR & 2)) tile_rows_dot_mma(qk_base + s * 2 * mat_bytes + mat_bytes, a.lk16 / 16, bq, pbuf, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qk_empty(s));
       float sj[8];
       float mx = sc0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int j = lane + 32 * i;
-        sj[i] = j < Lp ? swz_row_dot64(kst, j, w) * 0.125f : -INFINITY;
+        sj[i] = (j < Lp && !(VAR & 2)) ? pbuf[j] * 0.125f : -INFINITY;
         mx = fmaxf(mx, sj[i]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(qk_empty(s));
       mx = warp_max(mx);
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float p = __expf(sj[i] - mx);  // exp(-inf) = 0 for the padding keys
-        pbuf[lane + 32 * i] = p;
-        sum += p;
+        // exp(-inf) = 0 for the padding keys; rounded to bf16 like the probabilities of every other row, and the
+        // normaliser sums the ROUNDED values
+        const __nv_bfloat16 pb = __float2bfloat16_rn(__expf(sj[i] - mx));
+        pb16[lane + 32 * i] = pb;
+        sum += __bfloat162float(pb);
       }
       const float pc = __expf(sc0 - mx);
       sum = warp_sum(sum) + pc;
       __syncwarp();
       mbar_wait(v_full(s), ring_par);
-      // O = sum_j p_j V[j]: lane = (key group g = lane >> 3, dim chunk c = lane & 7); per step the warp reads four swizzled
-      // 128-byte V rows with one LDS.128 per lane (4 wavefronts: optimal), 8 FMAs per lane; the four key groups are
-      // reduced with two shuffle rounds at the end.
+      // O[64] = sum_j p_j V[j][:] on the warp-level tensor path: A = P (row 0 of the 16 x 16 fragment = 16 probabilities, the
+      // other rows zero: only lanes 0..3 hold non-zero A registers), B = V[16 keys x 8 dims] through ldmatrix.trans from
+      // the token-major swizzled tile (one x4 = two 8-dim blocks), fp32 accumulators: lane t < 4 ends up with dims
+      // 8 nb + 2 t, +1 of every 8-dim block nb.
       const uint32_t vst = v_base + s * mat_bytes;
-      const int g = lane >> 3;
-      const uint32_t c = (uint32_t)lane & 7u;
-      float acc[8];
+      float acc[8][4];
 #pragma unroll
-      for (int m = 0; m < 8; ++m) acc[m] = 0.f;
-#pragma unroll 2
-      for (int j0 = 0; j0 < a.lk16; j0 += 4) {
-        const int j = j0 + g;
-        const float pj = pbuf[j];
-        const uint4 v = lds128(vst + (uint32_t)j * 128u + ((c ^ (uint32_t)(j & 7)) << 4));
-        acc[0] = fmaf(pj, bf_lo(v.x), acc[0]); acc[1] = fmaf(pj, bf_hi(v.x), acc[1]);
-        acc[2] = fmaf(pj, bf_lo(v.y), acc[2]); acc[3] = fmaf(pj, bf_hi(v.y), acc[3]);
-        acc[4] = fmaf(pj, bf_lo(v.z), acc[4]); acc[5] = fmaf(pj, bf_hi(v.z), acc[5]);
-        acc[6] = fmaf(pj, bf_lo(v.w), acc[6]); acc[7] = fmaf(pj, bf_hi(v.w), acc[7]);
+      for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+      {
+        const uint32_t m = (uint32_t)lane >> 3, r = (uint32_t)lane & 7u;
+        const uint32_t rowoff = ((m & 1u) * 8u + r) * 128u;
+        const uint32_t pa = pb16_base + ((uint32_t)lane & 3u) * 4u;
+        for (int ks = 0; ks < ((VAR & 4) ? 0 : a.lk16 / 16); ++ks) {
+          uint32_t a0 = 0u, a2 = 0u;
+          if (lane < 4) {
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(pa + (uint32_t)ks * 32u));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a2) : "r"(pa + (uint32_t)ks * 32u + 16u));
+          }
+          const uint32_t ra = vst + (uint32_t)ks * 2048u + rowoff;
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            uint32_t b0, b1, b2, b3;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                         : "r"(ra + (((uint32_t(2 * np) + (m >> 1)) ^ r) << 4)));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[2 * np][0]), "+f"(acc[2 * np][1]), "+f"(acc[2 * np][2]), "+f"(acc[2 * np][3])
+                         : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[2 * np + 1][0]), "+f"(acc[2 * np + 1][1]), "+f"(acc[2 * np + 1][2]), "+f"(acc[2 * np + 1][3])
+                         : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b2), "r"(b3));
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(v_empty(s));
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 8);
-        acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 16);
-      }
-      if (lane < 8) {
+      if (lane < 4) {
         const float inv = 1.0f / sum;
-        uint4 o;
-        o.x = pack_bf16x2(fmaf(pc, bf_lo(vc8.x), acc[0]) * inv, fmaf(pc, bf_hi(vc8.x), acc[1]) * inv);
-        o.y = pack_bf16x2(fmaf(pc, bf_lo(vc8.y), acc[2]) * inv, fmaf(pc, bf_hi(vc8.y), acc[3]) * inv);
-        o.z = pack_bf16x2(fmaf(pc, bf_lo(vc8.z), acc[4]) * inv, fmaf(pc, bf_hi(vc8.z), acc[5]) * inv);
-        o.w = pack_bf16x2(fmaf(pc, bf_lo(vc8.w), acc[6]) * inv, fmaf(pc, bf_hi(vc8.w), acc[7]) * inv);
-        reinterpret_cast<uint4*>(a.out + (size_t)frame * a.L * a.d + (size_t)head * HD)[lane] = o;
+        uint32_t* orow = reinterpret_cast<uint32_t*>(a.out + (size_t)frame * a.L * a.d + (size_t)head * HD);
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+          orow[4 * nb + lane] = pack_bf16x2(fmaf(pc, bf_lo(vcw[nb]), acc[nb][0]) * inv, fmaf(pc, bf_hi(vcw[nb]), acc[nb][1]) * inv);
       }
+      __syncwarp();  // pbuf is rewritten by the next item's scores
     }
   } else if (warp >= 8) {
     // ===================== epilogue warps: drain O, add the CLS key, write the rows =====================
@@ -1510,7 +1536,13 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(s_empty(t));
-        if (warp_active && row < Lp) {
+        if (warp_active && row < Lp && (VAR & 8)) {
+          const float inv = 1.0f / __uint_as_float(rs);
+          __nv_bfloat16* orow = a.out + ((size_t)frame * a.L + row + 1) * a.d + (size_t)head * HD;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<uint4*>(orow)[i] = make_uint4(pack_bf16x2(__uint_as_float(o0[4 * i]) * inv, __uint_as_float(o0[4 * i + 1]) * inv), pack_bf16x2(__uint_as_float(o0[4 * i + 2]) * inv, __uint_as_float(o0[4 * i + 3]) * inv), pack_bf16x2(__uint_as_float(o1[4 * i]) * inv, __uint_as_float(o1[4 * i + 1]) * inv), pack_bf16x2(__uint_as_float(o1[4 * i + 2]) * inv, __uint_as_float(o1[4 * i + 3]) * inv));
+        } else if (warp_active && row < Lp) {
           const float inv = 1.0f / (__uint_as_float(rs) + pc);
           __nv_bfloat16* orow = a.out + ((size_t)frame * a.L + row + 1) * a.d + (size_t)head * HD;
           uint32_t vc[32];
@@ -1592,8 +1624,8 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         if (lane == 0) mbar_arrive_relaxed(pa_full(t));
       }
       // the CLS key, scored by warp 14: same stabiliser as the row's other keys; consumed by the epilogue warps
-      mbar_wait(c_full(k & 1), ((uint32_t)k >> 1) & 1u);
-      pcls[(k & 1) * 256 + row] = ex2_approx(fminf(fmaf(scls[(k & 1) * 256 + row], sc, -mxs), 120.f));
+      if (!(VAR & 16)) mbar_wait(c_full(k & 1), ((uint32_t)k >> 1) & 1u);
+      if (!(VAR & 16)) pcls[(k & 1) * 256 + row] = ex2_approx(fminf(fmaf(scls[(k & 1) * 256 + row], sc, -mxs), 120.f));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(c_empty(k & 1));
@@ -2056,6 +2088,11 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
   VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit: null pointer");
   VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 272, VMC_ERR_SHAPE,
                 "vmc_attention_vit: need 0 < L <= 272 tokens (L=%d)", L);
+  int var6 = 0;
+  if (impl >= 100 && impl < 132) {  // 100 + bits: what-if timing variants of v6 (wrong results)
+    var6 = impl - 100;
+    impl = 6;
+  }
   VMC_CHECK_ARG((impl >= 1 && impl <= 7) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 55), VMC_ERR_ARG,
                 "vmc_attention_vit: impl must be 1..7");
   const int d = heads * HD;
@@ -2103,6 +2140,7 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     a6.n_items = F * heads;
     a6.out = reinterpret_cast<__nv_bfloat16*>(out);
     a6.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    a6.var = var6;
     CUtensorMap tm6, tm6b;
     const uint64_t dims6[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)F};
     const uint64_t strides6[2] = {(uint64_t)3 * d * 2, (uint64_t)L * 3 * d * 2};
@@ -2110,13 +2148,18 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     const uint32_t box6b[3] = {HD, (uint32_t)(a6.lk16 - 128), 1};
     VMC_TRY(vmc_encode_tmap_bf16(&tm6, qkv, 3, dims6, strides6, box6));
     VMC_TRY(vmc_encode_tmap_bf16(&tm6b, qkv, 3, dims6, strides6, box6b));
-    const uint32_t smem6 = 6u * (uint32_t)a6.lk16 * 128u + 2048u + 5u * 1024u + 256u + 1024u;
+    const uint32_t smem6 = 6u * (uint32_t)a6.lk16 * 128u + 2048u + 5u * 1024u + 512u + 256u + 1024u;
     cudaStream_t st6 = reinterpret_cast<cudaStream_t>(stream);
     const int grid6 = a6.n_items < vmc_num_sms() ? a6.n_items : vmc_num_sms();
-    VMC_CUDA(cudaFuncSetAttribute(attention_vit6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6));
+    auto kern6 = var6 == 0 ? attention_vit6_kernel<0>
+                 : var6 == 1 ? attention_vit6_kernel<1>
+                 : var6 == 2 ? attention_vit6_kernel<2>
+                 : var6 == 4 ? attention_vit6_kernel<4>
+                 : var6 == 7 ? attention_vit6_kernel<7> : attention_vit6_kernel<31>;
+    VMC_CUDA(cudaFuncSetAttribute(kern6, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6));
     {
       VmcProfScope prof(VMC_K_ATTN_VIT, st6, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
-      attention_vit6_kernel<<<grid6, A6_THREADS, smem6, st6>>>(tm6, tm6b, a6);
+      kern6<<<grid6, A6_THREADS, smem6, st6>>>(tm6, tm6b, a6);
     }
     VMC_LAUNCH_CHECK();
     vmc_count_launch();
