@@ -857,3 +857,47 @@ def test_vit_tower_last_block_cls_only(cuda_device, name, nframes):
     cos = torch.nn.functional.cosine_similarity(full.double(), short.double(), dim=-1).min().item()
     assert cos >= 0.99999, cos  # the CLS path keeps the probabilities in fp32 where the tcgen05 path rounds them to bf16
     assert (full - short).abs().max().item() <= 5e-3 * full.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the launch-bound regime (inference.py:129: one clip at a time)
+# ------------------------------------------------------------------------------------------------
+def test_graphed_student_forward_matches_eager(cuda_device):
+    torch.manual_seed(3)
+    model = vmc.FlowStudentModel("ViT-B/32", device=cuda_device, num_classes=140).eval()
+    with torch.no_grad():
+        model.residual_mlp.fc2.weight.normal_(0, 0.02)
+    gen = torch.Generator().manual_seed(11)
+    clips = [torch.randint(0, 256, (1, 15, 3, 224, 224), dtype=torch.uint8, generator=gen).to(cuda_device) for _ in range(3)]
+    g = vmc.graphed(model, clips[0])
+    for c in clips + clips[:1]:  # replay with new contents, and again with the first clip
+        want = [t.clone() for t in model(c)]
+        got = g(c)
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and torch.equal(a, b)
+    with pytest.raises(ValueError):
+        g(clips[0][:, :7])
+
+
+def test_graphed_tfam_and_pipeline_match_eager(cuda_device):
+    torch.manual_seed(4)
+    tfam = vmc.AMO_CLIP(num_classes=140, device=cuda_device).to(cuda_device).eval()
+    gen = torch.Generator().manual_seed(12)
+    rgb = torch.randn(2, 16, 512, generator=gen).to(cuda_device)
+    mot = torch.randn(2, 15, 512, generator=gen).to(cuda_device)
+    mask_rgb = (torch.arange(16)[None, :] < torch.tensor([16, 12])[:, None]).to(cuda_device)
+    mask_mot = (torch.arange(15)[None, :] < torch.tensor([15, 11])[:, None]).to(cuda_device)
+    g = vmc.graphed(tfam, rgb, mot, mask_rgb, mask_mot)
+    for scale in (1.0, -0.5):
+        want = tfam(rgb * scale, mot * scale, mask_rgb, mask_mot).clone()
+        assert torch.equal(g(rgb * scale, mot * scale, mask_rgb, mask_mot), want)
+    g2 = vmc.graphed(tfam, rgb, mot, None, None)  # non-tensor arguments are baked in
+    assert torch.equal(g2(rgb, mot, None, None), tfam(rgb, mot))
+    pipe = vmc.ViMoCLIPPipeline("openai/clip-vit-base-patch32", "ViT-B/32", num_classes=140, device=cuda_device, clips_per_step=1)
+    r8 = torch.randint(0, 256, (1, 16, 3, 224, 224), dtype=torch.uint8, generator=gen).to(cuda_device)
+    m8 = torch.randint(0, 256, (1, 15, 3, 224, 224), dtype=torch.uint8, generator=gen).to(cuda_device)
+    gp = vmc.graphed(pipe, r8, m8)
+    want = [t.clone() for t in pipe(r8.flip(1).contiguous(), m8)]
+    got = gp(r8.flip(1).contiguous(), m8)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

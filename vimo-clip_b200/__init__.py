@@ -12,7 +12,8 @@ reference):
 All arithmetic of the path runs in hand-written sm_100a CUDA kernels reached through the C-ABI of
 ``include/vimoclip_b200.h`` (``libvimoclip_b200.so``).  There is no CPU fallback.
 """
-from . import _lib, indexing, ops, store  # noqa: F401
+from . import _lib, graphs, indexing, ops, store  # noqa: F401
+from .graphs import graphed  # noqa: F401
 from .clip_hf import CLIPImageProcessor, CLIPVisionFeatures  # noqa: F401
 from .losses import classification_loss, distillation_loss  # noqa: F401
 from .pipeline import ViMoCLIPPipeline  # noqa: F401
