@@ -938,11 +938,15 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
           const int s = kq & 1;
           const uint32_t q = qk_base + s * 2 * mat_bytes, kk_ = q + mat_bytes;
           VMC_DBG5(kq, 24);
-          mbar_arrive_expect_tx(qk_full(s), 2 * mat_bytes);
-          tma_load_3d(q, &tm, qk_full(s), a.cq + head * a.chead, 0, frame);
-          tma_load_3d(q + TILE, &tm1, qk_full(s), a.cq + head * a.chead, 128, frame);
-          tma_load_3d(kk_, &tm, qk_full(s), a.ck + head * a.chead, 0, frame);
-          tma_load_3d(kk_ + TILE, &tm1, qk_full(s), a.ck + head * a.chead, 128, frame);
+          if (VAR >= 4 && kq >= 2) {  // what-if: no loads after the first two items (ring contents reused): no HBM traffic
+            mbar_arrive(qk_full(s));
+          } else {
+            mbar_arrive_expect_tx(qk_full(s), 2 * mat_bytes);
+            tma_load_3d(q, &tm, qk_full(s), a.cq + head * a.chead, 0, frame);
+            tma_load_3d(q + TILE, &tm1, qk_full(s), a.cq + head * a.chead, 128, frame);
+            tma_load_3d(kk_, &tm, qk_full(s), a.ck + head * a.chead, 0, frame);
+            tma_load_3d(kk_ + TILE, &tm1, qk_full(s), a.ck + head * a.chead, 128, frame);
+          }
           ++kq;
         }
         if (kv < n_my && mbar_test_wait(v_empty(kv & 1), (((uint32_t)kv >> 1) & 1u) ^ 1u)) {
@@ -951,9 +955,13 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
           const int s = kv & 1;
           const uint32_t v = v_base + s * mat_bytes;
           VMC_DBG5(kv, 26);
-          mbar_arrive_expect_tx(v_full(s), mat_bytes);
-          tma_load_3d(v, &tm, v_full(s), a.cv + head * a.chead, 0, frame);
-          tma_load_3d(v + TILE, &tm1, v_full(s), a.cv + head * a.chead, 128, frame);
+          if (VAR >= 4 && kv >= 2) {
+            mbar_arrive(v_full(s));
+          } else {
+            mbar_arrive_expect_tx(v_full(s), mat_bytes);
+            tma_load_3d(v, &tm, v_full(s), a.cv + head * a.chead, 0, frame);
+            tma_load_3d(v + TILE, &tm1, v_full(s), a.cv + head * a.chead, 128, frame);
+          }
           ++kv;
         }
       }
@@ -1039,7 +1047,6 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       const uint32_t par = (uint32_t)k & 1u;
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {  // tile 0 leads tile 1 by half a period, so this is the completion order
-        const int row = t * 128 + q * 32 + lane;
         const bool warp_active = (t * 128 + q * 32) < a.L;  // warp-uniform
         const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
         mbar_wait(o_full(t), par);
@@ -1057,7 +1064,11 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(s_empty(t));
         if (q == 0 && lane == 0) VMC_DBG5(k, 12 + 8 * t);
-        if (warp_active && row < a.L) {
+        if (warp_active && (t * 128 + q * 32 + lane) < a.L && VAR != 6) {
+          // (A transposing epilogue -- 32 x 64 block through a swizzled smem tile so that a warp store covers 4 full 128-byte
+          // lines instead of 32 x 16 bytes -- was measured SLOWER, 0.395 vs 0.381 ms: the 12 % that what-if variant 6 (no
+          // stores) saves is the 0.31 GB of output traffic itself, not the store pattern.)
+          const int row = t * 128 + q * 32 + lane;
           const float inv = 1.0f / __uint_as_float(rs);
           __nv_bfloat16* orow = a.out + ((size_t)frame * a.L + row) * a.d + (size_t)head * HD;
 #pragma unroll
@@ -1096,7 +1107,7 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       mbar_wait(s_full(t), par);
       tc_fence_after();
       if (q == 0 && lane == 0) VMC_DBG5(k, 8 + 8 * t);
-      if (warp_active && VAR == 1) {
+      if (warp_active && (VAR == 1 || VAR == 5)) {
         if (lane == 0) mbar_arrive_relaxed(pa_full(t));
       } else if (warp_active) {
         // single pass over the score row, 32-column chunks double-buffered in registers; stabiliser = max of
@@ -1108,8 +1119,8 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
         for (int c = 0; c < n_chunks; c += 2) {
           if (c != 0) tmem_ld_wait();
           if (c + 1 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 1) * 32), r1);
-          if (c < n_full) chunk_exp_store5<false, VAR>(r0, sc, mxs, 32, pcol(c));
-          else chunk_exp_store5<true, VAR>(r0, sc, mxs, tail, pcol(c));
+          if (c < n_full) chunk_exp_store5<false, (VAR >= 4 ? 0 : VAR)>(r0, sc, mxs, 32, pcol(c));
+          else chunk_exp_store5<true, (VAR >= 4 ? 0 : VAR)>(r0, sc, mxs, tail, pcol(c));
           if (c == A5_PA_CHUNKS - 1) {
             // chunks 0..4 (keys 0..159) are stored: release part A of the PV MMA.  The load of chunk 5
             // issued above reads columns >= 160, disjoint from P_a and the accumulator.
@@ -1122,8 +1133,8 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
           if (c + 1 < n_chunks) {
             tmem_ld_wait();
             if (c + 2 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 2) * 32), r0);
-            if (c + 1 < n_full) chunk_exp_store5<false, VAR>(r1, sc, mxs, 32, pcol(c + 1));
-            else chunk_exp_store5<true, VAR>(r1, sc, mxs, tail, pcol(c + 1));
+            if (c + 1 < n_full) chunk_exp_store5<false, (VAR >= 4 ? 0 : VAR)>(r1, sc, mxs, 32, pcol(c + 1));
+            else chunk_exp_store5<true, (VAR >= 4 ? 0 : VAR)>(r1, sc, mxs, tail, pcol(c + 1));
           }
         }
         tmem_st_wait();
@@ -2093,7 +2104,7 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     var6 = impl - 100;
     impl = 6;
   }
-  VMC_CHECK_ARG((impl >= 1 && impl <= 7) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 55), VMC_ERR_ARG,
+  VMC_CHECK_ARG((impl >= 1 && impl <= 7) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
                 "vmc_attention_vit: impl must be 1..7");
   const int d = heads * HD;
   // v7 = two items packed per query tile in the v5 pipeline: default for short sequences (ViT-B/32: 50 tokens)
@@ -2191,6 +2202,9 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     cudaStream_t st5 = reinterpret_cast<cudaStream_t>(stream);
     const int grid5 = a5.n_items < vmc_num_sms() ? a5.n_items : vmc_num_sms();
     auto kern5 = impl == 5 ? attention_vit5_kernel<0>
+                 : impl == 56 ? attention_vit5_kernel<4>
+                 : impl == 57 ? attention_vit5_kernel<5>
+                 : impl == 58 ? attention_vit5_kernel<6>
                  : impl == 51 ? attention_vit5_kernel<1>
                  : impl == 52 ? attention_vit5_kernel<2>
                  : impl == 53 ? attention_vit5_kernel<3>
