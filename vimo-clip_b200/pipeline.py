@@ -25,13 +25,27 @@ class ViMoCLIPPipeline(nn.Module):
         self.clips_per_step = clips_per_step
         self.device = torch.device(device)
         self._copy_stream = None
+        self.ramp_first_chunk = True  # host inputs: small first chunk (see _chunks)
 
-    def _stage(self, rgb_u8, motion_u8, c0):
+    def _chunks(self, n_clips: int, on_host: bool):
+        """Clip ranges of the tower calls.  Device-resident inputs: ``clips_per_step`` clips each.  Host inputs: the FIRST chunk is
+        a quarter of that, because its host->device copy is the only one no kernel can overlap (128 clips of RGB frames = 308 MB,
+        ~12 ms of PCIe before the first kernel starts; 32 clips = 3 ms), then full chunks."""
+        cps = self.clips_per_step
+        first = max(1, cps // 4) if (on_host and self.ramp_first_chunk and n_clips > cps // 4 and cps >= 4) else cps
+        bounds, c0 = [], 0
+        while c0 < n_clips:
+            c1 = min(n_clips, c0 + (first if c0 == 0 else cps))
+            bounds.append((c0, c1))
+            c0 = c1
+        return bounds
+
+    def _stage(self, rgb_u8, motion_u8, c0, c1):
         """Queue the host->device copies of one clip chunk on the copy stream: RGB first, then motion, each with its own
         event, so the RGB tower starts as soon as ITS frames have arrived while the motion frames are still in flight.
         Returns (rgb, rgb_event, motion, motion_event)."""
-        r = rgb_u8[c0:c0 + self.clips_per_step]
-        m = motion_u8[c0:c0 + self.clips_per_step]
+        r = rgb_u8[c0:c1]
+        m = motion_u8[c0:c1]
         if r.is_cuda and m.is_cuda:
             return r, None, m, None
         if self._copy_stream is None:
@@ -59,12 +73,12 @@ class ViMoCLIPPipeline(nn.Module):
         kernels of chunk i; the towers batch every frame of a chunk."""
         N, T = rgb_u8.shape[:2]
         e_rgb, e_mot = [], []
-        starts = list(range(0, N, self.clips_per_step))
-        staged = self._stage(rgb_u8, motion_u8, starts[0])
-        for k, c0 in enumerate(starts):
+        chunks = self._chunks(N, on_host=not (rgb_u8.is_cuda and motion_u8.is_cuda))
+        staged = self._stage(rgb_u8, motion_u8, *chunks[0])
+        for k in range(len(chunks)):
             r, ev_r, m, ev_m = staged
-            if k + 1 < len(starts):
-                staged = self._stage(rgb_u8, motion_u8, starts[k + 1])
+            if k + 1 < len(chunks):
+                staged = self._stage(rgb_u8, motion_u8, *chunks[k + 1])
             compute = torch.cuda.current_stream(self.device)
             if ev_r is not None:
                 compute.wait_event(ev_r)
