@@ -233,6 +233,19 @@ int vmc_layernorm_bwd(const float* z, long long ldz, const float* gamma, float e
 int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* out, long long n, void* stream);
 /* y = bf16(QuickGELU(x)) over n contiguous fp32 elements (n % 4 == 0): the c_fc activation of the student's training forward */
 int vmc_qgelu_cast(const float* x, void* y, long long n, void* stream);
+/* Fused LayerNorm backward of the residual stream (d = 512 / 768 / 1024): dz = LN'(z; gamma)[dy] (+ add, the gradient arriving over
+ * the residual branch), dgamma_dbeta[0..d) = sum_r dy * xhat, [d..2d) = sum_r dy.  workspace: vmc_layernorm_bwd_fused_blocks(rows) * 2 * d
+ * floats (per-block partials, added in block order: deterministic). */
+int vmc_layernorm_bwd_fused_blocks(int rows);
+int vmc_layernorm_bwd_fused(const float* z, long long ldz, const float* gamma, float eps, const float* dy, long long lddy,
+                            const float* add, long long ldadd, float* dz, long long lddz, float* dgamma_dbeta, float* workspace,
+                            int rows, int d, void* stream);
+/* Fused pass of the bf16 Linear backward (train.py:104 loss.backward(), the nn.Linear grad of dY): y16 = bf16(v), colsum[c] = sum_r v[r,c]
+ * with v = x, or v = x * QuickGELU'(aux) when aux (the c_fc pre-activation) is given -- replaces an element-wise backward, a cast and a
+ * column sum (three passes over the fp32 gradient) by one.  workspace: vmc_cast_colsum_slices(R, C) * C floats. */
+int vmc_cast_colsum_slices(int R, int C);
+int vmc_cast_colsum(const float* x, long long ldx, const float* aux, long long ldaux, void* y16, long long ldy, float* colsum,
+                    int R, int C, float* workspace, void* stream);
 /* ViT self-attention backward for towers of at most 64 tokens (ViT-B/32), straight from the packed bf16 qkv buffer
  * [F*L, 3*heads*64]: dqkv fp32 [F*L, 3*heads*64] from dO fp32 [F*L, heads*64] (row stride lddo) */
 int vmc_attention_vit_bwd_short(const void* qkv, const float* dO, long long lddo, float* dqkv, int F, int L, int heads,

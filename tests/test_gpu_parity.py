@@ -901,3 +901,42 @@ def test_graphed_tfam_and_pipeline_match_eager(cuda_device):
     got = gp(r8.flip(1).contiguous(), m8)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("R,C,qgelu", [(25600, 768, False), (1000, 3072, True), (37, 96, True), (50, 2304, False), (300, 200, True)])
+def test_cast_colsum_fused_pass(cuda_device, R, C, qgelu):
+    """vmc_cast_colsum == (QuickGELU backward,) bf16 cast and fp32 column sum done separately."""
+    gen = torch.Generator(device="cuda").manual_seed(R + C)
+    x = torch.randn(R, C, device=cuda_device, generator=gen)
+    aux = torch.randn(R, C, device=cuda_device, generator=gen) * 2 if qgelu else None
+    y16, cs = ops.cast_colsum(x, aux)
+    v = x.double()
+    if qgelu:
+        sg = torch.sigmoid(1.702 * aux.double())
+        v = v * sg * (1 + 1.702 * aux.double() * (1 - sg))
+    assert (y16.double() - v).abs().max().item() <= 2.0 ** -8 * v.abs().max().item() + 1e-6  # one bf16 rounding (+ __expf)
+    ref = v.sum(0)
+    assert (cs.double() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    y2, cs2 = ops.cast_colsum(x, aux)
+    assert torch.equal(cs, cs2) and torch.equal(y16.view(torch.int16), y2.view(torch.int16))  # deterministic
+
+
+@pytest.mark.parametrize("rows,d,with_add", [(25600, 768, True), (300, 512, False), (77, 1024, True), (5000, 640, True)])
+def test_layernorm_backward_fused_matches_autograd(cuda_device, rows, d, with_add):
+    """Fused LayerNorm backward (dz + residual gradient, dgamma / dbeta partials in registers; d = 512 / 768 / 1024) and the generic
+    fallback (d = 640) against fp32 autograd."""
+    gen = torch.Generator(device="cuda").manual_seed(rows + d)
+    z = torch.randn(rows, d, device=cuda_device, generator=gen) * 1.5 + 0.3
+    gamma = torch.randn(d, device=cuda_device, generator=gen) * 0.2 + 1.0
+    beta = torch.randn(d, device=cuda_device, generator=gen) * 0.1
+    dy = torch.randn(rows, d, device=cuda_device, generator=gen)
+    add = torch.randn(rows, d, device=cuda_device, generator=gen) if with_add else None
+    zz, gg, bb = z.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    torch.nn.functional.layer_norm(zz, (d,), gg, bb, 1e-5).backward(dy)
+    want_dz = zz.grad + (add if with_add else 0)
+    dz, dg, db = ops.layernorm_bwd(z, gamma, 1e-5, dy, add=add)
+    assert (dz - want_dz).abs().max().item() <= 2e-5 * max(1.0, want_dz.abs().max().item())
+    assert (dg - gg.grad).abs().max().item() <= 2e-4 * max(1.0, gg.grad.abs().max().item())
+    assert (db - bb.grad).abs().max().item() <= 2e-4 * max(1.0, bb.grad.abs().max().item())
+    dz2, dg2, db2 = ops.layernorm_bwd(z, gamma, 1e-5, dy, add=add)
+    assert torch.equal(dz, dz2) and torch.equal(dg, dg2) and torch.equal(db, db2)  # deterministic

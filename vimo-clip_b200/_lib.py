@@ -93,6 +93,11 @@ _SIGNATURES = {
     "vmc_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     "vmc_eltwise": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
     "vmc_qgelu_cast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "vmc_layernorm_bwd_fused_blocks": (C.c_int, [C.c_int]),
+    "vmc_layernorm_bwd_fused": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+                                          C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vmc_cast_colsum_slices": (C.c_int, [C.c_int, C.c_int]),
+    "vmc_cast_colsum": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vmc_attention_vit_bwd_short": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vmc_broadcast_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "vmc_attention_masked_train": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -419,12 +419,42 @@ def colsum(x: torch.Tensor, y: torch.Tensor | None = None, out: torch.Tensor | N
     return out
 
 
-def layernorm_bwd(z: torch.Tensor, gamma: torch.Tensor, eps: float, dy: torch.Tensor):
-    """-> (dz, dgamma, dbeta) for y = LayerNorm(z) * gamma + beta; z is the saved LayerNorm input."""
-    _need_cuda(z, gamma, dy)
-    _f32_2d(z, dy)
+def cast_colsum(x: torch.Tensor, aux: torch.Tensor | None = None):
+    """One pass over an fp32 gradient [R, C] (C a multiple of 4): -> (bf16 copy [R, C], column sums [C] of the unrounded values);
+    with ``aux`` (the c_fc pre-activation) the QuickGELU backward ``x * qgelu'(aux)`` is applied first."""
+    _need_cuda(x, aux)
+    _f32_2d(x, aux)
+    R, Cn = x.shape
+    y = torch.empty((R, Cn), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(Cn, dtype=torch.float32, device=x.device)
+    slices = int(_lib.lib().vmc_cast_colsum_slices(R, Cn))
+    ws = torch.empty(max(1, slices) * Cn, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vmc_cast_colsum(_p(x), x.stride(0), _p(aux), 0 if aux is None else aux.stride(0), _p(y), y.stride(0), _p(out),
+                                              R, Cn, _p(ws), _stream()), "vmc_cast_colsum")
+    return y, out
+
+
+def layernorm_bwd(z: torch.Tensor, gamma: torch.Tensor, eps: float, dy: torch.Tensor, add: torch.Tensor | None = None):
+    """-> (dz [+ add], dgamma, dbeta) for y = LayerNorm(z) * gamma + beta; z is the saved LayerNorm input; ``add`` = the gradient
+    that reaches z over the residual branch (pre-LN blocks), summed in the same pass."""
+    _need_cuda(z, gamma, dy, add)
+    _f32_2d(z, dy, add)
     rows, d = z.shape
     dz = torch.empty_like(z)
+    if d in (512, 768, 1024) and gamma.dtype == torch.float32 and gamma.is_contiguous():
+        L = _lib.lib()
+        blocks = int(L.vmc_layernorm_bwd_fused_blocks(rows))
+        ws = torch.empty(blocks * 2 * d, dtype=torch.float32, device=z.device)
+        gb = torch.empty(2 * d, dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            _lib.check(L.vmc_layernorm_bwd_fused(_p(z), z.stride(0), _p(gamma), float(eps), _p(dy), dy.stride(0), _p(add),
+                                                 0 if add is None else add.stride(0), _p(dz), dz.stride(0), _p(gb), _p(ws), rows, d, _stream()),
+                       "vmc_layernorm_bwd_fused")
+        return dz, gb[:d], gb[d:]
+    if add is not None:
+        dz0, dg, db = layernorm_bwd(z, gamma, eps, dy)
+        return eltwise(ELT_ADD, add.contiguous(), dz0), dg, db
     xhat = torch.empty_like(z)
     with torch.cuda.device(z.device):
         _lib.check(_lib.lib().vmc_layernorm_bwd(_p(z), z.stride(0), _p(gamma), float(eps), _p(dy), dy.stride(0), _p(dz), dz.stride(0),

@@ -51,10 +51,17 @@ def _gemm16(a16, w16, **kw):
     return ops.gemm(a16, w16, **kw)
 
 
-def _lin_bwd16(dy32, x16, w32, need_dx=True):
+def _lin_bwd16(dy32, x16, w32, need_dx=True, qgelu_pre=None):
     """bf16 Linear backward: y = x W^T + b with x16 [M,K] bf16 (saved), W [N,K] fp32 parameter, dy fp32 [M,N].
-    Returns (dx fp32 | None, dW fp32 [N,K], db fp32 [N])."""
+    Returns (dx fp32 | None, dW fp32 [N,K], db fp32 [N]).  With ``qgelu_pre`` (the layer's pre-activation, fp32 [M,N]) ``dy32`` is
+    the gradient AFTER the QuickGELU and the activation backward is applied in the same pass that casts it and sums its columns."""
     M, N = dy32.shape
+    if N % 8 == 0 and dy32.is_contiguous():
+        dy16, db = ops.cast_colsum(dy32, qgelu_pre)  # one pass: (activation backward,) bf16 operand, bias gradient
+        dx = _gemm16(dy16, _bf(w32), w_t=True, out_dtype=torch.float32) if need_dx else None
+        return dx, _gemm16(dy16, x16, a_t=True, w_t=True, out_dtype=torch.float32), db
+    if qgelu_pre is not None:
+        dy32 = ops.eltwise(ops.ELT_QGELU_BWD, dy32, qgelu_pre)
     dy16 = ops.cast_bf16(dy32)[:, :N]  # (row stride padded to a multiple of 8 when N is not one)
     dx = None
     if need_dx:  # dx[M,K] = dy[M,N] W[N,K]: W [N,K] row-major IS the transposed "weight" operand (MN-major B)
@@ -158,16 +165,13 @@ class StudentTrainFunction(torch.autograd.Function):
             s = ctx.saved[li]
             # x_next = x_mid + c_proj(QuickGELU(c_fc(ln_2(x_mid))))
             dh, g_w2, g_b2 = _lin_bwd16(dx, s["h16"], w2)
-            dh_pre = ops.eltwise(ops.ELT_QGELU_BWD, dh, s["h_pre"])
-            dxn2, g_w1, g_b1 = _lin_bwd16(dh_pre, s["xn2"], w1)
-            dz2, g_g2, g_bt2 = ops.layernorm_bwd(s["x_mid"], g2.detach().float(), 1e-5, dxn2)
-            dx_mid = ops.eltwise(ops.ELT_ADD, dx, dz2)
+            dxn2, g_w1, g_b1 = _lin_bwd16(dh, s["xn2"], w1, qgelu_pre=s["h_pre"])  # QuickGELU backward fused into the cast pass
+            dx_mid, g_g2, g_bt2 = ops.layernorm_bwd(s["x_mid"], g2.detach().float(), 1e-5, dxn2, add=dx)  # + residual branch
             # x_mid = x + out_proj(attn(ln_1(x)))
             da, g_wo, g_bo = _lin_bwd16(dx_mid, s["a"], wo)
             dqkv = ops.attention_vit_bwd(s["qkv"], da, F_, L, heads)
             dxn, g_wqkv, g_bqkv = _lin_bwd16(dqkv, s["xn"], wqkv)
-            dz1, g_g1, g_bt1 = ops.layernorm_bwd(s["x"], g1.detach().float(), 1e-5, dxn)
-            dx = ops.eltwise(ops.ELT_ADD, dx_mid, dz1)
+            dx, g_g1, g_bt1 = ops.layernorm_bwd(s["x"], g1.detach().float(), 1e-5, dxn, add=dx_mid)
             grads_blocks[li] = [g_g1, g_bt1, g_wqkv, g_bqkv, g_wo, g_bo, g_g2, g_bt2, g_w1, g_b1, g_w2, g_b2]
         # ---- ln_pre, embeddings, patch embedding ----
         dz0, g_gpre, g_bpre = ops.layernorm_bwd(m["z0"], gpre.detach().float(), 1e-5, dx)
