@@ -32,7 +32,7 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel,
  * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row sums from the tensor core (L <= 224), 3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
  * Both implementations of each op are kept so the tests can cross-check them. */
-enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* 1 = first-generation shared-memory attention backward (cross-checks) */,
+enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* ViT attention backward, L <= 64: 0 = warp-level tensor-core kernel (ldmatrix + mma.sync), 2 = register-tiled fp32 kernel, 1 = first-generation shared-memory kernel (cross-checks) */,
        VMC_OPT_LAST_BLOCK_CLS = 5 /* ViT tower, opt-in: 1 = in the LAST block compute only what the output reads (the CLS row):
                                      K / V of all tokens, but query, out_proj, ln_2 and the MLP on the F CLS rows only */,
        VMC_OPT_ATTN_PREFETCH = 6 /* ViT attention: experiment, L <= 64 kernel: L2 prefetch distance of the TMA producer in CTA iterations (0 = off, the default: measured slower) */,

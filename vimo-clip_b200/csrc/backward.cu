@@ -1019,8 +1019,218 @@ int vmc_broadcast_rows(const float* g, float* out, int B, int T, int d, float sc
   return VMC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// ViT self-attention backward for short sequences (L <= 64: ViT-B/32, the reference's training default) on the warp-level
+// tensor path (ldmatrix + mma.sync.m16n8k16, bf16 operands, fp32 accumulation).  The register-tiled CUDA-core kernel above
+// runs the five 64 x 64 x 64 products of an item at 19 TFLOP/s (6.2 ms of a 30 ms training step).  One CTA of 4 warps per
+// (frame, head); Q, K, V (bf16, from the saved qkv buffer) and dO (fp32 -> bf16) are staged as 64 x 64 tiles with 128-byte
+// rows whose 16-byte chunks are XOR-swizzled with (row & 7), so every ldmatrix is conflict free.
+//   phase 1, warp w = queries 16 w .. 16 w + 15:  S = Q K^T / 8 and dP = dO V^T (A fragments of Q / dO, B fragments of K / V
+//     straight from the token-major tiles), row softmax P and delta = sum_j P dP in registers (a row lives in one lane quad),
+//     dS = P (dP - delta) / 8, then dQ = dS K with dS re-packed from accumulator to A-fragment layout and K through
+//     ldmatrix.trans; P and dS (bf16) go to shared memory;
+//   phase 2, warp w = keys 16 w .. 16 w + 15:  dV = P^T dO and dK = dS^T Q, the transposed A fragments through ldmatrix.trans.
+// Every sum runs in a fixed order: deterministic.  Operands are rounded to bf16 once (P, dS, dO), like every GEMM of the step.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t swz(uint32_t base, int row, int chunk) {
+  return base + (uint32_t)row * 128u + (((uint32_t)chunk ^ ((uint32_t)row & 7u)) << 4);
+}
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128)
+attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ dO, long long lddo,
+                         float* __restrict__ dqkv, int L, int heads) {
+  extern __shared__ __align__(1024) uint8_t bw_smem[];
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(bw_smem);
+  const uint32_t sQ = sb, sK = sb + 8192u, sV = sb + 16384u, sD = sb + 24576u, sP = sb + 32768u, sS = sb + 40960u;
+  const int head = blockIdx.x, frame = blockIdx.y;
+  const int d = heads * HD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const size_t row0 = (size_t)frame * L;
+
+  // ---- stage Q, K, V (bf16) and dO (fp32 -> bf16); rows >= L are zero ----
+  for (int i = tid; i < 3 * 64 * 8; i += 128) {
+    const int mat = i >> 9, r = (i >> 3) & 63, c = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < L) v = __ldg(reinterpret_cast<const uint4*>(qkv + (row0 + r) * 3 * d + (size_t)mat * d + head * HD) + c);
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(swz(sb + (uint32_t)mat * 8192u, r, c)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  for (int i = tid; i < 64 * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < L) {
+      const float4* src = reinterpret_cast<const float4*>(dO + (row0 + r) * lddo + head * HD + c * 8);
+      const float4 lo = __ldg(src), hi = __ldg(src + 1);
+      v = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+    }
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(swz(sD, r, c)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  __syncthreads();
+
+  const int lm = lane >> 3, lr = lane & 7;  // ldmatrix: this lane supplies row lr of matrix lm
+  // ================= phase 1: this warp's 16 queries =================
+  {
+    const int q0 = 16 * warp;
+    uint32_t aQ[4][4], aD[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      ldsm4(swz(sQ, q0 + (lm & 1) * 8 + lr, 2 * ks + (lm >> 1)), aQ[ks]);
+      ldsm4(swz(sD, q0 + (lm & 1) * 8 + lr, 2 * ks + (lm >> 1)), aD[ks]);
+    }
+    float sa[8][4], pa[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sa[nb][e] = pa[nb][e] = 0.f;
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {  // key blocks 2 np, 2 np + 1
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t bk[4], bv[4];
+        ldsm4(swz(sK, 8 * (2 * np + (lm >> 1)) + lr, 2 * ks + (lm & 1)), bk);
+        ldsm4(swz(sV, 8 * (2 * np + (lm >> 1)) + lr, 2 * ks + (lm & 1)), bv);
+        mma16816(sa[2 * np], aQ[ks], bk[0], bk[1]);
+        mma16816(sa[2 * np + 1], aQ[ks], bk[2], bk[3]);
+        mma16816(pa[2 * np], aD[ks], bv[0], bv[1]);
+        mma16816(pa[2 * np + 1], aD[ks], bv[2], bv[3]);
+      }
+    }
+    // softmax over the keys (rows g and g + 8 of the warp's block; a row is spread over the 4 lanes of a quad)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = 8 * nb + 2 * tig + e < L;
+        sa[nb][e] = ok ? sa[nb][e] * 0.125f : -INFINITY;
+        sa[nb][2 + e] = ok ? sa[nb][2 + e] * 0.125f : -INFINITY;
+        mx0 = fmaxf(mx0, sa[nb][e]);
+        mx1 = fmaxf(mx1, sa[nb][2 + e]);
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sm0 = 0.f, sm1 = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sa[nb][e] = __expf(sa[nb][e] - mx0);
+        sa[nb][2 + e] = __expf(sa[nb][2 + e] - mx1);
+        sm0 += sa[nb][e];
+        sm1 += sa[nb][2 + e];
+      }
+    sm0 += __shfl_xor_sync(0xffffffffu, sm0, 1); sm0 += __shfl_xor_sync(0xffffffffu, sm0, 2);
+    sm1 += __shfl_xor_sync(0xffffffffu, sm1, 1); sm1 += __shfl_xor_sync(0xffffffffu, sm1, 2);
+    const float i0 = 1.0f / sm0, i1 = 1.0f / sm1;
+    float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sa[nb][e] *= i0;
+        sa[nb][2 + e] *= i1;
+        dl0 = fmaf(sa[nb][e], pa[nb][e], dl0);
+        dl1 = fmaf(sa[nb][2 + e], pa[nb][2 + e], dl1);
+      }
+    dl0 += __shfl_xor_sync(0xffffffffu, dl0, 1); dl0 += __shfl_xor_sync(0xffffffffu, dl0, 2);
+    dl1 += __shfl_xor_sync(0xffffffffu, dl1, 1); dl1 += __shfl_xor_sync(0xffffffffu, dl1, 2);
+    // P and dS = P (dP - delta) / 8 as bf16: to shared memory for phase 2, dS also as the A operand of dQ = dS K
+    uint32_t pds[8][2];  // dS pairs of rows g / g + 8
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const float s00 = sa[nb][0] * (pa[nb][0] - dl0) * 0.125f, s01 = sa[nb][1] * (pa[nb][1] - dl0) * 0.125f;
+      const float s10 = sa[nb][2] * (pa[nb][2] - dl1) * 0.125f, s11 = sa[nb][3] * (pa[nb][3] - dl1) * 0.125f;
+      pds[nb][0] = pack_bf16x2(s00, s01);
+      pds[nb][1] = pack_bf16x2(s10, s11);
+      const uint32_t o = 4u * (uint32_t)tig;
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(swz(sP, q0 + g, nb) + o), "r"(pack_bf16x2(sa[nb][0], sa[nb][1])) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(swz(sP, q0 + g + 8, nb) + o), "r"(pack_bf16x2(sa[nb][2], sa[nb][3])) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(swz(sS, q0 + g, nb) + o), "r"(pds[nb][0]) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(swz(sS, q0 + g + 8, nb) + o), "r"(pds[nb][1]) : "memory");
+    }
+    // dQ = dS K: A = dS (k-step kk = key blocks 2 kk, 2 kk + 1), B[k = key][n = dim] through ldmatrix.trans of the K tile
+    float dq[8][4];
+#pragma unroll
+    for (int db = 0; db < 8; ++db) dq[db][0] = dq[db][1] = dq[db][2] = dq[db][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t a[4] = {pds[2 * kk][0], pds[2 * kk][1], pds[2 * kk + 1][0], pds[2 * kk + 1][1]};
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        uint32_t b[4];
+        ldsm4t(swz(sK, 16 * kk + (lm & 1) * 8 + lr, 2 * cp + (lm >> 1)), b);
+        mma16816(dq[2 * cp], a, b[0], b[1]);
+        mma16816(dq[2 * cp + 1], a, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int tok = q0 + g + 8 * h;
+      if (tok < L) {
+        float* o = dqkv + (row0 + tok) * 3 * d + head * HD + 2 * tig;
+#pragma unroll
+        for (int db = 0; db < 8; ++db) *reinterpret_cast<float2*>(o + 8 * db) = make_float2(dq[db][2 * h], dq[db][2 * h + 1]);
+      }
+    }
+  }
+  __syncthreads();
+  // ================= phase 2: this warp's 16 keys: dV = P^T dO, dK = dS^T Q =================
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const uint32_t sA = which == 0 ? sP : sS, sB = which == 0 ? sD : sQ;
+    float acc[8][4];
+#pragma unroll
+    for (int db = 0; db < 8; ++db) acc[db][0] = acc[db][1] = acc[db][2] = acc[db][3] = 0.f;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {  // 16 queries per k-step
+      uint32_t a[4];  // A[m = key][k = query] = transposed 8 x 8 blocks of the [query][key] tile
+      ldsm4t(swz(sA, 16 * kq + (lm >> 1) * 8 + lr, 2 * warp + (lm & 1)), a);
+#pragma unroll
+      for (int cp = 0; cp < 4; ++cp) {
+        uint32_t b[4];  // B[k = query][n = dim]
+        ldsm4t(swz(sB, 16 * kq + (lm & 1) * 8 + lr, 2 * cp + (lm >> 1)), b);
+        mma16816(acc[2 * cp], a, b[0], b[1]);
+        mma16816(acc[2 * cp + 1], a, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int tok = 16 * warp + g + 8 * h;
+      if (tok < L) {
+        float* o = dqkv + (row0 + tok) * 3 * d + (size_t)(which == 0 ? 2 : 1) * d + head * HD + 2 * tig;
+#pragma unroll
+        for (int db = 0; db < 8; ++db) *reinterpret_cast<float2*>(o + 8 * db) = make_float2(acc[db][2 * h], acc[db][2 * h + 1]);
+      }
+    }
+  }
+}
+
 int vmc_attention_vit_bwd_short(const void* qkv, const float* dO, long long lddo, float* dqkv, int F, int L, int heads,
                                 void* stream) {
+  if (vmc_get_option(VMC_OPT_ATTN_BWD_IMPL) == 0 && F > 0 && F <= 65535 && heads > 0 && L > 0 && L <= 64 && qkv && dO && dqkv &&
+      (lddo % 4) == 0 && (reinterpret_cast<uintptr_t>(dO) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dqkv) & 7) == 0) {
+    // default: warp-level tensor-core kernel (VMC_OPT_ATTN_BWD_IMPL = 2 selects the register-tiled CUDA-core kernel, 1 the first one)
+    cudaStream_t stm = reinterpret_cast<cudaStream_t>(stream);
+    {
+      VmcProfScope prof(VMC_K_ATTN_SMALL, stm, 10.0 * F * heads * (double)L * L * HD, 0.0);
+      attention_bwd_mma_kernel<<<dim3(heads, F), 128, 49152, stm>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), dO, lddo, dqkv, L, heads);
+    }
+    VMC_LAUNCH_CHECK();
+    vmc_count_launch();
+    return VMC_OK;
+  }
   VMC_CHECK_ARG(qkv && dO && dqkv, VMC_ERR_ARG, "vmc_attention_vit_bwd_short: null pointer");
   VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 64 && F <= 65535 && (lddo % 4) == 0, VMC_ERR_SHAPE,
                 "vmc_attention_vit_bwd_short: need 0 < L <= 64 tokens (L=%d); longer towers go through vmc_attention_masked_bwd", L);
