@@ -30,7 +30,7 @@ const char* vmc_last_error(void);
 int vmc_abi_version(void);
 int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel,
- * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL: 0/5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row sums from the tensor core (L <= 224), 3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
+ * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL (0 = by sequence length: 7 for L <= 64, 5 for 129..224, 6 for 225..257, else 2; 8 = warp-level mma.sync kernel for L <= 64): 0/5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row sums from the tensor core (L <= 224), 3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
  * Both implementations of each op are kept so the tests can cross-check them. */
 enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* ViT attention backward, L <= 64: 0 = warp-level tensor-core kernel (ldmatrix + mma.sync), 2 = register-tiled fp32 kernel, 1 = first-generation shared-memory kernel (cross-checks) */,
        VMC_OPT_LAST_BLOCK_CLS = 5 /* ViT tower, opt-in: 1 = in the LAST block compute only what the output reads (the CLS row):
@@ -166,6 +166,8 @@ int vmc_layernorm_stats(const float* x, long long ldx, const float* gamma, const
  * Replaces nn.MultiheadAttention inside OpenAI ResidualAttentionBlock / HF CLIPAttention.
  */
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream);
+/* short sequences (L <= 64) on the warp-level tensor path (ldmatrix + mma.sync), one CTA per (frame, head); = vmc_attention_vit_impl(..., 8, ...) */
+int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
 /* CLS-query attention of the last block (VMC_OPT_LAST_BLOCK_CLS): q_cls bf16 [F, d], kv bf16 [F*L, 2d] = [k | v] -> out bf16 [F, d] */
 int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L, int heads, void* stream);
 /* same, selecting the implementation: 3 = persistent, pipelined kernel with 8 softmax warps (default for

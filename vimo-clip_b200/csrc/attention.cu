@@ -2091,6 +2091,7 @@ uint32_t pow2_at_least(uint32_t v) {
 
 int vmc_get_option(int option);
 long long vmc_get_option64(int option);
+extern "C" int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
 
 extern "C" {
 
@@ -2104,9 +2105,13 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     var6 = impl - 100;
     impl = 6;
   }
-  VMC_CHECK_ARG((impl >= 1 && impl <= 7) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 1..7");
+  VMC_CHECK_ARG((impl >= 1 && impl <= 8) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 1..8");
   const int d = heads * HD;
+  if (impl == 8) {  // warp-level tensor path for short sequences (backward.cu)
+    if (L <= 64) return vmc_attention_vit_short_mma(qkv, out, F, L, heads, stream);
+    impl = 5;
+  }
   // v7 = two items packed per query tile in the v5 pipeline: default for short sequences (ViT-B/32: 50 tokens)
   if (impl == 5 && L <= 64) impl = 7;
   if (impl == 7 && L > 64) impl = 5;
@@ -2330,7 +2335,7 @@ int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L
 
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream) {
   const int opt = vmc_get_option(VMC_OPT_ATTN_IMPL);
-  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt >= 1 && opt <= 5) ? opt : 5, stream);
+  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt >= 1 && opt <= 8) ? opt : 5, stream);
 }
 
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk,

@@ -1237,6 +1237,131 @@ attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
   }
 }
 
+// Forward for short sequences on the same warp-level tensor path (VMC_OPT_ATTN_IMPL = 8): one CTA of 4 warps per (frame, head),
+// 24 KB of shared memory (Q, K, V tiles) -> nine CTAs per SM hide the staging latency that the persistent tcgen05 kernel (v7: two
+// tiles in flight per SM, bound by its S -> softmax -> PV -> drain chain) cannot.  A warp owns 16 queries: S = Q K^T (ldmatrix +
+// mma.sync), single-pass row softmax inside a lane quad, P kept in registers and re-packed from accumulator to A-fragment layout
+// (bf16, the normaliser sums the ROUNDED values), O = P V with V through ldmatrix.trans, rows staged through the warp's own
+// (dead) Q rows so that they leave as full 128-byte lines.
+__global__ void __launch_bounds__(128)
+attention_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int L, int heads) {
+  extern __shared__ __align__(1024) uint8_t fw_smem[];
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(fw_smem);
+  const uint32_t sQ = sb, sK = sb + 8192u, sV = sb + 16384u;
+  const int head = blockIdx.x, frame = blockIdx.y;
+  const int d = heads * HD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const size_t row0 = (size_t)frame * L;
+  {
+    uint4 v[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const int i = tid + 128 * j;
+      const int mat = i >> 9, r = (i >> 3) & 63, c = i & 7;
+      v[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < L) v[j] = __ldg(reinterpret_cast<const uint4*>(qkv + (row0 + r) * 3 * d + (size_t)mat * d + head * HD) + c);
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const int i = tid + 128 * j;
+      const int mat = i >> 9, r = (i >> 3) & 63, c = i & 7;
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(swz(sb + (uint32_t)mat * 8192u, r, c)), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w) : "memory");
+    }
+  }
+  __syncthreads();
+  const int q0 = 16 * warp;
+  if (q0 >= L) return;  // warp-uniform: no query of this warp exists (no further block-wide barrier below)
+  const int lm = lane >> 3, lr = lane & 7;
+  uint32_t aQ[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm4(swz(sQ, q0 + (lm & 1) * 8 + lr, 2 * ks + (lm >> 1)), aQ[ks]);
+  float sa[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) sa[nb][0] = sa[nb][1] = sa[nb][2] = sa[nb][3] = 0.f;
+#pragma unroll
+  for (int np = 0; np < 4; ++np)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bk[4];
+      ldsm4(swz(sK, 8 * (2 * np + (lm >> 1)) + lr, 2 * ks + (lm & 1)), bk);
+      mma16816(sa[2 * np], aQ[ks], bk[0], bk[1]);
+      mma16816(sa[2 * np + 1], aQ[ks], bk[2], bk[3]);
+    }
+  const float sc = 0.125f * 1.4426950408889634f;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool ok = 8 * nb + 2 * tig + e < L;
+      sa[nb][e] = ok ? sa[nb][e] * sc : -INFINITY;
+      sa[nb][2 + e] = ok ? sa[nb][2 + e] * sc : -INFINITY;
+      mx0 = fmaxf(mx0, sa[nb][e]);
+      mx1 = fmaxf(mx1, sa[nb][2 + e]);
+    }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  uint32_t pp[8][2];
+  float sm0 = 0.f, sm1 = 0.f;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const __nv_bfloat162 r0 = __floats2bfloat162_rn(exp2f(sa[nb][0] - mx0), exp2f(sa[nb][1] - mx0));
+    const __nv_bfloat162 r1 = __floats2bfloat162_rn(exp2f(sa[nb][2] - mx1), exp2f(sa[nb][3] - mx1));
+    sm0 += __low2float(r0) + __high2float(r0);
+    sm1 += __low2float(r1) + __high2float(r1);
+    pp[nb][0] = *reinterpret_cast<const uint32_t*>(&r0);
+    pp[nb][1] = *reinterpret_cast<const uint32_t*>(&r1);
+  }
+  sm0 += __shfl_xor_sync(0xffffffffu, sm0, 1); sm0 += __shfl_xor_sync(0xffffffffu, sm0, 2);
+  sm1 += __shfl_xor_sync(0xffffffffu, sm1, 1); sm1 += __shfl_xor_sync(0xffffffffu, sm1, 2);
+  float oa[8][4];
+#pragma unroll
+  for (int db = 0; db < 8; ++db) oa[db][0] = oa[db][1] = oa[db][2] = oa[db][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint32_t a[4] = {pp[2 * kk][0], pp[2 * kk][1], pp[2 * kk + 1][0], pp[2 * kk + 1][1]};
+#pragma unroll
+    for (int cp = 0; cp < 4; ++cp) {
+      uint32_t b[4];
+      ldsm4t(swz(sV, 16 * kk + (lm & 1) * 8 + lr, 2 * cp + (lm >> 1)), b);
+      mma16816(oa[2 * cp], a, b[0], b[1]);
+      mma16816(oa[2 * cp + 1], a, b[2], b[3]);
+    }
+  }
+  // rows g / g + 8 -> the warp's own Q rows (dead: the A fragments are in registers), then out as full 128-byte lines
+  const float i0 = 1.0f / sm0, i1 = 1.0f / sm1;
+  __syncwarp();
+#pragma unroll
+  for (int db = 0; db < 8; ++db) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(swz(sQ, q0 + g, db) + 4u * (uint32_t)tig), "r"(pack_bf16x2(oa[db][0] * i0, oa[db][1] * i0)) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(swz(sQ, q0 + g + 8, db) + 4u * (uint32_t)tig), "r"(pack_bf16x2(oa[db][2] * i1, oa[db][3] * i1)) : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = q0 + 4 * i + (lane >> 3), c = lane & 7;
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(swz(sQ, r, c)));
+    if (r < L) *reinterpret_cast<uint4*>(out + (row0 + r) * d + head * HD + c * 8) = v;
+  }
+}
+
+int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream) {
+  VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit_short_mma: null pointer");
+  VMC_CHECK_ARG(F > 0 && F <= 65535 && heads > 0 && L > 0 && L <= 64, VMC_ERR_SHAPE, "vmc_attention_vit_short_mma: need 0 < L <= 64 (L=%d)", L);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int d = heads * HD;
+  {
+    VmcProfScope prof(VMC_K_ATTN_VIT, st, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
+    attention_fwd_mma_kernel<<<dim3(heads, F), 128, 24576, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                reinterpret_cast<__nv_bfloat16*>(out), L, heads);
+  }
+  VMC_LAUNCH_CHECK();
+  vmc_count_launch();
+  return VMC_OK;
+}
+
 int vmc_attention_vit_bwd_short(const void* qkv, const float* dO, long long lddo, float* dqkv, int F, int L, int heads,
                                 void* stream) {
   if (vmc_get_option(VMC_OPT_ATTN_BWD_IMPL) == 0 && F > 0 && F <= 65535 && heads > 0 && L > 0 && L <= 64 && qkv && dO && dqkv &&
