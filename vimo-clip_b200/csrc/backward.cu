@@ -1243,6 +1243,10 @@ attention_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
 // mma.sync), single-pass row softmax inside a lane quad, P kept in registers and re-packed from accumulator to A-fragment layout
 // (bf16, the normaliser sums the ROUNDED values), O = P V with V through ldmatrix.trans, rows staged through the warp's own
 // (dead) Q rows so that they leave as full 128-byte lines.
+extern "C++" {
+// HM = true: what-if input layout [F, heads, 3, L, 64] (head-major: an item's Q, K, V are contiguous runs of L * 128 bytes) instead of
+// the packed [F * L, 3 d] rows the qkv GEMM writes -- tools/kernel_bench.py impl 81, to test whether the access pattern is the ceiling
+template <bool HM>
 __global__ void __launch_bounds__(128)
 attention_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int L, int heads) {
   extern __shared__ __align__(1024) uint8_t fw_smem[];
@@ -1260,7 +1264,9 @@ attention_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
       const int i = tid + 128 * j;
       const int mat = i >> 9, r = (i >> 3) & 63, c = i & 7;
       v[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (r < L) v[j] = __ldg(reinterpret_cast<const uint4*>(qkv + (row0 + r) * 3 * d + (size_t)mat * d + head * HD) + c);
+      if (r < L)
+        v[j] = HM ? __ldg(reinterpret_cast<const uint4*>(qkv + ((((size_t)frame * heads + head) * 3 + mat) * L + r) * HD) + c)
+                  : __ldg(reinterpret_cast<const uint4*>(qkv + (row0 + r) * 3 * d + (size_t)mat * d + head * HD) + c);
     }
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
@@ -1347,6 +1353,8 @@ attention_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
   }
 }
 
+}  // extern "C++"
+
 int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream) {
   VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit_short_mma: null pointer");
   VMC_CHECK_ARG(F > 0 && F <= 65535 && heads > 0 && L > 0 && L <= 64, VMC_ERR_SHAPE, "vmc_attention_vit_short_mma: need 0 < L <= 64 (L=%d)", L);
@@ -1354,8 +1362,12 @@ int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int he
   const int d = heads * HD;
   {
     VmcProfScope prof(VMC_K_ATTN_VIT, st, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
-    attention_fwd_mma_kernel<<<dim3(heads, F), 128, 24576, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                                reinterpret_cast<__nv_bfloat16*>(out), L, heads);
+    if (vmc_get_option(VMC_OPT_ATTN_PREFETCH) == 81)  // what-if: head-major input layout (timing experiment only)
+      attention_fwd_mma_kernel<true><<<dim3(heads, F), 128, 24576, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                        reinterpret_cast<__nv_bfloat16*>(out), L, heads);
+    else
+      attention_fwd_mma_kernel<false><<<dim3(heads, F), 128, 24576, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                         reinterpret_cast<__nv_bfloat16*>(out), L, heads);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
