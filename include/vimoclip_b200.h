@@ -35,7 +35,7 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* ViT attention backward, L <= 64: 0 = warp-level tensor-core kernel (ldmatrix + mma.sync), 2 = register-tiled fp32 kernel, 1 = first-generation shared-memory kernel (cross-checks) */,
        VMC_OPT_LAST_BLOCK_CLS = 5 /* ViT tower, opt-in: 1 = in the LAST block compute only what the output reads (the CLS row):
                                      K / V of all tokens, but query, out_proj, ln_2 and the MLP on the F CLS rows only */,
-       VMC_OPT_ATTN_PREFETCH = 6 /* ViT attention: experiment, L <= 64 kernel: L2 prefetch distance of the TMA producer in CTA iterations (0 = off, the default: measured slower) */,
+       VMC_OPT_ATTN_PREFETCH = 6 /* ViT attention: experiments, L <= 64 kernels: 1..8 = L2 prefetch distance of the v7 TMA producer in CTA iterations (measured slower; 0 = off, the default); 81 = impl 8 reads a head-major [F, heads, 3, L, 64] buffer (timing what-if only) */,
        VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
        VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged) */,
        VMC_OPT_LN_FUSE = 3 /* ViT tower: 0/4 = separate LayerNorm kernels (default); 5 = ln_1 FOLDED into the qkv GEMM (c_proj
