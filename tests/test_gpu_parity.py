@@ -951,3 +951,50 @@ def test_layernorm_backward_fused_matches_autograd(cuda_device, rows, d, with_ad
     assert (db - bb.grad).abs().max().item() <= 2e-4 * max(1.0, bb.grad.abs().max().item())
     dz2, dg2, db2 = ops.layernorm_bwd(z, gamma, 1e-5, dy, add=add)
     assert torch.equal(dz, dz2) and torch.equal(dg, dg2) and torch.equal(db, db2)  # deterministic
+
+
+def test_tfam_training_step_as_one_cuda_graph(cuda_device):
+    """Forward + BCE loss + backward (our kernels) + AdamW captured in ONE CUDA graph (tools/tfam_train_graph.py): replays must
+    produce the same parameters as the same number of eager steps (dropout off: the kernels are deterministic)."""
+    gen = torch.Generator().manual_seed(21)
+    B = 6
+    rgb = torch.randn(B, 16, 512, generator=gen).to(cuda_device)
+    mot = torch.randn(B, 15, 512, generator=gen).to(cuda_device)
+    m_r = (torch.arange(16)[None, :] < torch.tensor([16, 12, 9, 16, 5, 14])[:, None]).to(cuda_device)
+    m_m = (torch.arange(15)[None, :] < torch.tensor([15, 11, 8, 15, 4, 13])[:, None]).to(cuda_device)
+    labels = (torch.rand(B, 140, generator=gen) < 0.05).float().to(cuda_device)
+    crit = torch.nn.BCEWithLogitsLoss()
+
+    def make():
+        torch.manual_seed(5)
+        model = vmc.AMO_CLIP(num_classes=140, dropout=0.0, mlp_dropout=0.0, device=cuda_device).to(cuda_device).train()
+        return model, torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.1, capturable=True)
+
+    def eager(model, opt):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(rgb, mot, m_r, m_m), labels)
+        loss.backward()
+        opt.step()
+        return loss
+
+    ref_model, ref_opt = make()
+    for _ in range(5):
+        eager(ref_model, ref_opt)
+    model, opt = make()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eager(model, opt)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    opt.zero_grad(set_to_none=True)
+    with torch.cuda.graph(g):
+        loss = crit(model(rgb, mot, m_r, m_m), labels)
+        loss.backward()
+        opt.step()
+    g.replay()  # capture itself does not execute: 3 eager + 2 replays = 5 steps
+    g.replay()
+    torch.cuda.synchronize()
+    for (n, a), (_, b) in zip(model.named_parameters(), ref_model.named_parameters()):
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item()), n
