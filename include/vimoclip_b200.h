@@ -171,7 +171,7 @@ int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int he
 /* CLS-query attention of the last block (VMC_OPT_LAST_BLOCK_CLS): q_cls bf16 [F, d], kv bf16 [F*L, 2d] = [k | v] -> out bf16 [F, d] */
 int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L, int heads, void* stream);
 /* same, selecting the implementation: 3 = persistent, pipelined kernel with 8 softmax warps (default for
- * 128 < L <= 256; other L fall back to 2), 4 = the same pipeline with 16 softmax warps (measured slower), 2 = one CTA per (frame, head) with P kept in TMEM as the A operand of the PV MMA,
+ * 128 < L <= 256; other L fall back), 6 = v5 on the patch tokens + CLS token on mma.sync warps (145 <= L <= 257), 7 = two items per tile (L <= 64), 8 = mma.sync kernel (L <= 64), 4 = the same pipeline with 16 softmax warps (measured slower), 2 = one CTA per (frame, head) with P kept in TMEM as the A operand of the PV MMA,
  * 1 = P staged through shared memory (first version; kept as a cross-check in the tests) */
 int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, int impl, void* stream);
 
