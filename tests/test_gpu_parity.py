@@ -51,7 +51,7 @@ def test_prologue_bit_exact_all_regimes(cuda_device, golden):
     assert np.array_equal(ops.prologue(u8, wrap=False, dst="f32").cpu().numpy().view(np.uint32), ref.view(np.uint32))
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["gather", "direct", "band"])
+@pytest.fixture(params=[0, 1, 2, 4], ids=["gather", "direct", "band", "gather16"])
 def prologue_impl(request):
     ops.set_option(vmc._lib.OPT_PROLOGUE_IMPL, request.param)
     yield request.param
