@@ -189,6 +189,7 @@ def ours_main(args):
     ops.set_option(_lib.OPT_LN_FUSE, args.ln_fuse)
     ops.set_option(_lib.OPT_ATTN_IMPL, args.attn_impl)
     ops.set_option(_lib.OPT_LAST_BLOCK_CLS, 1 if args.last_block_cls else 0)
+    ops.set_option(_lib.OPT_PROLOGUE_IMPL, args.prologue_impl)
     torch.manual_seed(0)
     pipe = vmc.ViMoCLIPPipeline("openai/clip-vit-base-patch16", "ViT-B/32", num_classes=NUM_CLASSES, device=dev, clips_per_step=args.chunk)
     pipe.rgb.visual.frames_in_flight = args.frames_in_flight
@@ -334,6 +335,7 @@ def main():
     ap.add_argument("--last-block-cls", action="store_true",
                     help="opt-in exact shortcut: the last transformer block computes only the CLS row of its output (NOT the default: "
                          "the headline run does the reference's full per-token work)")
+    ap.add_argument("--prologue-impl", type=int, default=0, help="VMC_OPT_PROLOGUE_IMPL: 0 library default, 4 = 16-pixel-per-item gather kernel for uint8 frames (bit-identical output)")
     ap.add_argument("--attn-impl", type=int, default=0, help="VMC_OPT_ATTN_IMPL: 0 library default, 3 / 5 select a ViT attention kernel generation")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -37,7 +37,7 @@ enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* ViT attention backward, L <= 64: 0 = warp-le
                                      K / V of all tokens, but query, out_proj, ln_2 and the MLP on the F CLS rows only */,
        VMC_OPT_ATTN_PREFETCH = 6 /* ViT attention: experiments, L <= 64 kernels: 1..8 = L2 prefetch distance of the v7 TMA producer in CTA iterations (measured slower; 0 = off, the default); 81 = impl 8 reads a head-major [F, heads, 3, L, 64] buffer (timing what-if only) */,
        VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
-       VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged), 4 = gather with 16 pixels per item (uint8 sources; fewer instructions per pixel for the power-capped in-step clock) */,
+       VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged), 4 = gather with 16 pixels per item (uint8 sources; bit-identical, measured slower: experiment) */,
        VMC_OPT_LN_FUSE = 3 /* ViT tower: 0/4 = separate LayerNorm kernels (default); 5 = ln_1 FOLDED into the qkv GEMM (c_proj
                               emits bf16 rows + row statistics, no ln_1 pass); 3 = ln_2 folded into c_fc as well (-1.7 % step
                               time, but the LayerNorm work moves into the GEMM epilogues); 1 = ln_1/ln_2 fused into the

@@ -1121,7 +1121,7 @@ int vmc_prologue(const void* frames, int src_kind, void* dst, int dst_kind, int 
     const int bands = F * (H / patch);
     __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dst);
     VmcProfScope prof(VMC_K_PROLOGUE, st, 0.0, px * ((f32_src ? 4.0 : 1.0) + 2.0));
-    // uint8 sources: 16-pixel items -- opt-in (VMC_OPT_PROLOGUE_IMPL = 4) until measured inside the step on a B200
+    // uint8 sources: 16-pixel items -- opt-in only (VMC_OPT_PROLOGUE_IMPL = 4): measured SLOWER inside the step (1.07-1.12 vs 0.82 ms)
     const int g16_items = g_items / 2;
     const int g16_block = ((g16_items + 6) / 7 + 31) / 32 * 32;
     if (!f32_src && impl == 4 && (W % 16) == 0 && (((size_t)H * W) % 16) == 0 && g16_block <= 384) {
