@@ -23,25 +23,29 @@
 extern "C" {
 #endif
 
-#define VMC_ABI_VERSION 2
+#define VMC_ABI_VERSION 3
 
 /* ---- runtime ---------------------------------------------------------------- */
 const char* vmc_last_error(void);
 int vmc_abi_version(void);
 int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel,
- * 1 = single-CTA kernel.  VMC_OPT_ATTN_IMPL (0 = by sequence length: 7 for L <= 64, 5 for 129..224, 6 for 225..257, else 2; 8 = warp-level mma.sync kernel for L <= 64): 0/5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row sums from the tensor core (L <= 224), 3 = persistent pipelined (8 softmax warps), 4 = 16 softmax warps, 2 = per-item CTA with P in TMEM, 1 = P through shared memory.
- * Both implementations of each op are kept so the tests can cross-check them. */
+/* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel, 1 = single-CTA kernel
+ * (kept as an independent cross-check for the tests).  VMC_OPT_ATTN_IMPL: 0 = by sequence length (7 for L <= 64, 5 for
+ * 129..224, 6 for 225..257, else 2); 5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row
+ * sums from the tensor core; 6 = v5 on the patch tokens + the CLS token on mma.sync warps; 7 = two items per query tile;
+ * 8 = warp-level mma.sync kernel for L <= 64; 2 = one CTA per (frame, head) with P in TMEM (any L <= 272). */
+/* vmc_set_option sets PROCESS-WIDE defaults (relaxed atomics; meant for tests, A/B runs and tools).  The per-model
+ * selectors of vmc_vit_model take precedence, so two models in one process can run different variants concurrently. */
 enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* ViT attention backward, L <= 64: 0 = warp-level tensor-core kernel (ldmatrix + mma.sync), 2 = register-tiled fp32 kernel, 1 = first-generation shared-memory kernel (cross-checks) */,
-       VMC_OPT_LAST_BLOCK_CLS = 5 /* ViT tower, opt-in: 1 = in the LAST block compute only what the output reads (the CLS row):
-                                     K / V of all tokens, but query, out_proj, ln_2 and the MLP on the F CLS rows only */,
+       VMC_OPT_LAST_BLOCK_CLS = 5 /* ViT tower: 0 / 1 = in the LAST block compute only what the output reads (the CLS row): K / V of
+                                     all tokens, but query, out_proj, ln_2 and the MLP on the F CLS rows only (default; the
+                                     embeddings are the same numbers); 2 = the full last block */,
        VMC_OPT_ATTN_PREFETCH = 6 /* ViT attention: experiments, L <= 64 kernels: 1..8 = L2 prefetch distance of the v7 TMA producer in CTA iterations (measured slower; 0 = off, the default); 81 = impl 8 reads a head-major [F, heads, 3, L, 64] buffer (timing what-if only) */,
        VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
        VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged), 4 = gather with 16 pixels per item (uint8 sources; bit-identical, measured slower: experiment) */,
-       VMC_OPT_LN_FUSE = 3 /* ViT tower: 0/4 = separate LayerNorm kernels (default); 5 = ln_1 FOLDED into the qkv GEMM (c_proj
-                              emits bf16 rows + row statistics, no ln_1 pass); 3 = ln_2 folded into c_fc as well (-1.7 % step
-                              time, but the LayerNorm work moves into the GEMM epilogues); 1 = ln_1/ln_2 fused into the
-                              residual GEMM epilogues (row-owner tile order, measured slower), 2 = only c_proj -> ln_1 fused */ };
+       VMC_OPT_LN_FUSE = 3 /* ViT tower variant (vmc_vit_model.ln_mode): 0 / 6 = bf16 residual stream, ln_1 and ln_2 FOLDED into
+                              the qkv / c_fc GEMMs (default); 3 = fp32 residual stream + bf16 copy, both folded; 5 = fp32
+                              stream, only ln_1 folded; 4 = fp32 stream, separate LayerNorm kernels (round-1 default) */ };
 int vmc_set_option(int option, long long value);
 /* kernels launched by this library since the last reset (bench.py "gpu_launches") */
 long long vmc_launch_count(void);
@@ -106,15 +110,7 @@ typedef struct vmc_gemm_epilogue {
   float alpha;
   int row_group;      /* 0: orow = rrow = m.  g > 0 (patch embed): f = m / g, orow = m + f + 1,
                          rrow = m - f*g + 1 (token rows of frame f skip the CLS row; resid = pos-emb) */
-  /* Optional fused LayerNorm of the output rows (fp32 out + bias + residual epilogue only, N <= 1024, N % 128 == 0):
-   * after a CTA pair has written all N columns of a row block it normalises those rows (read back from L2) and
-   * writes ln_out[m, :] = bf16(LayerNorm(out[m, :]) * ln_gamma + ln_beta): the A operand of the next GEMM, without
-   * the separate LayerNorm pass over HBM.  ln_out NULL = off. */
-  const float* ln_gamma;
-  const float* ln_beta;
-  void* ln_out;       /* bf16 [M, ln_ldo] */
-  long long ln_ldo;
-  float ln_eps;      /* also the epsilon of the folded LayerNorm below */
+  float ln_eps;         /* epsilon of the folded LayerNorm below (consumer side) */
   /* LayerNorm FOLDING (no LayerNorm pass at all; CTA-pair kernel only).  For y = LayerNorm(x) * gamma + beta,
    *   y W^T + b = rstd * (x W'^T - mean * colsum) + b',   W' = gamma (.) W,  colsum[n] = sum_k W'[n,k],  b' = b + W beta,
    * so the GEMM that consumes LayerNorm(x) runs on the RAW rows x (bf16) with W', and its epilogue applies the per-row
@@ -129,6 +125,11 @@ typedef struct vmc_gemm_epilogue {
   int stats_parts;
   long long stats_ld;
   const float* colsum;   /* consumer: [N] fp32 */
+  /* bf16 RESIDUAL STREAM (ViT tower default): resid_bf16 = 1 means `resid` points to bf16 rows.  With out_bf16 = 1, bias,
+   * no activation and stats_out set, the epilogue writes out = bf16(acc + bias + resid) -- the residual stream AND the A
+   * operand of the next (LayerNorm-folded) GEMM in one buffer, may alias resid -- plus the per-row partial statistics of
+   * the ROUNDED values (raw16_out must be NULL).  With an fp32 out it is only a dtype switch of the residual read. */
+  int resid_bf16;
 } vmc_gemm_epilogue;
 /* number of column slices (partials per row) a producer GEMM of this shape writes to stats_out */
 int vmc_gemm_stats_parts(int M, int N);
@@ -160,6 +161,12 @@ int vmc_layernorm_stats(const float* x, long long ldx, const float* gamma, const
                         float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows,
                         int d, const float* cls_row, int cls_every, float* stats_out, void* stream);
 
+/* General form: x_bf16 = 1 reads bf16 input rows (cls_every must be 0); stats_rounded = 1 makes stats_out the statistics
+ * of the bf16-ROUNDED output row, i.e. of the values a LayerNorm-folded GEMM reading y16 multiplies. */
+int vmc_layernorm_ex(const void* x, int x_bf16, long long ldx, const float* gamma, const float* beta, float eps,
+                     float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows, int d,
+                     const float* cls_row, int cls_every, float* stats_out, int stats_rounded, void* stream);
+
 /* ---- A1: ViT self-attention (no mask), head_dim 64 ------------------------------
  * qkv bf16 [F*L, 3*d] (q | k | v, heads contiguous inside each), out bf16 [F*L, d].
  * softmax(q k^T / 8) v per (frame, head); QK^T and PV on tcgen05, S/O in TMEM.
@@ -170,9 +177,7 @@ int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void*
 int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
 /* CLS-query attention of the last block (VMC_OPT_LAST_BLOCK_CLS): q_cls bf16 [F, d], kv bf16 [F*L, 2d] = [k | v] -> out bf16 [F, d] */
 int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L, int heads, void* stream);
-/* same, selecting the implementation: 3 = persistent, pipelined kernel with 8 softmax warps (default for
- * 128 < L <= 256; other L fall back), 6 = v5 on the patch tokens + CLS token on mma.sync warps (145 <= L <= 257), 7 = two items per tile (L <= 64), 8 = mma.sync kernel (L <= 64), 4 = the same pipeline with 16 softmax warps (measured slower), 2 = one CTA per (frame, head) with P kept in TMEM as the A operand of the PV MMA,
- * 1 = P staged through shared memory (first version; kept as a cross-check in the tests) */
+/* same, selecting the implementation (see VMC_OPT_ATTN_IMPL above); kernels that do not cover L fall back to one that does */
 int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, int impl, void* stream);
 
 /* ---- small masked attention (TFAM), fp32 in, bf16 out ---------------------------
@@ -206,6 +211,49 @@ int vmc_student_heads(const float* emb, const float* w_fc1_t, const float* b_fc1
                       const float* b_c2, float* distill, float* logits, int B, int T, int D, int H, int C, void* stream);
 int vmc_tfam_head(const float* x, const float* ln_g, const float* ln_b, float eps, const float* w1_t, const float* b1,
                   const float* w2_t, const float* b2, float* logits, int B, int T, int D, int H, int C, void* stream);
+
+/* ---- TFAM block as ONE fused kernel (north star piece 4) ------------------------------------------
+ * Replaces the whole of AMO_CLIP.forward after the mode selection: the AttentionLayer stack (TFAM/models/AMO_CLIP.py:37-51,
+ * :146-150 -- self-attention, optional cross-attention, FFN, post-LN) and `classifier(x.mean(dim=1))` (:170).  One cluster
+ * of 8 CTAs (one per head) per clip, or per pair of clips in large batches; weights streamed from L2 in a host-packed
+ * fragment-major fp16 order; activations stay in (distributed) shared memory; fp32 accumulation, residual stream,
+ * LayerNorm and softmax.  Geometry: d_model 512, nhead 8, dim_feedforward 2048 (every configuration of the reference,
+ * TFAM/cfg_AK), at most 32 frames per clip and stream; vmc_tfam_fused_supported() tells, other shapes take the batched
+ * GEMM path of the host code.
+ * wstream: vmc_tfam_wstream_bytes(layers) bytes = [8 CTAs][8 warps][layers][256 blocks][32 lanes][8 fp16].  Per (CTA c,
+ * warp w, layer) the blocks are, in order, (k-pair p major, column tile i minor), for
+ *   self in_proj   (16 k-pairs x 3 tiles): rows {0, 512, 1024} + 64 c + 8 w + [0, 8) of self_attn.in_proj_weight
+ *   self out_proj  (16 x 1): rows 64 c + 8 w + [0, 8) of self_attn.out_proj.weight
+ *   cross q        (16 x 1): rows 64 c + 8 w + [0, 8) of cross_attn.in_proj_weight
+ *   cross k | v    (16 x 2): rows {512, 1024} + 64 c + 8 w + [0, 8) of cross_attn.in_proj_weight
+ *   cross out_proj (16 x 1): rows 64 c + 8 w + [0, 8) of cross_attn.out_proj.weight
+ *   ffn.0          (16 x 4): rows 256 c + 32 w + 8 i + [0, 8) of ffn.0.weight
+ *   ffn.3          ( 8 x 8): rows 64 w + 8 i + [0, 8), columns 256 c + [0, 256) of ffn.3.weight
+ * and block (p, i) holds for lane (g = lane / 4, t = lane % 4) the 8 values W_i[g][32 p + {2t, 2t+1, 2t+8, 2t+9, 16+2t,
+ * 17+2t, 24+2t, 25+2t}] (the mma.m16n8k16 B fragments of two k steps).  vimoclip_b200.tfam packs it. */
+#define VMC_TFAM_MAX_LAYERS 8
+typedef struct vmc_tfam_layer {
+  const float *b_sin, *b_sout, *b_cin, *b_cout, *b_f1, *b_f2; /* in_proj_bias [1536], out_proj.bias [512] (self, cross), ffn biases */
+  const float *ns_g, *ns_b, *nc_g, *nc_b, *nf_g, *nf_b;        /* norm_self / norm_cross / norm_ffn weight, bias */
+  float ns_eps, nc_eps, nf_eps;
+} vmc_tfam_layer;
+typedef struct vmc_tfam_model {
+  int d_model, nhead, dim_ff, layers, num_classes, hidden; /* hidden = classifier.1 out_features (d_model / 2) */
+  int act;                        /* FFN activation: VMC_ACT_RELU (reference default) or VMC_ACT_GELU_ERF */
+  const void* wstream;            /* device, fp16, layout above */
+  const vmc_tfam_layer* layer;    /* HOST array of `layers` entries */
+  const float *cls_ln_g, *cls_ln_b; /* classifier.0 */
+  float cls_ln_eps;
+  const float *w1t, *b1;          /* classifier.1: weight TRANSPOSED [512, hidden] fp32, bias */
+  const float *w2t, *b2;          /* classifier.4: weight TRANSPOSED [hidden, C] fp32, bias */
+} vmc_tfam_model;
+long long vmc_tfam_wstream_bytes(int layers);
+int vmc_tfam_fused_supported(const vmc_tfam_model* m, int B, int T, int Tm);
+/* x [B, T, 512] fp32 (layer-0 input: rgb / flow / concatenated / projected rows per AMO_CLIP.py:136-167), motion [B, Tm, 512]
+ * fp32 = cross-attention source or NULL (self-attention-only modes), valid_x [B, T] / valid_m [B, Tm] uint8 (1 = real frame)
+ * or NULL, logits [B, C] fp32.  ONE kernel launch. */
+int vmc_tfam_forward(const vmc_tfam_model* m, const float* x, const float* motion, const uint8_t* valid_x,
+                     const uint8_t* valid_m, float* logits, int B, int T, int Tm, void* stream);
 
 /* ---- TFAM training step: backward kernels -------------------------------
  * TFAM/train_and_eval.py:66-101 (`loss.backward()` through TFAM/models/AMO_CLIP.py:37-51,99-171).  Every nn.Linear
@@ -293,6 +341,12 @@ typedef struct vmc_vit_model {
   const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
   const void* w_proj;       /* [out_dim, width] bf16 = proj.T */
   const vmc_vit_layer* layer; /* HOST array of `layers` entries */
+  /* Per-model variant selectors (0 = process default, see vmc_set_option).
+   * ln_mode: 6 = bf16 residual stream with both LayerNorms folded into the consuming GEMMs (the default), 3 = fp32 residual
+   *   stream + bf16 copy with both LayerNorms folded, 5 = fp32 stream with ln_1 folded, 4 = fp32 stream with separate
+   *   LayerNorm kernels.  last_block_cls: 1 = the last block computes only what the output reads, the CLS row (default:
+   *   identical embeddings), 2 = full last block.  attn_impl: see vmc_attention_vit_impl (0 = by sequence length). */
+  int ln_mode, last_block_cls, attn_impl;
 } vmc_vit_model;
 /* bytes of workspace needed for F frames in flight */
 long long vmc_vit_workspace_bytes(const vmc_vit_model* m, int F);

@@ -22,7 +22,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(vmc._lib.EXPORTED_SYMBOLS), declared ^ set(vmc._lib.EXPORTED_SYMBOLS)
-    assert vmc._lib.lib().vmc_abi_version() == 2
+    assert vmc._lib.lib().vmc_abi_version() == vmc._lib.ABI_VERSION == 3
 
 
 def test_no_cpu_fallback():
@@ -212,3 +212,52 @@ def test_embedding_store_layout_and_roundtrip(tmp_path):
         assert f["trimmed_videos/clipA"]["embeddings"].shape == (7, 512)
         with pytest.raises(ImportError):
             f.to_hdf5(str(tmp_path / "x.h5"))  # h5py is absent here; on a machine that has it this writes the reference layout
+
+
+def test_tfam_weight_stream_packing_matches_mma_fragment_order():
+    """The fused TFAM kernel's weight stream (vimoclip_b200.tfam.pack_weight_stream): replaying, per (CTA, warp), the 512-byte
+    blocks in stream order with the mma.m16n8k16 B-fragment lane mapping reproduces x @ W_slice^T for every projection."""
+    import numpy as np
+
+    from vimoclip_b200 import tfam
+
+    torch.manual_seed(0)
+    m = tfam.AMO_CLIP(device="cpu", num_layers=2)
+    ws = tfam.pack_weight_stream(m.layers)
+    assert tuple(ws.shape) == (8, 8, 2, 256, 32, 8) and ws.dtype == torch.float16
+    lay = {"sin": (0, 3, 16), "sout": (48, 1, 16), "cq": (64, 1, 16), "ckv": (80, 2, 16), "cout": (112, 1, 16), "f1": (128, 4, 16),
+           "f2": (192, 8, 8)}
+    lane = np.arange(32)
+    g, t = lane >> 2, lane & 3
+    koff = np.stack([2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9, 16 + 2 * t, 17 + 2 * t, 24 + 2 * t, 25 + 2 * t], 1)  # [32, 8]
+
+    def replay(a, blocks, nt, kp):
+        out = np.zeros((a.shape[0], nt * 8))
+        for b in range(nt * kp):
+            p, i = divmod(b, nt)
+            blk = blocks[b].astype(np.float64)  # [32, 8]
+            for ln in range(32):
+                out[:, 8 * i + g[ln]] += a[:, 32 * p + koff[ln]] @ blk[ln]
+        return out
+
+    rs = np.random.RandomState(0)
+    a512, a256 = rs.randn(4, 512), rs.randn(4, 256)
+    w16 = lambda w: w.detach().to(torch.float16).double().numpy()  # noqa: E731
+    ly, layer = m.layers[1], 1
+    for c, w in [(0, 0), (5, 2), (7, 7)]:
+        st = ws[c, w, layer].numpy()
+        take = lambda k: st[lay[k][0]:lay[k][0] + lay[k][1] * lay[k][2]]  # noqa: E731
+        r0 = 64 * c + 8 * w
+        wi, wc = w16(ly.self_attn.in_proj_weight), w16(ly.cross_attn.in_proj_weight)
+        want = {
+            "sin": np.concatenate([a512 @ wi[512 * i + r0:512 * i + r0 + 8].T for i in range(3)], 1),
+            "sout": a512 @ w16(ly.self_attn.out_proj.weight)[r0:r0 + 8].T,
+            "cq": a512 @ wc[r0:r0 + 8].T,
+            "ckv": np.concatenate([a512 @ wc[512 * (i + 1) + r0:512 * (i + 1) + r0 + 8].T for i in range(2)], 1),
+            "cout": a512 @ w16(ly.cross_attn.out_proj.weight)[r0:r0 + 8].T,
+            "f1": np.concatenate([a512 @ w16(ly.ffn[0].weight)[256 * c + 32 * w + 8 * i:256 * c + 32 * w + 8 * i + 8].T for i in range(4)], 1),
+            "f2": np.concatenate([a256 @ w16(ly.ffn[3].weight)[64 * w + 8 * i:64 * w + 8 * i + 8, 256 * c:256 * c + 256].T for i in range(8)], 1),
+        }
+        for k, (_, nt, kp) in lay.items():
+            got = replay(a256 if k == "f2" else a512, take(k), nt, kp)
+            assert np.abs(got - want[k]).max() < 1e-9, (c, w, k)

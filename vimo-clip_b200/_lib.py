@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libvimoclip_b200.so")
 SRC_U8, SRC_U8_WRAP, SRC_F32_WRAP, SRC_F32_NORM = 0, 1, 2, 3
 DST_U8, DST_F32_NCHW, DST_BF16_PATCH = 0, 1, 2
 ACT_NONE, ACT_QUICKGELU, ACT_GELU_ERF, ACT_RELU = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 OPT_GEMM_IMPL, OPT_ATTN_IMPL, OPT_PROLOGUE_IMPL, OPT_LN_FUSE, OPT_ATTN_BWD_IMPL, OPT_LAST_BLOCK_CLS = 0, 1, 2, 3, 4, 5
 OPT_ATTN_PREFETCH = 6
 
@@ -32,10 +32,6 @@ class GemmEpilogue(C.Structure):
         ("act", C.c_int),
         ("alpha", C.c_float),
         ("row_group", C.c_int),
-        ("ln_gamma", C.c_void_p),
-        ("ln_beta", C.c_void_p),
-        ("ln_out", C.c_void_p),
-        ("ln_ldo", C.c_longlong),
         ("ln_eps", C.c_float),
         ("raw16_out", C.c_void_p),
         ("raw16_ld", C.c_longlong),
@@ -44,6 +40,7 @@ class GemmEpilogue(C.Structure):
         ("stats_parts", C.c_int),
         ("stats_ld", C.c_longlong),
         ("colsum", C.c_void_p),
+        ("resid_bf16", C.c_int),
     ]
 
 
@@ -60,8 +57,26 @@ class VitModel(C.Structure):
         ("w_patch", C.c_void_p), ("cls_pos0", C.c_void_p), ("pos", C.c_void_p),
         ("ln_pre_g", C.c_void_p), ("ln_pre_b", C.c_void_p), ("ln_post_g", C.c_void_p), ("ln_post_b", C.c_void_p),
         ("w_proj", C.c_void_p), ("layer", C.POINTER(VitLayer)),
+        ("ln_mode", C.c_int), ("last_block_cls", C.c_int), ("attn_impl", C.c_int),
     ]
 
+
+class TfamLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("b_sin", "b_sout", "b_cin", "b_cout", "b_f1", "b_f2", "ns_g", "ns_b", "nc_g", "nc_b",
+                                          "nf_g", "nf_b")] + [("ns_eps", C.c_float), ("nc_eps", C.c_float), ("nf_eps", C.c_float)]
+
+
+class TfamModel(C.Structure):
+    _fields_ = [
+        ("d_model", C.c_int), ("nhead", C.c_int), ("dim_ff", C.c_int), ("layers", C.c_int), ("num_classes", C.c_int),
+        ("hidden", C.c_int), ("act", C.c_int),
+        ("wstream", C.c_void_p), ("layer", C.POINTER(TfamLayer)),
+        ("cls_ln_g", C.c_void_p), ("cls_ln_b", C.c_void_p), ("cls_ln_eps", C.c_float),
+        ("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
+    ]
+
+
+TFAM_MAX_LAYERS = 8
 
 _SIGNATURES = {
     "vmc_last_error": (C.c_char_p, []),
@@ -80,6 +95,7 @@ _SIGNATURES = {
     "vmc_gemm_bf16_ex": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(GemmEpilogue), C.c_void_p]),
     "vmc_layernorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "vmc_layernorm_stats": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "vmc_layernorm_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "vmc_gemm_stats_parts": (C.c_int, [C.c_int, C.c_int]),
     "vmc_attention_vit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vmc_attention_vit_short_mma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -108,6 +124,9 @@ _SIGNATURES = {
     "vmc_cosine_distill_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vmc_student_heads": (C.c_int, [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p]),
     "vmc_tfam_head": (C.c_int, [C.c_void_p] * 3 + [C.c_float] + [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_void_p]),
+    "vmc_tfam_wstream_bytes": (C.c_longlong, [C.c_int]),
+    "vmc_tfam_fused_supported": (C.c_int, [C.POINTER(TfamModel), C.c_int, C.c_int, C.c_int]),
+    "vmc_tfam_forward": (C.c_int, [C.POINTER(TfamModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vmc_vit_workspace_bytes": (C.c_longlong, [C.POINTER(VitModel), C.c_int]),
     "vmc_vit_forward": (C.c_int, [C.POINTER(VitModel), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
 }

@@ -249,18 +249,8 @@ attention_vit_kernel(const __grid_constant__ CUtensorMap tm, const AttnArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// A1, third generation (129 <= L <= 256 tokens, i.e. ViT-B/16): persistent and pipelined.
-//
-// ncu on the one-CTA-per-(frame, head) kernel above showed 26 % of the samples waiting on the load /
-// MMA mbarriers and the tensor pipe 15 % active: each CTA runs load -> S MMA -> softmax -> PV MMA ->
-// store strictly in sequence.  Here one CTA per SM loops over (frame, head) items with
-//   warps 0-3   softmax of query tile 0 (one thread per row)      warp 8  TMA producer: Q/K/V of the
-//   warps 4-7   softmax of query tile 1                                   NEXT item into the other
-//   warp  9     MMA issuer (+ TMEM allocator, all 512 columns)            shared-memory stage
-// TMEM: S_t at columns [256 t, 256 t + Lk16); P_t (bf16, packed) over S_t's first Lk16/2 columns;
-// O_t at [256 t + 128, +64) (S columns that are dead once the tile's softmax has finished).
-// While tile 0 is in its softmax the tensor core computes S of tile 1, the PV MMAs overlap the other
-// tile's softmax, and the loads of the next item are already in flight.
+// (Generations 3 and 4 -- the first persistent pipeline with 8 / 16 softmax warps marching in lockstep -- were measured
+// against v5 in round 1 and removed from the library in round 2.)
 // ---------------------------------------------------------------------------------------
 // max over one 32-column chunk of a score row (columns >= valid are padding)
 template <bool MASK>
@@ -270,523 +260,6 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], float mx, in
     if (!MASK || j < valid) mx = fmaxf(mx, __uint_as_float(r[j]));
   return mx;
 }
-// p = 2^(s*sc - mxs) for one chunk, packed to bf16 and written over the dead S columns; returns the
-// chunk's (fp32) sum in two independent accumulators to keep the FADD chains short
-// VAR: 0 = production; 1, 2 = what-if timing variants (WRONG results; tools/kernel_bench.py only):
-//      1 replaces MUFU.EX2 by an FMA, 2 sums the unrounded values (drops the LOP per element)
-template <bool MASK, int VAR = 0>
-__device__ __forceinline__ void chunk_exp_store(const uint32_t (&r)[32], float sc, float mxs, int valid,
-                                                uint32_t taddr, float& s0, float& s1) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float e0 = 0.f, e1 = 0.f;
-    if (!MASK || 2 * j < valid) {  // warp-uniform: padding columns cost no MUFU work
-      if (VAR == 1) {
-        e0 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f), 0.001f, 1.0f);
-        e1 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f), 0.001f, 1.0f);
-      } else {
-        e0 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f));
-        e1 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f));
-      }
-      if (MASK && 2 * j + 1 >= valid) e1 = 0.f;
-    }
-    // fp32 -> bf16 in the integer ALU (round half up: + 0x8000, keep the high half; differs from
-    // round-to-nearest-even only on exact ties).  ncu: the XU pipe (MUFU.EX2 and F2FP conversions)
-    // is the busiest pipe of this kernel, so the conversion is moved off it.
-    // The normaliser sums the bf16-ROUNDED values the PV MMA will actually see: with a stabiliser
-    // below the true row max the dominant probability is no longer exactly 1.0, and an unrounded sum
-    // would leave its 2^-9 rounding error in the ratio.
-    const uint32_t b0 = __float_as_uint(e0) + 0x8000u;
-    const uint32_t b1 = __float_as_uint(e1) + 0x8000u;
-    pk[j] = __byte_perm(b0, b1, 0x7632);  // {b1.hi16, b0.hi16}
-    if (VAR == 2) {
-      s0 += e0;
-      s1 += e1;
-    } else {
-      s0 += __uint_as_float(b0 & 0xffff0000u);
-      s1 += __uint_as_float(b1 & 0xffff0000u);
-    }
-  }
-  tmem_st_32x32b_x16(taddr, pk);
-}
-
-struct Attn3Args {
-  int L, heads, d, lk16, n_items;
-  __nv_bfloat16* out;
-  long long* dbg;  // optional timeline (clock64 per phase of CTA 0), tools/attn_timeline.py
-};
-#ifdef VMC_ATTN_TIMELINE  // make NVCCFLAGS+=-DVMC_ATTN_TIMELINE: phase stamps for tools/attn_timeline.py
-#define VMC_DBG(slot)                                                                         \
-  do {                                                                                        \
-    if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0 && k < 16) a.dbg[(k * 32) + (slot)] = clock64(); \
-  } while (0)
-#else  // the stamps cost 10 % of the kernel (0.441 vs 0.398 ms), so they are compiled out by default
-#define VMC_DBG(slot) do { } while (0)
-#endif
-
-// TMEM column plan of one query tile (base = 256 t), Lk16 <= 256 keys:
-//   S   [0, Lk16)            fp32 scores
-//   P_a [0, 64)              bf16 pairs of keys 0..127 (chunks 0-3), over S columns already consumed
-//   O   [64, 128)            fp32 output accumulator, also over consumed S columns
-//   P_b [32 c, 32 c + 16)    bf16 pairs of chunk c >= 4, written in place over its own chunk
-// so the PV MMA of the first 128 keys is issued while the softmax is still working on keys >= 128.
-template <int VAR>
-__global__ void __launch_bounds__(320, 1)
-attention_vit3_kernel(const __grid_constant__ CUtensorMap tm, const Attn3Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  constexpr uint32_t STAGE = 6 * TILE;  // Q0 Q1 | K0 K1 | V0 V1
-  const uint32_t bar_base = base + 2 * STAGE;
-  auto kv_full = [&](int s) { return bar_base + 8u * s; };
-  auto kv_empty = [&](int s) { return bar_base + 16u + 8u * s; };
-  auto s_full = [&](int t) { return bar_base + 32u + 8u * t; };
-  auto pa_full = [&](int t) { return bar_base + 48u + 8u * t; };
-  auto pb_full = [&](int t) { return bar_base + 64u + 8u * t; };
-  auto o_full = [&](int t) { return bar_base + 80u + 8u * t; };
-  auto s_empty = [&](int t) { return bar_base + 96u + 8u * t; };
-  const uint32_t tmem_ptr_addr = bar_base + 112u;
-  volatile uint32_t* tmem_ptr_generic =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tm);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(kv_full(i), 1);
-      mbar_init(kv_empty(i), 1);
-      mbar_init(s_full(i), 1);
-      mbar_init(pa_full(i), 4);  // one arrive per softmax warp of the tile
-      mbar_init(pb_full(i), 4);
-      mbar_init(o_full(i), 1);
-      mbar_init(s_empty(i), 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_ptr_addr, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_generic;
-  const int n_chunks = (a.lk16 + 31) / 32;  // 5..8 for 129 <= L <= 256
-
-  if (warp == 8) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int k = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-        const int s = k & 1;
-        const int head = item % a.heads;
-        const int frame = item / a.heads;
-        mbar_wait(kv_empty(s), (((uint32_t)k >> 1) & 1u) ^ 1u);
-        const uint32_t st = base + s * STAGE;
-        mbar_arrive_expect_tx(kv_full(s), STAGE);
-        for (int mt = 0; mt < 2; ++mt) {
-          tma_load_3d(st + mt * TILE, &tm, kv_full(s), head * HD, mt * 128, frame);
-          tma_load_3d(st + (2 + mt) * TILE, &tm, kv_full(s), a.d + head * HD, mt * 128, frame);
-          tma_load_3d(st + (4 + mt) * TILE, &tm, kv_full(s), 2 * a.d + head * HD, mt * 128, frame);
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, a.lk16, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
-      const int nkk = a.lk16 / 16;  // 16-key steps of the PV MMA; the first 8 belong to part A
-      int k = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-        const int s = k & 1;
-        const uint32_t st = base + s * STAGE;
-        const uint32_t par = (uint32_t)k & 1u;
-        VMC_DBG(0);
-        mbar_wait(kv_full(s), ((uint32_t)k >> 1) & 1u);
-        tc_fence_after();
-        VMC_DBG(1);
-        const uint64_t dk = umma_desc_sw128(st + 2 * TILE);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(s_empty(t), par ^ 1u);
-          tc_fence_after();
-          VMC_DBG(2 + t);
-          const uint64_t dq = umma_desc_sw128(st + t * TILE);
-#pragma unroll
-          for (int kq = 0; kq < HD / 16; ++kq)
-            umma_ss(tmem_base + uint32_t(t * 256), dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s,
-                    kq != 0);
-          umma_commit(s_full(t));
-        }
-        for (int t = 0; t < 2; ++t) {  // part A: keys 0..127
-          mbar_wait(pa_full(t), par);
-          tc_fence_after();
-          VMC_DBG(4 + t);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ts(tmem_base + uint32_t(t * 256 + 64), tmem_base + uint32_t(t * 256 + kk * 8),
-                    umma_desc_sw128(st + 4 * TILE + kk * 2048), idesc_pv, kk != 0);
-        }
-        for (int t = 0; t < 2; ++t) {  // part B: keys 128.., P stored in place over its own chunk
-          mbar_wait(pb_full(t), par);
-          tc_fence_after();
-          VMC_DBG(6 + t);
-          for (int kk = 8; kk < nkk; ++kk) {
-            const int c = kk >> 1;
-            umma_ts(tmem_base + uint32_t(t * 256 + 64), tmem_base + uint32_t(t * 256 + c * 32 + (kk & 1) * 8),
-                    umma_desc_sw128(st + 4 * TILE + kk * 2048), idesc_pv, 1u);
-          }
-          umma_commit(o_full(t));
-        }
-        umma_commit(kv_empty(s));  // every MMA that reads this stage has retired
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================== softmax warps =====================
-    const int t = warp >> 2;
-    const int q = warp & 3;
-    const int row = t * 128 + q * 32 + lane;
-    const bool warp_active = (t * 128 + q * 32) < a.L;  // warp-uniform
-    const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
-    const float sc = 0.125f * 1.4426950408889634f;
-    const int n_full = a.L >> 5;           // chunks with 32 valid columns
-    const int tail = a.L - (n_full << 5);  // valid columns of the last, partial chunk (0: none)
-    int k = 0;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-      const int head = item % a.heads;
-      const int frame = item / a.heads;
-      const uint32_t par = (uint32_t)k & 1u;
-      if (q == 0) VMC_DBG(8 + t * 8);
-      mbar_wait(s_full(t), par);
-      tc_fence_after();
-      if (q == 0) VMC_DBG(9 + t * 8);
-      float row_sum = 1.0f;
-      if (warp_active) {
-        // Both passes stream the score row out of TMEM in 32-column chunks, double-buffered in
-        // registers: the tcgen05.ld of chunk c+1 is in flight while chunk c is reduced.  Only the last
-        // chunk can hold padding columns (>= L), so only it pays for the masking.
-        // SINGLE pass over the score row.  tcgen05.ld moves ~64 B/cycle/SM, and reading S twice
-        // (max pass + exp pass) made the kernel TMEM-read bound (measured 8.3k cycles per item against
-        // ~7.7k cycles of tcgen05.ld traffic).  Softmax is shift invariant, so instead of the exact row
-        // max the stabiliser is the max of the FIRST 32 keys (already in registers, includes the CLS
-        // key): it is <= the true max, so the row sum is >= 1 (no underflow to zero), and fp32 / bf16
-        // share an 8-bit exponent, so the result has the same relative precision as the two-pass form.
-        // The exponent argument is clamped at +120 so a pathological row (scores spread by more than
-        // ~83 after scaling) saturates instead of producing inf.
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tb, r0);
-        tmem_ld_wait();
-        float mx = chunk_max<false>(r0, -INFINITY, 32);
-        const float mxs = mx * sc;
-        float s0 = 0.f, s1 = 0.f;
-        for (int c = 0; c < n_chunks; c += 2) {
-          // chunk c < 4 -> P_a column 16 c; chunk c >= 4 -> in place at column 32 c
-          if (c != 0) tmem_ld_wait();
-          if (c + 1 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 1) * 32), r1);
-          {
-            const uint32_t pcol = tb + uint32_t(c < 4 ? c * 16 : c * 32);
-            if (c < n_full) chunk_exp_store<false, VAR>(r0, sc, mxs, 32, pcol, s0, s1);
-            else chunk_exp_store<true, VAR>(r0, sc, mxs, tail, pcol, s0, s1);
-          }
-          if (c + 1 < n_chunks) {
-            tmem_ld_wait();
-            if (c + 2 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 2) * 32), r0);
-            const uint32_t pcol = tb + uint32_t(c + 1 < 4 ? (c + 1) * 16 : (c + 1) * 32);
-            if (c + 1 < n_full) chunk_exp_store<false, VAR>(r1, sc, mxs, 32, pcol, s0, s1);
-            else chunk_exp_store<true, VAR>(r1, sc, mxs, tail, pcol, s0, s1);
-          }
-          if (c == 2) {
-            // chunks 0..3 (keys 0..127) are stored: release part A of the PV MMA.  The loads of
-            // chunk 4 already issued above read columns >= 128, disjoint from P_a and O.
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_relaxed(pa_full(t));
-          }
-        }
-        row_sum = s0 + s1;
-        tmem_st_wait();
-      } else {
-        if (lane == 0) mbar_arrive_relaxed(pa_full(t));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (q == 0) VMC_DBG(10 + t * 8);
-      if (lane == 0) mbar_arrive_relaxed(pb_full(t));
-      mbar_wait(o_full(t), par);
-      tc_fence_after();
-      if (q == 0) VMC_DBG(11 + t * 8);
-      uint32_t o0[32], o1[32];
-      if (warp_active) {
-        tmem_ld_32x32b_x32(tb + 64u, o0);
-        tmem_ld_32x32b_x32(tb + 96u, o1);
-        tmem_ld_wait();
-      }
-      // the accumulator is in registers: hand the tile's TMEM back before the global stores
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(s_empty(t));
-      if (q == 0) VMC_DBG(12 + t * 8);
-      if (warp_active && row < a.L) {
-        const float inv = 1.0f / row_sum;
-        __nv_bfloat16* orow = a.out + ((size_t)frame * a.L + row) * a.d + (size_t)head * HD;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
-          reinterpret_cast<uint4*>(orow)[i] = o;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
-          o.y = pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
-          o.z = pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
-          o.w = pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
-          reinterpret_cast<uint4*>(orow + 32)[i] = o;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// A1, fourth generation: the persistent pipeline above with SIXTEEN softmax warps.
-//
-// ncu on attention_vit3_kernel: neither the MUFU pipe (40 %) nor the issue slots are saturated; with 8
-// softmax warps there are 2 warps per scheduler and each runs a serial chain (wait S -> 2 passes ->
-// wait O), so fixed-latency stalls and barrier waits stay exposed.  TMEM (2 x 256 columns) does not
-// allow more tiles in flight, but two warps may share a TMEM lane quarter: warp (t, h, q) handles
-// rows of tile t / quarter q and the key-column half h (h = 0: keys 0..127 = P_a, h = 1: keys
-// 128.. = P_b).  The pair exchanges its partial row max / row sum through shared memory with a
-// 64-thread named barrier.  Four warps per scheduler hide each other's latencies.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// 20 warps: registers are allocated in groups of four warps, so 18 warps cost as much as 20
-__global__ void __launch_bounds__(640, 1)
-attention_vit4_kernel(const __grid_constant__ CUtensorMap tm, const Attn3Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  constexpr uint32_t STAGE = 6 * TILE;  // Q0 Q1 | K0 K1 | V0 V1
-  const uint32_t bar_base = base + 2 * STAGE;
-  auto kv_full = [&](int s) { return bar_base + 8u * s; };
-  auto kv_empty = [&](int s) { return bar_base + 16u + 8u * s; };
-  auto s_full = [&](int t) { return bar_base + 32u + 8u * t; };
-  auto pa_full = [&](int t) { return bar_base + 48u + 8u * t; };
-  auto pb_full = [&](int t) { return bar_base + 64u + 8u * t; };
-  auto o_full = [&](int t) { return bar_base + 80u + 8u * t; };
-  auto s_empty = [&](int t) { return bar_base + 96u + 8u * t; };
-  const uint32_t tmem_ptr_addr = bar_base + 112u;
-  volatile uint32_t* tmem_ptr_generic =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
-  float* xch = reinterpret_cast<float*>(smem_raw + (bar_base + 128u - raw_addr));  // [2][8 pairs][2][32]
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tm);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(kv_full(i), 1);
-      mbar_init(kv_empty(i), 1);
-      mbar_init(s_full(i), 1);
-      mbar_init(pa_full(i), 4);  // the four h = 0 warps of the tile
-      mbar_init(pb_full(i), 4);  // the four h = 1 warps
-      mbar_init(o_full(i), 1);
-      mbar_init(s_empty(i), 8);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 17) {
-    tmem_alloc(tmem_ptr_addr, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_generic;
-  const int n_chunks = (a.lk16 + 31) / 32;  // 5..8 for 129 <= L <= 256
-
-  if (warp == 16) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int k = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-        const int s = k & 1;
-        const int head = item % a.heads;
-        const int frame = item / a.heads;
-        mbar_wait(kv_empty(s), (((uint32_t)k >> 1) & 1u) ^ 1u);
-        const uint32_t st = base + s * STAGE;
-        mbar_arrive_expect_tx(kv_full(s), STAGE);
-        for (int mt = 0; mt < 2; ++mt) {
-          tma_load_3d(st + mt * TILE, &tm, kv_full(s), head * HD, mt * 128, frame);
-          tma_load_3d(st + (2 + mt) * TILE, &tm, kv_full(s), a.d + head * HD, mt * 128, frame);
-          tma_load_3d(st + (4 + mt) * TILE, &tm, kv_full(s), 2 * a.d + head * HD, mt * 128, frame);
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 17) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, a.lk16, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
-      const int nkk = a.lk16 / 16;
-      int k = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-        const int s = k & 1;
-        const uint32_t st = base + s * STAGE;
-        const uint32_t par = (uint32_t)k & 1u;
-        mbar_wait(kv_full(s), ((uint32_t)k >> 1) & 1u);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(st + 2 * TILE);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(s_empty(t), par ^ 1u);
-          tc_fence_after();
-          const uint64_t dq = umma_desc_sw128(st + t * TILE);
-#pragma unroll
-          for (int kq = 0; kq < HD / 16; ++kq)
-            umma_ss(tmem_base + uint32_t(t * 256), dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s,
-                    kq != 0);
-          umma_commit(s_full(t));
-        }
-        for (int t = 0; t < 2; ++t) {  // part A: keys 0..127
-          mbar_wait(pa_full(t), par);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_ts(tmem_base + uint32_t(t * 256 + 64), tmem_base + uint32_t(t * 256 + kk * 8),
-                    umma_desc_sw128(st + 4 * TILE + kk * 2048), idesc_pv, kk != 0);
-        }
-        for (int t = 0; t < 2; ++t) {  // part B: keys 128.., P in place over its own chunk
-          mbar_wait(pb_full(t), par);
-          tc_fence_after();
-          for (int kk = 8; kk < nkk; ++kk) {
-            const int c = kk >> 1;
-            umma_ts(tmem_base + uint32_t(t * 256 + 64), tmem_base + uint32_t(t * 256 + c * 32 + (kk & 1) * 8),
-                    umma_desc_sw128(st + 4 * TILE + kk * 2048), idesc_pv, 1u);
-          }
-          umma_commit(o_full(t));
-        }
-        umma_commit(kv_empty(s));
-      }
-    }
-    __syncwarp();
-  } else if (warp < 16) {
-    // ===================== softmax warps: (tile t, key half h, lane quarter q) =====================
-    const int t = warp >> 3;
-    const int h = (warp >> 2) & 1;
-    const int q = warp & 3;
-    const int pair = t * 4 + q;
-    const int row = t * 128 + q * 32 + lane;
-    const bool warp_active = (t * 128 + q * 32) < a.L;  // warp-uniform, same for both warps of a pair
-    const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
-    const float sc = 0.125f * 1.4426950408889634f;
-    const int n_full = a.L >> 5;
-    const int tail = a.L - (n_full << 5);
-    const int c_begin = h ? 4 : 0;
-    const int c_end = h ? n_chunks : 4;
-    float* xmax = xch + pair * 64;
-    float* xsum = xch + 512 + pair * 64;
-    int k = 0;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-      const int head = item % a.heads;
-      const int frame = item / a.heads;
-      const uint32_t par = (uint32_t)k & 1u;
-      mbar_wait(s_full(t), par);
-      tc_fence_after();
-      float row_sum = 1.0f;
-      if (warp_active) {
-        // single register buffer: with four warps per scheduler the other warps cover the
-        // tcgen05.ld latency, and two 32-register buffers would spill at the 112-register cap
-        uint32_t r0[32];
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          tmem_ld_32x32b_x32(tb + uint32_t(c * 32), r0);
-          tmem_ld_wait();
-          mx = (c < n_full) ? chunk_max<false>(r0, mx, 32) : chunk_max<true>(r0, mx, tail);
-        }
-        // first chunk of pass 2 is already in flight while the pair exchanges its maxima
-        tmem_ld_32x32b_x32(tb + uint32_t(c_begin * 32), r0);
-        xmax[h * 32 + lane] = mx;
-        named_bar_sync(1 + pair, 64);
-        mx = fmaxf(mx, xmax[(h ^ 1) * 32 + lane]);
-        const float mxs = mx * sc;
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          if (c != c_begin) tmem_ld_32x32b_x32(tb + uint32_t(c * 32), r0);
-          tmem_ld_wait();
-          const uint32_t pcol = tb + uint32_t(c < 4 ? c * 16 : c * 32);
-          if (c < n_full) chunk_exp_store<false>(r0, sc, mxs, 32, pcol, s0, s1);
-          else chunk_exp_store<true>(r0, sc, mxs, tail, pcol, s0, s1);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_relaxed(h ? pb_full(t) : pa_full(t));
-        xsum[h * 32 + lane] = s0 + s1;
-        named_bar_sync(1 + pair, 64);
-        row_sum = (s0 + s1) + xsum[(h ^ 1) * 32 + lane];
-      } else {
-        if (lane == 0) mbar_arrive_relaxed(h ? pb_full(t) : pa_full(t));
-      }
-      mbar_wait(o_full(t), par);
-      tc_fence_after();
-      uint32_t o[32];
-      if (warp_active) {
-        tmem_ld_32x32b_x32(tb + uint32_t(64 + h * 32), o);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(s_empty(t));
-      if (warp_active && row < a.L) {
-        const float inv = 1.0f / row_sum;
-        __nv_bfloat16* orow = a.out + ((size_t)frame * a.L + row) * a.d + (size_t)head * HD + h * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-          v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-          v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-          v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          reinterpret_cast<uint4*>(orow)[i] = v;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // ---------------------------------------------------------------------------------------
 // A1, fifth generation (129 <= L <= 256): the two query tiles run OUT OF PHASE and the softmax warps do
 // nothing but softmax.
@@ -2101,12 +1574,16 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
   VMC_CHECK_ARG(F > 0 && heads > 0 && L > 0 && L <= 272, VMC_ERR_SHAPE,
                 "vmc_attention_vit: need 0 < L <= 272 tokens (L=%d)", L);
   int var6 = 0;
-  if (impl >= 100 && impl < 132) {  // 100 + bits: what-if timing variants of v6 (wrong results)
+#ifdef VMC_WHATIF  // timing experiments that produce WRONG results: never part of the shipped library (make WHATIF=1)
+  if (impl >= 100 && impl < 132) {  // 100 + bits: what-if timing variants of v6
     var6 = impl - 100;
     impl = 6;
   }
-  VMC_CHECK_ARG((impl >= 1 && impl <= 8) || impl == 31 || impl == 32 || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 1..8");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8) || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
+#else
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
+#endif
   const int d = heads * HD;
   if (impl == 8) {  // warp-level tensor path for short sequences (backward.cu)
     if (L <= 64) return vmc_attention_vit_short_mma(qkv, out, F, L, heads, stream);
@@ -2167,11 +1644,15 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     const uint32_t smem6 = 6u * (uint32_t)a6.lk16 * 128u + 2048u + 5u * 1024u + 512u + 256u + 1024u;
     cudaStream_t st6 = reinterpret_cast<cudaStream_t>(stream);
     const int grid6 = a6.n_items < vmc_num_sms() ? a6.n_items : vmc_num_sms();
+#ifdef VMC_WHATIF
     auto kern6 = var6 == 0 ? attention_vit6_kernel<0>
                  : var6 == 1 ? attention_vit6_kernel<1>
                  : var6 == 2 ? attention_vit6_kernel<2>
                  : var6 == 4 ? attention_vit6_kernel<4>
                  : var6 == 7 ? attention_vit6_kernel<7> : attention_vit6_kernel<31>;
+#else
+    auto kern6 = attention_vit6_kernel<0>;
+#endif
     VMC_CUDA(cudaFuncSetAttribute(kern6, cudaFuncAttributeMaxDynamicSharedMemorySize, smem6));
     {
       VmcProfScope prof(VMC_K_ATTN_VIT, st6, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
@@ -2181,8 +1662,7 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     vmc_count_launch();
     return VMC_OK;
   }
-  if (impl >= 3 && (L <= 128 || L > 256)) impl = 2;
-  if ((impl == 5 || impl >= 51) && L > 224) impl = 3;  // v5 keeps two Q/K and two V slots + the ones tile in smem  // the persistent kernels cover two query tiles
+  if (impl >= 5 && (L <= 128 || L > 224)) impl = 2;  // v5 covers 129..224 tokens (two Q/K and two V slots + the ones tile in smem)
   if (impl == 5 || impl >= 51) {
     Attn5Args a5;
     a5.L = L;
@@ -2206,6 +1686,7 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     const uint32_t smem5 = 6u * (uint32_t)a5.lk16 * 128u + (uint32_t)(a5.lk16 / 16) * 2048u + 256 + 1024;
     cudaStream_t st5 = reinterpret_cast<cudaStream_t>(stream);
     const int grid5 = a5.n_items < vmc_num_sms() ? a5.n_items : vmc_num_sms();
+#ifdef VMC_WHATIF
     auto kern5 = impl == 5 ? attention_vit5_kernel<0>
                  : impl == 56 ? attention_vit5_kernel<4>
                  : impl == 57 ? attention_vit5_kernel<5>
@@ -2214,6 +1695,9 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
                  : impl == 52 ? attention_vit5_kernel<2>
                  : impl == 53 ? attention_vit5_kernel<3>
                  : impl == 54 ? attention_vit5_kernel<1, true> : attention_vit5_kernel<0, true>;  // 54 / 55: timeline stamps
+#else
+    auto kern5 = attention_vit5_kernel<0>;
+#endif
     VMC_CUDA(cudaFuncSetAttribute(kern5, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
     {
       VmcProfScope prof(VMC_K_ATTN_VIT, st5, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
@@ -2223,55 +1707,6 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     vmc_count_launch();
     return VMC_OK;
   }
-  if (impl >= 3) {
-    Attn3Args a3;
-    a3.L = L;
-    a3.heads = heads;
-    a3.d = d;
-    a3.lk16 = ((L + 15) / 16) * 16;
-    a3.n_items = F * heads;
-    a3.out = reinterpret_cast<__nv_bfloat16*>(out);
-    a3.dbg = reinterpret_cast<long long*>((uintptr_t)(unsigned long long)vmc_get_option64(VMC_OPT_DEBUG_PTR));
-    CUtensorMap tm3;
-    const uint64_t dims3[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)F};
-    const uint64_t strides3[2] = {(uint64_t)3 * d * 2, (uint64_t)L * 3 * d * 2};
-    const uint32_t box3[3] = {HD, 128, 1};
-    VMC_TRY(vmc_encode_tmap_bf16(&tm3, qkv, 3, dims3, strides3, box3));
-    const uint32_t smem3 = 12 * TILE + 128 + 4096 + 1024;
-    cudaStream_t st3 = reinterpret_cast<cudaStream_t>(stream);
-    const int grid3 = a3.n_items < vmc_num_sms() ? a3.n_items : vmc_num_sms();
-    {
-      VmcProfScope prof(VMC_K_ATTN_VIT, st3, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
-      if (impl == 3) {
-        VMC_CUDA(cudaFuncSetAttribute(attention_vit3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-        attention_vit3_kernel<0><<<grid3, 320, smem3, st3>>>(tm3, a3);
-      } else if (impl == 31) {  // what-if timing variants, wrong results (tools/kernel_bench.py)
-        VMC_CUDA(cudaFuncSetAttribute(attention_vit3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-        attention_vit3_kernel<1><<<grid3, 320, smem3, st3>>>(tm3, a3);
-      } else if (impl == 32) {
-        VMC_CUDA(cudaFuncSetAttribute(attention_vit3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-        attention_vit3_kernel<2><<<grid3, 320, smem3, st3>>>(tm3, a3);
-      } else {
-        VMC_CUDA(cudaFuncSetAttribute(attention_vit4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-        attention_vit4_kernel<<<grid3, 640, smem3, st3>>>(tm3, a3);
-      }
-    }
-    {
-      cudaError_t le = cudaGetLastError();
-      if (le != cudaSuccess) {
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, attention_vit4_kernel);
-        vmc_set_error("attention_vit%d launch failed: %s (regs %d, maxThreads %d, static smem %zu, dyn %u, maxDyn %d)",
-                      impl, cudaGetErrorString(le), fa.numRegs, fa.maxThreadsPerBlock, fa.sharedSizeBytes, smem3,
-                      fa.maxDynamicSharedSizeBytes);
-        return (int)le;
-      }
-    }
-    VMC_LAUNCH_CHECK();
-    vmc_count_launch();
-    return VMC_OK;
-  }
-  const bool p_tmem = impl == 2;
   AttnArgs a;
   a.F = F;
   a.L = L;
@@ -2280,16 +1715,10 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
   a.n_mt = (L + 127) / 128;
   a.lk16 = ((L + 15) / 16) * 16;
   const int lk32 = ((a.lk16 + 31) / 32) * 32;
-  if (p_tmem) {
-    a.n_pkb = 0;
-    a.o_col = ((lk32 / 2 + 31) / 32) * 32;  // first 32-aligned column past the packed P
-    const int need = lk32 > a.o_col + HD ? lk32 : a.o_col + HD;
-    a.tmem_cols = pow2_at_least(need);
-  } else {
-    a.n_pkb = (lk32 + 63) / 64;
-    a.o_col = 0;
-    a.tmem_cols = pow2_at_least(lk32 > 64 ? lk32 : 64);
-  }
+  a.n_pkb = 0;
+  a.o_col = ((lk32 / 2 + 31) / 32) * 32;  // first 32-aligned column past the packed P
+  const int need = lk32 > a.o_col + HD ? lk32 : a.o_col + HD;
+  a.tmem_cols = pow2_at_least(need);
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   CUtensorMap tm;
   const uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)F};
@@ -2302,16 +1731,11 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const double fl = 4.0 * F * heads * (double)L * L * HD;
   const unsigned grid = (unsigned)((long long)F * heads);
-  if (p_tmem) {
+  {
     VMC_CUDA(cudaFuncSetAttribute(attention_vit_kernel<true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VmcProfScope prof(VMC_K_ATTN_VIT, st, fl, 8.0 * F * L * d);
     attention_vit_kernel<true><<<grid, 128, smem, st>>>(tm, a);
-  } else {
-    VMC_CUDA(cudaFuncSetAttribute(attention_vit_kernel<false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VmcProfScope prof(VMC_K_ATTN_VIT, st, fl, 8.0 * F * L * d);
-    attention_vit_kernel<false><<<grid, 128, smem, st>>>(tm, a);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
@@ -2335,7 +1759,7 @@ int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L
 
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream) {
   const int opt = vmc_get_option(VMC_OPT_ATTN_IMPL);
-  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt >= 1 && opt <= 8) ? opt : 5, stream);
+  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt == 2 || (opt >= 5 && opt <= 8)) ? opt : 5, stream);
 }
 
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk,

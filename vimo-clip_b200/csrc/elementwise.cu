@@ -839,17 +839,20 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* row, int d, int j, f
 // ---------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row cached in registers, fp32 two-pass statistics.
 // ---------------------------------------------------------------------------------------
-template <int NV>  // float4 per lane; supports d <= NV * 128
+// XB16: the input rows are bf16 (the bf16 residual stream of the ViT tower; cls_every must be 0).
+// stats_rounded: stats_out holds the statistics of the bf16-ROUNDED output row (what a GEMM reading y16 multiplies).
+template <int NV, bool XB16>  // float4 per lane; supports d <= NV * 128
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+layernorm_kernel(const void* __restrict__ x_, long long ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* y32, long long ld32,
                  __nv_bfloat16* y16, long long ld16, int y16_split, int rows, int d,
-                 const float* __restrict__ cls_row, int cls_every, float2* __restrict__ stats_out) {
+                 const float* __restrict__ cls_row, int cls_every, float2* __restrict__ stats_out, int stats_rounded) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float* xr = x + (size_t)row * ldx;
-  if (cls_every > 0 && (row % cls_every) == 0) xr = cls_row;
+  const float* xr = XB16 ? nullptr : reinterpret_cast<const float*>(x_) + (size_t)row * ldx;
+  const __nv_bfloat16* xr16 = XB16 ? reinterpret_cast<const __nv_bfloat16*>(x_) + (size_t)row * ldx : nullptr;
+  if (!XB16 && cls_every > 0 && (row % cls_every) == 0) xr = cls_row;
   const int nv = d >> 2;
   float4 v[NV];
   float s = 0.f;
@@ -857,7 +860,13 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
   for (int i = 0; i < NV; ++i) {
     const int j = lane + 32 * i;
     if (j < nv) {
-      v[i] = reinterpret_cast<const float4*>(xr)[j];
+      if constexpr (XB16) {
+        const uint2 u = reinterpret_cast<const uint2*>(xr16)[j];
+        v[i] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                           __uint_as_float(u.y & 0xFFFF0000u));
+      } else {
+        v[i] = reinterpret_cast<const float4*>(xr)[j];
+      }
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -886,8 +895,15 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      so += (o.x + o.y) + (o.z + o.w);
-      qo += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+      if (stats_rounded) {
+        const float r0 = __bfloat162float(__float2bfloat16_rn(o.x)), r1 = __bfloat162float(__float2bfloat16_rn(o.y));
+        const float r2 = __bfloat162float(__float2bfloat16_rn(o.z)), r3 = __bfloat162float(__float2bfloat16_rn(o.w));
+        so += (r0 + r1) + (r2 + r3);
+        qo += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
+      } else {
+        so += (o.x + o.y) + (o.z + o.w);
+        qo += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+      }
       if (y32 != nullptr) reinterpret_cast<float4*>(y32 + (size_t)row * ld32)[j] = o;
       if (y16 != nullptr) {
         if (y16_split) {
@@ -1218,6 +1234,13 @@ int vmc_layernorm(const float* x, long long ldx, const float* gamma, const float
 int vmc_layernorm_stats(const float* x, long long ldx, const float* gamma, const float* beta, float eps,
                         float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows,
                         int d, const float* cls_row, int cls_every, float* stats_out, void* stream) {
+  return vmc_layernorm_ex(x, 0, ldx, gamma, beta, eps, y32, ld32, y16, ld16, y16_split, rows, d, cls_row, cls_every,
+                          stats_out, 0, stream);
+}
+
+int vmc_layernorm_ex(const void* x, int x_bf16, long long ldx, const float* gamma, const float* beta, float eps,
+                     float* y32, long long ld32, void* y16, long long ld16, int y16_split, int rows, int d,
+                     const float* cls_row, int cls_every, float* stats_out, int stats_rounded, void* stream) {
   VMC_CHECK_ARG(x && gamma && beta && (y32 || y16), VMC_ERR_ARG, "vmc_layernorm: null pointer");
   VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(stats_out) & 7) == 0, VMC_ERR_ALIGN,
                 "vmc_layernorm_stats: stats_out must be 8-byte aligned");
@@ -1225,17 +1248,26 @@ int vmc_layernorm_stats(const float* x, long long ldx, const float* gamma, const
                 "vmc_layernorm: need d %% 4 == 0 and d <= 4096 (rows=%d d=%d)", rows, d);
   VMC_CHECK_ARG((ldx % 4) == 0 && (!y32 || (ld32 % 4) == 0) && (!y16 || (ld16 % 4) == 0),
                 VMC_ERR_ALIGN, "vmc_layernorm: row strides must be multiples of 4 elements");
-  VMC_CHECK_ARG(cls_every <= 0 || cls_row != nullptr, VMC_ERR_ARG,
-                "vmc_layernorm: cls_every set without cls_row");
+  VMC_CHECK_ARG(cls_every <= 0 || (cls_row != nullptr && !x_bf16), VMC_ERR_ARG,
+                "vmc_layernorm: cls_every needs cls_row and an fp32 input");
+  VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & (x_bf16 ? 7 : 15)) == 0, VMC_ERR_ALIGN,
+                "vmc_layernorm: input rows must be 16-byte (fp32) / 8-byte (bf16) aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (rows + 7) / 8;
   __nv_bfloat16* y16b = reinterpret_cast<__nv_bfloat16*>(y16);
-#define LN_LAUNCH(NV)                                                                            \
-  layernorm_kernel<NV><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, y32, ld32, y16b, ld16,    \
-                                             y16_split, rows, d, cls_row, cls_every,         \
-                                             reinterpret_cast<float2*>(stats_out))
+#define LN_LAUNCH(NV)                                                                                              \
+  do {                                                                                                             \
+    if (x_bf16)                                                                                                    \
+      layernorm_kernel<NV, true><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, y32, ld32, y16b, ld16, y16_split, \
+                                                       rows, d, cls_row, cls_every,                                \
+                                                       reinterpret_cast<float2*>(stats_out), stats_rounded);       \
+    else                                                                                                           \
+      layernorm_kernel<NV, false><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, eps, y32, ld32, y16b, ld16, y16_split, \
+                                                        rows, d, cls_row, cls_every,                               \
+                                                        reinterpret_cast<float2*>(stats_out), stats_rounded);      \
+  } while (0)
   VmcProfScope prof(VMC_K_LAYERNORM, st, 0.0,
-                    (double)rows * d * (4.0 + (y32 ? 4.0 : 0.0) + (y16 ? 2.0 : 0.0)));
+                    (double)rows * d * ((x_bf16 ? 2.0 : 4.0) + (y32 ? 4.0 : 0.0) + (y16 ? 2.0 : 0.0)));
   if (d <= 512) LN_LAUNCH(4);
   else if (d <= 768) LN_LAUNCH(6);
   else if (d <= 1024) LN_LAUNCH(8);

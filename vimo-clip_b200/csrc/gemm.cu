@@ -375,8 +375,8 @@ extern "C" int vmc_gemm_bf16_ex(const void* A, long long lda, int a_transposed, 
                 VMC_ERR_ALIGN, "vmc_gemm_bf16: out must be 16-byte aligned with ldo %% %d == 0",
                 oalign);
   if (epi->resid)
-    VMC_CHECK_ARG((epi->ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(epi->resid) & 15) == 0,
-                  VMC_ERR_ALIGN, "vmc_gemm_bf16: resid must be 16-byte aligned with ldr %% 4 == 0");
+    VMC_CHECK_ARG((epi->ldr % 4) == 0 && (reinterpret_cast<uintptr_t>(epi->resid) & (epi->resid_bf16 ? 7 : 15)) == 0,
+                  VMC_ERR_ALIGN, "vmc_gemm_bf16: resid must be 16-byte (fp32) / 8-byte (bf16) aligned with ldr %% 4 == 0");
   if (epi->bias)
     VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(epi->bias) & 15) == 0, VMC_ERR_ALIGN,
                   "vmc_gemm_bf16: bias must be 16-byte aligned");
@@ -387,8 +387,8 @@ extern "C" int vmc_gemm_bf16_ex(const void* A, long long lda, int a_transposed, 
     return vmc_gemm2_dispatch(A, lda, W, ldw, M, N, K, epi, st, a_transposed ? 1 : 0, w_transposed ? 1 : 0);
   VMC_CHECK_ARG(!a_transposed && !w_transposed, VMC_ERR_ARG,
                 "vmc_gemm_bf16_ex: transposed (MN-major) operands exist only in the CTA-pair kernel");
-  VMC_CHECK_ARG(epi->ln_out == nullptr && epi->raw16_out == nullptr && epi->stats_out == nullptr &&
-                    epi->stats_in == nullptr,
+  VMC_CHECK_ARG(epi->raw16_out == nullptr && epi->stats_out == nullptr &&
+                    epi->stats_in == nullptr && !epi->resid_bf16,
                 VMC_ERR_ARG, "vmc_gemm_bf16: the fused / folded LayerNorm epilogues exist only in the CTA-pair kernel");
   // single-CTA kernel: 128x256 tiles when there are enough to fill the machine twice; 128x128 otherwise.
   const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);

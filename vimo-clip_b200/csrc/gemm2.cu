@@ -17,6 +17,8 @@
 // Epilogue: tcgen05.ld gives a thread one accumulator ROW; the chunk is transposed through a private
 // XOR-swizzled 4 KB shared-memory tile so global loads (residual, bias) and stores are issued with 8
 // lanes per 128-byte row segment (4 full lines per warp instruction).
+#include <type_traits>
+
 #include "common.cuh"
 #include "vimoclip_b200.h"
 
@@ -146,21 +148,24 @@ __device__ __forceinline__ float quickgelu_fast(float x) {
 //       before the bias; mean / rstd come from the producer's partial row sums (statistics over K columns).
 // STATS (producer, MODE 3): also write the bf16 copy of the output rows and this warp's partial
 //       (sum, sum of squares) of each row over its HALF_N columns.
-template <int MODE, int HALF_N, bool LNF = false, bool STATS = false>
+// R16   (MODE 3 + STATS): the residual stream itself is bf16 -- resid is read as bf16, out is written as bf16 (it IS the A
+//       operand of the next GEMM: no separate raw16 copy) and the statistics are those of the ROUNDED values.
+template <int MODE, int HALF_N, bool LNF = false, bool STATS = false, bool R16 = false>
 __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M, int N, int K, int row0,
                                               int n_base, uint32_t t_acc, uint8_t* stg, int lane) {
   const int lr = lane >> 3, lc = lane & 7;
   const int m_first = row0 + lr;
   int nvalid = (M - m_first + 3) >> 2;  // rows m_first + 4 i, i < nvalid, are inside the matrix
   nvalid = nvalid < 0 ? 0 : (nvalid > 8 ? 8 : nvalid);
-  constexpr int ESZ = (MODE == 3) ? 4 : 2;
+  constexpr int ESZ = (MODE == 3 && !R16) ? 4 : 2;
+  constexpr int RSZ = R16 ? 2 : 4;  // bytes per residual element
   char* optr = reinterpret_cast<char*>(e.out) + ((long long)m_first * e.ldo + n_base + lc * 4) * ESZ;
   const long long ostride = 4 * e.ldo * ESZ;
   const char* rptr = nullptr;
   long long rstride = 0;
   if constexpr (MODE == 3) {
-    rptr = reinterpret_cast<const char*>(e.resid) + ((long long)m_first * e.ldr + n_base + lc * 4) * 4;
-    rstride = 4 * e.ldr * 4;
+    rptr = reinterpret_cast<const char*>(e.resid) + ((long long)m_first * e.ldr + n_base + lc * 4) * RSZ;
+    rstride = 4 * e.ldr * RSZ;
   }
   const float* bptr = e.bias + n_base + lc * 4;
   // folded LayerNorm: every thread derives mean / rstd of ONE row (row0 + lane) from the producer's partial sums;
@@ -193,15 +198,27 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
   if constexpr (STATS) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) psum[i] = psq[i] = 0.f;
-    r16ptr = reinterpret_cast<char*>(e.raw16_out) + ((long long)m_first * e.raw16_ld + n_base + lc * 4) * 2;
-    r16stride = 4 * e.raw16_ld * 2;
+    if constexpr (!R16) {
+      r16ptr = reinterpret_cast<char*>(e.raw16_out) + ((long long)m_first * e.raw16_ld + n_base + lc * 4) * 2;
+      r16stride = 4 * e.raw16_ld * 2;
+    }
   }
-  float4 res_next[8];
+  // residual rows of one 32-column chunk: 4 consecutive elements per lane and row (float4, or 4 bf16 kept packed in a uint2)
+  using ResT = typename std::conditional<R16, uint2, float4>::type;
+  auto res_f4 = [](const ResT& u) -> float4 {
+    if constexpr (R16) {
+      return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                         __uint_as_float(u.y & 0xFFFF0000u));
+    } else {
+      return u;
+    }
+  };
+  ResT res_next[8];
   if constexpr (MODE == 3) {
     const char* rp = rptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (i < nvalid && n_base < N) res_next[i] = *reinterpret_cast<const float4*>(rp);
+      if (i < nvalid && n_base < N) res_next[i] = *reinterpret_cast<const ResT*>(rp);
       rp += rstride;
     }
   }
@@ -213,17 +230,17 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + c * 32));
     float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (LNF) cs4 = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base + c * 32 + lc * 4));
-    float4 res[8];
+    ResT res[8];
     if constexpr (MODE == 3) {
       // the residual rows of the NEXT chunk are requested while this one is processed: the epilogue of the
       // K = 768 residual GEMMs is bound by bytes in flight (8 warps x 4 KB per SM), not by HBM bandwidth
 #pragma unroll
       for (int i = 0; i < 8; ++i) res[i] = res_next[i];
       if (c + 1 < HALF_N / 32 && n_base + (c + 1) * 32 < N) {
-        const char* rp = rptr + (c + 1) * 128;
+        const char* rp = rptr + (c + 1) * 32 * RSZ;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (i < nvalid) res_next[i] = *reinterpret_cast<const float4*>(rp);
+          if (i < nvalid) res_next[i] = *reinterpret_cast<const ResT*>(rp);
           rp += rstride;
         }
       }
@@ -242,7 +259,7 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
     }
     __syncwarp();
     char* op = optr + c * 32 * ESZ;
-    char* r16p = STATS ? r16ptr + c * 64 : nullptr;
+    char* r16p = (STATS && !R16) ? r16ptr + c * 64 : nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 v = w[i];
@@ -264,19 +281,33 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
         v.w = quickgelu_fast(v.w);
       }
       if constexpr (MODE == 3) {
-        v.x += res[i].x;
-        v.y += res[i].y;
-        v.z += res[i].z;
-        v.w += res[i].w;
-        if (i < nvalid) *reinterpret_cast<float4*>(op) = v;
-        if constexpr (STATS) {
-          psum[i] += (v.x + v.y) + (v.z + v.w);
-          psq[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        const float4 rr = res_f4(res[i]);
+        v.x += rr.x;
+        v.y += rr.y;
+        v.z += rr.z;
+        v.w += rr.w;
+        if constexpr (R16) {
           uint2 o;
           o.x = pack_bf16x2(v.x, v.y);
           o.y = pack_bf16x2(v.z, v.w);
-          if (i < nvalid) *reinterpret_cast<uint2*>(r16p) = o;
-          r16p += r16stride;
+          if (i < nvalid) *reinterpret_cast<uint2*>(op) = o;
+          if constexpr (STATS) {  // of the values the next GEMM will read
+            const float r0 = __uint_as_float(o.x << 16), r1 = __uint_as_float(o.x & 0xFFFF0000u);
+            const float r2 = __uint_as_float(o.y << 16), r3 = __uint_as_float(o.y & 0xFFFF0000u);
+            psum[i] += (r0 + r1) + (r2 + r3);
+            psq[i] += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
+          }
+        } else {
+          if (i < nvalid) *reinterpret_cast<float4*>(op) = v;
+          if constexpr (STATS) {
+            psum[i] += (v.x + v.y) + (v.z + v.w);
+            psq[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            uint2 o;
+            o.x = pack_bf16x2(v.x, v.y);
+            o.y = pack_bf16x2(v.z, v.w);
+            if (i < nvalid) *reinterpret_cast<uint2*>(r16p) = o;
+            r16p += r16stride;
+          }
         }
       } else {
         uint2 o;
@@ -330,27 +361,12 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int num_tiles = g.tiles_m * g.tiles_n;
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  // Tile order.  Default: tile t = pair + i * num_pairs with N fastest, so the pairs running together
-  // share one A block.  MODE 4 (fused LayerNorm) needs a pair to OWN whole rows: it walks all N tiles of
-  // row block (pair + j * num_pairs) back to back; after the last one the CTA holds complete rows of x.
-  constexpr bool kRowOwner = (MODE == 4);
-  int my_tiles;
-  if (kRowOwner) {
-    const int my_blocks = pair < g.tiles_m ? (g.tiles_m - pair + num_pairs - 1) / num_pairs : 0;
-    my_tiles = my_blocks * g.tiles_n;
-  } else {
-    my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
-  }
+  // Tile order: tile t = pair + i * num_pairs with N fastest, so the pairs running together share one A block.
+  const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
   auto tile_of = [&](int i, int& m_blk, int& n_blk) {
-    if (kRowOwner) {
-      const int j = i / g.tiles_n;
-      n_blk = i - j * g.tiles_n;
-      m_blk = pair + j * num_pairs;
-    } else {
-      const int t = pair + i * num_pairs;
-      n_blk = t % g.tiles_n;
-      m_blk = t / g.tiles_n;
-    }
+    const int t = pair + i * num_pairs;
+    n_blk = t % g.tiles_n;
+    m_blk = t / g.tiles_n;
   };
 
   if (warp == 0 && lane == 0) {
@@ -468,12 +484,14 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       tc_fence_after();
       const uint32_t t_acc =
           tmem_base + uint32_t(acc * BN + half * HALF_N) + (uint32_t(quarter * 32) << 16);
-      if constexpr (MODE == 5) {
+      if constexpr (MODE == 8) {
+        epilogue_fast<3, HALF_N, false, true, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
+      } else if constexpr (MODE == 5) {
         epilogue_fast<3, HALF_N, false, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else if constexpr (MODE == 6 || MODE == 7) {
         epilogue_fast<MODE - 5, HALF_N, true, false>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else if constexpr (MODE != 0) {
-        epilogue_fast<(MODE == 4 ? 3 : MODE), HALF_N>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
+        epilogue_fast<MODE, HALF_N>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else {
         // ---- generic path: any activation / alpha / ragged N / patch-embed row remap ----
 #pragma unroll 1
@@ -499,8 +517,15 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             }
             ooff[i] = (m < g.M) ? orow * e.ldo + col : -1;
             res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_res && m < g.M && col_full)
-              res[i] = *reinterpret_cast<const float4*>(e.resid + rrow * e.ldr + col);
+            if (has_res && m < g.M && col_full) {
+              if (e.resid_bf16) {
+                const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.resid) + rrow * e.ldr + col);
+                res[i] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+              } else {
+                res[i] = *reinterpret_cast<const float4*>(e.resid + rrow * e.ldr + col);
+              }
+            }
           }
           tmem_ld_wait();
 #pragma unroll
@@ -556,7 +581,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                   float x = wv[q];
                   if (e.bias != nullptr) x += __ldg(e.bias + col + q);
                   x = act2(x, e.act) * e.alpha;
-                  if (has_res) x += e.resid[rrow * e.ldr + col + q];
+                  if (has_res)
+                    x += e.resid_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.resid)[rrow * e.ldr + col + q])
+                                      : e.resid[rrow * e.ldr + col + q];
                   if (e.out_bf16)
                     reinterpret_cast<__nv_bfloat16*>(e.out)[ooff[i] + q] = __float2bfloat16_rn(x);
                   else
@@ -572,57 +599,6 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
-      if constexpr (MODE == 4) {
-        if (n_blk == g.tiles_n - 1) {
-          // Fused LayerNorm of the NEXT op's input.  The 8 epilogue warps of this CTA have just written
-          // all N columns of its 128 rows of x (fp32): wait for each other, then normalise the rows
-          // straight out of L2 (same arithmetic as layernorm_kernel: one warp per row, row in
-          // registers, two-pass fp32 statistics) and write the bf16 A operand of the next GEMM.
-          // The accumulator was already handed back, so the next row block's MMAs run underneath.
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const int nv = g.N >> 2;  // float4 per row (N <= 1024, N % 128 == 0)
-          const int cta_row0 = m_blk * (2 * BM) + (int)rank * BM;
-          for (int rr = ew; rr < BM; rr += 8) {
-            const int m = cta_row0 + rr;
-            if (m >= g.M) break;
-            const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) + (long long)m * e.ldo);
-            float4 v[8];
-            float sum = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int j = lane + 32 * q;
-              if (j < nv) {
-                v[q] = __ldcg(xr + j);  // L2: written moments ago by the other epilogue warps of this CTA
-                sum += (v[q].x + v[q].y) + (v[q].z + v[q].w);
-              }
-            }
-            const float mean = warp_sum(sum) / (float)g.N;
-            float sq = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int j = lane + 32 * q;
-              if (j < nv) {
-                const float a0 = v[q].x - mean, a1 = v[q].y - mean, a2 = v[q].z - mean, a3 = v[q].w - mean;
-                sq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-              }
-            }
-            const float rstd = rsqrtf(warp_sum(sq) / (float)g.N + e.ln_eps);
-            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(e.ln_out) + (long long)m * e.ln_ldo;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int j = lane + 32 * q;
-              if (j < nv) {
-                const float4 gm = __ldg(reinterpret_cast<const float4*>(e.ln_gamma) + j);
-                const float4 bt = __ldg(reinterpret_cast<const float4*>(e.ln_beta) + j);
-                uint2 pk;
-                pk.x = pack_bf16x2((v[q].x - mean) * rstd * gm.x + bt.x, (v[q].y - mean) * rstd * gm.y + bt.y);
-                pk.y = pack_bf16x2((v[q].z - mean) * rstd * gm.z + bt.z, (v[q].w - mean) * rstd * gm.w + bt.w);
-                reinterpret_cast<uint2*>(orow)[j] = pk;
-              }
-            }
-          }
-        }
-      }
     }
   }
 
@@ -678,7 +654,7 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
   {
     const double out_b = (double)M * N * (epi->out_bf16 ? 2 : 4);
     VmcProfScope prof(VMC_K_GEMM, stream, 2.0 * M * N * K,
-                      2.0 * ((double)M * K + (double)N * K) + out_b + (epi->resid ? 4.0 * M * N : 0.0) +
+                      2.0 * ((double)M * K + (double)N * K) + out_b + (epi->resid ? (epi->resid_bf16 ? 2.0 : 4.0) * M * N : 0.0) +
                           (epi->raw16_out ? 2.0 * M * N : 0.0));
     gemm2_bf16_tcgen05_kernel<BN, MODE><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, g);
   }
@@ -708,10 +684,22 @@ int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ld
   if (fast_ok) {
     if (epi->out_bf16 && !epi->resid && epi->act == VMC_ACT_NONE) mode = 1;
     else if (epi->out_bf16 && !epi->resid && epi->act == VMC_ACT_QUICKGELU) mode = 2;
-    else if (!epi->out_bf16 && epi->resid && epi->act == VMC_ACT_NONE) mode = 3;
+    else if (!epi->out_bf16 && epi->resid && !epi->resid_bf16 && epi->act == VMC_ACT_NONE) mode = 3;
+  }
+  if (epi->resid && epi->resid_bf16 && epi->out_bf16 && epi->stats_out != nullptr) {
+    // bf16 residual stream: out = bf16(acc + bias + resid), row statistics of the rounded values
+    VMC_CHECK_ARG(fast_ok && epi->act == VMC_ACT_NONE && epi->raw16_out == nullptr &&
+                      epi->stats_in == nullptr && (N % (big ? 128 : 64)) == 0 && epi->stats_ld >= M &&
+                      (epi->ldr % 4) == 0 && (epi->ldo % 4) == 0 && (reinterpret_cast<uintptr_t>(epi->resid) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(epi->out) & 7) == 0 && (reinterpret_cast<uintptr_t>(epi->stats_out) & 7) == 0,
+                  VMC_ERR_ARG,
+                  "vmc_gemm_bf16: the bf16 residual-stream epilogue needs bias, alpha 1, no activation, N a multiple of the "
+                  "column slice (%d), stats_ld >= M and 8-byte aligned rows", big ? 128 : 64);
+    if (big) return launch_gemm2<256, 8>(A, lda, W, ldw, M, N, K, epi, stream, a_mn, b_mn);
+    return launch_gemm2<128, 8>(A, lda, W, ldw, M, N, K, epi, stream, a_mn, b_mn);
   }
   if (epi->raw16_out != nullptr || epi->stats_out != nullptr) {
-    VMC_CHECK_ARG(mode == 3 && epi->raw16_out && epi->stats_out && epi->ln_out == nullptr && (N % (big ? 128 : 64)) == 0 &&
+    VMC_CHECK_ARG(mode == 3 && epi->raw16_out && epi->stats_out && (N % (big ? 128 : 64)) == 0 &&
                       (epi->raw16_ld % 4) == 0 && epi->raw16_ld >= N && epi->stats_ld >= M &&
                       (reinterpret_cast<uintptr_t>(epi->raw16_out) & 7) == 0 &&
                       (reinterpret_cast<uintptr_t>(epi->stats_out) & 7) == 0,
@@ -729,21 +717,12 @@ int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ld
                   "stats_parts > 0");
     mode += 5;
   }
-  if (epi->ln_out != nullptr) {
-    VMC_CHECK_ARG(mode == 3 && big && N <= 1024 && (N % 128) == 0 && epi->ln_gamma && epi->ln_beta &&
-                      epi->ldo >= N && (epi->ln_ldo % 4) == 0,
-                  VMC_ERR_ARG,
-                  "vmc_gemm_bf16: the fused LayerNorm needs the fp32 bias+residual epilogue, N %% 128 == 0, N <= 1024 "
-                  "and enough tiles for 128x256 pair tiles");
-    mode = 4;
-  }
 #define VMC_G2(BN_, MODE_) return launch_gemm2<BN_, MODE_>(A, lda, W, ldw, M, N, K, epi, stream, a_mn, b_mn)
   if (big) {
     switch (mode) {
       case 1: VMC_G2(256, 1);
       case 2: VMC_G2(256, 2);
       case 3: VMC_G2(256, 3);
-      case 4: VMC_G2(256, 4);
       case 5: VMC_G2(256, 5);
       case 6: VMC_G2(256, 6);
       case 7: VMC_G2(256, 7);

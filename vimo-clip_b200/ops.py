@@ -162,11 +162,12 @@ def frame_diff(bgr: torch.Tensor, *, dst: str | None = None, patch: int = 0, wan
 # ---------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, alpha: float = 1.0, resid=None,
          out: torch.Tensor | None = None, out_dtype=torch.bfloat16, n: int | None = None, k: int | None = None,
-         row_group: int = 0, out_rows: int | None = None, ln=None, emit_stats=None, fold=None, a_t: bool = False,
+         row_group: int = 0, out_rows: int | None = None, emit_stats=None, fold=None, a_t: bool = False,
          w_t: bool = False) -> torch.Tensor:
     """out = alpha * act(a @ w.T + bias) + resid.  a [M, lda] bf16, w [N, ldw] bf16 (nn.Linear layout).
-    ln = (gamma, beta, eps, ln_out bf16 [M, N]): fused LayerNorm of the output rows (see vmc_gemm_epilogue).
-    emit_stats = (raw16 bf16 [M, N], stats fp32 [parts, M, 2]): producer side of a folded LayerNorm.
+    resid may be fp32 or bf16 (bf16 residual stream of the ViT tower).
+    emit_stats = (raw16 bf16 [M, N] | None, stats fp32 [parts, M, 2]): producer side of a folded LayerNorm; raw16 None with
+    a bf16 resid and a bf16 out: the output IS the bf16 row copy and the statistics are those of the rounded values.
     fold = (stats fp32 [parts, M, 2], colsum fp32 [N], eps): consumer side (a = raw rows, w = gamma-folded weights).
     a_t / w_t: the operand is given transposed in memory (a = A^T [K, M], w = W^T [K, N], row-major): MN-major UMMA
     operands, no transposing pass (the dW = dY^T X and dX = dY W GEMMs of the backward)."""
@@ -190,19 +191,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, al
     e.out_bf16 = 1 if out.dtype == torch.bfloat16 else 0
     if out.dtype not in (torch.bfloat16, torch.float32):
         raise TypeError("gemm output must be bf16 or fp32")
-    if bias is not None and bias.dtype != torch.float32 or resid is not None and resid.dtype != torch.float32:
-        raise TypeError("bias / resid must be fp32")
+    if bias is not None and bias.dtype != torch.float32:
+        raise TypeError("bias must be fp32")
+    if resid is not None and resid.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("resid must be fp32 or bf16")
+    e.resid_bf16 = 1 if (resid is not None and resid.dtype == torch.bfloat16) else 0
     e.act = act
     e.alpha = alpha
     e.row_group = row_group
-    if ln is not None:
-        g_, b_, eps_, ln_out = ln
-        _need_cuda(g_, b_, ln_out)
-        e.ln_gamma, e.ln_beta, e.ln_out, e.ln_ldo, e.ln_eps = g_.data_ptr(), b_.data_ptr(), ln_out.data_ptr(), ln_out.stride(0), eps_
     if emit_stats is not None:
         raw16, stats = emit_stats
         _need_cuda(raw16, stats)
-        e.raw16_out, e.raw16_ld, e.stats_out, e.stats_ld = raw16.data_ptr(), raw16.stride(0), stats.data_ptr(), stats.shape[1]
+        if raw16 is not None:
+            e.raw16_out, e.raw16_ld = raw16.data_ptr(), raw16.stride(0)
+        e.stats_out, e.stats_ld = stats.data_ptr(), stats.shape[1]
     if fold is not None:
         stats, colsum, eps_ = fold
         _need_cuda(stats, colsum)
@@ -219,18 +221,21 @@ def gemm_stats_parts(M: int, N: int) -> int:
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5, want32: bool = False,
-              want16: bool = True, out32: torch.Tensor | None = None, split16: bool = False):
-    """x fp32 [rows, d] -> (y32 | None, y16 | None).  split16: y16 is the [rows, 3d] split operand [hi|lo|hi]."""
-    _need_cuda(x, gamma, beta, out32)
-    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
-        raise ValueError("layernorm input must be fp32 [rows, d] row-major")
+              want16: bool = True, out32: torch.Tensor | None = None, split16: bool = False, stats: torch.Tensor | None = None,
+              stats_rounded: bool = False):
+    """x fp32 or bf16 [rows, d] -> (y32 | None, y16 | None).  split16: y16 is the [rows, 3d] split operand [hi|lo|hi].
+    stats fp32 [rows, 2]: (sum, sum of squares) of the output row (of its bf16 rounding when stats_rounded)."""
+    _need_cuda(x, gamma, beta, out32, stats)
+    if x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("layernorm input must be fp32 or bf16 [rows, d] row-major")
     rows, d = x.shape
     y32 = out32 if out32 is not None else (torch.empty((rows, d), dtype=torch.float32, device=x.device) if want32 else None)
     y16 = torch.empty((rows, 3 * d if split16 else d), dtype=torch.bfloat16, device=x.device) if want16 else None
     with torch.cuda.device(x.device):
         _lib.check(
-            _lib.lib().vmc_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), eps, _p(y32), 0 if y32 is None else y32.stride(0),
-                                     _p(y16), 0 if y16 is None else y16.stride(0), 1 if split16 else 0, rows, d, None, 0, _stream()),
+            _lib.lib().vmc_layernorm_ex(_p(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _p(gamma), _p(beta), eps, _p(y32),
+                                        0 if y32 is None else y32.stride(0), _p(y16), 0 if y16 is None else y16.stride(0),
+                                        1 if split16 else 0, rows, d, None, 0, _p(stats), 1 if stats_rounded else 0, _stream()),
             "vmc_layernorm",
         )
     return y32, y16

@@ -7,7 +7,14 @@ Inference forward on the sm_100a kernels (dropout is inactive in eval, AMO_CLIP.
   post-LN layer (AMO_CLIP.py:37-51):  x = LN(x + SelfMHA(x));  x = LN(x + CrossMHA(x, motion));
                                       x = LN(x + W2 relu(W1 x))
   head (AMO_CLIP.py:170):             logits = classifier(mean over ALL T rows, padded ones included)
-GEMMs run on the tcgen05 kernel in "split-bf16" form (activations [hi|lo|hi] x weights [Whi|Whi|Wlo] in
+
+DEFAULT: ONE fused kernel for the whole block (``vmc_tfam_forward``, csrc/tfam_fused.cu): a cluster of 8 CTAs (one per
+head) per clip, weights streamed from L2 in the fragment-major fp16 order ``pack_weight_stream`` produces, activations in
+(distributed) shared memory, fp32 accumulation / residual / LayerNorm / softmax.  It covers the reference's geometry
+(d_model 512, nhead 8, dim_feedforward 2048: every TFAM/cfg_AK configuration) up to 32 frames per clip and stream;
+anything else, and ``model.fused = False``, takes the BATCHED path below.
+
+Batched path: GEMMs run on the tcgen05 kernel in "split-bf16" form (activations [hi|lo|hi] x weights [Whi|Whi|Wlo] in
 one K = 3d GEMM, fp32 accumulation in TMEM: plain bf16 operands measured 1.1e-2 logit error on config 1,
 over the 1e-2 bar, because the post-LN block has no residual path around the LayerNorms); the residual
 stream, the LayerNorms, the attention scores/softmax and the pooling stay fp32.  TFAM is 0.08% of the
@@ -24,6 +31,43 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+
+
+def _frag_blocks(wsel: torch.Tensor) -> torch.Tensor:
+    """wsel [8 (CTA), 8 (warp), NT, 8 (row g), K] -> [8, 8, (K / 32) * NT, 32 lanes, 8] fp16: per (CTA, warp) the 512-byte blocks
+    in consumption order (k-pair p major, column tile i minor); lane (g, t) of block (p, i) holds
+    W_i[g][32 p + 16 ks + 8 half + 2 t + pair] for (ks, half, pair) in C order -- the mma.m16n8k16 B fragments (b0, b1) of
+    k-steps 2p and 2p + 1 (include/vimoclip_b200.h, vmc_tfam_forward)."""
+    c_, w_, nt, g_, K = wsel.shape
+    kp = K // 32
+    v = wsel.reshape(c_, w_, nt, g_, kp, 2, 2, 4, 2)  # (c, w, i, g, p, ks, half, t, pair)
+    v = v.permute(0, 1, 4, 2, 3, 7, 5, 6, 8)          # (c, w, p, i, g, t, ks, half, pair)
+    return v.reshape(c_, w_, kp * nt, 32, 8)
+
+
+@torch.no_grad()
+def pack_weight_stream(layers) -> torch.Tensor:
+    """fp16 weight stream of the fused kernel for a list of ``AttentionLayer`` (d_model 512, 8 heads, ffn 2048):
+    [8 CTAs][8 warps][layers][256 blocks][32 lanes][8 halfs]; one-time packing at load time."""
+    per_layer = []
+    for ly in layers:
+        f = lambda t: t.detach().float().clamp(-65504.0, 65504.0)  # noqa: E731
+        wsi, wso = f(ly.self_attn.in_proj_weight), f(ly.self_attn.out_proj.weight)
+        wci, wco = f(ly.cross_attn.in_proj_weight), f(ly.cross_attn.out_proj.weight)
+        w1, w2 = f(ly.ffn[0].weight), f(ly.ffn[3].weight)
+        d = wso.shape[0]
+        rows8 = lambda w: w.reshape(8, 8, 8, w.shape[1]).unsqueeze(2)  # noqa: E731  [c, w, 1, g, K]: row = 64 c + 8 w + g
+        parts = [
+            _frag_blocks(wsi.reshape(3, 8, 8, 8, d).permute(1, 2, 0, 3, 4)),       # q | k | v of head c
+            _frag_blocks(rows8(wso)),
+            _frag_blocks(rows8(wci[:d])),
+            _frag_blocks(wci[d:].reshape(2, 8, 8, 8, d).permute(1, 2, 0, 3, 4)),   # k | v of head c (cross)
+            _frag_blocks(rows8(wco)),
+            _frag_blocks(w1.reshape(8, 8, 4, 8, d)),                               # row = 256 c + 32 w + 8 i + g
+            _frag_blocks(w2.reshape(8, 8, 8, 8, 256).permute(3, 0, 1, 2, 4)),      # row = 64 w + 8 i + g, column = 256 c + k
+        ]
+        per_layer.append(torch.cat(parts, dim=2))  # [8, 8, 256, 32, 8]
+    return torch.stack(per_layer, dim=2).to(torch.float16).contiguous()  # [8, 8, L, 256, 32, 8]
 
 
 class AttentionLayer(nn.Module):
@@ -80,6 +124,8 @@ class AMO_CLIP(nn.Module):
         )
         self.projection_layer = nn.Linear(2 * self.d_model, self.d_model)
         self._cache = None
+        self._fcache = None
+        self.fused = True  # one fused kernel per forward where the geometry allows (False: batched GEMM path)
 
     def positional_encoding(self, seq_len, device=None):
         """Sinusoidal PE, AMO_CLIP.py:88-97 (host-side table build; added in place by forward)."""
@@ -118,6 +164,68 @@ class AMO_CLIP(nn.Module):
                     wp=bf(self.projection_layer.weight), bp=f32(self.projection_layer.bias))
         self._cache = (sig, (layers, head))
         return self._cache[1]
+
+    # ---- fused kernel: packed fp16 weight stream + parameter table, rebuilt when parameters change ----
+    def _fused_model(self):
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._fcache is not None and self._fcache[0] == sig:
+            return self._fcache[1]
+        import ctypes as C
+
+        keep = []
+
+        def f32(t):
+            t = t.detach().float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        n = len(self.layers)
+        arr = (_lib.TfamLayer * n)()
+        for i, ly in enumerate(self.layers):
+            e = arr[i]
+            e.b_sin, e.b_sout = f32(ly.self_attn.in_proj_bias), f32(ly.self_attn.out_proj.bias)
+            e.b_cin, e.b_cout = f32(ly.cross_attn.in_proj_bias), f32(ly.cross_attn.out_proj.bias)
+            e.b_f1, e.b_f2 = f32(ly.ffn[0].bias), f32(ly.ffn[3].bias)
+            e.ns_g, e.ns_b, e.ns_eps = f32(ly.norm_self.weight), f32(ly.norm_self.bias), ly.norm_self.eps
+            e.nc_g, e.nc_b, e.nc_eps = f32(ly.norm_cross.weight), f32(ly.norm_cross.bias), ly.norm_cross.eps
+            e.nf_g, e.nf_b, e.nf_eps = f32(ly.norm_ffn.weight), f32(ly.norm_ffn.bias), ly.norm_ffn.eps
+        m = _lib.TfamModel()
+        c = self.classifier
+        m.d_model, m.nhead, m.dim_ff, m.layers = self.d_model, self.nhead, self.layers[0].ffn[0].out_features, n
+        m.num_classes, m.hidden = c[4].out_features, c[1].out_features
+        m.act = ops.ACT_GELU_ERF if self.layers[0].activation == "gelu" else ops.ACT_RELU
+        m.layer = C.cast(arr, C.POINTER(_lib.TfamLayer))
+        m.cls_ln_g, m.cls_ln_b, m.cls_ln_eps = f32(c[0].weight), f32(c[0].bias), c[0].eps
+        m.w1t, m.b1 = f32(c[1].weight.detach().float().t()), f32(c[1].bias)
+        m.w2t, m.b2 = f32(c[4].weight.detach().float().t()), f32(c[4].bias)
+        geometry_ok = (self.d_model == 512 and self.nhead == 8 and m.dim_ff == 2048 and n <= _lib.TFAM_MAX_LAYERS
+                       and all(ly.ffn[0].out_features == 2048 and ly.activation == self.layers[0].activation for ly in self.layers))
+        if geometry_ok:
+            ws = pack_weight_stream(self.layers)
+            assert ws.numel() * 2 == _lib.lib().vmc_tfam_wstream_bytes(n)
+            keep.append(ws)
+            m.wstream = ws.data_ptr()
+        self._fcache = (sig, (m if geometry_ok else None, arr, keep))
+        return self._fcache[1]
+
+    def _forward_fused(self, x, motion, valid_x, valid_m):
+        """x [B,T,512] fp32 contiguous, motion [B,Tm,512] or None -> logits [B,C]; None if the fused kernel does not cover the shape."""
+        import ctypes as C
+
+        if not self.fused:
+            return None
+        m = self._fused_model()[0]
+        B, T = x.shape[0], x.shape[1]
+        Tm = 0 if motion is None else motion.shape[1]
+        L = _lib.lib()
+        if m is None or not L.vmc_tfam_fused_supported(C.byref(m), B, T, Tm):
+            return None
+        logits = torch.empty((B, m.num_classes), dtype=torch.float32, device=x.device)
+        vp = lambda t: C.c_void_p(0 if t is None else t.data_ptr())  # noqa: E731
+        with torch.cuda.device(x.device):
+            _lib.check(L.vmc_tfam_forward(C.byref(m), vp(x), vp(motion), vp(valid_x), vp(valid_m), vp(logits), B, T, Tm,
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vmc_tfam_forward")
+        return logits
 
     @staticmethod
     def _ln(y, norm):
@@ -185,7 +293,6 @@ class AMO_CLIP(nn.Module):
         raise ValueError("concat_dim must be 1 or -1")
 
     def _forward_eval(self, rgb_emb, motion_emb, mask_rgb, mask_flow, dev):
-        layers, head = self._packed()
         d = self.d_model
         if self.use_pe:  # AMO_CLIP.py:129-134: added IN PLACE to the caller's tensors
             rgb_emb += self.positional_encoding(rgb_emb.size(1), rgb_emb.device).unsqueeze(0)
@@ -194,16 +301,15 @@ class AMO_CLIP(nn.Module):
         mot = motion_emb.to(dev).float()
         v_rgb, v_mot = self._valid(mask_rgb, dev), self._valid(mask_flow, dev)
         B = rgb.shape[0]
-        cross16, Tm, cross_valid = None, 0, None
+        # mode selection of AMO_CLIP.py:136-167: layer-0 rows x, their key mask, and the cross-attention source
+        cross, cross_valid = None, None
         if self.use_only_rgb:
             x, valid = rgb, v_rgb
         elif self.use_only_flow:
             x, valid = mot, v_mot
         elif self.use_cross_attention:
             x, valid = rgb, v_rgb
-            Tm = mot.shape[1]
-            cross16 = ops.cast_bf16(mot.reshape(B * Tm, d).contiguous(), split=True)
-            cross_valid = v_mot
+            cross, cross_valid = mot, v_mot
         else:
             rgb = rgb[:, :-1, :]  # AMO_CLIP.py:153-154 (masks are indexed: None is an error there too)
             v_rgb = v_rgb[:, :-1]
@@ -212,12 +318,25 @@ class AMO_CLIP(nn.Module):
                 x = torch.cat([rgb, mot], dim=1)
             elif self.concat_dim == -1:
                 valid = v_mot
+                head = self._packed()[1]
                 cat16 = ops.cast_bf16(torch.cat([rgb, mot], dim=-1).reshape(B * mot.shape[1], 2 * d).contiguous(), split=True)
                 x = ops.gemm(cat16, head["wp"], bias=head["bp"], out_dtype=torch.float32).view(B, mot.shape[1], d)
             else:
                 raise ValueError("concat_dim must be 1 or -1")
+        x = x.contiguous()
+        if cross is not None:
+            cross = cross.contiguous()
+        out = self._forward_fused(x, cross, valid, cross_valid)
+        if out is not None:
+            return out
+        # ---- batched path (other geometries, more than 32 frames, model.fused = False) ----
+        layers, head = self._packed()
         T = x.shape[1]
-        x32 = x.reshape(B * T, d).contiguous()
+        cross16, Tm = None, 0
+        if cross is not None:
+            Tm = cross.shape[1]
+            cross16 = ops.cast_bf16(cross.reshape(B * Tm, d), split=True)
+        x32 = x.reshape(B * T, d)
         x16 = ops.cast_bf16(x32, split=True)
         for w in layers:
             x32, x16 = self._layer(x32, x16, B, T, w, valid, cross16, Tm, cross_valid)

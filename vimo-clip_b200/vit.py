@@ -87,6 +87,12 @@ class VisionTower(nn.Module):
         self._packed = None
         self._packed_sig = None
         self._workspace = None
+        # per-model kernel variants (0 = library default; vmc_vit_model in include/vimoclip_b200.h):
+        # ln_mode 6 = bf16 residual stream + folded LayerNorms (default), 3 / 5 = fp32 stream with folds, 4 = fp32 stream with
+        # separate LayerNorm kernels; last_block_cls 1 = last block on the CLS rows only (default), 2 = full last block
+        self.ln_mode = 0
+        self.last_block_cls = 0
+        self.attn_impl = 0
 
     @classmethod
     def from_name(cls, name: str, **kw) -> "VisionTower":
@@ -167,6 +173,7 @@ class VisionTower(nn.Module):
     def forward_patches(self, patches: torch.Tensor, n_frames: int) -> torch.Tensor:
         """patches bf16 [F*n, ld_patch] (from ``ops.prologue(..., dst='patch')``) -> fp32 [F, output_dim]."""
         m, _, _ = self._pack()
+        m.ln_mode, m.last_block_cls, m.attn_impl = int(self.ln_mode), int(self.last_block_cls), int(self.attn_impl)
         n = self.tokens - 1
         out = torch.empty((n_frames, self.output_dim), dtype=torch.float32, device=patches.device)
         L = _lib.lib()
