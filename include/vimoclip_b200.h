@@ -91,6 +91,12 @@ int vmc_frame_diff_prologue(const uint8_t* bgr, uint8_t* diff_u8, void* dst, int
 int vmc_resize_geometry(int H, int W, int size, int* new_h, int* new_w, int* top, int* left);
 int vmc_resize_center_crop(const void* frames, int src_kind, uint8_t* out, uint8_t* tmp, int F, int H, int W,
                            int size, void* stream);
+/* crop_floor = 1: the crop offset of HF CLIPImageProcessor, (dim - size) // 2 (extract_embeddings.py:18,91), instead of
+ * torchvision's round-half-to-even; they differ by one pixel when dim - size is 3 mod 4.  Frames smaller than `size` are
+ * scaled up by the same resampler (Resize scales the SHORT side to `size`, so the crop never pads). */
+int vmc_resize_geometry_ex(int H, int W, int size, int crop_floor, int* new_h, int* new_w, int* top, int* left);
+int vmc_resize_center_crop_ex(const void* frames, int src_kind, uint8_t* out, uint8_t* tmp, int F, int H, int W,
+                              int size, int crop_floor, void* stream);
 
 /* ---- G: tcgen05/TMEM GEMM fed by TMA ------------------------------------------
  * out[orow, n] = alpha * act(sum_k A[m,k] * W[n,k] + bias[n]) + resid[rrow, n]

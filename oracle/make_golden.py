@@ -269,10 +269,33 @@ def golden_resize():
 
     tf = Compose([Resize(224, interpolation=InterpolationMode.BICUBIC), CenterCrop(224)])
     out = {}
-    for tag, (H, W) in {"360x640": (360, 640), "240x320": (240, 320), "500x375": (500, 375)}.items():
+    # the last four: frames SMALLER than 224 (Resize scales the short side UP to 224; CenterCrop then never pads)
+    sizes = {"360x640": (360, 640), "240x320": (240, 320), "500x375": (500, 375), "120x160": (120, 160), "100x300": (100, 300),
+             "223x225": (223, 225), "64x64": (64, 64)}
+    for tag, (H, W) in sizes.items():
         img = np.random.default_rng(len(tag) * 7 + H).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
         out["pil_" + tag] = np.asarray(tf(Image.fromarray(img))).transpose(2, 0, 1)
         out["seed_" + tag] = np.int64(len(tag) * 7 + H)
+    # HF CLIPImageProcessor (extract_embeddings.py:18,91): same resampler, crop offset (dim - 224) // 2 -- differs from
+    # torchvision's round-half-to-even when the margin is 3 mod 4 (360x648 -> 224x403: margin 179 -> 89 vs 90; 227x224 ->
+    # margin 3 -> 1 vs 2).  Frozen from the installed processor as the uint8 crop (pixel_values de-normalised exactly).
+    # The reference pins transformers 4.53.2, whose CLIPImageProcessor is the PIL ("slow") processor; the installed 5.5 keeps
+    # that implementation as CLIPImageProcessorPil (its default class resizes with torchvision on tensors instead).
+    from transformers.models.clip import CLIPImageProcessorPil
+
+    proc = CLIPImageProcessorPil()
+    mean = np.array(clip_shim.CLIP_MEAN, dtype=np.float64)[:, None, None]
+    std = np.array(clip_shim.CLIP_STD, dtype=np.float64)[:, None, None]
+    for tag, (H, W) in {"360x648": (360, 648), "227x224": (227, 224)}.items():
+        img = np.random.default_rng(len(tag) * 11 + W).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        pv = proc(images=[Image.fromarray(img)], return_tensors="np")["pixel_values"][0].astype(np.float64)
+        u8 = np.rint((pv * std + mean) * 255.0)
+        assert np.abs((pv * std + mean) * 255.0 - u8).max() < 1e-3
+        u8 = u8.astype(np.uint8)
+        tv = np.asarray(tf(Image.fromarray(img))).transpose(2, 0, 1)
+        assert not np.array_equal(u8, tv), "these geometries are chosen so that HF's and torchvision's crops differ"
+        out["hf_" + tag] = u8
+        out["hfseed_" + tag] = np.int64(len(tag) * 11 + W)
     clip_shim.install()
     sys.path.insert(0, REF)
     mod = load_ref_module("ref_fd_resize", "models/student_model_frame_diff.py")
@@ -306,9 +329,44 @@ def golden_losses():
     print("losses.npz")
 
 
+def golden_sampling():
+    """extract_embeddings.py:77-81 (frame sampling) -- the module cannot be imported (module-level ``from_pretrained`` needs the
+    network; decord / h5py are absent), so the `if (max_frames is None) or ...: indices = ... else: ...` statement is cut
+    out of the reference SOURCE with ``ast`` and executed on its own."""
+    import ast
+
+    src = open(os.path.join(REF, "extract_embeddings.py")).read()
+    tree = ast.parse(src)
+    stmt = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and "max_frames" in ast.unparse(node.test) and "total_frames" in ast.unparse(node.test):
+            targets = {t.id for b in (node.body, node.orelse) for st in b if isinstance(st, ast.Assign) for t in st.targets if isinstance(t, ast.Name)}
+            if "indices" in targets:
+                stmt = node
+                break
+    assert stmt is not None, "frame-sampling statement not found in extract_embeddings.py"
+    assert 77 <= stmt.lineno <= 78, stmt.lineno  # the lines SURVEY.md section 8 a4 cites
+    code = compile(ast.Module(body=[stmt], type_ignores=[]), "extract_embeddings.py:77-81", "exec")
+    cases = [(t, m) for t in (1, 5, 15, 16, 17, 31, 32, 33, 47, 64, 100, 250, 1000) for m in (None, 1, 8, 16, 32)]
+    tot, mx, rows = [], [], []
+    width = max(t for t, _ in cases)
+    for t, m in cases:
+        ns = {"np": np, "total_frames": t, "max_frames": m}
+        exec(code, ns)
+        idx = np.asarray(ns["indices"], dtype=np.int64)
+        row = np.full(width, -1, dtype=np.int64)
+        row[: len(idx)] = idx
+        tot.append(t)
+        mx.append(-1 if m is None else m)
+        rows.append(row)
+    np.savez_compressed(os.path.join(OUT, "sampling.npz"), total_frames=np.array(tot), max_frames=np.array(mx),
+                        indices_flat_split=np.stack(rows), source_lines=np.array([stmt.lineno, stmt.end_lineno]))
+    print("sampling.npz", len(cases), "cases from lines", stmt.lineno, stmt.end_lineno)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
-    which = sys.argv[1:] or ["prologue", "framediff", "student", "vit_hf", "tfam", "indexing", "losses", "resize"]
+    which = sys.argv[1:] or ["prologue", "framediff", "student", "vit_hf", "tfam", "indexing", "losses", "resize", "sampling"]
     for w in which:
         globals()["golden_" + w]()

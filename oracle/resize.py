@@ -77,8 +77,10 @@ def resized_size(h: int, w: int, size: int = 224):
     return size, int(size * w / h)
 
 
-def resize_center_crop_u8(frames: np.ndarray, size: int = 224) -> np.ndarray:
-    """uint8 [..., H, W] -> uint8 [..., size, size]: PIL bicubic resize (short side -> size) then CenterCrop."""
+def resize_center_crop_u8(frames: np.ndarray, size: int = 224, hf_crop: bool = False) -> np.ndarray:
+    """uint8 [..., H, W] -> uint8 [..., size, size]: PIL bicubic resize (short side -> size, up or down) then CenterCrop
+    (torchvision: int(round(margin / 2)), Python round-half-to-even; hf_crop: HF image_transforms.center_crop, margin // 2,
+    the CLIPImageProcessor of extract_embeddings.py:18,91)."""
     H, W = frames.shape[-2:]
     nh, nw = resized_size(H, W, size)
     out = frames
@@ -86,6 +88,6 @@ def resize_center_crop_u8(frames: np.ndarray, size: int = 224) -> np.ndarray:
         out = _pass(out, *precompute_coeffs(W, nw), axis=-1)  # horizontal first (Resample.c)
     if nh != H:
         out = _pass(out, *precompute_coeffs(H, nh), axis=-2)
-    top = int(round((nh - size) / 2.0))
-    left = int(round((nw - size) / 2.0))
+    top = (nh - size) // 2 if hf_crop else int(round((nh - size) / 2.0))
+    left = (nw - size) // 2 if hf_crop else int(round((nw - size) / 2.0))
     return np.ascontiguousarray(out[..., top:top + size, left:left + size])

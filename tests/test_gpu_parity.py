@@ -101,9 +101,11 @@ def test_frame_difference_bit_exact(cuda_device, golden, prologue_impl):
     assert torch.equal(pt.cpu().view(torch.int16), torch.from_numpy(prologue.patchify(n_ref, 32)).to(torch.bfloat16).view(torch.int16))
 
 
-@pytest.mark.parametrize("H,W", [(360, 640), (240, 320), (500, 375), (224, 224), (300, 224), (1080, 1920)])
+@pytest.mark.parametrize("H,W", [(360, 640), (240, 320), (500, 375), (224, 224), (300, 224), (1080, 1920), (120, 160), (100, 300),
+                                 (223, 225), (64, 64), (30, 500)])
 def test_resize_center_crop_bit_exact(cuda_device, golden, H, W):
-    """Pillow bicubic Resize(224) + CenterCrop(224): bit-exact against the oracle (itself pinned to PIL)."""
+    """Pillow bicubic Resize(224) + CenterCrop(224): bit-exact against the oracle (itself pinned to PIL), frames smaller
+    than 224 included (scaled up: the short side becomes 224, so the crop never pads)."""
     from oracle import resize
 
     g = golden("resize.npz")
@@ -122,6 +124,27 @@ def test_resize_center_crop_bit_exact(cuda_device, golden, H, W):
     got_f = ops.resize_center_crop(f, wrap=True).cpu().numpy()[0]
     assert np.array_equal(got_f, got)  # regime B round-trips to the original uint8
     assert ops.resize_geometry(H, W)[:2] == resize.resized_size(H, W)
+
+
+@pytest.mark.parametrize("H,W", [(360, 648), (227, 224), (360, 640), (500, 375)])
+def test_resize_center_crop_hf_floor_offset(cuda_device, golden, H, W):
+    """HF CLIPImageProcessor crop offset (margin // 2; extract_embeddings.py:18,91), against crops frozen from the installed
+    processor where it differs from torchvision's round-half-to-even (margin 3 mod 4)."""
+    from oracle import resize
+
+    g = golden("resize.npz")
+    tag = f"{H}x{W}"
+    seed = int(g["hfseed_" + tag]) if "hfseed_" + tag in g.files else H * 5 + W
+    img = np.random.default_rng(seed).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    chw = np.ascontiguousarray(img.transpose(2, 0, 1))[None]
+    got = ops.resize_center_crop(torch.from_numpy(chw).to(cuda_device), wrap=False, hf_crop=True).cpu().numpy()[0]
+    assert np.array_equal(got, resize.resize_center_crop_u8(chw[0], hf_crop=True))
+    if "hf_" + tag in g.files:
+        assert np.array_equal(got, g["hf_" + tag])
+    feats = vmc.CLIPVisionFeatures("openai/clip-vit-base-patch32").to(cuda_device)
+    a = feats.get_image_features_u8(torch.from_numpy(chw).to(cuda_device))
+    b = feats.get_image_features_u8(torch.from_numpy(got[None]).to(cuda_device))
+    assert torch.equal(a, b)  # the drop-in applies exactly this resize + crop
 
 
 def test_prologue_full_size_properties(cuda_device):
@@ -506,8 +529,12 @@ def test_student_config1_against_reference_golden(cuda_device, golden):
     embR, _, logR = ours(big)
     assert _cos_min(embR, torch.from_numpy(gr["student_emb"])) >= COS_MIN
     assert (logR.cpu() - torch.from_numpy(gr["student_logits"])).abs().max().item() <= LOGIT_TOL
-    with pytest.raises(NotImplementedError):
-        ours(torch.zeros(1, 1, 3, 100, 640, dtype=torch.uint8))
+    # frames smaller than 224 are scaled up by the same resampler (the oracle applies PIL's arithmetic)
+    small = torch.randint(0, 256, (1, 2, 3, 120, 160), dtype=torch.uint8, generator=gen)
+    embS, _, logS = ours(small)
+    with torch.no_grad():
+        eS, _, lS = oracle(small)
+    assert _cos_min(embS, eS) >= COS_MIN and (logS.cpu() - lS).abs().max().item() <= LOGIT_TOL
 
 
 MODES = {

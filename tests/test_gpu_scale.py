@@ -1,0 +1,113 @@
+"""GPU parity at BASELINE size and on the composed chains ("parity at scale").
+
+The persistent multi-tile scheduling paths the bench exercises (many live A blocks, ragged last pair tile, attention CTAs
+with dozens of items, two clips per TFAM cluster pass) are compared with the CPU oracle on SAMPLED clips / frames of a
+full-size batch, so the oracle stays within seconds while the kernels run the real shapes.
+"""
+import numpy as np
+import pytest
+import torch
+
+import vimoclip_b200 as vmc
+from oracle import clip_shim, losses as olosses, prologue, student as ostudent, tfam as otfam, weights
+from vimoclip_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.9995  # north_star: per-frame embedding cosine
+LOGIT_TOL = 1e-2  # north_star: logit max-abs
+
+
+def _cos_min(a, b):
+    return float(torch.nn.functional.cosine_similarity(a.double().cpu(), b.double().cpu(), dim=-1).min())
+
+
+def test_config4_256_clips_sampled_against_oracle(cuda_device):
+    """BASELINE config 4 at full size: 256 clips x (16 RGB + 15 motion) frames through ViMoCLIPPipeline.forward (two
+    128-clip chunks, 2048 frames per tower call), then clips 0 / 127 / 128 / 255 (first, last, both sides of the chunk
+    boundary) against the fp32 oracle chain."""
+    torch.manual_seed(0)
+    pipe = vmc.ViMoCLIPPipeline("ViT-B/16", "ViT-B/32", device=cuda_device, clips_per_step=128)
+    o_rgb = clip_shim.build_visual("ViT-B/16", seed=1)
+    o_st = ostudent.StudentOracle("ViT-B/32", seed=2)
+    weights.randomise_heads_(o_st, 2)
+    o_tf = otfam.TfamOracle().eval()
+    weights.randomise_tfam_(o_tf, 3)
+    pipe.rgb.visual.load_state_dict(o_rgb.state_dict())
+    pipe.student.load_state_dict(o_st.state_dict())
+    pipe.tfam.load_state_dict(o_tf.state_dict())
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    rgb = torch.randint(0, 256, (256, 16, 3, 224, 224), dtype=torch.uint8, device=cuda_device, generator=gen)
+    mot = torch.randint(0, 256, (256, 15, 3, 224, 224), dtype=torch.uint8, device=cuda_device, generator=gen)
+    logits, er, em = pipe(rgb, mot)
+    assert logits.shape == (256, 140) and er.shape == (256, 16, 512) and em.shape == (256, 15, 512)
+    assert bool(torch.isfinite(logits).all())
+    pick = [0, 127, 128, 255]
+    with torch.no_grad():
+        x = torch.from_numpy(prologue.normalise_u8(rgb[pick].reshape(-1, 3, 224, 224).cpu().numpy()))
+        er_ref = o_rgb(x).view(len(pick), 16, -1)
+        em_ref, _, _ = o_st(mot[pick].cpu())
+        lg_stage = o_tf(er[pick].cpu(), em[pick].cpu())  # stage-3 parity on identical inputs
+        lg_ref = o_tf(er_ref, em_ref)                    # fp32 chain end to end
+    assert _cos_min(er[pick], er_ref) >= COS_MIN
+    assert _cos_min(em[pick], em_ref) >= COS_MIN
+    assert (logits[pick].cpu() - lg_stage).abs().max().item() <= LOGIT_TOL
+    assert (logits[pick].cpu() - lg_ref).abs().max().item() <= 5e-2  # looser, stated: bf16 embedding error through the fusion block
+    # the whole batch through the oracle's TFAM on OUR embeddings (cheap on the CPU: 0.5 GFLOP per clip)
+    with torch.no_grad():
+        lg_all = o_tf(er.cpu(), em.cpu())
+    assert (logits.cpu() - lg_all).abs().max().item() <= LOGIT_TOL
+
+
+def test_vit_l14_64_frames_in_flight_sampled_against_oracle(cuda_device):
+    """BASELINE config 5 tower (ViT-L/14, 257 tokens: attention v6, K = 588 patch GEMM) with 64 frames in flight; frames
+    0 and 63 against the oracle."""
+    o = clip_shim.build_visual("ViT-L/14", seed=4)
+    tower = vmc.VisionTower.from_name("ViT-L/14").to(cuda_device)
+    tower.load_state_dict(o.state_dict())
+    gen = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (64, 3, 224, 224), dtype=torch.uint8, generator=gen)
+    patches = ops.prologue(u8.to(cuda_device), wrap=False, dst="patch", patch=14)
+    emb = tower.forward_patches(patches, 64)
+    pick = [0, 63]
+    with torch.no_grad():
+        ref = o(torch.from_numpy(prologue.normalise_u8(u8[pick].numpy())))
+    assert _cos_min(emb[pick], ref) >= COS_MIN
+    # the same frames alone (one M tile, other scheduling) give the same embeddings up to bf16 rounding differences
+    alone = tower.forward_patches(ops.prologue(u8[pick].to(cuda_device), wrap=False, dst="patch", patch=14), 2)
+    assert _cos_min(alone, emb[pick]) >= 0.99995
+
+
+def test_config3_chain_frame_diff_student_distillation_against_oracle(cuda_device):
+    """BASELINE config 3: BGR clips -> fused frame-difference prologue -> ViT-B/32 student + heads (forward_bgr) ->
+    cosine distillation loss against CLIP ViT-B/16 teacher embeddings sliced [:, :-1] (train.py:98;
+    utils/generate_frame_diff_video.py:37-49; losses.py:27-40)."""
+    o_teacher = clip_shim.build_visual("ViT-B/16", seed=7)
+    o_st = ostudent.StudentOracle("ViT-B/32", seed=8)
+    weights.randomise_heads_(o_st, 8)
+    teacher = vmc.CLIPVisionFeatures("openai/clip-vit-base-patch16").to(cuda_device)
+    teacher.visual.load_state_dict(o_teacher.state_dict())
+    student = vmc.FrameDiffStudentModel("ViT-B/32", device=cuda_device, num_classes=140)
+    student.load_state_dict(o_st.state_dict(), strict=True)
+    student.eval()
+    gen = torch.Generator().manual_seed(9)
+    clips, T1 = 2, 17
+    # frame-difference-like content: a base frame plus small per-frame perturbations
+    base = torch.randint(0, 256, (clips, 1, 224, 224, 3), generator=gen)
+    bgr = (base + torch.randint(-12, 13, (clips, T1, 224, 224, 3), generator=gen)).clamp(0, 255).to(torch.uint8)
+    rgb = bgr.flip(-1).permute(0, 1, 4, 2, 3).contiguous()
+    emb_gt = teacher.get_image_features_u8(rgb.view(-1, 3, 224, 224).to(cuda_device)).view(clips, T1, -1)[:, :-1, :].contiguous()
+    emb, dist, logits = student.forward_bgr(bgr.to(cuda_device))
+    loss = vmc.distillation_loss(dist, emb_gt, "cosine")
+    # oracle chain
+    with torch.no_grad():
+        t_ref = o_teacher(torch.from_numpy(prologue.normalise_u8(rgb.view(-1, 3, 224, 224).numpy()))).view(clips, T1, -1)[:, :-1, :]
+        gray = prologue.bgr2gray(bgr.numpy())
+        diff = np.abs(gray[:, 1:].astype(np.int16) - gray[:, :-1].astype(np.int16)).astype(np.uint8)  # [clips, 16, H, W]
+        videos = torch.from_numpy(np.repeat(diff[:, :, None], 3, axis=2))  # three identical channels, uint8 (regime A)
+        e_ref, d_ref, l_ref = o_st(videos)
+        loss_ref = olosses.distillation_loss(d_ref, t_ref, "cosine")
+    assert _cos_min(emb_gt, t_ref) >= COS_MIN
+    assert _cos_min(emb, e_ref) >= COS_MIN and _cos_min(dist, d_ref) >= COS_MIN
+    assert (logits.cpu() - l_ref).abs().max().item() <= LOGIT_TOL
+    assert abs(float(loss) - float(loss_ref)) <= 2e-3, (float(loss), float(loss_ref))

@@ -161,10 +161,18 @@ def test_resize_oracle_matches_pil(golden):
     from oracle import resize
 
     g = golden("resize.npz")
-    for tag, (H, W) in {"360x640": (360, 640), "240x320": (240, 320), "500x375": (500, 375)}.items():
+    # the last four are SMALLER than 224: Resize scales the short side up, CenterCrop never pads
+    for tag, (H, W) in {"360x640": (360, 640), "240x320": (240, 320), "500x375": (500, 375), "120x160": (120, 160),
+                        "100x300": (100, 300), "223x225": (223, 225), "64x64": (64, 64)}.items():
         img = np.random.default_rng(int(g["seed_" + tag])).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
         got = resize.resize_center_crop_u8(np.ascontiguousarray(img.transpose(2, 0, 1)))
         assert np.array_equal(got, g["pil_" + tag]), tag
+    # HF CLIPImageProcessor (extract_embeddings.py:18,91): same resampler, floor crop offset
+    for tag, (H, W) in {"360x648": (360, 648), "227x224": (227, 224)}.items():
+        img = np.random.default_rng(int(g["hfseed_" + tag])).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        chw = np.ascontiguousarray(img.transpose(2, 0, 1))
+        assert np.array_equal(resize.resize_center_crop_u8(chw, hf_crop=True), g["hf_" + tag]), tag
+        assert not np.array_equal(resize.resize_center_crop_u8(chw), g["hf_" + tag]), tag
     assert resize.resized_size(360, 640) == (224, 398) and resize.resized_size(640, 360) == (398, 224)
     # same-size frames are untouched (PIL's identity shortcut), and bicubic at scale 1 is an exact identity
     x = np.random.default_rng(0).integers(0, 256, size=(3, 224, 224), dtype=np.uint8)
@@ -180,3 +188,21 @@ def test_student_oracle_on_640x360_frames(golden):
     frames = torch.randint(0, 256, (1, 2, 3, 360, 640), dtype=torch.uint8, generator=gen)
     emb, _, logits = m(frames)
     assert np.allclose(emb.numpy(), g["student_emb"], atol=2e-5) and np.allclose(logits.numpy(), g["student_logits"], atol=2e-5)
+
+
+def test_frame_sampling_indices_match_reference_source(golden):
+    """extract_embeddings.py:77-81 cannot be imported (module-level from_pretrained), so oracle/make_golden.py cut the
+    statement out of the reference SOURCE with `ast`, executed it and froze the results: the oracle and the product's host
+    function reproduce them bit for bit."""
+    import numpy as np
+
+    from oracle import indexing as oidx
+    from vimoclip_b200 import indexing
+
+    g = golden("sampling.npz")
+    assert list(g["source_lines"]) == [77, 81]
+    for total, mx, want in zip(g["total_frames"], g["max_frames"], g["indices_flat_split"]):
+        want = want[want >= 0]
+        m = None if mx < 0 else int(mx)
+        assert np.array_equal(np.asarray(oidx.sample_frame_indices(int(total), m)), want), (total, mx)
+        assert np.array_equal(indexing.sample_frame_indices(int(total), m), want), (total, mx)

@@ -50,9 +50,8 @@ class CLIPVisionFeatures(nn.Module):
         frames_u8 = frames_u8.to(dev, non_blocking=True)
         res = self.visual.input_resolution
         if frames_u8.shape[-2] != res or frames_u8.shape[-1] != res:
-            # CLIPImageProcessor: bicubic resize of the shortest edge to 224 + centre crop (PIL resampler; torchvision's
-            # crop rounding, identical to HF's for the reference's 640x360 -> 398x224 geometry)
-            frames_u8 = ops.resize_center_crop(frames_u8, wrap=False, size=res)
+            # CLIPImageProcessor: bicubic resize of the shortest edge to 224 + centre crop (PIL resampler, HF's floor crop offset)
+            frames_u8 = ops.resize_center_crop(frames_u8, wrap=False, size=res, hf_crop=True)
         patches = ops.prologue(frames_u8, wrap=False, dst="patch", patch=self.visual.patch_size)
         return self.visual.forward_patches(patches, frames_u8.shape[0])
 
@@ -74,7 +73,7 @@ class _ProcessorOutput(dict):
             raise _lib.VmcError("the image processor runs on CUDA only (no CPU fallback)")
         u8 = self._u8.to(dev, non_blocking=True)
         if u8.shape[-2] != self._size or u8.shape[-1] != self._size:
-            u8 = ops.resize_center_crop(u8, wrap=False, size=self._size)
+            u8 = ops.resize_center_crop(u8, wrap=False, size=self._size, hf_crop=True)
         self["pixel_values"] = ops.prologue(u8, wrap=False, dst="f32")
         return self
 

@@ -1397,8 +1397,13 @@ int get_table(int in_size, int out_size, ResizeTable* out) {
 extern "C" {
 
 int vmc_resize_geometry(int H, int W, int size, int* new_h, int* new_w, int* top, int* left) {
+  return vmc_resize_geometry_ex(H, W, size, 0, new_h, new_w, top, left);
+}
+
+int vmc_resize_geometry_ex(int H, int W, int size, int crop_floor, int* new_h, int* new_w, int* top, int* left) {
   VMC_CHECK_ARG(H > 0 && W > 0 && size > 0, VMC_ERR_SHAPE, "vmc_resize_geometry: bad geometry");
-  // torchvision Resize(int): short side -> size, long side -> int(size * long / short)
+  // torchvision Resize(int) / HF get_resize_output_image_size: short side -> size, long side -> int(size * long / short)
+  // (frames smaller than `size` are scaled UP, so the centre crop never has to pad)
   int nh, nw;
   if (W <= H) {
     nw = size;
@@ -1407,8 +1412,9 @@ int vmc_resize_geometry(int H, int W, int size, int* new_h, int* new_w, int* top
     nh = size;
     nw = (int)((double)size * W / H);
   }
-  // CenterCrop: int(round((dim - size) / 2.0)) with Python's round-half-to-even
-  auto crop = [&](int dim) { return (int)nearbyint((dim - size) / 2.0); };
+  // torchvision CenterCrop: int(round((dim - size) / 2.0)) with Python's round-half-to-even;
+  // HF image_transforms.center_crop (extract_embeddings.py:91): (dim - size) // 2
+  auto crop = [&](int dim) { return crop_floor ? (dim - size) / 2 : (int)nearbyint((dim - size) / 2.0); };
   if (new_h) *new_h = nh;
   if (new_w) *new_w = nw;
   if (top) *top = crop(nh);
@@ -1418,14 +1424,17 @@ int vmc_resize_geometry(int H, int W, int size, int* new_h, int* new_w, int* top
 
 int vmc_resize_center_crop(const void* frames, int src_kind, uint8_t* out, uint8_t* tmp, int F, int H,
                            int W, int size, void* stream) {
+  return vmc_resize_center_crop_ex(frames, src_kind, out, tmp, F, H, W, size, 0, stream);
+}
+
+int vmc_resize_center_crop_ex(const void* frames, int src_kind, uint8_t* out, uint8_t* tmp, int F, int H,
+                              int W, int size, int crop_floor, void* stream) {
   VMC_CHECK_ARG(frames && out && tmp, VMC_ERR_ARG, "vmc_resize_center_crop: null pointer");
   VMC_CHECK_ARG(src_kind >= VMC_SRC_U8 && src_kind <= VMC_SRC_F32_WRAP, VMC_ERR_ARG,
                 "vmc_resize_center_crop: unknown src_kind %d", src_kind);
-  VMC_CHECK_ARG(F > 0 && H >= size && W >= size, VMC_ERR_SHAPE,
-                "vmc_resize_center_crop: frames must be at least %dx%d (CenterCrop padding is not implemented)",
-                size, size);
+  VMC_CHECK_ARG(F > 0 && H > 0 && W > 0 && size > 0, VMC_ERR_SHAPE, "vmc_resize_center_crop: bad geometry %dx%d -> %d", H, W, size);
   int nh, nw, top, left;
-  VMC_TRY(vmc_resize_geometry(H, W, size, &nh, &nw, &top, &left));
+  VMC_TRY(vmc_resize_geometry_ex(H, W, size, crop_floor, &nh, &nw, &top, &left));
   ResizeTable th, tv;
   VMC_TRY(get_table(W, nw, &th));
   VMC_TRY(get_table(H, nh, &tv));

@@ -14,8 +14,14 @@
 //     flight in a register ring that runs ahead across GEMM boundaries and cluster barriers;
 //   * activations never leave the SMs: the fp16 A operand [rows, 512] is replicated in every CTA's shared memory, the
 //     fp32 residual stream is column-sharded (64 columns per CTA); slices are exchanged through distributed shared
-//     memory (st.shared::cluster) between barrier.cluster phases: attention output all-gather, FFN2 partial-sum
-//     reduce-scatter (fixed order: deterministic), LayerNorm row statistics, normalised rows all-gather;
+//     memory: attention output all-gather, FFN2 partial-sum reduce-scatter (fixed order: deterministic), LayerNorm row
+//     statistics, normalised rows all-gather.  Every exchange is st.async (SASS STAS) with mbarrier complete_tx on the
+//     RECEIVER's barrier: a CTA waits on its own mbarrier for the bytes of all eight senders, no cluster-wide barrier
+//     and no fence.  (The first version used barrier.cluster.arrive.release / wait.acquire between phases: the release
+//     compiles to MEMBAR.ALL.GPU, which also waits for the warp's 16 in-flight weight loads -- ncu: 27 % of the stall
+//     samples on the 38 barriers of a pass, profiles/r02_tfam_fused_v1_ncu_summary.txt.)  Buffer reuse is safe without
+//     extra handshakes because consecutive uses of a buffer are always separated by another all-to-all exchange: a
+//     CTA can only be one exchange ahead of its slowest peer;
 //   * the attention of head c (<= 32 keys) runs in fp32 on the CUDA cores of CTA c out of shared memory.
 // Operands are fp16 (not bf16): with one rounding per operand the config-1 logits are within 2.4e-3 of fp32 (bf16:
 // 1.2e-2, over the 1e-2 bar; tools/emulate_tfam_precision.py), fp32 accumulation, fp32 residual / LayerNorm / softmax.
@@ -24,6 +30,8 @@
 // Throughput regime (B = 256): 16 co-resident clusters, two clips (32 rows, two M tiles) per pass so the weight
 // stream is read from L2 once per two clips.
 #include <cuda_fp16.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "vimoclip_b200.h"
@@ -82,14 +90,28 @@ __device__ __forceinline__ uint32_t tf_mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void tf_st_remote_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+// st.async: the store and its byte count travel together; the receiver's mbarrier phase completes when the expected
+// bytes of all senders have landed (and its own arrive.expect_tx has been posted)
+__device__ __forceinline__ void tf_sta_u32(uint32_t addr, uint32_t v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(bar)
+               : "memory");
 }
-__device__ __forceinline__ void tf_st_remote_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+__device__ __forceinline__ void tf_sta_f32(uint32_t addr, float v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(addr), "f"(v), "r"(bar)
+               : "memory");
 }
-__device__ __forceinline__ void tf_st_remote_f32x2(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void tf_sta_f32x2(uint32_t addr, float a, float b, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(a),
+               "f"(b), "r"(bar)
+               : "memory");
+}
+enum { XB_OH = 0, XB_STATS = 1, XB_XH = 2, XB_RECV = 3, XB_POOL = 4, XB_UH = 5, XB_COUNT = 6 };
+// receiver side of an exchange: thread 0 posts the expected byte count (one arrival), everybody waits for the phase
+__device__ __forceinline__ void tf_xchg_wait(uint32_t bar_base, uint32_t& parity_bits, int which, uint32_t bytes, int tid) {
+  const uint32_t bar = bar_base + 8u * which;
+  if (tid == 0) mbar_arrive_expect_tx(bar, bytes);
+  mbar_wait(bar, (parity_bits >> which) & 1u);
+  parity_bits ^= 1u << which;
 }
 __device__ __forceinline__ uint4 tf_ldg_w(const uint4* p) {  // weights: read once per pass, keep them out of L1
   uint4 v;
@@ -173,14 +195,17 @@ struct TfSmem {
   static constexpr uint32_t POOL = STATS + 8 * RM * 2 * 4;            // float [MAXG][512] temporal mean
   static constexpr uint32_t UH = POOL + TF_MAXG * TF_D * 4;           // float [MAXG][256] classifier hidden
   static constexpr uint32_t RED = UH + TF_MAXG * 256 * 4;             // float [8][32]     head reduction scratch
-  static constexpr uint32_t TOTAL = RED + 8 * 32 * 4;
+  static constexpr uint32_t PB = RED + 8 * 32 * 4;                    // float [8 warps][32] attention probabilities of a row
+  static constexpr uint32_t BAR = PB + 8 * 32 * 4;                    // mbarrier [XB_COUNT]: one per exchange buffer
+  static constexpr uint32_t TOTAL = BAR + 64;
 };
 
 // y (already in the x32 slice) -> LayerNorm over the 512 columns held by the 8 CTAs -> x32 slice (fp32, next residual) and
-// the fp16 rows of every CTA's xh.  Two cluster barriers: statistics exchange, normalised-row all-gather.
+// the fp16 rows of every CTA's xh.  Two exchanges: row statistics, normalised-row all-gather.
 template <int MT>
 __device__ __forceinline__ void tf_layernorm_exchange(uint8_t* sm, uint32_t sm_addr, int R, uint32_t c, const float* gamma,
-                                                      const float* beta, float eps, int warp, int lane) {
+                                                      const float* beta, float eps, int warp, int lane, int tid,
+                                                      uint32_t& parity_bits) {
   using S = TfSmem<MT>;
   float* x32 = reinterpret_cast<float*>(sm + S::X32);
   const float* stats = reinterpret_cast<const float*>(sm + S::STATS);
@@ -190,11 +215,15 @@ __device__ __forceinline__ void tf_layernorm_exchange(uint8_t* sm, uint32_t sm_a
     const float s = warp_sum(v.x + v.y);
     const float q = warp_sum(v.x * v.x + v.y * v.y);
     if (lane < TF_NC)  // lane = destination CTA
-      tf_st_remote_f32x2(tf_mapa(sm_addr + S::STATS + (uint32_t)((c * S::RM + r) * 2) * 4u, (uint32_t)lane), s, q);
+      tf_sta_f32x2(tf_mapa(sm_addr + S::STATS + (uint32_t)((c * S::RM + r) * 2) * 4u, (uint32_t)lane), s, q,
+                   tf_mapa(sm_addr + S::BAR + 8u * XB_STATS, (uint32_t)lane));
   }
-  tf_cluster_sync();
+  tf_xchg_wait(sm_addr + S::BAR, parity_bits, XB_STATS, (uint32_t)R * 64u, tid);
   const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma + c * 64) + lane);
   const float2 bt = __ldg(reinterpret_cast<const float2*>(beta + c * 64) + lane);
+  uint32_t rbar[TF_NC];
+#pragma unroll
+  for (int j = 0; j < TF_NC; ++j) rbar[j] = tf_mapa(sm_addr + S::BAR + 8u * XB_XH, (uint32_t)j);
   for (int r = warp; r < R; r += TF_NW) {
     float s = 0.f, q = 0.f;
     if (lane < TF_NC) {
@@ -219,9 +248,9 @@ __device__ __forceinline__ void tf_layernorm_exchange(uint8_t* sm, uint32_t sm_a
     const uint32_t h2 = tf_pack_h2(v.x, v.y);
     const uint32_t dst = sm_addr + S::XH + (uint32_t)(r * TF_LDA + c * 64 + 2 * lane) * 2u;
 #pragma unroll
-    for (int j = 0; j < TF_NC; ++j) tf_st_remote_u32(tf_mapa(dst, (uint32_t)j), h2);
+    for (int j = 0; j < TF_NC; ++j) tf_sta_u32(tf_mapa(dst, (uint32_t)j), h2, rbar[j]);
   }
-  tf_cluster_sync();
+  tf_xchg_wait(sm_addr + S::BAR, parity_bits, XB_XH, (uint32_t)R * 1024u, tid);
 }
 
 // attention of head c for the rows of this group (fp32, CUDA cores): one warp per query row, lane = key.
@@ -233,35 +262,59 @@ __device__ __forceinline__ void tf_attention(uint8_t* sm, uint32_t sm_addr, int 
   const float* qs = reinterpret_cast<const float*>(sm + S::QS);
   const float* ks = reinterpret_cast<const float*>(sm + S::KS);
   const float* vs = reinterpret_cast<const float*>(sm + S::VS);
+  float* pb = reinterpret_cast<float*>(sm + S::PB) + warp * 32;
+  uint32_t rbar[TF_NC];
+#pragma unroll
+  for (int j = 0; j < TF_NC; ++j) rbar[j] = tf_mapa(sm_addr + S::BAR + 8u * XB_OH, (uint32_t)j);
   for (int r = warp; r < R; r += TF_NW) {
     const int gi = r / Tq;
-    const int krow = gi * Tk + lane;
-    float s = 0.f;
     const bool in = lane < Tk;
+    float s = -INFINITY;
     if (in) {
-      const float* qr = qs + r * 64;
-      const float* kr = ks + krow * TF_LDK;
-#pragma unroll 16
-      for (int d = 0; d < TF_HD; ++d) s = fmaf(qr[d], kr[d], s);
-      s *= 0.125f;
+      // 64-deep dot product as four independent chains (the first version's single chain was 8 % of the kernel's stall samples)
+      const float4* qr = reinterpret_cast<const float4*>(qs + r * 64);
+      const float* kr = ks + (gi * Tk + lane) * TF_LDK;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int d = 0; d < TF_HD / 4; ++d) {
+        const float4 qv = qr[d];
+        s0 = fmaf(qv.x, kr[4 * d], s0);
+        s1 = fmaf(qv.y, kr[4 * d + 1], s1);
+        s2 = fmaf(qv.z, kr[4 * d + 2], s2);
+        s3 = fmaf(qv.w, kr[4 * d + 3], s3);
+      }
+      if (valid == nullptr || valid[(size_t)(clip0 + gi) * Tk + lane]) s = ((s0 + s1) + (s2 + s3)) * 0.125f;
     }
-    if (!in || (valid != nullptr && !valid[(size_t)(clip0 + gi) * Tk + lane])) s = -INFINITY;
     const float m = warp_max(s);
     const float p = (s == -INFINITY) ? 0.f : __expf(s - m);
     const float l = warp_sum(p);
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < Tk; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, p, j);
-      const float2 vv = *reinterpret_cast<const float2*>(vs + (gi * Tk + j) * 64 + 2 * lane);
-      o0 = fmaf(pj, vv.x, o0);
-      o1 = fmaf(pj, vv.y, o1);
+    __syncwarp();
+    pb[lane] = p;
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    const float* vrow = vs + (gi * Tk) * 64 + 2 * lane;
+    int j = 0;
+    for (; j + 1 < Tk; j += 2) {  // p broadcast from shared memory, two independent accumulator pairs
+      const float pa = pb[j], pc = pb[j + 1];
+      const float2 va = *reinterpret_cast<const float2*>(vrow + j * 64);
+      const float2 vc = *reinterpret_cast<const float2*>(vrow + (j + 1) * 64);
+      o0 = fmaf(pa, va.x, o0);
+      o1 = fmaf(pa, va.y, o1);
+      o2 = fmaf(pc, vc.x, o2);
+      o3 = fmaf(pc, vc.y, o3);
+    }
+    if (j < Tk) {
+      const float pa = pb[j];
+      const float2 va = *reinterpret_cast<const float2*>(vrow + j * 64);
+      o0 = fmaf(pa, va.x, o0);
+      o1 = fmaf(pa, va.y, o1);
     }
     // all keys masked: l = 0 -> 0 * inf = NaN, as torch's softmax over an all -inf row (and vmc_attention_masked)
     const float inv = 1.0f / l;
-    const uint32_t h2 = tf_pack_h2(o0 * inv, o1 * inv);
+    const uint32_t h2 = tf_pack_h2((o0 + o2) * inv, (o1 + o3) * inv);
     const uint32_t dst = sm_addr + S::OH + (uint32_t)(r * TF_LDA + c * 64 + 2 * lane) * 2u;
 #pragma unroll
-    for (int j = 0; j < TF_NC; ++j) tf_st_remote_u32(tf_mapa(dst, (uint32_t)j), h2);
+    for (int jj = 0; jj < TF_NC; ++jj) tf_sta_u32(tf_mapa(dst, (uint32_t)jj), h2, rbar[jj]);
   }
 }
 
@@ -293,13 +346,18 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
 
   // rows past the group's last one are multiplied too (M tiles of 16): keep every operand row finite
   for (uint32_t i = tid; i < S::X32 / 16; i += TF_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < XB_COUNT; ++i) mbar_init(sm_addr + S::BAR + 8u * i, 1);  // one arrival: the local arrive.expect_tx
+    fence_mbar_init();
+  }
+  uint32_t parity_bits = 0;  // phase parity of each exchange barrier (tracked identically by every thread)
   // the warp's weight stream: [CTA][warp][layers * 256 blocks][32 lanes]
   const uint4* wbase = a.wstream + ((size_t)(c * TF_NW + warp) * a.layers * NB_LAYER) * 32 + lane;
   uint4 ring[TF_PD];
 #pragma unroll
   for (int j = 0; j < TF_PD; ++j) ring[j] = tf_ldg_w(wbase + (size_t)j * 32);
   __syncthreads();
-  tf_cluster_sync();  // every CTA of the cluster is resident before the first remote store
+  tf_cluster_sync();  // every CTA of the cluster is resident and its barriers initialised before the first remote store
 
   for (int grp = cluster_id; grp < n_groups; grp += num_clusters) {
     const int clip0 = grp * a.G;
@@ -367,7 +425,7 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
       }
       __syncthreads();
       tf_attention<MT>(sm, sm_addr, R, a.T, a.T, a.valid_x, clip0, c, warp, lane);
-      tf_cluster_sync();  // oh complete in every CTA
+      tf_xchg_wait(sm_addr + S::BAR, parity_bits, XB_OH, (uint32_t)R * 1024u, tid);  // all eight heads' output rows are here
       {  // this CTA's 64 columns of out_proj + residual
         float acc[MT][1][4];
         tf_gemm<MT, 1, 16>(sm_addr + S::OH, TF_LDA, w_sout, cross ? w_cq : w_f1, ring, acc, lane);
@@ -382,7 +440,7 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
             x32[r * 64 + col + 1] += acc[mt][0][2 * hf + 1] + bo.y;
           }
       }
-      tf_layernorm_exchange<MT>(sm, sm_addr, R, c, ly.ns_g, ly.ns_b, ly.ns_eps, warp, lane);
+      tf_layernorm_exchange<MT>(sm, sm_addr, R, c, ly.ns_g, ly.ns_b, ly.ns_eps, warp, lane, tid, parity_bits);
 
       // ================= cross-attention: x = LN(x + out_proj(MHA(q = x, k = v = motion))) =================
       if (cross) {
@@ -419,7 +477,7 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
         }
         __syncthreads();
         tf_attention<MT>(sm, sm_addr, R, a.T, a.Tm, a.valid_m, clip0, c, warp, lane);
-        tf_cluster_sync();
+        tf_xchg_wait(sm_addr + S::BAR, parity_bits, XB_OH, (uint32_t)R * 1024u, tid);
         {
           float acc[MT][1][4];
           tf_gemm<MT, 1, 16>(sm_addr + S::OH, TF_LDA, w_cout, w_f1, ring, acc, lane);
@@ -434,7 +492,7 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
               x32[r * 64 + col + 1] += acc[mt][0][2 * hf + 1] + bo.y;
             }
         }
-        tf_layernorm_exchange<MT>(sm, sm_addr, R, c, ly.nc_g, ly.nc_b, ly.nc_eps, warp, lane);
+        tf_layernorm_exchange<MT>(sm, sm_addr, R, c, ly.nc_g, ly.nc_b, ly.nc_eps, warp, lane, tid, parity_bits);
       }
 
       // ================= feed-forward: x = LN(x + W2 act(W1 x + b1) + b2) =================
@@ -467,6 +525,7 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
         float acc[MT][8][4];
         tf_gemm<MT, 8, 8>(sm_addr + S::HH, TF_LDH, w_f2, w_next_layer, ring, acc, lane);
         const uint32_t dst_cta = tf_mapa(sm_addr + S::RECV, (uint32_t)warp);
+        const uint32_t dst_bar = tf_mapa(sm_addr + S::BAR + 8u * XB_RECV, (uint32_t)warp);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -474,11 +533,12 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               const int r = mt * 16 + g + 8 * hf;
-              tf_st_remote_f32x2(dst_cta + (uint32_t)((c * RM + r) * 64 + 8 * i + 2 * t) * 4u, acc[mt][i][2 * hf],
-                                 acc[mt][i][2 * hf + 1]);
+              if (r < R)  // the receiver expects exactly R rows from every CTA
+                tf_sta_f32x2(dst_cta + (uint32_t)((c * RM + r) * 64 + 8 * i + 2 * t) * 4u, acc[mt][i][2 * hf],
+                             acc[mt][i][2 * hf + 1], dst_bar);
             }
       }
-      tf_cluster_sync();  // every CTA's partial sums have arrived
+      tf_xchg_wait(sm_addr + S::BAR, parity_bits, XB_RECV, (uint32_t)R * 2048u, tid);  // every CTA's partial sums have arrived
       {
         const float2 b2 = __ldg(reinterpret_cast<const float2*>(ly.b_f2 + c * 64) + lane);
         for (int r = warp; r < R; r += TF_NW) {
@@ -494,7 +554,7 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
           *reinterpret_cast<float2*>(x32 + r * 64 + 2 * lane) = v;
         }
       }
-      tf_layernorm_exchange<MT>(sm, sm_addr, R, c, ly.nf_g, ly.nf_b, ly.nf_eps, warp, lane);
+      tf_layernorm_exchange<MT>(sm, sm_addr, R, c, ly.nf_g, ly.nf_b, ly.nf_eps, warp, lane, tid, parity_bits);
     }
 
     // ================= head: mean over ALL T rows -> LayerNorm -> Linear -> GELU(erf) -> Linear =================
@@ -505,9 +565,10 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
       s /= (float)a.T;
       const uint32_t dst = sm_addr + S::POOL + (uint32_t)(gi * TF_D + c * 64 + col) * 4u;
 #pragma unroll
-      for (int j = 0; j < TF_NC; ++j) tf_st_remote_f32(tf_mapa(dst, (uint32_t)j), s);
+      for (int j = 0; j < TF_NC; ++j)
+        tf_sta_f32(tf_mapa(dst, (uint32_t)j), s, tf_mapa(sm_addr + S::BAR + 8u * XB_POOL, (uint32_t)j));
     }
-    tf_cluster_sync();
+    tf_xchg_wait(sm_addr + S::BAR, parity_bits, XB_POOL, (uint32_t)nclip * 2048u, tid);
     if (warp < nclip) {  // LayerNorm of the pooled row (every CTA redundantly: 512 values)
       float* pr = pool + warp * TF_D;
       float v[16];
@@ -529,18 +590,21 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
       }
     }
     __syncthreads();
-    {  // Linear 512 -> hidden: this CTA computes hidden / 8 units (32 for hidden = 256); thread = (k slice, unit)
+    const int o = tid & 31, kp = tid >> 5;  // thread = (k slice, output unit): weight reads coalesced over the units
+    {  // Linear 512 -> hidden: this CTA computes hidden / 8 units (32 for hidden = 256)
       const int per = a.hidden / TF_NC;  // <= 32
-      const int o = tid & 31, kp = tid >> 5;
       for (int gi = 0; gi < nclip; ++gi) {
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f;
         if (o < per) {
           const float* w = a.w1t + (size_t)(kp * 64) * a.hidden + c * per + o;
           const float* pr = pool + gi * TF_D + kp * 64;
-#pragma unroll 8
-          for (int k = 0; k < 64; ++k) s = fmaf(pr[k], __ldg(w + (size_t)k * a.hidden), s);
+#pragma unroll 16
+          for (int k = 0; k < 64; k += 2) {
+            s0 = fmaf(pr[k], __ldg(w + (size_t)k * a.hidden), s0);
+            s1 = fmaf(pr[k + 1], __ldg(w + (size_t)(k + 1) * a.hidden), s1);
+          }
         }
-        red[kp * 32 + o] = s;
+        red[kp * 32 + o] = s0 + s1;
         __syncthreads();
         if (tid < per) {
           float u = __ldg(a.b1 + c * per + tid);
@@ -549,44 +613,78 @@ tfam_fused_kernel(const __grid_constant__ TfArgs a) {
           u = 0.5f * u * (1.0f + erff(u * 0.70710678118654752440f));
           const uint32_t dst = sm_addr + S::UH + (uint32_t)(gi * 256 + c * per + tid) * 4u;
 #pragma unroll
-          for (int j = 0; j < TF_NC; ++j) tf_st_remote_f32(tf_mapa(dst, (uint32_t)j), u);
+          for (int j = 0; j < TF_NC; ++j)
+            tf_sta_f32(tf_mapa(dst, (uint32_t)j), u, tf_mapa(sm_addr + S::BAR + 8u * XB_UH, (uint32_t)j));
         }
         __syncthreads();
       }
     }
-    tf_cluster_sync();
-    {  // Linear hidden -> C: class j is computed by CTA j % 8, one warp per class
+    tf_xchg_wait(sm_addr + S::BAR, parity_bits, XB_UH, (uint32_t)(nclip * a.hidden) * 4u, tid);
+    {  // Linear hidden -> C: this CTA computes classes [c * cper, (c + 1) * cper)
+      const int cper = (a.C + TF_NC - 1) / TF_NC;
+      const int ksl = a.hidden / 8;  // k slice of one warp
       for (int gi = 0; gi < nclip; ++gi)
-        for (int j = (int)c + TF_NC * warp; j < a.C; j += TF_NC * TF_NW) {
-          float s = 0.f;
-          for (int k = lane; k < a.hidden; k += 32) s = fmaf(uh[gi * 256 + k], __ldg(a.w2t + (size_t)k * a.C + j), s);
-          s = warp_sum(s);
-          if (lane == 0) a.logits[(size_t)(clip0 + gi) * a.C + j] = s + __ldg(a.b2 + j);
+        for (int o0 = 0; o0 < cper; o0 += 32) {
+          const int cls = (int)c * cper + o0 + o;
+          const bool ok = (o0 + o) < cper && cls < a.C;
+          float s0 = 0.f, s1 = 0.f;
+          if (ok) {
+            const float* w = a.w2t + (size_t)(kp * ksl) * a.C + cls;
+            const float* ur = uh + gi * 256 + kp * ksl;
+#pragma unroll 8
+            for (int k = 0; k + 1 < ksl; k += 2) {
+              s0 = fmaf(ur[k], __ldg(w + (size_t)k * a.C), s0);
+              s1 = fmaf(ur[k + 1], __ldg(w + (size_t)(k + 1) * a.C), s1);
+            }
+            if (ksl & 1) s0 = fmaf(ur[ksl - 1], __ldg(w + (size_t)(ksl - 1) * a.C), s0);
+          }
+          red[kp * 32 + o] = s0 + s1;
+          __syncthreads();
+          if (tid < 32 && ok) {
+            float u = __ldg(a.b2 + cls);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u += red[k * 32 + tid];
+            a.logits[(size_t)(clip0 + gi) * a.C + cls] = u;
+          }
+          __syncthreads();
         }
     }
-    // the next group's first remote stores (attention output) come after its own barriers; pool / uh are rewritten only
-    // after three more cluster barriers -- but x32 / xh are rewritten right away, and only by this CTA's own threads
-    __syncthreads();
   }
   tf_cluster_sync();  // no CTA exits while a peer may still store into its shared memory
 }
 
 int tf_max_clusters(int mt, size_t smem) {
+  static std::mutex mu;
   static int cached[64][2];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 8;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 16;
+  std::lock_guard<std::mutex> lock(mu);
   int& slot = cached[dev][mt - 1];
   if (slot > 0) return slot;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(TF_NC * 16, 1, 1);
-  cfg.blockDim = dim3(TF_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
+  // co-resident clusters of 8 CTAs (one CTA per SM: ~220 KB of shared memory).  More clusters than that would only queue
+  // (clusters never wait for one another), so an over-estimate costs balance, not correctness.
   int n = 0;
-  cudaError_t e = mt == 1 ? cudaOccupancyMaxActiveClusters(&n, tfam_fused_kernel<1>, &cfg)
-                          : cudaOccupancyMaxActiveClusters(&n, tfam_fused_kernel<2>, &cfg);
+  cudaError_t e = mt == 1 ? cudaFuncSetAttribute(tfam_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(tfam_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(TF_NC * 32, 1, 1);
+    cfg.blockDim = dim3(TF_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = TF_NC;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    e = mt == 1 ? cudaOccupancyMaxActiveClusters(&n, tfam_fused_kernel<1>, &cfg)
+                : cudaOccupancyMaxActiveClusters(&n, tfam_fused_kernel<2>, &cfg);
+  }
   if (e != cudaSuccess || n <= 0) {
     (void)cudaGetLastError();
-    n = 8;
+    n = vmc_num_sms() / TF_NC - 2;  // 148 SMs in GPCs of 16-20: two clusters per GPC
+    if (n < 1) n = 1;
   }
   slot = n;
   return n;

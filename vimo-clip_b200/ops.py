@@ -94,16 +94,17 @@ def prologue(frames: torch.Tensor, *, wrap: bool, dst: str, patch: int = 0, norm
     return out
 
 
-def resize_geometry(H: int, W: int, size: int = 224):
-    """torchvision Resize(size) + CenterCrop(size) geometry: (new_h, new_w, top, left)."""
+def resize_geometry(H: int, W: int, size: int = 224, hf_crop: bool = False):
+    """torchvision Resize(size) + CenterCrop(size) geometry: (new_h, new_w, top, left); hf_crop: HF's floor crop offset."""
     v = [C.c_int() for _ in range(4)]
-    _lib.check(_lib.lib().vmc_resize_geometry(H, W, size, *[C.byref(x) for x in v]), "vmc_resize_geometry")
+    _lib.check(_lib.lib().vmc_resize_geometry_ex(H, W, size, 1 if hf_crop else 0, *[C.byref(x) for x in v]), "vmc_resize_geometry")
     return tuple(x.value for x in v)
 
 
-def resize_center_crop(frames: torch.Tensor, *, wrap: bool, size: int = 224) -> torch.Tensor:
+def resize_center_crop(frames: torch.Tensor, *, wrap: bool, size: int = 224, hf_crop: bool = False) -> torch.Tensor:
     """frames [F,3,H,W] uint8/float32 -> uint8 [F,3,size,size]: (optional student wrap) -> Pillow bicubic resize of the
-    short side to ``size`` -> centre crop, bit-exact with ``Resize(224, BICUBIC)`` + ``CenterCrop(224)`` on PIL images."""
+    short side to ``size`` (up or down) -> centre crop, bit-exact with ``Resize(224, BICUBIC)`` + ``CenterCrop(224)`` on PIL
+    images; hf_crop = True takes HF CLIPImageProcessor's crop offset ((dim - size) // 2) instead of torchvision's round."""
     _need_cuda(frames)
     if frames.dim() != 4 or frames.shape[1] != 3:
         raise ValueError("frames must be [F,3,H,W]")
@@ -118,8 +119,8 @@ def resize_center_crop(frames: torch.Tensor, *, wrap: bool, size: int = 224) -> 
     out = torch.empty((F_, 3, size, size), dtype=torch.uint8, device=frames.device)
     tmp = torch.empty((F_, 3, H, size), dtype=torch.uint8, device=frames.device)
     with torch.cuda.device(frames.device):
-        _lib.check(_lib.lib().vmc_resize_center_crop(_p(frames), src_kind, _p(out), _p(tmp), F_, H, W, size, _stream()),
-                   "vmc_resize_center_crop")
+        _lib.check(_lib.lib().vmc_resize_center_crop_ex(_p(frames), src_kind, _p(out), _p(tmp), F_, H, W, size, 1 if hf_crop else 0,
+                                                        _stream()), "vmc_resize_center_crop")
     return out
 
 

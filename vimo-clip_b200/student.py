@@ -126,8 +126,6 @@ class _StudentBase(nn.Module):
             raise ValueError("expected videos of shape (B, T, 3, H, W)")
         B, T, C, H, W = videos.shape
         res = self.visual_encoder.input_resolution
-        if H < res or W < res:
-            raise NotImplementedError(f"{H}x{W} input: frames smaller than {res}x{res} need CenterCrop padding (not implemented)")
         dev = self.visual_encoder.proj.device
         if dev.type != "cuda":
             raise _lib.VmcError("the student runs on CUDA only (no CPU fallback)")
@@ -136,7 +134,8 @@ class _StudentBase(nn.Module):
             frames = frames.float()  # student_model.py:74
         frames = frames.to(dev, non_blocking=True)
         if H != res or W != res:
-            # Resize(224, BICUBIC) -> CenterCrop(224) of the reference preprocess, after the to_pil_image wrap
+            # Resize(224, BICUBIC) -> CenterCrop(224) of the reference preprocess, after the to_pil_image wrap; smaller frames are
+            # scaled UP by the same resampler (the short side becomes 224, so CenterCrop never pads)
             u8 = ops.resize_center_crop(frames, wrap=True, size=res)
             patches = ops.prologue(u8, wrap=False, dst="patch", patch=self.visual_encoder.patch_size)
         else:
