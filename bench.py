@@ -230,6 +230,63 @@ def workload_config(clips):
             "l2": "inputs (1.19 GB/step) and activations (>8 GB) are larger than the 126 MB L2"}
 
 
+def other_configs(vmc, ops, dev, rank, world, timed, peaks):
+    """Short measurements of BASELINE configs 2, 3 and 5 (config 1 is the CPU parity case, config 4 the headline): one dict
+    each, per-GPU batch fixed (weak scaling), `frames_per_s` aggregated over the N GPUs.  tools/configs_bench.py is the
+    long form (sweeps, training step, per-class times)."""
+    import torch
+
+    FL = {"ViT-B/32": 8.818e9, "ViT-B/16": 35.127e9, "ViT-L/14": 162.03e9}
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    out = []
+
+    def rec(name, ms, frames, flops, extra):
+        tf = flops / (ms * 1e9)
+        out.append({"config": name, "frames_per_s": world * frames / (ms / 1e3), "ms_per_step": ms, "steps": 3, "warmup": 3, "tflops_per_gpu": tf,
+                    "frac_of_bf16_sustained": tf / peaks["bf16_sustained"], **extra})
+
+    torch.manual_seed(0)
+    # config 2: CLIP ViT-B/16 per-frame embedding extraction (extract_embeddings.py:89-94), 256 clips x 16 frames of uint8
+    clip = vmc.CLIPVisionFeatures("openai/clip-vit-base-patch16").to(dev)
+    frames = torch.randint(0, 256, (256 * 16, 3, RES, RES), dtype=torch.uint8, device=dev, generator=gen)
+    ms = timed(lambda: clip.get_image_features_u8(frames), 3, 3)
+    rec("config2: CLIP ViT-B/16 per-frame embedding extraction, 256 clips x 16 frames x 224x224 uint8 per GPU", ms, 256 * 16, 256 * 16 * FL["ViT-B/16"],
+        {"clips_per_gpu": 256})
+    # config 3: BGR clips -> fused frame-difference prologue -> ViT-B/32 student + heads -> cosine distillation loss vs the teacher [:, :-1]
+    student = vmc.FrameDiffStudentModel("ViT-B/32", device=dev, num_classes=NUM_CLASSES).eval()
+    bgr = torch.randint(0, 256, (128, 17, RES, RES, 3), dtype=torch.uint8, device=dev, generator=gen)
+    with torch.no_grad():  # teacher embeddings are precomputed (HDF5) in the reference; sliced as train.py:98
+        emb_gt = clip.get_image_features_u8(frames[: 128 * 17]).view(128, 17, -1)[:, :-1, :].contiguous()
+
+    def fn3():
+        with torch.no_grad():
+            _, e_distill, _ = student.forward_bgr(bgr)
+            return vmc.distillation_loss(e_distill, emb_gt, "cosine")
+
+    ms = timed(fn3, 3, 3)
+    rec("config3: MoCLIP frame-difference student (uint8 BGR frame-diff prologue + ViT-B/32 + heads) + cosine distillation loss vs CLIP teacher, 128 clips x 16 "
+        "difference frames per GPU", ms, 128 * 16, 128 * 16 * FL["ViT-B/32"], {"clips_per_gpu": 128})
+    del clip, student, frames, bgr, emb_gt
+    torch.cuda.empty_cache()
+    # config 5: CLIP ViT-L/14 at 32 frames per clip, clip-sharded, NCCL all-gather of the [clips * 32, 768] fp32 embeddings in the step
+    big = vmc.CLIPVisionFeatures("openai/clip-vit-large-patch14").to(dev)
+    big.visual.frames_in_flight = 1024
+    clips5 = 64
+    frames = torch.randint(0, 256, (clips5 * 32, 3, RES, RES), dtype=torch.uint8, device=dev, generator=gen)
+
+    def fn5():
+        e = big.get_image_features_u8(frames).view(clips5, 32, -1)
+        return vmc.sharding.gather_clips(e, clips5 * world) if world > 1 else e
+
+    ms = timed(fn5, 3, 3)
+    rec("config5: CLIP ViT-L/14 frame encoder, 32 frames per clip, 64 clips per GPU, NCCL all-gather of the embeddings in the step", ms, clips5 * 32,
+        clips5 * 32 * FL["ViT-L/14"], {"clips_per_gpu": clips5, "sweep_scale": f"{clips5 * world} of MammalNet's 20033 clips per step",
+                                       "gather_bytes": clips5 * world * 32 * 768 * 4})
+    del big, frames
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
@@ -324,6 +381,39 @@ def ours_main(args):
     h2d = rgb_host.numel() + mot_host.numel()
     d2h = sum(t.numel() * t.element_size() for t in out_host)
 
+    # ---- strong scaling of BASELINE config 4 as it is written: ONE batch of 256 clips, clip-sharded over the N GPUs ----
+    strong = None
+    if not args.no_strong:
+        sc = args.strong_clips
+        n_local = len(vmc.indexing.shard_ids(sc, rank, world))
+        if n_local > clips:
+            raise SystemExit("--strong-clips needs at most --clips clips per GPU")
+        rgb_s, mot_s = rgb_dev[:n_local], mot_dev[:n_local]
+
+        def step_strong():
+            return pipe.forward_sharded(rgb_s, mot_s, sc)  # towers + TFAM on the local clips, three NCCL all-gathers
+
+        ops.reset_launch_count()
+        ms_strong = timed(step_strong, args.steps, 3)
+        strong = {"clips_total": sc, "clips_per_gpu": n_local, "value": sc * T_RGB / (ms_strong / 1e3), "unit": "frames/s", "ms_per_step": ms_strong,
+                  "scaling": "strong", "gpu_launches_per_step": ops.launch_count() // (args.steps + 3),
+                  "note": "ViMoCLIPPipeline.forward_sharded: rank r owns clips r::N; all_gather_into_tensor of logits and both embedding sets inside the step"}
+
+    # ---- the same step with the round-1 defaults, in the same process (N = 1): what the new defaults buy ----
+    ab = None
+    if world == 1 and not args.no_ab:
+        def with_variant(ln_mode, cls, fused):
+            for tower in (pipe.rgb.visual, pipe.student.visual_encoder):
+                tower.ln_mode, tower.last_block_cls = ln_mode, cls
+            pipe.tfam.fused = fused
+            return timed(step_resident, 3, 3)
+
+        ab = {"full_last_block_ms": with_variant(args.ln_mode, 2, not args.tfam_batched),
+              "round1_defaults_ms": with_variant(4, 2, False),
+              "note": "full_last_block: last_block_cls = 2 (every token of the last block computed, identical embeddings); round1_defaults: fp32 residual "
+                      "stream + separate LayerNorm kernels + full last block + batched TFAM; 3 timed steps each after 3 warm-ups"}
+        with_variant(args.ln_mode, args.last_block_cls, not args.tfam_batched)
+
     # ---- per-kernel-class profile of one extra step (roofline of the dominant kernel) ----
     L = _lib.lib()
     L.vmc_profile_begin()
@@ -339,12 +429,15 @@ def ours_main(args):
     # DRAM traffic per launch of the GEMM class: dram__bytes_read + dram__bytes_write summed over the launches of one step
     # in the committed ncu launch list (same command line), divided by the launch count -- ncu cannot run inside the bench
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_step_launches_dram.json")
-    if os.path.exists(tpath) and clips == 256 and args.frames_in_flight == 2048 and args.ln_mode == 4 and args.last_block_cls == 2:
+    default_variant = args.ln_mode in (0, 6) and args.last_block_cls in (0, 1) and not args.tfam_batched
+    tpath = os.path.join(ROOT, "profiles", "r02_step_launches_dram.json" if default_variant else "r01_step_launches_dram.json")
+    round1_variant = args.ln_mode == 4 and args.last_block_cls == 2
+    if os.path.exists(tpath) and clips == 256 and args.frames_in_flight == 2048 and (default_variant or round1_variant):
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj["gemm_class"]["dram_bytes_per_launch"]
-        traffic_src = "profiles/r01_step_launches_dram.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the %d GEMM launches of one step)" % tj["gemm_class"]["launches"]
+        traffic_src = ("STATIC: %s -- ncu dram__bytes_read.sum + dram__bytes_write.sum over the %d GEMM launches of one step of this command line, "
+                       "captured once and committed (ncu cannot run inside the timed bench)" % (os.path.relpath(tpath, ROOT), tj["gemm_class"]["launches"]))
     roofline = {"bound": "tensor", "kernel": "gemm2_bf16_tcgen05_kernel", "achieved": gemm["tflops"], "peak": peaks["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": (gemm["tflops"] / peaks["bf16_sustained"]) if gemm["tflops"] else None, "traffic": traffic,
                 "traffic_unit": "bytes per launch (DRAM, ncu)", "traffic_source": traffic_src,
@@ -354,8 +447,17 @@ def ours_main(args):
                 "share_of_step": gemm["ms"] / sum(c["ms"] for c in classes.values()),
                 "hbm_kernels": {k: {"gbs": classes[k]["gbs"], "frac_of_hbm_peak": (classes[k]["gbs"] / peaks["hbm"]) if classes[k]["gbs"] else None}
                                 for k in ("prologue", "layernorm")}}
+    # algorithmic FLOPs of the REFERENCE's work per step (every token of every block); the default path skips the dead part of
+    # the last block (only its CLS row is read), so the executed FLOPs -- the sum over the launches -- are lower
     flops_step = clips * (T_RGB * FLOPS_B16 + T_MOT * FLOPS_B32 + FLOPS_TFAM_CLIP + FLOPS_HEADS_CLIP)
     step_tflops = flops_step / (ms_step * 1e9)
+    executed_flops = sum(fl_c[i] for i in range(n))
+
+    # ---- the other BASELINE configurations, short (configs 2, 3, 5; same timing rules) ----
+    other = None
+    if not args.no_configs:
+        del rgb_host, mot_host
+        other = other_configs(vmc, ops, dev, rank, world, timed, peaks)
 
     if rank != 0:
         if world > 1:
@@ -383,7 +485,13 @@ def ours_main(args):
         "roofline": roofline,
         "step_tflops": step_tflops,
         "step_frac_of_bf16_sustained": step_tflops / peaks["bf16_sustained"],
+        "step_tflops_executed": executed_flops / (ms_step * 1e9),
+        "step_flops_note": "step_tflops counts the reference's algorithmic FLOPs (all tokens of all blocks); step_tflops_executed the FLOPs of the launches "
+                           "(the last block runs on the CLS rows only: same embeddings)",
         "kernel_classes": classes,
+        "strong": strong,
+        "ab_same_process": ab,
+        "configs": other,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -403,6 +511,10 @@ def main():
     ap.add_argument("--frames-in-flight", type=int, default=2048, help="frames per vmc_vit_forward call (workspace size)")
     ap.add_argument("--ref-clips", type=int, default=12, help="clips per CPU-baseline step (bounded sample: ~10 s per pass on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (one 256-clip batch sharded over the N GPUs)")
+    ap.add_argument("--strong-clips", type=int, default=256, help="total clips of the strong-scaling batch")
+    ap.add_argument("--no-ab", action="store_true", help="skip the same-process timing of the round-1 defaults / the full last block (N = 1)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short measurements of BASELINE configs 2, 3, 5")
     ap.add_argument("--ln-mode", type=int, default=0, help="tower variant (vmc_vit_model.ln_mode): 0 / 6 = bf16 residual stream + LayerNorms folded into the "
                     "qkv / c_fc GEMMs (default), 3 = fp32 stream + folds, 5 = fp32 stream + ln_1 fold, 4 = fp32 stream + separate LayerNorm kernels (round 1)")
     ap.add_argument("--last-block-cls", type=int, default=0, help="0 / 1 = the last transformer block computes only the CLS row of its output, all the "

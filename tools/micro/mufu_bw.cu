@@ -70,7 +70,65 @@ void run(const char* name, int elems) {
   cudaFree(cyc);
 }
 
+// mma.sync.m16n8k16 (bf16 -> fp32) issue rate: NACC independent accumulator chains per warp, 8 warps per block, 4 blocks per SM
+template <int NACC>
+__global__ void __launch_bounds__(256) hmma_bench(float* out, int iters, long long* cycles) {
+  float acc[NACC][4];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  uint32_t a[4] = {0x3c003c00u + threadIdx.x, 0x3c003c00u, 0x3c003c01u, 0x3c003c02u};
+  uint32_t b[2] = {0x3c003c00u, 0x3c003c03u + threadIdx.x};
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i)
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                   : "+f"(acc[i][0]), "+f"(acc[i][1]), "+f"(acc[i][2]), "+f"(acc[i][3])
+                   : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) s += acc[i][0] + acc[i][1] + acc[i][2] + acc[i][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int NACC>
+void run_hmma(int blocks_per_sm) {
+  const int blocks = 148 * blocks_per_sm, threads = 256, iters = 2048;
+  float* out;
+  long long* cyc;
+  cudaMalloc(&out, blocks * threads * 4);
+  cudaMalloc(&cyc, blocks * 8);
+  hmma_bench<NACC><<<blocks, threads>>>(out, 16, cyc);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  hmma_bench<NACC><<<blocks, threads>>>(out, iters, cyc);
+  cudaEventRecord(e1);
+  cudaDeviceSynchronize();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  const double flops = 2.0 * 16 * 8 * 16 * (double)NACC * iters * 8.0 * blocks;
+  long long h[148 * 4];
+  cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
+  double avg = 0;
+  for (int i = 0; i < blocks; ++i) avg += h[i];
+  avg /= blocks;
+  printf("mma.sync m16n8k16 bf16: %d chains/warp, %d warps/SM: %8.3f ms  %7.1f TFLOP/s  %.2f clk per HMMA per SM (%s)\n", NACC,
+         8 * blocks_per_sm, ms, flops / ms / 1e9, avg / ((double)NACC * iters * 8 * blocks_per_sm), cudaGetErrorString(cudaGetLastError()));
+  cudaFree(out);
+  cudaFree(cyc);
+}
+
 int main() {
+  run_hmma<1>(1);
+  run_hmma<4>(1);
+  run_hmma<8>(1);
+  run_hmma<8>(2);
+  run_hmma<8>(4);
   run<0>("ex2.approx.ftz.f32", 1);
   run<1>("ex2.approx.f16x2", 2);
   run<2>("ex2.approx.ftz.bf16x2", 2);
