@@ -1565,6 +1565,7 @@ uint32_t pow2_at_least(uint32_t v) {
 int vmc_get_option(int option);
 long long vmc_get_option64(int option);
 extern "C" int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
+extern "C" int vmc_attention_vit_long_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
 
 extern "C" {
 
@@ -1579,14 +1580,15 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     var6 = impl - 100;
     impl = 6;
   }
-  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8) || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 9) || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 2, 5, 6, 7, 8 or 9");
 #else
-  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 9), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7, 8 or 9");
 #endif
   const int d = heads * HD;
-  if (impl == 8) {  // warp-level tensor path for short sequences (backward.cu)
+  if (impl == 8 || impl == 9) {  // warp-level tensor path (backward.cu): 8 = short sequences, 9 = up to 272 tokens
     if (L <= 64) return vmc_attention_vit_short_mma(qkv, out, F, L, heads, stream);
+    if (impl == 9 && L <= 272 && F <= 65535) return vmc_attention_vit_long_mma(qkv, out, F, L, heads, stream);
     impl = 5;
   }
   // v7 = two items packed per query tile in the v5 pipeline: default for short sequences (ViT-B/32: 50 tokens)
@@ -1759,7 +1761,7 @@ int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L
 
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream) {
   const int opt = vmc_get_option(VMC_OPT_ATTN_IMPL);
-  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt == 2 || (opt >= 5 && opt <= 8)) ? opt : 5, stream);
+  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt == 2 || (opt >= 5 && opt <= 9)) ? opt : 5, stream);
 }
 
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk,

@@ -25,7 +25,7 @@ struct Workspace {
   void* xn2;
   void* big;
   void* cls;
-  float* stats;  // float2 [8][rows]: partial row statistics for the folded LayerNorms
+  float* stats;  // float2 [16][rows]: partial row statistics for the folded LayerNorms (one plane per 64- / 128-column slice)
   long long total;
 };
 
@@ -48,7 +48,7 @@ Workspace carve(const vmc_vit_model* m, int F, void* base) {
   w.cls = p + off;
   off += align_up((long long)F * d * 2, 1024);
   w.stats = reinterpret_cast<float*>(p + off);
-  off += align_up(rows * 8 * 8, 1024);
+  off += align_up(rows * 16 * 8, 1024);
   w.total = off;
   return w;
 }
@@ -126,7 +126,7 @@ int vmc_vit_forward(const vmc_vit_model* m, const void* patches, float* out, int
     have_folded = m->layer[i].w_qkv_f && m->layer[i].b_qkv_f && m->layer[i].cs_qkv && m->layer[i].w_fc1_f &&
                   m->layer[i].b_fc1_f && m->layer[i].cs_fc1;
   const int res_parts = vmc_gemm_stats_parts(rows, d);  // column slices written by the out_proj / c_proj GEMMs
-  have_folded = have_folded && res_parts > 0 && res_parts <= 8 && (d % (d / res_parts)) == 0;
+  have_folded = have_folded && res_parts > 0 && res_parts <= 16 && (d % (d / res_parts)) == 0;
   if (!have_folded) ln_mode = 4;
   const bool cls_only = tower_last_block_cls(m) == 1 && (ln_mode == 6 || ln_mode == 4);
   float* xcls = nullptr;  // [F, d] fp32: the CLS rows after the last block

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from ._params import SharedCache
 from .vit import VisionTower
 
 
@@ -86,19 +87,20 @@ class _StudentBase(nn.Module):
             nn.ReLU(),
             nn.Linear(embed_dim // 2, num_classes),
         )
-        self._head_cache = None
+        self._head_cache = SharedCache(self)
         self.to(device)
 
     def _heads(self):
         ps = [self.residual_mlp.fc1.weight, self.residual_mlp.fc1.bias, self.residual_mlp.fc2.weight, self.residual_mlp.fc2.bias,
               self.classification_head[0].weight, self.classification_head[0].bias,
               self.classification_head[2].weight, self.classification_head[2].bias]
-        sig = tuple((p.data_ptr(), p._version) for p in ps)
-        if self._head_cache is None or self._head_cache[0] != sig:
+
+        def build():
             # one fused fp32 kernel per clip (vmc_student_heads): weights transposed to [K, N] fp32 once
-            packed = [p.detach().float().t().contiguous() if p.dim() == 2 else p.detach().float().contiguous() for p in ps]
-            self._head_cache = (sig, packed)
-        return self._head_cache[1]
+            return [p.detach().float().t().contiguous() if p.dim() == 2 else p.detach().float().contiguous() for p in ps]
+
+        self._head_cache.bind(self)
+        return self._head_cache.get(("heads", ps[0].device.index), self._head_cache.signature(self), build)
 
     @torch.no_grad()
     def encode_patches(self, patches: torch.Tensor, B: int, T: int):

@@ -24,6 +24,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from ._params import named_tensors
 from .tfam_train import _lin_bwd, _lin_fwd
 
 _PER_BLOCK = ("ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",
@@ -35,7 +36,7 @@ _HEADS = ("residual_mlp.fc1.weight", "residual_mlp.fc1.bias", "residual_mlp.fc2.
 
 
 def trainable_parameters(model):
-    named = dict(model.named_parameters())
+    named = dict(named_tensors(model))  # also on DataParallel replicas (train.py:64), whose _parameters are empty
     n_layers = model.visual_encoder.layers
     names = [f"visual_encoder.{n}" for n in _TOWER_HEAD]
     names += [f"visual_encoder.transformer.resblocks.{i}.{n}" for i in range(n_layers) for n in _PER_BLOCK]

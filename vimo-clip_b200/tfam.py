@@ -31,6 +31,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from ._params import SharedCache
 
 
 def _frag_blocks(wsel: torch.Tensor) -> torch.Tensor:
@@ -123,8 +124,7 @@ class AMO_CLIP(nn.Module):
             nn.LayerNorm(d_model), nn.Linear(d_model, d_model // 2), nn.GELU(), nn.Dropout(mlp_dropout), nn.Linear(d_model // 2, num_classes)
         )
         self.projection_layer = nn.Linear(2 * self.d_model, self.d_model)
-        self._cache = None
-        self._fcache = None
+        self._cache = SharedCache(self)  # packed weights per device, shared with DataParallel replicas
         self.fused = True  # one fused kernel per forward where the geometry allows (False: batched GEMM path)
 
     def positional_encoding(self, seq_len, device=None):
@@ -139,9 +139,10 @@ class AMO_CLIP(nn.Module):
 
     # ---- packed weights (bf16 GEMM operands, fp32 vectors), rebuilt when parameters change ----
     def _packed(self):
-        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self._cache is not None and self._cache[0] == sig:
-            return self._cache[1]
+        self._cache.bind(self)
+        return self._cache.get(("batched", self.classifier[0].weight.device.index), self._cache.signature(self), self._build_packed)
+
+    def _build_packed(self):
         bf = ops.split_weight  # [N, 3K] = [Whi | Whi | Wlo]
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
         layers = []
@@ -162,14 +163,14 @@ class AMO_CLIP(nn.Module):
         head = dict(ln=(f32(c[0].weight), f32(c[0].bias), c[0].eps), w1t=tr(c[1].weight), b1=f32(c[1].bias),
                     w2t=tr(c[4].weight), b2=f32(c[4].bias),
                     wp=bf(self.projection_layer.weight), bp=f32(self.projection_layer.bias))
-        self._cache = (sig, (layers, head))
-        return self._cache[1]
+        return (layers, head)
 
     # ---- fused kernel: packed fp16 weight stream + parameter table, rebuilt when parameters change ----
     def _fused_model(self):
-        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self._fcache is not None and self._fcache[0] == sig:
-            return self._fcache[1]
+        self._cache.bind(self)
+        return self._cache.get(("fused", self.classifier[0].weight.device.index), self._cache.signature(self), self._build_fused_model)
+
+    def _build_fused_model(self):
         import ctypes as C
 
         keep = []
@@ -205,8 +206,7 @@ class AMO_CLIP(nn.Module):
             assert ws.numel() * 2 == _lib.lib().vmc_tfam_wstream_bytes(n)
             keep.append(ws)
             m.wstream = ws.data_ptr()
-        self._fcache = (sig, (m if geometry_ok else None, arr, keep))
-        return self._fcache[1]
+        return (m if geometry_ok else None, arr, keep)
 
     def _forward_fused(self, x, motion, valid_x, valid_m):
         """x [B,T,512] fp32 contiguous, motion [B,Tm,512] or None -> logits [B,C]; None if the fused kernel does not cover the shape."""

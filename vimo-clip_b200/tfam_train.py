@@ -21,6 +21,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from ._params import named_tensors
 
 _PER_LAYER = ("self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight", "self_attn.out_proj.bias",
               "cross_attn.in_proj_weight", "cross_attn.in_proj_bias", "cross_attn.out_proj.weight", "cross_attn.out_proj.bias",
@@ -31,7 +32,7 @@ _HEAD = ("classifier.0.weight", "classifier.0.bias", "classifier.1.weight", "cla
 
 def trainable_parameters(model, proj: bool = False):
     """The parameters in the order TfamTrainFunction takes them (projection_layer only in the embedding-concat mode)."""
-    named = dict(model.named_parameters())
+    named = dict(named_tensors(model))  # also on DataParallel replicas (TFAM/train_and_eval.py:392), whose _parameters are empty
     names = [f"layers.{i}.{n}" for i in range(len(model.layers)) for n in _PER_LAYER] + list(_HEAD)
     if proj:
         names += ["projection_layer.weight", "projection_layer.bias"]

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from ._params import SharedCache
 
 # name -> (patch, width, layers, heads, output_dim); 224x224 input
 VIT_CONFIGS = {
@@ -84,9 +85,7 @@ class VisionTower(nn.Module):
         self.transformer.resblocks = nn.ModuleList([_Block(width) for _ in range(layers)])
         self.ln_post = _ln_holder(width)
         self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
-        self._packed = None
-        self._packed_sig = None
-        self._workspace = None
+        self._cache = SharedCache(self)  # packed weights / workspace per device, shared with DataParallel replicas
         # per-model kernel variants (0 = library default; vmc_vit_model in include/vimoclip_b200.h):
         # ln_mode 6 = bf16 residual stream + folded LayerNorms (default), 3 / 5 = fp32 stream with folds, 4 = fp32 stream with
         # separate LayerNorm kernels; last_block_cls 1 = last block on the CLS rows only (default), 2 = full last block
@@ -101,17 +100,17 @@ class VisionTower(nn.Module):
         return cls(*VIT_CONFIGS[name], **kw)
 
     # ---- weight packing: fp32 state_dict -> bf16 K-major GEMM operands + fp32 vectors ----
-    def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
-
     @torch.no_grad()
     def _pack(self):
-        sig = self._signature()
-        if self._packed is not None and sig == self._packed_sig:
-            return self._packed
         dev = self.proj.device
         if dev.type != "cuda":
             raise _lib.VmcError("VisionTower runs on CUDA only (no CPU fallback); call .to('cuda') first")
+        self._cache.bind(self)
+        return self._cache.get(("pack", dev.index), self._cache.signature(self), self._build_pack)
+
+    @torch.no_grad()
+    def _build_pack(self):
+        dev = self.proj.device
         keep = []  # tensors referenced by raw pointers below
 
         def bf(w):
@@ -158,15 +157,13 @@ class VisionTower(nn.Module):
         m.ln_post_g, m.ln_post_b = f32(self.ln_post.weight), f32(self.ln_post.bias)
         m.w_proj = bf(self.proj.detach().t())
         m.layer = C.cast(layers, C.POINTER(_lib.VitLayer))
-        self._packed = (m, layers, keep)
-        self._packed_sig = sig
-        return self._packed
+        return (m, layers, keep)
 
     def _get_workspace(self, nbytes: int, device) -> torch.Tensor:
-        ws = self._workspace
-        if ws is None or ws.numel() < nbytes or ws.device != device:
+        ws = self._cache.peek(("workspace", device.index))
+        if ws is None or ws.numel() < nbytes:
             ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-            self._workspace = ws
+            self._cache.put(("workspace", device.index), ws)
         return ws
 
     @torch.no_grad()
