@@ -33,8 +33,7 @@ int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * (kept as an independent cross-check for the tests).  VMC_OPT_ATTN_IMPL: 0 = by sequence length (7 for L <= 64, 5 for
  * 129..224, 6 for 225..257, else 2); 5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row
  * sums from the tensor core; 6 = v5 on the patch tokens + the CLS token on mma.sync warps; 7 = two items per query tile;
- * 8 = warp-level mma.sync kernel for L <= 64; 9 = warp-level mma.sync kernel for 64 < L <= 272 (scores / P / O in registers);
- * 2 = one CTA per (frame, head) with P in TMEM (any L <= 272). */
+ * 8 = warp-level mma.sync kernel for L <= 64; 2 = one CTA per (frame, head) with P in TMEM (any L <= 272). */
 /* vmc_set_option sets PROCESS-WIDE defaults (relaxed atomics; meant for tests, A/B runs and tools).  The per-model
  * selectors of vmc_vit_model take precedence, so two models in one process can run different variants concurrently. */
 enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* ViT attention backward, L <= 64: 0 = warp-level tensor-core kernel (ldmatrix + mma.sync), 2 = register-tiled fp32 kernel, 1 = first-generation shared-memory kernel (cross-checks) */,
@@ -182,9 +181,6 @@ int vmc_layernorm_ex(const void* x, int x_bf16, long long ldx, const float* gamm
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream);
 /* short sequences (L <= 64) on the warp-level tensor path (ldmatrix + mma.sync), one CTA per (frame, head); = vmc_attention_vit_impl(..., 8, ...) */
 int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
-/* 64 < L <= 272 on the same warp-level path, flash-attention-2 style (scores, probabilities and the output accumulator in
- * registers, keys walked in chunks of 64, two CTAs per SM); = vmc_attention_vit_impl(..., 9, ...) */
-int vmc_attention_vit_long_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
 /* CLS-query attention of the last block (VMC_OPT_LAST_BLOCK_CLS): q_cls bf16 [F, d], kv bf16 [F*L, 2d] = [k | v] -> out bf16 [F, d] */
 int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L, int heads, void* stream);
 /* same, selecting the implementation (see VMC_OPT_ATTN_IMPL above); kernels that do not cover L fall back to one that does */

@@ -87,7 +87,9 @@ def test_dataparallel_replicas_reuse_packed_weights_and_train():
     rep = replicate(tfam, [0])[0]
     torch.nn.functional.binary_cross_entropy_with_logits(rep(rgb, mot), labels).backward()
     got = {n: p.grad for n, p in tfam.named_parameters() if p.grad is not None}
-    assert set(got) == set(want) and len(want) > 50
+    assert set(want) <= set(got) and len(want) > 50
+    for n in set(got) - set(want):  # Broadcast.backward hands the parameters this mode does not use a zero gradient
+        assert float(got[n].abs().max()) == 0.0, n
     for n in want:
         assert torch.allclose(got[n], want[n], rtol=1e-4, atol=1e-6), n
     # ---- student ----

@@ -1,8 +1,8 @@
 set -x
 mkdir -p gpurun_out
-(nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/mufu_bw tools/micro/mufu_bw.cu && /tmp/mufu_bw) > gpurun_out/r02_mufu2.log 2>&1
-timeout 600 python tools/tower_margins.py > gpurun_out/r02_tower_margins.log 2>&1
-timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -k "scale or resize or student_config1 or tfam_fused" > gpurun_out/r02_pytest3.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest3.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench3_default.json 2> gpurun_out/r02_bench3_default.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench3_reference.json 2> gpurun_out/r02_bench3_reference.err
-tail -n 4 gpurun_out/r02_pytest3.log; cat gpurun_out/r02_mufu2.log | tail -n 6; cat gpurun_out/r02_tower_margins.log
+KB_WHICH=attn KB_ATTN_IMPLS=5,9,6,2 python tools/kernel_bench.py > gpurun_out/r02_kb_attn.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -x > gpurun_out/r02_pytest4.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest4.log
+timeout 600 python tools/tower_margins.py > gpurun_out/r02_tower_margins2.log 2>&1
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs --no-strong --no-ab > gpurun_out/r02_bench4_attn5.json 2> gpurun_out/r02_bench4_attn5.err
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs --no-strong --no-ab --attn-impl 9 > gpurun_out/r02_bench4_attn9.json 2> gpurun_out/r02_bench4_attn9.err
+cat gpurun_out/r02_kb_attn.log; tail -n 5 gpurun_out/r02_pytest4.log; cat gpurun_out/r02_tower_margins2.log

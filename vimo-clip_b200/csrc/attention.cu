@@ -1565,7 +1565,6 @@ uint32_t pow2_at_least(uint32_t v) {
 int vmc_get_option(int option);
 long long vmc_get_option64(int option);
 extern "C" int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
-extern "C" int vmc_attention_vit_long_mma(const void* qkv, void* out, int F, int L, int heads, void* stream);
 
 extern "C" {
 
@@ -1580,15 +1579,18 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     var6 = impl - 100;
     impl = 6;
   }
-  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 9) || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 2, 5, 6, 7, 8 or 9");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8) || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
 #else
-  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 9), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7, 8 or 9");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
 #endif
   const int d = heads * HD;
-  if (impl == 8 || impl == 9) {  // warp-level tensor path (backward.cu): 8 = short sequences, 9 = up to 272 tokens
+  if (impl == 8) {  // warp-level tensor path for short sequences (backward.cu)
+    // (The same flash-attention-2 style kernel for 64 < L <= 272 -- scores / P / O in registers, keys in chunks of 64, two
+    // CTAs per SM -- was built and measured in round 2: 0.730 ms per 1024 ViT-B/16 frames against 0.381 ms for v5.  Each of
+    // the 13 sixteen-row tiles re-reads the item's K and V fragments from shared memory: 0.7 MB per item, ~5.4 k cycles at
+    // 128 B/clk, more than v5's whole item.  Removed; profiles/r02_kernel_bench_attention.txt.)
     if (L <= 64) return vmc_attention_vit_short_mma(qkv, out, F, L, heads, stream);
-    if (impl == 9 && L <= 272 && F <= 65535) return vmc_attention_vit_long_mma(qkv, out, F, L, heads, stream);
     impl = 5;
   }
   // v7 = two items packed per query tile in the v5 pipeline: default for short sequences (ViT-B/32: 50 tokens)
@@ -1761,7 +1763,7 @@ int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L
 
 int vmc_attention_vit(const void* qkv, void* out, int F, int L, int heads, void* stream) {
   const int opt = vmc_get_option(VMC_OPT_ATTN_IMPL);
-  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt == 2 || (opt >= 5 && opt <= 9)) ? opt : 5, stream);
+  return vmc_attention_vit_impl(qkv, out, F, L, heads, (opt == 2 || (opt >= 5 && opt <= 8)) ? opt : 5, stream);
 }
 
 int vmc_attention_masked(const float* q, long long ldq, const float* k, long long ldk,

@@ -1354,149 +1354,6 @@ attention_fwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// ViT self-attention for 64 < L <= 272 tokens on the warp-level tensor path (impl 9; flash-attention-2 style).
-//
-// Why, next to the tcgen05 kernel v5: that pipeline keeps two 128-row query tiles in flight per SM (TMEM holds two 208-column
-// score tiles) and is bound by the per-tile S -> softmax -> PV -> drain dependency chain: ~7.5 k cycles per (frame, head) item
-// against ~1.9 k cycles of tensor work and ~1.7 k of MUFU work.  Here an item is one CTA of 7 warps; a warp
-// owns 16 query rows at a time (13 row tiles at L = 197: warps take tiles w and w + 7), keeps its scores, probabilities and the
-// output accumulator in REGISTERS (no TMEM round trip, no mbarrier hand-overs), and walks the keys in chunks of 64:
-//   S = Q K^T (32 HMMA) -> p = 2^(s * sc - m) -> P V (32 HMMA), O and the row sums accumulate over the chunks.
-// m is the row maximum of the FIRST chunk (64 keys) -- as in v5 the stabiliser need not be the true maximum: the exponent is
-// clamped at +120 and the normaliser sums the bf16-rounded probabilities the MMA consumes, so no rescaling pass is needed.
-// Two CTAs (80 KB of shared memory each) are resident per SM: one loads its Q / K / V with cp.async while the other computes.
-// mma.sync peaks at ~530 TFLOP/s on this part (tools/micro/mufu_bw.cu) -- a quarter of tcgen05 -- but attention at 197 tokens
-// is bound by the softmax and by latency, not by the tensor pipe.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int AL_WARPS = 7;
-__device__ __forceinline__ float ex2_fast(float x) {  // one MUFU.EX2 (exp2f adds range handling around it)
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__global__ void __launch_bounds__(AL_WARPS * 32, 2)
-attention_fwd_mma_long_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int L, int heads, int lk16) {
-  extern __shared__ __align__(1024) uint8_t fl_smem[];
-  const uint32_t sb = ((uint32_t)__cvta_generic_to_shared(fl_smem) + 1023u) & ~1023u;
-  const uint32_t mat_bytes = (uint32_t)lk16 * 128u;
-  const uint32_t sQ = sb, sK = sb + mat_bytes, sV = sb + 2u * mat_bytes;
-  const int head = blockIdx.x, frame = blockIdx.y;
-  const int d = heads * HD;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, tig = lane & 3;
-  const size_t row0 = (size_t)frame * L;
-  // ---- Q | K | V head slices -> swizzled 128-byte rows (cp.async, 16 bytes per request); rows L .. lk16-1 zeroed ----
-  for (int i = tid; i < 3 * lk16 * 8; i += AL_WARPS * 32) {
-    const int mat = i / (lk16 * 8), rem = i - mat * lk16 * 8;
-    const int r = rem >> 3, c = rem & 7;
-    const uint32_t dst = swz(sb + (uint32_t)mat * mat_bytes, r, c);
-    if (r < L) {
-      const __nv_bfloat16* src = qkv + (row0 + r) * 3 * d + (size_t)mat * d + head * HD + c * 8;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    } else {
-      asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  const int lm = lane >> 3, lr = lane & 7;
-  const float sc = 0.125f * 1.4426950408889634f;
-  const int n_chunks = (lk16 + 63) >> 6;
-  for (int rt = warp; 16 * rt < L; rt += AL_WARPS) {  // warp-uniform; no block-wide barrier below
-    const int q0 = 16 * rt;
-    uint32_t aQ[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) ldsm4(swz(sQ, q0 + (lm & 1) * 8 + lr, 2 * ks + (lm >> 1)), aQ[ks]);
-    float oa[8][4];
-#pragma unroll
-    for (int db = 0; db < 8; ++db) oa[db][0] = oa[db][1] = oa[db][2] = oa[db][3] = 0.f;
-    float mx0 = 0.f, mx1 = 0.f, sm0 = 0.f, sm1 = 0.f;
-    for (int kc = 0; kc < n_chunks; ++kc) {
-      const int k0 = 64 * kc;
-      const int nkt = min(8, (lk16 - k0) >> 3);  // 8-key tiles of this chunk (8, or 2 / 4 / 6 in the last one)
-      float sa[8][4];
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb) sa[nb][0] = sa[nb][1] = sa[nb][2] = sa[nb][3] = 0.f;
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        if (2 * np < nkt) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            uint32_t bk[4];
-            ldsm4(swz(sK, k0 + 8 * (2 * np + (lm >> 1)) + lr, 2 * ks + (lm & 1)), bk);
-            mma16816(sa[2 * np], aQ[ks], bk[0], bk[1]);
-            mma16816(sa[2 * np + 1], aQ[ks], bk[2], bk[3]);
-          }
-        }
-      }
-      // scale; keys >= L are padding (-inf -> probability 0)
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const bool ok = k0 + 8 * nb + 2 * tig + e < L;
-          sa[nb][e] = ok ? sa[nb][e] * sc : -INFINITY;
-          sa[nb][2 + e] = ok ? sa[nb][2 + e] * sc : -INFINITY;
-        }
-      if (kc == 0) {  // stabiliser: row maximum of the first 64 keys (all of them real: L > 64)
-        float a0 = -INFINITY, a1 = -INFINITY;
-#pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
-          a0 = fmaxf(a0, fmaxf(sa[nb][0], sa[nb][1]));
-          a1 = fmaxf(a1, fmaxf(sa[nb][2], sa[nb][3]));
-        }
-        a0 = fmaxf(a0, __shfl_xor_sync(0xffffffffu, a0, 1)); a0 = fmaxf(a0, __shfl_xor_sync(0xffffffffu, a0, 2));
-        a1 = fmaxf(a1, __shfl_xor_sync(0xffffffffu, a1, 1)); a1 = fmaxf(a1, __shfl_xor_sync(0xffffffffu, a1, 2));
-        mx0 = a0;
-        mx1 = a1;
-      }
-      uint32_t pp[8][2];
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        const __nv_bfloat162 r0 = __floats2bfloat162_rn(ex2_fast(fminf(sa[nb][0] - mx0, 120.f)), ex2_fast(fminf(sa[nb][1] - mx0, 120.f)));
-        const __nv_bfloat162 r1 = __floats2bfloat162_rn(ex2_fast(fminf(sa[nb][2] - mx1, 120.f)), ex2_fast(fminf(sa[nb][3] - mx1, 120.f)));
-        sm0 += __low2float(r0) + __high2float(r0);  // the normaliser sums what the MMA will multiply
-        sm1 += __low2float(r1) + __high2float(r1);
-        pp[nb][0] = *reinterpret_cast<const uint32_t*>(&r0);
-        pp[nb][1] = *reinterpret_cast<const uint32_t*>(&r1);
-      }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (2 * kk < nkt) {
-          const uint32_t a[4] = {pp[2 * kk][0], pp[2 * kk][1], pp[2 * kk + 1][0], pp[2 * kk + 1][1]};
-#pragma unroll
-          for (int cp = 0; cp < 4; ++cp) {
-            uint32_t b[4];
-            ldsm4t(swz(sV, k0 + 16 * kk + (lm & 1) * 8 + lr, 2 * cp + (lm >> 1)), b);
-            mma16816(oa[2 * cp], a, b[0], b[1]);
-            mma16816(oa[2 * cp + 1], a, b[2], b[3]);
-          }
-        }
-      }
-    }
-    sm0 += __shfl_xor_sync(0xffffffffu, sm0, 1); sm0 += __shfl_xor_sync(0xffffffffu, sm0, 2);
-    sm1 += __shfl_xor_sync(0xffffffffu, sm1, 1); sm1 += __shfl_xor_sync(0xffffffffu, sm1, 2);
-    // rows g / g + 8 -> the warp's own Q rows (dead: the A fragments are in registers), then out as full 128-byte lines
-    const float i0 = 1.0f / sm0, i1 = 1.0f / sm1;
-    __syncwarp();
-#pragma unroll
-    for (int db = 0; db < 8; ++db) {
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(swz(sQ, q0 + g, db) + 4u * (uint32_t)tig), "r"(pack_bf16x2(oa[db][0] * i0, oa[db][1] * i0)) : "memory");
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(swz(sQ, q0 + g + 8, db) + 4u * (uint32_t)tig), "r"(pack_bf16x2(oa[db][2] * i1, oa[db][3] * i1)) : "memory");
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = q0 + 4 * i + (lane >> 3), c = lane & 7;
-      uint4 v;
-      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(swz(sQ, r, c)));
-      if (r < L) *reinterpret_cast<uint4*>(out + (row0 + r) * d + head * HD + c * 8) = v;
-    }
-  }
-}
-
 }  // extern "C++"
 
 int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int heads, void* stream) {
@@ -1512,26 +1369,6 @@ int vmc_attention_vit_short_mma(const void* qkv, void* out, int F, int L, int he
     else
       attention_fwd_mma_kernel<false><<<dim3(heads, F), 128, 24576, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                                          reinterpret_cast<__nv_bfloat16*>(out), L, heads);
-  }
-  VMC_LAUNCH_CHECK();
-  vmc_count_launch();
-  return VMC_OK;
-}
-
-int vmc_attention_vit_long_mma(const void* qkv, void* out, int F, int L, int heads, void* stream) {
-  VMC_CHECK_ARG(qkv && out, VMC_ERR_ARG, "vmc_attention_vit_long_mma: null pointer");
-  VMC_CHECK_ARG(F > 0 && F <= 65535 && heads > 0 && L > 64 && L <= 272, VMC_ERR_SHAPE, "vmc_attention_vit_long_mma: need 64 < L <= 272 (L=%d)", L);
-  VMC_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, VMC_ERR_ALIGN,
-                "vmc_attention_vit_long_mma: qkv / out must be 16-byte aligned");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int d = heads * HD;
-  const int lk16 = (L + 15) / 16 * 16;
-  const int smem = 3 * lk16 * 128 + 1024;
-  VMC_CUDA(cudaFuncSetAttribute(attention_fwd_mma_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  {
-    VmcProfScope prof(VMC_K_ATTN_VIT, st, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
-    attention_fwd_mma_long_kernel<<<dim3(heads, F), AL_WARPS * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                                               reinterpret_cast<__nv_bfloat16*>(out), L, heads, lk16);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
