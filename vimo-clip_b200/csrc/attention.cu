@@ -327,8 +327,9 @@ constexpr int A5_THREADS = 448;  // 8 softmax + 4 epilogue + TMA + MMA warps
 constexpr int A5_PA_CHUNKS = 5;  // chunks (32 keys) whose P is packed into [0, 80): part A of the PV MMA
 constexpr int A5_OCOL = 80;      // accumulator columns [80, 160): 64 of O + 16 copies of the row sum
 
+constexpr int A5B_THREADS = 480;  // v5: + a second MMA issuer warp (one per query tile)
 template <int VAR, bool DBG = false>
-__global__ void __launch_bounds__(A5_THREADS, 1)
+__global__ void __launch_bounds__(A5B_THREADS, 1)
 attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm1,
                       const Attn5Args a) {
   // Shared memory: two rings, released at different times.  The timeline of the first v5 (one Q/K/V stage
@@ -369,7 +370,7 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
   // the all-ones "second MN atom" of the PV B operand (bf16 1.0 everywhere; any layout reads ones)
   {
     uint4* ones = reinterpret_cast<uint4*>(smem_raw + (ones_base - raw_addr));
-    for (uint32_t i = tid; i < ones_bytes / 16; i += A5_THREADS)
+    for (uint32_t i = tid; i < ones_bytes / 16; i += A5B_THREADS)
       ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
@@ -378,9 +379,9 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     tma_prefetch_desc(&tm1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(qk_full(i), 1);
-      mbar_init(qk_empty(i), 1);
+      mbar_init(qk_empty(i), 2);  // one tcgen05.commit per tile's MMA issuer
       mbar_init(v_full(i), 1);
-      mbar_init(v_empty(i), 1);
+      mbar_init(v_empty(i), 2);
       mbar_init(s_full(i), 1);
       mbar_init(pa_full(i), 4);  // one arrive per softmax warp of the tile
       mbar_init(pb_full(i), 4);
@@ -440,73 +441,57 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == 13) {
-    // ===================== MMA issuer (event driven, non-blocking polls) =====================
+  } else if (warp == 13 || warp == 14) {
+    // ===================== MMA issuers: one warp per query tile =====================
+    // Round 1 had ONE thread serve both tiles by polling their barriers round-robin with mbarrier.test_wait (~150 cycles
+    // per probe, two to four probes per turn): every hand-over on a tile's S -> softmax -> PV -> drain chain waited for the
+    // poller to come round, and an MMA burst for one tile delayed the other.  Each tile now has its own issuer that BLOCKS
+    // on that tile's barriers (try_wait: the thread sleeps in hardware and wakes ~60 cycles after the arrive).  The shared
+    // rings are released by both: qk_empty / v_empty count two arrivals, each issuer's tcgen05.commit covering its own MMAs.
+    const int t = warp - 13;
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, a.lk16, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 80, 0, 1);  // B = [V | ones], MN-major
       const int nka = nkk < 2 * A5_PA_CHUNKS ? nkk : 2 * A5_PA_CHUNKS;
-      int kt[2] = {0, 0};   // next item (local index) of each tile
-      int ph[2] = {0, 0};   // 0: S to issue, 1: waiting for P_a, 2: waiting for P_b
-      int sdone[2] = {0, 0};  // tiles whose S MMAs of the item in Q/K ring slot s have been issued
-      int fin[2] = {0, 0};    // tiles that have issued the last PV MMA of the item in V ring slot s
-      while (kt[0] < n_my || kt[1] < n_my) {
+      const uint32_t tcol = tmem_base + uint32_t(t * 256);
+      for (int k = 0; k < n_my; ++k) {
+        const int s = k & 1;
+        const uint32_t par = (uint32_t)k & 1u;
+        const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
+        const uint32_t vst = v_base + s * mat_bytes;
+        // V descriptor: atom 0 = the TMA tile (64 head dims x 16 keys), atom 1 (N = 64..79) = LBO further = ones
+        const uint64_t dv0 = (umma_desc_sw128(vst) & ~(uint64_t(0x3FFF) << 16)) |
+                             (uint64_t((ones_base - vst) >> 4) << 16);
+        // ---- S = Q K^T ----
+        mbar_wait(qk_full(s), ring_par);
+        if (t == 0) VMC_DBG5(k, 25);
+        mbar_wait(s_empty(t), par ^ 1u);
+        tc_fence_after();
+        VMC_DBG5(k, 0 + t);
+        const uint32_t qst = qk_base + s * 2 * mat_bytes;
+        const uint64_t dq = umma_desc_sw128(qst + t * TILE);
+        const uint64_t dk = umma_desc_sw128(qst + mat_bytes);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (kt[t] >= n_my) continue;
-          const int k = kt[t];
-          const int s = k & 1;
-          const uint32_t par = (uint32_t)k & 1u;
-          const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
-          const uint32_t vst = v_base + s * mat_bytes;
-          // V descriptor: atom 0 = the TMA tile (64 head dims x 16 keys), atom 1 (N = 64..79) = LBO further = ones
-          const uint64_t dv0 = (umma_desc_sw128(vst) & ~(uint64_t(0x3FFF) << 16)) |
-                               (uint64_t((ones_base - vst) >> 4) << 16);
-          const uint32_t tcol = tmem_base + uint32_t(t * 256);
-          if (ph[t] == 0) {
-            // start tile 1 half a period late so that its softmax covers tile 0's MMA / drain tail
-            if (t == 1 && k == 0 && kt[0] == 0 && ph[0] < 2) continue;
-            if (!mbar_test_wait(qk_full(s), ring_par)) continue;
-            if (t == 0) VMC_DBG5(k, 25);
-            if (!mbar_test_wait(s_empty(t), par ^ 1u)) continue;
-            tc_fence_after();
-            VMC_DBG5(k, 0 + t);
-            const uint32_t qst = qk_base + s * 2 * mat_bytes;
-            const uint64_t dq = umma_desc_sw128(qst + t * TILE);
-            const uint64_t dk = umma_desc_sw128(qst + mat_bytes);
-#pragma unroll
-            for (int kq = 0; kq < HD / 16; ++kq)
-              umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s, kq != 0);
-            umma_commit(s_full(t));
-            if (++sdone[s] == 2) {  // both tiles' score MMAs are in flight: Q and K die when they retire
-              sdone[s] = 0;
-              umma_commit(qk_empty(s));
-            }
-            ph[t] = 1;
-          } else if (ph[t] == 1) {
-            if (!mbar_test_wait(pa_full(t), par)) continue;
-            if (!mbar_test_wait(v_full(s), ring_par)) continue;
-            tc_fence_after();
-            VMC_DBG5(k, 2 + t);
-            for (int kk = 0; kk < nka; ++kk)
-              umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv0 + uint64_t(kk * 128), idesc_pv, kk != 0);
-            ph[t] = 2;
-          } else {
-            if (!mbar_test_wait(pb_full(t), par)) continue;
-            tc_fence_after();
-            VMC_DBG5(k, 4 + t);
-            for (int kk = nka; kk < nkk; ++kk)
-              umma_ts(tcol + A5_OCOL, tcol + uint32_t((kk >> 1) * 32 + (kk & 1) * 8), dv0 + uint64_t(kk * 128),
-                      idesc_pv, 1u);
-            umma_commit(o_full(t));
-            if (++fin[s] == 2) {  // both tiles are done with this slot's V
-              fin[s] = 0;
-              umma_commit(v_empty(s));
-            }
-            kt[t] = k + 1;
-            ph[t] = 0;
-          }
-        }
+        for (int kq = 0; kq < HD / 16; ++kq)
+          umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s, kq != 0);
+        umma_commit(s_full(t));
+        umma_commit(qk_empty(s));  // second arrival (the other tile's issuer) frees Q and K
+        // ---- O = P V, keys of part A (their probabilities are stored while the softmax still works on part B) ----
+        mbar_wait(pa_full(t), par);
+        mbar_wait(v_full(s), ring_par);
+        tc_fence_after();
+        VMC_DBG5(k, 2 + t);
+        for (int kk = 0; kk < nka; ++kk)
+          umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv0 + uint64_t(kk * 128), idesc_pv, kk != 0);
+        // ---- part B ----
+        mbar_wait(pb_full(t), par);
+        tc_fence_after();
+        VMC_DBG5(k, 4 + t);
+        for (int kk = nka; kk < nkk; ++kk)
+          umma_ts(tcol + A5_OCOL, tcol + uint32_t((kk >> 1) * 32 + (kk & 1) * 8), dv0 + uint64_t(kk * 128),
+                  idesc_pv, 1u);
+        umma_commit(o_full(t));
+        umma_commit(v_empty(s));  // second arrival frees V
       }
     }
     __syncwarp();
@@ -809,7 +794,9 @@ attention_vit6_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     }
     __syncwarp();
   } else if (warp == 13) {
-    // ===================== MMA issuer (event driven, as v5) =====================
+    // ===================== MMA issuer (event driven: one thread polls both tiles' barriers) =====================
+    // (v5 / v7 moved to one BLOCKING issuer warp per tile in round 2: 0.381 -> 0.30 ms and 0.087 -> 0.056 ms.  The same change
+    // here needs a 17th warp, which caps the kernel at 120 registers: measured 0.387 vs 0.354 ms, so v6 keeps the poller.)
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, a.lk16, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 80, 0, 1);  // B = [V | ones], MN-major
@@ -1143,7 +1130,7 @@ struct Attn7Args {
   __nv_bfloat16* out;
 };
 
-__global__ void __launch_bounds__(A5_THREADS, 1)
+__global__ void __launch_bounds__(A5B_THREADS, 1)
 attention_vit7_kernel(const __grid_constant__ CUtensorMap tm, const Attn7Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -1172,21 +1159,21 @@ attention_vit7_kernel(const __grid_constant__ CUtensorMap tm, const Attn7Args a)
 
   {
     uint4* ones = reinterpret_cast<uint4*>(smem_raw + (ones_base - raw_addr));
-    for (uint32_t i = tid; i < 2048u / 16; i += A5_THREADS)
+    for (uint32_t i = tid; i < 2048u / 16; i += A5B_THREADS)
       ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     // rows of a half tile that no TMA box ever writes (a group's missing items) must not hold NaN patterns: K / V
     // garbage would reach valid rows through 0 * NaN.  Zero the rings once.
     uint4* ring = reinterpret_cast<uint4*>(smem_raw + (base - raw_addr));
-    for (uint32_t i = tid; i < 12u * TILE / 16; i += A5_THREADS) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = tid; i < 12u * TILE / 16; i += A5B_THREADS) ring[i] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
   if (tid == 0) {
     tma_prefetch_desc(&tm);
     for (int i = 0; i < 2; ++i) {
       mbar_init(qk_full(i), 1);
-      mbar_init(qk_empty(i), 1);
+      mbar_init(qk_empty(i), 2);  // one tcgen05.commit per tile's MMA issuer
       mbar_init(v_full(i), 1);
-      mbar_init(v_empty(i), 1);
+      mbar_init(v_empty(i), 2);
       mbar_init(s_full(i), 1);
       mbar_init(p_full(i), 4);
       mbar_init(o_full(i), 1);
@@ -1252,61 +1239,40 @@ attention_vit7_kernel(const __grid_constant__ CUtensorMap tm, const Attn7Args a)
       }
     }
     __syncwarp();
-  } else if (warp == 13) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 13 || warp == 14) {
+    // ===================== MMA issuers: one blocking issuer per query tile (see attention_vit5_kernel) =====================
+    const int t = warp - 13;
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 80, 0, 1);  // B = [V | ones], MN-major
-      int kt[2] = {0, 0};
-      int ph[2] = {0, 0};  // 0: S to issue, 1: waiting for P
-      int sdone[2] = {0, 0};
-      int fin[2] = {0, 0};
-      while (kt[0] < n_my || kt[1] < n_my) {
+      const uint32_t tcol = tmem_base + uint32_t(t * 256);
+      for (int k = 0; k < n_my; ++k) {
+        const int s = k & 1;
+        const uint32_t par = (uint32_t)k & 1u;
+        const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
+        mbar_wait(qk_full(s), ring_par);
+        mbar_wait(s_empty(t), par ^ 1u);
+        tc_fence_after();
+        const uint32_t qst = qk_base + s * 4 * TILE;
+        const uint64_t dq = umma_desc_sw128(qst + t * TILE);
+        const uint64_t dk = umma_desc_sw128(qst + 2 * TILE + t * TILE);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (kt[t] >= n_my) continue;
-          const int k = kt[t];
-          const int s = k & 1;
-          const uint32_t par = (uint32_t)k & 1u;
-          const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
-          const uint32_t tcol = tmem_base + uint32_t(t * 256);
-          if (ph[t] == 0) {
-            if (t == 1 && k == 0 && kt[0] == 0 && ph[0] < 1) continue;  // tile 1 starts after tile 0's scores are issued
-            if (!mbar_test_wait(qk_full(s), ring_par)) continue;
-            if (!mbar_test_wait(s_empty(t), par ^ 1u)) continue;
-            tc_fence_after();
-            const uint32_t qst = qk_base + s * 4 * TILE;
-            const uint64_t dq = umma_desc_sw128(qst + t * TILE);
-            const uint64_t dk = umma_desc_sw128(qst + 2 * TILE + t * TILE);
+        for (int kq = 0; kq < HD / 16; ++kq)
+          umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s, kq != 0);
+        umma_commit(s_full(t));
+        umma_commit(qk_empty(s));  // two arrivals (one per tile) free Q and K
+        mbar_wait(p_full(t), par);
+        mbar_wait(v_full(s), ring_par);
+        tc_fence_after();
+        const uint32_t vst = v_base + s * 2 * TILE + t * TILE;
 #pragma unroll
-            for (int kq = 0; kq < HD / 16; ++kq)
-              umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s, kq != 0);
-            umma_commit(s_full(t));
-            if (++sdone[s] == 2) {
-              sdone[s] = 0;
-              umma_commit(qk_empty(s));
-            }
-            ph[t] = 1;
-          } else {
-            if (!mbar_test_wait(p_full(t), par)) continue;
-            if (!mbar_test_wait(v_full(s), ring_par)) continue;
-            tc_fence_after();
-            const uint32_t vst = v_base + s * 2 * TILE + t * TILE;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint32_t va = vst + (uint32_t)kk * 2048u;
-              const uint64_t dv = (umma_desc_sw128(va) & ~(uint64_t(0x3FFF) << 16)) | (uint64_t((ones_base - va) >> 4) << 16);
-              umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv, idesc_pv, kk != 0);
-            }
-            umma_commit(o_full(t));
-            if (++fin[s] == 2) {
-              fin[s] = 0;
-              umma_commit(v_empty(s));
-            }
-            kt[t] = k + 1;
-            ph[t] = 0;
-          }
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t va = vst + (uint32_t)kk * 2048u;
+          const uint64_t dv = (umma_desc_sw128(va) & ~(uint64_t(0x3FFF) << 16)) | (uint64_t((ones_base - va) >> 4) << 16);
+          umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv, idesc_pv, kk != 0);
         }
+        umma_commit(o_full(t));
+        umma_commit(v_empty(s));
       }
     }
     __syncwarp();
@@ -1619,7 +1585,7 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     VMC_CUDA(cudaFuncSetAttribute(attention_vit7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem7));
     {
       VmcProfScope prof(VMC_K_ATTN_VIT, st7, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
-      attention_vit7_kernel<<<grid7, A5_THREADS, smem7, st7>>>(tm7, a7);
+      attention_vit7_kernel<<<grid7, A5B_THREADS, smem7, st7>>>(tm7, a7);
     }
     VMC_LAUNCH_CHECK();
     vmc_count_launch();
@@ -1705,7 +1671,7 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     VMC_CUDA(cudaFuncSetAttribute(kern5, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
     {
       VmcProfScope prof(VMC_K_ATTN_VIT, st5, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
-      kern5<<<grid5, A5_THREADS, smem5, st5>>>(tm5, tm5b, a5);
+      kern5<<<grid5, A5B_THREADS, smem5, st5>>>(tm5, tm5b, a5);
     }
     VMC_LAUNCH_CHECK();
     vmc_count_launch();
