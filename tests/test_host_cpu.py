@@ -261,3 +261,36 @@ def test_tfam_weight_stream_packing_matches_mma_fragment_order():
         for k, (_, nt, kp) in lay.items():
             got = replay(a256 if k == "f2" else a512, take(k), nt, kp)
             assert np.abs(got - want[k]).max() < 1e-9, (c, w, k)
+
+
+def test_embedding_store_flush_per_video_is_journalled_and_crash_safe(tmp_path):
+    """inference_frame_diff.py:299,395,404 flushes after EVERY video and opens with h5py keyword arguments: each flush appends
+    only the change to journal.jsonl (not the whole index), a reader that arrives after a crash (no close()) sees every
+    flushed video, close() compacts, and mode 'w' removes only the files the old index lists."""
+    import json
+
+    from vimoclip_b200.store import EmbeddingStore, write_video
+
+    path = tmp_path / "frame_diff_embeddings.vmc"
+    keep = tmp_path / "frame_diff_embeddings.vmc" / "dont_touch.npy"
+    rng = np.random.default_rng(1)
+    hf = EmbeddingStore(path, "a", libver="latest")  # h5py.File(path, 'a', libver='latest')
+    np.save(keep, np.arange(3))  # a foreign file whose name looks like ours
+    sizes = []
+    for i in range(40):
+        write_video(hf, f"v{i:03d}", rng.standard_normal((3, 8)).astype(np.float32), np.zeros(5, np.float32), 3, 30)
+        hf.flush()
+        sizes.append(os.path.getsize(path / "journal.jsonl"))
+    growth = np.diff(sizes)
+    assert growth.max() < 2 * growth.min() + 64  # every flush appends O(1) bytes: no O(N) index rewrite per video
+    # "crash": no close().  A new reader replays snapshot + journal.
+    with EmbeddingStore(path, "r") as f:
+        assert len(f.keys()) == 40 and f["v039"].attrs["original_frames"] == 30
+        assert f["v017"]["embeddings"].shape == (3, 8)
+    hf.close()
+    assert not os.path.exists(path / "journal.jsonl")
+    with open(path / "index.json") as fh:
+        assert len(json.load(fh)["datasets"]) == 80
+    with EmbeddingStore(path, "w") as f:  # truncate: our datasets go, the foreign file stays
+        assert len(f.keys()) == 0
+    assert os.path.exists(keep) and len([n for n in os.listdir(path) if n.endswith(".npy")]) == 1

@@ -23,17 +23,19 @@ import tempfile
 import numpy as np
 
 _INDEX = "index.json"
+_JOURNAL = "journal.jsonl"  # index changes since the last snapshot, one JSON object per flush()
 
 
 class _Attrs(dict):
-    def __init__(self, owner, *a):
+    def __init__(self, owner, group, *a):
         super().__init__(*a)
-        self._owner = owner
+        self._owner, self._group = owner, group
 
     def __setitem__(self, k, v):
         if isinstance(v, (np.generic,)):
             v = v.item()
         super().__setitem__(k, v)
+        self._owner._dirty_groups.add(self._group)
         self._owner._dirty()
 
 
@@ -68,25 +70,42 @@ class Dataset:
         out = self._load()[key]
         return np.array(out) if isinstance(out, np.memmap) else out
 
+    def _writable(self):
+        arr = self._load()
+        if isinstance(arr, np.memmap) or not arr.flags.writeable or arr.base is None and not arr.flags.owndata:
+            arr = np.array(arr)
+            self._data = arr
+        return arr
+
     def __setitem__(self, key, value):
         self._store._need_write()
-        arr = np.array(self._load())
-        arr[key] = value
-        self._data = arr
+        self._writable()[key] = value  # in place: the chunk loop of extract_embeddings_mammalNet.py:137-141 stays linear
         self._store._pending[self.name] = self
 
     def resize(self, size, axis=0):
-        """Grow (or shrink) along ``axis`` like an extendable HDF5 dataset (extract_embeddings_mammalNet.py:137-141)."""
+        """Grow (or shrink) along ``axis`` like an extendable HDF5 dataset (extract_embeddings_mammalNet.py:137-141).  Growth
+        along axis 0 doubles a hidden capacity buffer, so appending chunk after chunk copies O(N) bytes in total."""
         self._store._need_write()
-        arr = np.array(self._load())
+        arr = self._writable()
         shape = list(arr.shape)
         shape[axis] = int(size)
-        new = np.zeros(shape, dtype=arr.dtype)
-        sl = tuple(slice(0, min(a, b)) for a, b in zip(arr.shape, shape))
-        new[sl] = arr[sl]
+        cap = getattr(self, "_cap", None)
+        if axis == 0 and cap is not None and cap.shape[1:] == arr.shape[1:] and cap.shape[0] >= shape[0] and arr.base is cap:
+            if shape[0] > arr.shape[0]:
+                cap[arr.shape[0]:shape[0]] = 0
+            new = cap[:shape[0]]
+        else:
+            grow = list(shape)
+            if axis == 0:
+                grow[0] = max(shape[0], 2 * arr.shape[0])
+            self._cap = np.zeros(grow, dtype=arr.dtype)
+            sl = tuple(slice(0, min(a, b)) for a, b in zip(arr.shape, shape))
+            self._cap[sl] = arr[sl]
+            new = self._cap[tuple(slice(0, n) for n in shape)]
         self._data = new
         self._meta["shape"] = shape
         self._store._pending[self.name] = self
+        self._store._dirty_ds.add(self.name)
         self._store._dirty()
 
 
@@ -133,7 +152,10 @@ class Group:
             raise ValueError(f"unable to create group (name '{full}' already exists)")  # h5py raises ValueError too
         parts = full.split("/")
         for i in range(1, len(parts) + 1):  # intermediate groups, as h5py creates them
-            self._store._index["groups"].setdefault("/".join(parts[:i]), {})
+            name = "/".join(parts[:i])
+            if name not in self._store._index["groups"]:
+                self._store._index["groups"][name] = {}
+                self._store._dirty_groups.add(name)
         self._store._dirty()
         return Group(self._store, full)
 
@@ -169,6 +191,7 @@ class Group:
         ds._data = arr
         self._store._cache[full] = ds
         self._store._pending[full] = ds
+        self._store._dirty_ds.add(full)
         self._store._dirty()
         return ds
 
@@ -176,29 +199,80 @@ class Group:
 class EmbeddingStore(Group):
     """``EmbeddingStore(path, mode)`` ~ ``h5py.File(path, mode)`` for modes ``"w"``, ``"a"`` (resume) and ``"r"``.
 
-    ``flush()`` / ``close()`` / leaving the ``with`` block write pending datasets (atomic rename) and the index, so a crash
-    loses at most the groups written since the last flush (``inference_frame_diff.py`` flushes after every video)."""
+    ``flush()`` writes pending datasets (atomic rename) and appends the index changes to ``journal.jsonl``; ``close()`` / leaving
+    the ``with`` block compacts them into ``index.json``.  A crash loses at most the groups written since the last flush
+    (``inference_frame_diff.py`` flushes after every video)."""
 
-    def __init__(self, path, mode="r"):
-        if mode not in ("r", "w", "a"):
-            raise ValueError("mode must be 'r', 'w' or 'a'")
+    def __init__(self, path, mode="r", **_h5py_kwargs):
+        """``_h5py_kwargs`` (``libver=``, ``swmr=``, ``driver=`` ...) are accepted and ignored, so ``h5py.File(path, 'a',
+        libver='latest')`` call sites (inference_frame_diff.py) carry over unchanged."""
+        if mode not in ("r", "w", "a", "r+", "w-", "x"):
+            raise ValueError("mode must be 'r', 'r+', 'w', 'w-' / 'x' or 'a'")
         self.path, self.mode = str(path), mode
         self._cache, self._pending, self._is_dirty, self._closed = {}, {}, False, False
+        self._dirty_groups, self._dirty_ds, self._journal_lines = set(), set(), 0
         idx = os.path.join(self.path, _INDEX)
-        if mode == "r" or (mode == "a" and os.path.exists(idx)):
+        if mode in ("w-", "x") and os.path.exists(idx):
+            raise FileExistsError(f"unable to create store '{self.path}' (it exists)")
+        if mode in ("r", "r+") or (mode == "a" and os.path.exists(idx)):
             if not os.path.exists(idx):
                 raise FileNotFoundError(f"unable to open store '{self.path}' (no {_INDEX})")
-            with open(idx, encoding="utf-8") as f:
-                self._index = json.load(f)
+            self._index = self._read_index()
+            if mode == "r+":
+                self.mode = "a"
         else:
             os.makedirs(self.path, exist_ok=True)
-            for fn in os.listdir(self.path):  # mode 'w' truncates, like h5py
-                if fn == _INDEX or (fn.startswith("d") and fn.endswith((".npy", ".json"))):
-                    os.remove(os.path.join(self.path, fn))
+            if os.path.exists(idx):  # mode 'w' truncates, like h5py -- but removes only what the old index lists
+                try:
+                    old = self._read_index()
+                    for meta in old["datasets"].values():
+                        fn = os.path.join(self.path, meta["file"])
+                        if os.path.exists(fn):
+                            os.remove(fn)
+                except (OSError, ValueError, KeyError):
+                    pass
+                for fn in (_INDEX, _JOURNAL):
+                    if os.path.exists(os.path.join(self.path, fn)):
+                        os.remove(os.path.join(self.path, fn))
             self._index = {"format": "vimoclip_b200.EmbeddingStore/1", "attrs": {}, "groups": {"": {}}, "datasets": {}, "next_file": 0}
             self._is_dirty = True
+            self._snapshot()
+            self.mode = "a" if mode != "w" else "w"
         super().__init__(self, "")
         self._attr_objs = {}
+
+    def _read_index(self):
+        """Snapshot + the journal of later flushes (a crash between flushes loses nothing that was flushed)."""
+        with open(os.path.join(self.path, _INDEX), encoding="utf-8") as f:
+            index = json.load(f)
+        jp = os.path.join(self.path, _JOURNAL)
+        if os.path.exists(jp):
+            with open(jp, encoding="utf-8") as f:
+                for line in f:
+                    line = line.strip()
+                    if not line:
+                        continue
+                    try:
+                        d = json.loads(line)
+                    except ValueError:
+                        break  # torn last line of an interrupted flush
+                    index["groups"].update(d.get("groups", {}))
+                    index["datasets"].update(d.get("datasets", {}))
+                    if "attrs" in d:
+                        index["attrs"] = d["attrs"]
+                    index["next_file"] = max(index["next_file"], d.get("next_file", 0))
+                    self._journal_lines += 1
+        return index
+
+    def _snapshot(self):
+        fd, tmp = tempfile.mkstemp(dir=self.path, suffix=".tmp")
+        with os.fdopen(fd, "w", encoding="utf-8") as f:
+            json.dump(self._index, f)
+        os.replace(tmp, os.path.join(self.path, _INDEX))
+        jp = os.path.join(self.path, _JOURNAL)
+        if os.path.exists(jp):
+            os.remove(jp)
+        self._journal_lines = 0
 
     # -- internals --
     def _need_write(self):
@@ -213,7 +287,7 @@ class EmbeddingStore(Group):
     def _attrs_of(self, group):
         if group not in self._attr_objs:
             raw = self._index["attrs"] if group == "" else self._index["groups"][group]
-            self._attr_objs[group] = _Attrs(self, raw)
+            self._attr_objs[group] = _Attrs(self, group, raw)
         return self._attr_objs[group]
 
     def _dataset(self, full):
@@ -241,15 +315,25 @@ class EmbeddingStore(Group):
                 self._index["attrs"] = dict(obj)
             else:
                 self._index["groups"][group] = dict(obj)
-        fd, tmp = tempfile.mkstemp(dir=self.path, suffix=".tmp")
-        with os.fdopen(fd, "w", encoding="utf-8") as f:
-            json.dump(self._index, f)
-        os.replace(tmp, os.path.join(self.path, _INDEX))
+        # Only what changed since the last flush is appended to the journal: the reference flushes after EVERY video
+        # (inference_frame_diff.py:299,395,404), and rewriting a whole index of 30 k videos each time would be O(N^2).
+        delta = {"groups": {g: self._index["groups"][g] for g in self._dirty_groups if g and g in self._index["groups"]},
+                 "datasets": {n: self._index["datasets"][n] for n in self._dirty_ds if n in self._index["datasets"]},
+                 "next_file": self._index["next_file"]}
+        if "" in self._dirty_groups:
+            delta["attrs"] = self._index["attrs"]
+        with open(os.path.join(self.path, _JOURNAL), "a", encoding="utf-8") as f:
+            f.write(json.dumps(delta) + "\n")
+        self._journal_lines += 1
+        self._dirty_groups.clear()
+        self._dirty_ds.clear()
         self._is_dirty = False
 
     def close(self):
         if not self._closed:
             self.flush()
+            if self.mode != "r" and self._journal_lines:
+                self._snapshot()  # compact: one index.json, no journal
             self._closed = True
 
     def __enter__(self):
