@@ -285,7 +285,7 @@ int vmc_layernorm_bwd(const float* z, long long ldz, const float* gamma, float e
                       void* stream);
 /* mode 0: out = a*b (dropout mask), 1: ReLU backward (b = activation output or pre-activation), 2: GELU(erf)
  * backward (b = pre-activation), 3: out = a+b, 4: out = a*scale, 5: QuickGELU forward a*sigmoid(1.702a), 6: QuickGELU
- * backward (b = pre-activation), 7: out = scale*a + b */
+ * backward (b = pre-activation), 7: out = scale*a + b, 8: GELU(erf) forward of a */
 int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* out, long long n, void* stream);
 /* y = bf16(QuickGELU(x)) over n contiguous fp32 elements (n % 4 == 0): the c_fc activation of the student's training forward */
 int vmc_qgelu_cast(const float* x, void* y, long long n, void* stream);

@@ -300,7 +300,7 @@ layernorm_bwd_fused_kernel(const float* __restrict__ z, long long ldz, const flo
 
 // element-wise helpers of the backward pass
 enum { ELT_MUL = 0, ELT_RELU_BWD = 1, ELT_GELU_BWD = 2, ELT_ADD = 3, ELT_SCALE = 4, ELT_QGELU_FWD = 5, ELT_QGELU_BWD = 6,
-       ELT_AXPY = 7 };
+       ELT_AXPY = 7, ELT_GELU_FWD = 8 };
 __global__ void __launch_bounds__(256)
 eltwise_kernel(int mode, const float* __restrict__ a, const float* __restrict__ b, float scale,
                float* __restrict__ out, size_t n) {
@@ -324,6 +324,7 @@ eltwise_kernel(int mode, const float* __restrict__ a, const float* __restrict__ 
         break;
       }
       case ELT_AXPY: r = fmaf(scale, x, b[i]); break;  // scale * a + b
+      case ELT_GELU_FWD: r = 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); break;
       default: r = x * scale; break;
     }
     out[i] = r;
@@ -986,8 +987,8 @@ int vmc_layernorm_bwd_fused(const float* z, long long ldz, const float* gamma, f
 }
 
 int vmc_eltwise(int mode, const float* a, const float* b, float scale, float* out, long long n, void* stream) {
-  VMC_CHECK_ARG(a && out && n > 0 && mode >= ELT_MUL && mode <= ELT_AXPY, VMC_ERR_ARG, "vmc_eltwise: bad argument");
-  VMC_CHECK_ARG(b != nullptr || mode == ELT_SCALE || mode == ELT_QGELU_FWD, VMC_ERR_ARG,
+  VMC_CHECK_ARG(a && out && n > 0 && mode >= ELT_MUL && mode <= ELT_GELU_FWD, VMC_ERR_ARG, "vmc_eltwise: bad argument");
+  VMC_CHECK_ARG(b != nullptr || mode == ELT_SCALE || mode == ELT_QGELU_FWD || mode == ELT_GELU_FWD, VMC_ERR_ARG,
                 "vmc_eltwise: mode %d needs a second operand", mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VmcProfScope prof(VMC_K_OTHER, st, 0.0, 0.0);

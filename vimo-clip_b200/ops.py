@@ -364,7 +364,7 @@ def tfam_head(x: torch.Tensor, ln_g, ln_b, eps: float, w1_t, b1, w2_t, b2) -> to
 
 
 # ---- backward-pass ops of the TFAM training step (csrc/backward.cu) ----
-ELT_MUL, ELT_RELU_BWD, ELT_GELU_BWD, ELT_ADD, ELT_SCALE, ELT_QGELU_FWD, ELT_QGELU_BWD, ELT_AXPY = 0, 1, 2, 3, 4, 5, 6, 7
+ELT_MUL, ELT_RELU_BWD, ELT_GELU_BWD, ELT_ADD, ELT_SCALE, ELT_QGELU_FWD, ELT_QGELU_BWD, ELT_AXPY, ELT_GELU_FWD = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 
 def _f32_2d(*ts):

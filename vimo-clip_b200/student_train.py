@@ -25,7 +25,7 @@ import torch
 
 from . import ops
 from ._params import named_tensors
-from .tfam_train import _lin_bwd, _lin_fwd
+from .tfam_train import _activate, _lin_bwd, _lin_fwd
 
 _PER_BLOCK = ("ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",
               "ln_2.weight", "ln_2.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias")
@@ -112,20 +112,21 @@ class StudentTrainFunction(torch.autograd.Function):
         D = emb.shape[1]
         # heads (models/student_model.py:90-96): distill = emb + alpha * fc2(GELU(fc1(emb))); logits = head(mean_T(emb))
         r_pre = _lin_fwd(emb, fc1w, fc1b)
-        r_act = _lin_fwd(emb, fc1w, fc1b, act=ops.ACT_GELU_ERF)
+        r_act = _activate(r_pre, ops.ACT_GELU_ERF)  # element-wise pass on the saved pre-activation (no second GEMM)
         distill = ops.eltwise(ops.ELT_AXPY, _lin_fwd(r_act, fc2w, fc2b), emb, scale=cfg["alpha"])
         pooled, _ = ops.mean_rows(emb.view(B, T, D), want32=True)
         c_pre = _lin_fwd(pooled, c1w, c1b)
-        c_act = _lin_fwd(pooled, c1w, c1b, act=ops.ACT_RELU)
+        c_act = _activate(c_pre, ops.ACT_RELU)
         logits = _lin_fwd(c_act, c2w, c2b)
-        ctx.cfg, ctx.params, ctx.saved = cfg, params, saved
+        ctx.cfg, ctx.saved = cfg, saved
+        ctx.save_for_backward(*params)  # version-checked by autograd
         ctx.misc = dict(patches=patches, z0=z0, z_cls=z_cls, cls16=cls16, emb=emb, r_pre=r_pre, r_act=r_act, pooled=pooled,
                         c_pre=c_pre, c_act=c_act)
         return emb.view(B, T, D), distill.view(B, T, D), logits
 
     @staticmethod
     def backward(ctx, d_emb, d_distill, d_logits):
-        cfg, params, m = ctx.cfg, ctx.params, ctx.misc
+        cfg, params, m = ctx.cfg, ctx.saved_tensors, ctx.misc
         p, d, heads, n_layers, F_, B, T = cfg["patch"], cfg["d"], cfg["heads"], cfg["layers"], cfg["F"], cfg["B"], cfg["T"]
         g = cfg["res"] // p
         n, L = g * g, g * g + 1
@@ -184,7 +185,6 @@ class StudentTrainFunction(torch.autograd.Function):
         for gb in grads_blocks:
             grads += gb
         grads += [g_gpost, g_bpost, g_proj, g_fc1w, g_fc1b, g_fc2w, g_fc2b, g_c1w, g_c1b, g_c2w, g_c2b]
-        ctx.saved = None
         return (None, None, *grads)
 
 

@@ -54,6 +54,13 @@ def _lin_bwd(dy, x32, w, need_dx=True, dw_out=None):
     return dx, dw, ops.colsum(dy)
 
 
+def _activate(pre, act):
+    """ReLU / GELU(erf) of a saved pre-activation (one element-wise kernel instead of a second GEMM with the activation epilogue)."""
+    if act == ops.ACT_RELU:
+        return ops.eltwise(ops.ELT_RELU_BWD, pre, pre)  # pre * (pre > 0)
+    return ops.eltwise(ops.ELT_GELU_FWD, pre, None)
+
+
 def _dropout_mask(shape, p, dev):
     if p <= 0.0:
         return None
@@ -107,8 +114,8 @@ class TfamTrainFunction(torch.autograd.Function):
                 z2 = ops.eltwise(ops.ELT_ADD, x1, _drop(_lin_fwd(a2, w_co, b_co), dm2))
                 x2, _ = ops.layernorm(z2, gc, bc, eps=e_c, want32=True, want16=False)
             # feed-forward block (AMO_CLIP.py:48-49)
-            h_pre = _lin_fwd(x2, w1, b1)
-            h_act = _lin_fwd(x2, w1, b1, act=cfg["act"][li])
+            h_pre = _lin_fwd(x2, w1, b1)  # one GEMM: the backward needs the pre-activation, the activation is an element-wise pass
+            h_act = _activate(h_pre, cfg["act"][li])
             dmh = _dropout_mask(tuple(h_act.shape), p_drop, dev)
             h_d = _drop(h_act, dmh)
             dm3 = _dropout_mask((M, d), p_drop, dev)
@@ -121,18 +128,19 @@ class TfamTrainFunction(torch.autograd.Function):
         pooled, _ = ops.mean_rows(x.view(B, T, d), want32=True)  # ALL rows, padded ones included (AMO_CLIP.py:170)
         n32, _ = ops.layernorm(pooled, g0, b0, eps=cfg["head_eps"], want32=True, want16=False)
         u_pre = _lin_fwd(n32, wc1, bc1)
-        u = _lin_fwd(n32, wc1, bc1, act=ops.ACT_GELU_ERF)
+        u = _activate(u_pre, ops.ACT_GELU_ERF)
         dmu = _dropout_mask(tuple(u.shape), p_mlp, dev)
         u_d = _drop(u, dmu)
         logits = _lin_fwd(u_d, wc2, bc2)
         ctx.cfg, ctx.saved, ctx.head = cfg, saved, dict(pooled=pooled, n32=n32, u_pre=u_pre, u_d=u_d, dmu=dmu)
         ctx.m32, ctx.v_rgb, ctx.v_mot, ctx.shape = m32, v_rgb, v_mot, (B, T, Tm)
-        ctx.params, ctx.proj_in, ctx.cross = params, proj_in, cross
+        ctx.proj_in, ctx.cross = proj_in, cross
+        ctx.save_for_backward(*params)  # version-checked: an in-place parameter update between forward and backward is an error
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        cfg, params = ctx.cfg, ctx.params
+        cfg, params = ctx.cfg, ctx.saved_tensors
         d, h, n_layers = cfg["d"], cfg["heads"], cfg["layers"]
         B, T, Tm = ctx.shape
         M, Mm = B * T, B * Tm
@@ -192,7 +200,6 @@ class TfamTrainFunction(torch.autograd.Function):
             wp = params[n_layers * k + len(_HEAD)]
             _, g_wp, g_bp = _lin_bwd(dx, ctx.proj_in, wp, need_dx=False)
             grads[n_layers * k + len(_HEAD):] = [g_wp, g_bp]
-        ctx.saved = None
         return (None, None, None, None, None, *grads)
 
 
