@@ -150,9 +150,28 @@ __device__ __forceinline__ float quickgelu_fast(float x) {
 //       (sum, sum of squares) of each row over its HALF_N columns.
 // R16   (MODE 3 + STATS): the residual stream itself is bf16 -- resid is read as bf16, out is written as bf16 (it IS the A
 //       operand of the next GEMM: no separate raw16 copy) and the statistics are those of the ROUNDED values.
+// row statistics of a folded LayerNorm for row m: (rstd, -mean * rstd) from the producer's partial (sum, sum of squares)
+__device__ __forceinline__ void ln_row_stats(const vmc_gemm_epilogue& e, int m, int M, int K, float& rstd, float& shift) {
+  rstd = 1.f;
+  shift = 0.f;
+  if (m < M) {
+    float s = 0.f, q = 0.f;
+    for (int p = 0; p < e.stats_parts; ++p) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(e.stats_in) + (long long)p * e.stats_ld + m);
+      s += v.x;
+      q += v.y;
+    }
+    const float mean = s / (float)K;
+    const float var = fmaxf(q / (float)K - mean * mean, 0.f);
+    rstd = rsqrtf(var + e.ln_eps);
+    shift = -mean * rstd;
+  }
+}
+
 template <int MODE, int HALF_N, bool LNF = false, bool STATS = false, bool R16 = false>
 __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M, int N, int K, int row0,
-                                              int n_base, uint32_t t_acc, uint8_t* stg, int lane) {
+                                              int n_base, uint32_t t_acc, uint8_t* stg, int lane, float rstd = 1.f,
+                                              float shift = 0.f) {
   const int lr = lane >> 3, lc = lane & 7;
   const int m_first = row0 + lr;
   int nvalid = (M - m_first + 3) >> 2;  // rows m_first + 4 i, i < nvalid, are inside the matrix
@@ -168,24 +187,11 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
     rstride = 4 * e.ldr * RSZ;
   }
   const float* bptr = e.bias + n_base + lc * 4;
-  // folded LayerNorm: every thread derives mean / rstd of ONE row (row0 + lane) from the producer's partial sums;
-  // after the transpose a lane holds rows 4 i + lr, so the 8 (rstd, -mean * rstd) pairs it needs come by shuffle
+  // folded LayerNorm: the caller derived rstd / -mean * rstd of ONE row per thread (row0 + lane) from the producer's partial
+  // sums BEFORE waiting for the accumulator (ln_row_stats: the loads are off the tile's critical path); after the
+  // transpose a lane holds rows 4 i + lr, so the 8 (rstd, -mean * rstd) pairs it needs come by shuffle
   float ln_rs[8], ln_sh[8];
   if constexpr (LNF) {
-    const int m = row0 + lane;
-    float rstd = 1.f, shift = 0.f;
-    if (m < M) {
-      float s = 0.f, q = 0.f;
-      for (int p = 0; p < e.stats_parts; ++p) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(e.stats_in) + (long long)p * e.stats_ld + m);
-        s += v.x;
-        q += v.y;
-      }
-      const float mean = s / (float)K;
-      const float var = fmaxf(q / (float)K - mean * mean, 0.f);
-      rstd = rsqrtf(var + e.ln_eps);
-      shift = -mean * rstd;
-    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       ln_rs[i] = __shfl_sync(0xffffffffu, rstd, i * 4 + lr);
@@ -222,14 +228,24 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
       rp += rstride;
     }
   }
+  // bias / column sums of the NEXT chunk are requested while this one is processed (ncu: the FMAs that consume them were
+  // 13 % of the c_fc kernel's stall samples, waiting on these two loads)
+  float4 b4n = make_float4(0.f, 0.f, 0.f, 0.f), cs4n = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n_base < N) {
+    b4n = __ldg(reinterpret_cast<const float4*>(bptr));
+    if constexpr (LNF) cs4n = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base + lc * 4));
+  }
 #pragma unroll 1
   for (int c = 0; c < HALF_N / 32; ++c) {
     if (n_base + c * 32 >= N) break;  // warp-uniform
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + c * 32));
-    float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (LNF) cs4 = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base + c * 32 + lc * 4));
+    const float4 b4 = b4n;
+    const float4 cs4 = cs4n;
+    if (c + 1 < HALF_N / 32 && n_base + (c + 1) * 32 < N) {
+      b4n = __ldg(reinterpret_cast<const float4*>(bptr + (c + 1) * 32));
+      if constexpr (LNF) cs4n = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base + (c + 1) * 32 + lc * 4));
+    }
     ResT res[8];
     if constexpr (MODE == 3) {
       // the residual rows of the NEXT chunk are requested while this one is processed: the epilogue of the
@@ -480,6 +496,8 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       tile_of(i, m_blk, n_blk);
       const int row0 = m_blk * (2 * BM) + (int)rank * BM + quarter * 32;
       const int n_base = n_blk * BN + half * HALF_N;
+      float ln_rstd = 1.f, ln_shift = 0.f;
+      if constexpr (MODE == 6 || MODE == 7) ln_row_stats(e, row0 + lane, g.M, g.K, ln_rstd, ln_shift);  // before the wait
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_acc =
@@ -489,7 +507,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       } else if constexpr (MODE == 5) {
         epilogue_fast<3, HALF_N, false, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else if constexpr (MODE == 6 || MODE == 7) {
-        epilogue_fast<MODE - 5, HALF_N, true, false>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
+        epilogue_fast<MODE - 5, HALF_N, true, false>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane, ln_rstd, ln_shift);
       } else if constexpr (MODE != 0) {
         epilogue_fast<MODE, HALF_N>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else {

@@ -9,10 +9,11 @@ reads ``f.keys()``, ``f[key]["embeddings"].shape`` / ``[:]`` and ``f[key]["label
 ``trimmed_videos/`` (``dataset_frame_diff_mn.py:42``).
 
 No HDF5 library exists in this image (``h5py``, ``tables`` and ``libhdf5`` are all absent), so ``EmbeddingStore`` keeps the SAME
-logical layout and the subset of the ``h5py.File`` API those call sites use, on a sidecar format: a directory with one ``.npy``
-per dataset (memory-mappable, written atomically) and ``index.json`` for the hierarchy and attributes.  ``to_hdf5`` /
-``from_hdf5`` convert to and from the reference's exact HDF5 layout where ``h5py`` is installed.  Host-side I/O only: nothing
-here touches the GPU path.
+logical layout and the subset of the ``h5py.File`` API those call sites use, on a working format made for resumable appends: a
+directory with one ``.npy`` per dataset (memory-mappable, written atomically) and ``index.json`` + ``journal.jsonl`` for the
+hierarchy and attributes.  ``to_hdf5`` / ``from_hdf5`` convert to and from the reference's exact HDF5 files -- through h5py where it
+is installed, otherwise through the built-in writer / reader of ``hdf5_min`` (specification-following, pinned against a
+libhdf5-written file found in the image).  Host-side I/O only: nothing here touches the GPU path.
 """
 from __future__ import annotations
 
@@ -34,6 +35,8 @@ class _Attrs(dict):
     def __setitem__(self, k, v):
         if isinstance(v, (np.generic,)):
             v = v.item()
+        elif isinstance(v, np.ndarray):
+            v = v.item() if v.ndim == 0 else v.tolist()
         super().__setitem__(k, v)
         self._owner._dirty_groups.add(self._group)
         self._owner._dirty()
@@ -342,14 +345,44 @@ class EmbeddingStore(Group):
     def __exit__(self, *exc):
         self.close()
 
-    # -- HDF5 interchange (needs h5py; the exact layout of extract_embeddings.py:50-55,106-119) --
+    # -- HDF5 interchange: the exact layout of extract_embeddings.py:50-55,106-119 --
+    def _tree(self):
+        """The store as the nested structure vimoclip_b200.hdf5_min.write_hdf5 takes."""
+        root = {"attrs": dict(self._index["attrs"]), "children": {}}
+
+        def node_of(path):
+            cur = root
+            for part in path.split("/"):
+                cur = cur["children"].setdefault(part, {"attrs": {}, "children": {}})
+            return cur
+
+        for g, attrs in self._index["groups"].items():
+            if g:
+                node_of(g)["attrs"] = dict(attrs)
+        for name, meta in self._index["datasets"].items():
+            parent, _, leaf = name.rpartition("/")
+            holder = node_of(parent) if parent else root
+            ds = self._dataset(name)
+            if meta["kind"] == "str":
+                holder["children"][leaf] = ("dataset", [str(x) for x in ds[:]], {})
+            else:
+                storage = {"chunks": tuple(meta["chunks"]) if meta.get("chunks") else None, "compression": meta.get("compression")}
+                holder["children"][leaf] = ("dataset", np.asarray(ds[...]), {}, storage)
+        return root
+
     def to_hdf5(self, hdf5_path):
+        """Write the reference's HDF5 file: one group per video with ``embeddings`` (chunked + gzip as recorded), ``labels``,
+        attributes, root attributes, ``video_ids`` as variable-length strings.  With h5py installed it does the writing;
+        without it (this image) the built-in writer of ``hdf5_min`` produces the same layout."""
+        self.flush()
         try:
             import h5py
-        except ImportError as e:  # pragma: no cover - h5py is absent from the build image
-            raise ImportError("EmbeddingStore.to_hdf5 needs h5py (not installed in this environment)") from e
-        self.flush()
-        with h5py.File(hdf5_path, "w") as hf:
+        except ImportError:
+            from .hdf5_min import write_hdf5
+
+            write_hdf5(hdf5_path, self._tree())
+            return
+        with h5py.File(hdf5_path, "w") as hf:  # pragma: no cover - h5py is absent from the build image
             for k, v in self._index["attrs"].items():
                 hf.attrs[k] = v
             for g, attrs in self._index["groups"].items():
@@ -373,11 +406,31 @@ class EmbeddingStore(Group):
 
     @classmethod
     def from_hdf5(cls, hdf5_path, path):
+        """Import an HDF5 file written by the reference (default ``libver``): h5py when installed, else the built-in reader."""
         try:
             import h5py
-        except ImportError as e:  # pragma: no cover
-            raise ImportError("EmbeddingStore.from_hdf5 needs h5py (not installed in this environment)") from e
-        with h5py.File(hdf5_path, "r") as hf, cls(path, "w") as st:
+        except ImportError:
+            from .hdf5_min import read_hdf5
+
+            tree = read_hdf5(hdf5_path)
+            with cls(path, "w") as st:
+                def put(node, group):
+                    for k, v in node["attrs"].items():
+                        group.attrs[k] = v
+                    for name, child in node["children"].items():
+                        if isinstance(child, tuple):
+                            data = child[1]
+                            if data.dtype.kind == "O":
+                                data = [str(x) for x in data.ravel()]
+                            elif data.dtype.kind == "S":
+                                data = [x.decode("utf-8") for x in data.ravel()]
+                            group.create_dataset(name, data=data)
+                        else:
+                            put(child, group.require_group(name))
+
+                put(tree, st)
+            return cls(path, "r")
+        with h5py.File(hdf5_path, "r") as hf, cls(path, "w") as st:  # pragma: no cover
             for k, v in hf.attrs.items():
                 st.attrs[k] = v
 
