@@ -1,8 +1,8 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider -k "gemm or tower or pipeline or config4" > gpurun_out/r02_pytest9.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest9.log
-python tools/ncu_probe_r02.py > gpurun_out/r02_probe_plain.log 2>&1
-python - > gpurun_out/r02_gemm_times.log 2>&1 <<'PY'
+timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider -k "gemm or tower or pipeline or config or tfam or student_config1" > gpurun_out/r02_pytest10.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest10.log
+true
+python - > gpurun_out/r02_gemm_times2.log 2>&1 <<'PY'
 import sys, torch
 sys.path.insert(0, ".")
 from vimoclip_b200 import ops
@@ -36,5 +36,5 @@ for name, fn, fl in [
     ms = timeit(fn)
     print(f"{name:28s} M={M}: {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s", flush=True)
 PY
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs --no-strong --no-ab > gpurun_out/r02_bench6.json 2> gpurun_out/r02_bench6.err
-tail -n 3 gpurun_out/r02_pytest9.log; cat gpurun_out/r02_gemm_times.log
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs --no-strong --no-ab > gpurun_out/r02_bench7.json 2> gpurun_out/r02_bench7.err
+tail -n 3 gpurun_out/r02_pytest10.log; cat gpurun_out/r02_gemm_times2.log

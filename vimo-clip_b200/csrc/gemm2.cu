@@ -350,6 +350,76 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
   }
 }
 
+// bf16-output epilogues without a residual (MODE 1 / 2, LayerNorm-folded 6 / 7: qkv, c_fc -- 58 % of the tower's GEMM FLOPs).
+// ncu / cycle accounting of round 2: at K = 768 a pair tile is 6 144 tensor cycles during which the UMMA operand reads already take
+// the whole 128 B/clk of shared-memory bandwidth; epilogue_fast stages the fp32 accumulator through shared memory to transpose it
+// (128 KB written + 128 KB read per tile and CTA = 2 048 more cycles of that pipe) -- which is where the K = 768 GEMMs lose their
+// ~25 % against K = 3072.  Here ALL the arithmetic runs in the TMEM-native layout (a thread owns one accumulator row: its rstd /
+// shift are per-thread scalars, bias / colsum are warp-uniform and come as broadcast reads of a 1 KB per-warp shared copy), and
+// only the PACKED bf16 result is transposed: half the staging traffic, 4 + 4 shared-memory and 4 global instructions per
+// 32-column chunk instead of 8 + 8 + 8.
+//   stg (4 KB per warp): [0, 2048) swizzled 32 x 64-byte tile; [2048, 2560) bias of the warp's HALF_N columns; [2560, 3072) colsum
+template <int MODE, int HALF_N, bool LNF>
+__device__ __forceinline__ void epilogue_rowmajor(const vmc_gemm_epilogue& e, int M, int N, int row0, int n_base, uint32_t t_acc,
+                                                  uint8_t* stg, int lane, float rstd, float shift) {
+  float* sb = reinterpret_cast<float*>(stg + 2048);
+  float* scs = sb + 128;
+  if (4 * lane < HALF_N && n_base + 4 * lane < N) {
+    *reinterpret_cast<float4*>(sb + 4 * lane) = __ldg(reinterpret_cast<const float4*>(e.bias + n_base) + lane);
+    if constexpr (LNF) *reinterpret_cast<float4*>(scs + 4 * lane) = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base) + lane);
+  }
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;           // write side: this thread's row = lane
+  const int rrow = lane >> 2, rch = lane & 3;  // read side: rows 8 i + rrow, 16-byte chunk rch
+  __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)(row0 + rrow) * e.ldo + n_base + rch * 8;
+#pragma unroll 1
+  for (int c = 0; c < HALF_N / 32; ++c) {
+    if (n_base + c * 32 >= N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + 4 * q);  // same address in every lane: broadcast
+      float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                             __uint_as_float(r[4 * q + 3]));
+      if constexpr (LNF) {  // rstd * acc - mean * rstd * colsum[n] + bias'[n]
+        const float4 cs4 = *reinterpret_cast<const float4*>(scs + c * 32 + 4 * q);
+        v.x = fmaf(v.x, rstd, fmaf(shift, cs4.x, b4.x));
+        v.y = fmaf(v.y, rstd, fmaf(shift, cs4.y, b4.y));
+        v.z = fmaf(v.z, rstd, fmaf(shift, cs4.z, b4.z));
+        v.w = fmaf(v.w, rstd, fmaf(shift, cs4.w, b4.w));
+      } else {
+        v.x += b4.x;
+        v.y += b4.y;
+        v.z += b4.z;
+        v.w += b4.w;
+      }
+      if constexpr (MODE == 2) {
+        v.x = quickgelu_fast(v.x);
+        v.y = quickgelu_fast(v.y);
+        v.z = quickgelu_fast(v.z);
+        v.w = quickgelu_fast(v.w);
+      }
+      pk[2 * q] = pack_bf16x2(v.x, v.y);
+      pk[2 * q + 1] = pack_bf16x2(v.z, v.w);
+    }
+    // row `lane` of the 32 x 32 bf16 tile: four 16-byte chunks, chunk index XOR ((row >> 1) & 3): conflict-free both ways
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      *reinterpret_cast<uint4*>(stg + lane * 64 + ((ch ^ sw) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = 8 * i + rrow;
+      const uint4 o = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((rch ^ ((rl >> 1) & 3)) << 4));
+      if (row0 + rl < M) *reinterpret_cast<uint4*>(obase + (long long)(8 * i) * e.ldo + c * 32) = o;  // 4 lanes = one 64-byte row segment
+    }
+    __syncwarp();
+  }
+}
+
 template <int BN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -507,7 +577,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       } else if constexpr (MODE == 5) {
         epilogue_fast<3, HALF_N, false, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else if constexpr (MODE == 6 || MODE == 7) {
-        epilogue_fast<MODE - 5, HALF_N, true, false>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane, ln_rstd, ln_shift);
+        epilogue_rowmajor<MODE - 5, HALF_N, true>(e, g.M, g.N, row0, n_base, t_acc, stg, lane, ln_rstd, ln_shift);
+      } else if constexpr (MODE == 1 || MODE == 2) {
+        epilogue_rowmajor<MODE, HALF_N, false>(e, g.M, g.N, row0, n_base, t_acc, stg, lane, 1.f, 0.f);
       } else if constexpr (MODE != 0) {
         epilogue_fast<MODE, HALF_N>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else {
