@@ -312,6 +312,29 @@ __device__ __forceinline__ void chunk_exp_store5(const uint32_t (&r)[32], float 
   tmem_st_32x32b_x16(taddr, pk);
 }
 
+// the same, probabilities left in registers (the caller issues the next chunk's load before the store)
+template <bool MASK, int VAR = 0>
+__device__ __forceinline__ void chunk_exp_pack5(const uint32_t (&r)[32], float sc, float mxs, int valid, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float e0 = 0.f, e1 = 0.f;
+    if (VAR == 2) {
+      e0 = __uint_as_float(r[2 * j]);
+      e1 = __uint_as_float(r[2 * j + 1]);
+    } else if (!MASK || 2 * j < valid) {
+      if (VAR == 3) {
+        e0 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f), 0.001f, 1.0f);
+        e1 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f), 0.001f, 1.0f);
+      } else {
+        e0 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f));
+        e1 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f));
+      }
+      if (MASK && 2 * j + 1 >= valid) e1 = 0.f;
+    }
+    pk[j] = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);
+  }
+}
+
 struct Attn5Args {
   int L, heads, d, lk16, n_items;
   __nv_bfloat16* out;
@@ -328,8 +351,11 @@ constexpr int A5_PA_CHUNKS = 5;  // chunks (32 keys) whose P is packed into [0, 
 constexpr int A5_OCOL = 80;      // accumulator columns [80, 160): 64 of O + 16 copies of the row sum
 
 constexpr int A5B_THREADS = 480;  // v5: + a second MMA issuer warp (one per query tile)
-template <int VAR, bool DBG = false>
-__global__ void __launch_bounds__(A5B_THREADS, 1)
+// SPLIT = softmax warps per (query tile, TMEM lane quarter): 1 -> 8 softmax warps; 2 -> 16, the two warps of a pair taking
+// the even and the odd 32-key chunks of the same 32 score rows (see the softmax branch).
+constexpr int a5_threads(int split) { return (8 * split + 7) * 32; }
+template <int VAR, bool DBG = false, int SPLIT = 1>
+__global__ void __launch_bounds__(a5_threads(SPLIT), 1)
 attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm1,
                       const Attn5Args a) {
   // Shared memory: two rings, released at different times.  The timeline of the first v5 (one Q/K/V stage
@@ -361,7 +387,12 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
   const uint32_t tmem_ptr_addr = bar_base + 144u;
   volatile uint32_t* tmem_ptr_generic =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
+  float* mx_sh = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));  // SPLIT = 2: row stabilisers, [2][128]
 
+  constexpr int NSW = 8 * SPLIT;       // softmax warps 0 .. NSW-1, epilogue warps NSW .. NSW+3
+  constexpr int W_TMA = NSW + 4;       // then the TMA producer and one MMA issuer per query tile
+  constexpr int W_MMA = NSW + 5;
+  constexpr int NTHREADS = a5_threads(SPLIT);
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -370,7 +401,7 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
   // the all-ones "second MN atom" of the PV B operand (bf16 1.0 everywhere; any layout reads ones)
   {
     uint4* ones = reinterpret_cast<uint4*>(smem_raw + (ones_base - raw_addr));
-    for (uint32_t i = tid; i < ones_bytes / 16; i += A5B_THREADS)
+    for (uint32_t i = tid; i < ones_bytes / 16; i += NTHREADS)
       ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
@@ -383,14 +414,14 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       mbar_init(v_full(i), 1);
       mbar_init(v_empty(i), 2);
       mbar_init(s_full(i), 1);
-      mbar_init(pa_full(i), 4);  // one arrive per softmax warp of the tile
-      mbar_init(pb_full(i), 4);
+      mbar_init(pa_full(i), 4 * SPLIT);  // one arrive per softmax warp of the tile
+      mbar_init(pb_full(i), 4 * SPLIT);
       mbar_init(o_full(i), 1);
       mbar_init(s_empty(i), 4);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
-  if (warp == 13) {
+  if (warp == W_MMA) {
     tmem_alloc(tmem_ptr_addr, 512);
     tmem_relinquish();
   }
@@ -400,7 +431,7 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
   const uint32_t tmem_base = *tmem_ptr_generic;
   const int n_chunks = (a.lk16 + 31) / 32;  // 5..7
 
-  if (warp == 12) {
+  if (warp == W_TMA) {
     // ===================== TMA producer: serves both rings, never blocks on one of them =====================
     // (hot polling: a nanosleep between polls reacts in ~700 cycles and was measured neither faster nor slower)
     if (lane == 0) {
@@ -441,14 +472,14 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == 13 || warp == 14) {
+  } else if (warp == W_MMA || warp == W_MMA + 1) {
     // ===================== MMA issuers: one warp per query tile =====================
     // Round 1 had ONE thread serve both tiles by polling their barriers round-robin with mbarrier.test_wait (~150 cycles
     // per probe, two to four probes per turn): every hand-over on a tile's S -> softmax -> PV -> drain chain waited for the
     // poller to come round, and an MMA burst for one tile delayed the other.  Each tile now has its own issuer that BLOCKS
     // on that tile's barriers (try_wait: the thread sleeps in hardware and wakes ~60 cycles after the arrive).  The shared
     // rings are released by both: qk_empty / v_empty count two arrivals, each issuer's tcgen05.commit covering its own MMAs.
-    const int t = warp - 13;
+    const int t = warp - W_MMA;
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, a.lk16, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 80, 0, 1);  // B = [V | ones], MN-major
@@ -495,9 +526,9 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp >= 8) {
+  } else if (warp >= NSW) {
     // ===================== epilogue warps: drain O, release the tile, write the rows =====================
-    const int q = warp - 8;
+    const int q = warp - NSW;
     for (int k = 0; k < n_my; ++k) {
       const int item = blockIdx.x + k * gridDim.x;
       const int head = item % a.heads;
@@ -552,8 +583,9 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     }
   } else {
     // ===================== softmax warps =====================
-    const int t = warp >> 2;
+    const int t = (warp >> 2) & 1;
     const int q = warp & 3;
+    const int half = warp >> 3;  // SPLIT = 2: 0 = even chunks, 1 = odd chunks of the same rows
     const bool warp_active = (t * 128 + q * 32) < a.L;  // warp-uniform
     const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
     const float sc = 0.125f * 1.4426950408889634f;
@@ -564,9 +596,45 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       const uint32_t par = (uint32_t)k & 1u;
       mbar_wait(s_full(t), par);
       tc_fence_after();
-      if (q == 0 && lane == 0) VMC_DBG5(k, 8 + 8 * t);
+      if (q == 0 && half == 0 && lane == 0) VMC_DBG5(k, 8 + 8 * t);
       if (warp_active && (VAR == 1 || VAR == 5)) {
         if (lane == 0) mbar_arrive_relaxed(pa_full(t));
+      } else if (warp_active && SPLIT == 2) {
+        // Two warps per 32 rows.  With one softmax warp per scheduler and tile the exponentials of a row ran at well under half
+        // the MUFU rate (ncu: XU pipe 45 % busy, the warp alone on its scheduler for a third of the time), and the softmax is
+        // the longest link of the tile's S -> softmax -> PV -> drain chain.  Warp `half` takes chunks half, half + 2, ...; one
+        // register buffer per warp (the partner and the other tile's pair hide the TMEM latency).
+        // Hazards between the two warps: P of chunk c < 5 is stored over the scores of chunk c / 2, so P(1) (odd warp) lands on
+        // chunk 0 and P(2) (even warp) on chunk 1: both first loads are complete before either warp stores (named barrier of
+        // the pair, 64 threads); every later store lands on a chunk its own warp has already consumed.  The stabiliser (max
+        // of chunk 0) goes from the even to the odd warp through shared memory across the same barrier.
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tb + uint32_t(half * 32), r);
+        tmem_ld_wait();
+        float mxs = 0.f;
+        if (half == 0) {
+          mxs = chunk_max<false>(r, -INFINITY, 32) * sc;
+          mx_sh[t * 128 + q * 32 + lane] = mxs;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + q) : "memory");
+        if (half == 1) mxs = mx_sh[t * 128 + q * 32 + lane];
+        for (int c = half; c < n_chunks; c += 2) {
+          if (c != half) tmem_ld_wait();
+          uint32_t pk[16];
+          if (c < n_full) chunk_exp_pack5<false, (VAR >= 4 ? 0 : VAR)>(r, sc, mxs, 32, pk);
+          else chunk_exp_pack5<true, (VAR >= 4 ? 0 : VAR)>(r, sc, mxs, tail, pk);
+          if (c + 2 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 2) * 32), r);  // r is dead: next chunk in flight during the store
+          tmem_st_32x32b_x16(pcol(c), pk);
+          if (c == A5_PA_CHUNKS - 1 - half) {
+            // this warp's last part-A chunk (4 for the even warp, 3 for the odd one) is stored
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(pa_full(t));
+            if (q == 0 && half == 0 && lane == 0) VMC_DBG5(k, 9 + 8 * t);
+          }
+        }
+        tmem_st_wait();
       } else if (warp_active) {
         // single pass over the score row, 32-column chunks double-buffered in registers; stabiliser = max of
         // the first 32 keys (<= row max, so the row sum is >= 1; argument clamped at +120), see v3
@@ -602,13 +670,13 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(pb_full(t));
-      if (q == 0 && lane == 0) VMC_DBG5(k, 10 + 8 * t);
+      if (q == 0 && half == 0 && lane == 0) VMC_DBG5(k, 10 + 8 * t);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -1545,11 +1613,16 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     var6 = impl - 100;
     impl = 6;
   }
-  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8) || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 9) || (impl >= 51 && impl <= 59), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 2, 5, 6, 7, 8 or 9");
 #else
-  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 9), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7, 8 or 9");
 #endif
+  bool v5_split = impl == 59;  // 9: v5 with 16 softmax warps (two per query tile and TMEM lane quarter)
+  if (impl == 9) {
+    v5_split = true;
+    impl = 5;
+  }
   const int d = heads * HD;
   if (impl == 8) {  // warp-level tensor path for short sequences (backward.cu)
     // (The same flash-attention-2 style kernel for 64 < L <= 272 -- scores / P / O in registers, keys in chunks of 64, two
@@ -1653,7 +1726,7 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     CUtensorMap tm5b;  // second Q / K / V tile: rows 128 .. Lk16 - 1
     const uint32_t box5b[3] = {HD, (uint32_t)(a5.lk16 - 128), 1};
     VMC_TRY(vmc_encode_tmap_bf16(&tm5b, qkv, 3, dims5, strides5, box5b));
-    const uint32_t smem5 = 6u * (uint32_t)a5.lk16 * 128u + (uint32_t)(a5.lk16 / 16) * 2048u + 256 + 1024;
+    const uint32_t smem5 = 6u * (uint32_t)a5.lk16 * 128u + (uint32_t)(a5.lk16 / 16) * 2048u + 256 + 1024 /* row stabilisers */ + 1024;
     cudaStream_t st5 = reinterpret_cast<cudaStream_t>(stream);
     const int grid5 = a5.n_items < vmc_num_sms() ? a5.n_items : vmc_num_sms();
 #ifdef VMC_WHATIF
@@ -1665,13 +1738,15 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
                  : impl == 52 ? attention_vit5_kernel<2>
                  : impl == 53 ? attention_vit5_kernel<3>
                  : impl == 54 ? attention_vit5_kernel<1, true> : attention_vit5_kernel<0, true>;  // 54 / 55: timeline stamps
+    if (v5_split) kern5 = impl == 59 ? attention_vit5_kernel<0, true, 2> : attention_vit5_kernel<0, false, 2>;
 #else
-    auto kern5 = attention_vit5_kernel<0>;
+    auto kern5 = v5_split ? attention_vit5_kernel<0, false, 2> : attention_vit5_kernel<0>;
 #endif
+    const bool split5 = v5_split;
     VMC_CUDA(cudaFuncSetAttribute(kern5, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
     {
       VmcProfScope prof(VMC_K_ATTN_VIT, st5, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
-      kern5<<<grid5, A5B_THREADS, smem5, st5>>>(tm5, tm5b, a5);
+      kern5<<<grid5, a5_threads(split5 ? 2 : 1), smem5, st5>>>(tm5, tm5b, a5);
     }
     VMC_LAUNCH_CHECK();
     vmc_count_launch();
