@@ -384,7 +384,7 @@ def test_gemm_layernorm_fold(cuda_device, M, d, N, act):
     assert err_fold < max(2.0 * err_base, 3e-2), (err_fold, err_base)
 
 
-@pytest.mark.parametrize("impl", [9, 8, 7, 6, 5, 2])
+@pytest.mark.parametrize("impl", [8, 7, 6, 5, 2])
 @pytest.mark.parametrize("L,heads,F_", [(50, 12, 5), (197, 12, 3), (257, 16, 2), (128, 2, 2), (16, 1, 1), (129, 3, 2), (272, 1, 1), (197, 12, 40), (256, 4, 75), (200, 1, 1),
                                         (257, 16, 60), (226, 2, 3), (241, 3, 7), (145, 1, 2), (50, 12, 200), (50, 1, 7), (64, 3, 5), (33, 2, 3), (7, 1, 1)])
 def test_attention_vit(cuda_device, L, heads, F_, impl):
@@ -399,7 +399,7 @@ def test_attention_vit(cuda_device, L, heads, F_, impl):
     assert err < 2e-2, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("impl,L", [(5, 197), (9, 197), (2, 197), (6, 257), (6, 197), (7, 50), (8, 50)])
+@pytest.mark.parametrize("impl,L", [(5, 197), (5, 224), (5, 160), (2, 197), (6, 257), (6, 197), (7, 50), (8, 50)])
 def test_attention_vit_peaky_and_shifted_scores(cuda_device, impl, L):
     """Large score spread and a large common offset: the single-pass softmax (stabiliser = max of the
     first 32 keys) must stay as accurate as the exact-max reference.  (impl 6: the CLS token is handled outside the
@@ -420,7 +420,7 @@ def test_attention_vit_peaky_and_shifted_scores(cuda_device, impl, L):
     assert err < 3e-2, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("impl,L,heads,F_", [(7, 50, 12, 700), (8, 50, 12, 700), (5, 197, 12, 300), (9, 197, 12, 300), (9, 160, 12, 200), (6, 257, 16, 260), (6, 230, 4, 500)])
+@pytest.mark.parametrize("impl,L,heads,F_", [(7, 50, 12, 700), (8, 50, 12, 700), (5, 197, 12, 300), (5, 160, 12, 200), (5, 224, 3, 500), (5, 129, 2, 400), (5, 208, 5, 333), (6, 257, 16, 260), (6, 230, 4, 500)])
 def test_attention_vit_persistent_kernels_deterministic_at_scale(cuda_device, impl, L, heads, F_):
     """Many items per CTA (ring slots, TMEM tiles and hand-over buffers reused dozens of times): the persistent kernels
     must give bit-identical results run to run (a race shows up as run-to-run noise) and agree with the first-generation

@@ -261,15 +261,14 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], float mx, in
   return mx;
 }
 // ---------------------------------------------------------------------------------------
-// A1, fifth generation (129 <= L <= 256): the two query tiles run OUT OF PHASE and the softmax warps do
+// A1, fifth generation (129 <= L <= 224): the two query tiles run OUT OF PHASE and the softmax warps do
 // nothing but softmax.
 //
 // What the v3 timeline showed: both tiles march in lockstep through  S MMA -> softmax -> PV -> O drain ->
 // next S MMA, because one MMA thread serves them in a fixed order, and the ~3k-cycle tail (PV part B,
 // accumulator drain, next S MMA) of BOTH tiles sits idle on the MUFU pipe at the same time (XU 54 % busy).
 // TMEM (512 columns) cannot hold a third score tile, so the bubble is hidden by phase instead:
-//   * warp 13, the MMA issuer, is event driven: it serves whichever tile's barrier completes next
-//     (try_wait with a short suspend hint, no spinning), and starts tile 1 half a period after tile 0;
+//   * warps 13 / 14 are the MMA issuers, one per query tile, each blocking on its own tile's barriers;
 //   * warps 8-11 are EPILOGUE warps (one per TMEM lane quarter, both tiles): they drain O, release the
 //     tile's TMEM and write the output rows, so a softmax warp goes straight from its last chunk to the
 //     next item's scores;
@@ -277,15 +276,19 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], float mx, in
 //     its B operand being a constant all-ones tile reached through the descriptor's leading-dimension
 //     offset, so column 64 of the accumulator is the row sum of exactly the bf16 probabilities the MMA
 //     consumed.  This removes the rounded-sum bookkeeping (2 LOP + 2 FADD of 13 instructions per pair) and
-//     the softmax -> epilogue hand-over of the row sums.
-// TMEM plan of one query tile (base = 256 t, n_chunks = ceil(Lk16 / 32) in 5..8):
-//   S    [0, Lk16)              fp32 scores
+//     the softmax -> epilogue hand-over of the row sums.  The rows of that tile which belong to padding keys
+//     (>= L) are ZERO, like the zero-filled V rows, so whatever P holds for them contributes nothing;
+//   * [r2] the score MMA of an item is issued in two key ranges, the first one ahead of time (see the MMA
+//     issuers).
+// TMEM plan of one query tile (base = 256 t, n_chunks = ceil(Lk16 / 32) in 5..7):
+//   S_a  [0, 64)   S_b [64, Lk16)   fp32 scores of keys 0..63 / 64..
 //   P_a  [16 c, 16 c + 16)      bf16 pairs of chunk c < 5 (keys 0..159), over S columns already consumed
 //   O    [80, 144) sum [144,160) fp32 accumulator of the N = 80 PV MMA, over consumed S columns
 //   P_b  [32 c, 32 c + 16)      chunk c >= 5, in place over its own scores
 // ---------------------------------------------------------------------------------------
-// VAR: 0 = production; what-if timing variants (WRONG results; tools/kernel_bench.py only):
-//      1 = softmax warps only signal (pipeline floor), 2 = TMEM load + store without the math, 3 = FMA instead of MUFU
+// VAR: 0 = production; what-if timing variants (WRONG results; make WHATIF=1, tools/kernel_bench.py only):
+//      1 = softmax warps only signal (pipeline floor), 2 = TMEM load + store without the math, 3 = FMA instead of MUFU,
+//      4 = no loads after the first items, 5 = 1 + 4, 6 = no output stores
 template <bool MASK, int VAR = 0>
 __device__ __forceinline__ void chunk_exp_store5(const uint32_t (&r)[32], float sc, float mxs, int valid,
                                                  uint32_t taddr) {
@@ -306,37 +309,17 @@ __device__ __forceinline__ void chunk_exp_store5(const uint32_t (&r)[32], float 
       }
       if (MASK && 2 * j + 1 >= valid) e1 = 0.f;
     }
-    // fp32 -> bf16 in the integer ALU (round half up; the XU pipe is the busy one)
-    pk[j] = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);
+    // one F2FP per pair (round to nearest even).  Round 1 rounded in the integer ALU (2 IADD + PRMT per pair) to keep the
+    // conversion off the MUFU pipe; with the softmax warps bound by their own instruction stream rather than by that pipe
+    // (round-2 timeline) the shorter sequence is 1 - 3 % faster.
+    pk[j] = pack_bf16x2(e0, e1);
   }
   tmem_st_32x32b_x16(taddr, pk);
 }
 
-// the same, probabilities left in registers (the caller issues the next chunk's load before the store)
-template <bool MASK, int VAR = 0>
-__device__ __forceinline__ void chunk_exp_pack5(const uint32_t (&r)[32], float sc, float mxs, int valid, uint32_t (&pk)[16]) {
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float e0 = 0.f, e1 = 0.f;
-    if (VAR == 2) {
-      e0 = __uint_as_float(r[2 * j]);
-      e1 = __uint_as_float(r[2 * j + 1]);
-    } else if (!MASK || 2 * j < valid) {
-      if (VAR == 3) {
-        e0 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f), 0.001f, 1.0f);
-        e1 = fmaf(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f), 0.001f, 1.0f);
-      } else {
-        e0 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j]), sc, -mxs), 120.f));
-        e1 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j + 1]), sc, -mxs), 120.f));
-      }
-      if (MASK && 2 * j + 1 >= valid) e1 = 0.f;
-    }
-    pk[j] = __byte_perm(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632);
-  }
-}
-
 struct Attn5Args {
   int L, heads, d, lk16, n_items;
+  int qk_stages;  // depth of the Q / K ring: 3 where shared memory allows (<= 208 keys), else 2
   __nv_bfloat16* out;
   long long* dbg;  // timeline of CTA 0 (DBG instantiation only; tools/attn_timeline.py)
   int cq, ck, cv, chead;  // column of head h's Q / K / V slice = c{q,k,v} + h * chead
@@ -346,82 +329,86 @@ struct Attn5Args {
     if (DBG && a.dbg != nullptr && blockIdx.x == 0 && (k_) < 16) a.dbg[((k_) * 32) + (slot)] = clock64(); \
   } while (0)
 
-constexpr int A5_THREADS = 448;  // 8 softmax + 4 epilogue + TMA + MMA warps
 constexpr int A5_PA_CHUNKS = 5;  // chunks (32 keys) whose P is packed into [0, 80): part A of the PV MMA
 constexpr int A5_OCOL = 80;      // accumulator columns [80, 160): 64 of O + 16 copies of the row sum
+constexpr int A5B_THREADS = 480;  // 8 softmax + 4 epilogue + TMA + 2 MMA issuer warps (one per query tile)
 
-constexpr int A5B_THREADS = 480;  // v5: + a second MMA issuer warp (one per query tile)
-// SPLIT = softmax warps per (query tile, TMEM lane quarter): 1 -> 8 softmax warps; 2 -> 16, the two warps of a pair taking
-// the even and the odd 32-key chunks of the same 32 score rows (see the softmax branch).
-constexpr int a5_threads(int split) { return (8 * split + 7) * 32; }
-template <int VAR, bool DBG = false, int SPLIT = 1>
-__global__ void __launch_bounds__(a5_threads(SPLIT), 1)
+template <int VAR, bool DBG = false>
+__global__ void __launch_bounds__(A5B_THREADS, 1)
 attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm1,
                       const Attn5Args a) {
   // Shared memory: two rings, released at different times.  The timeline of the first v5 (one Q/K/V stage
   // per item, freed when the item's last PV MMA retires) showed the NEXT-NEXT item's load being issued
   // ~6k cycles (its own latency under load) before tile 0 needed it: the kernel was bound by the latency
-  // of one 96 KB load per SM.  Q and K are dead as soon as both S MMAs of the item have retired, i.e. a
+  // of one 96 KB load per SM.  Q and K are dead as soon as both score MMAs of the item have retired, i.e. a
   // whole softmax earlier, so they get their own ring; the second tiles are loaded with (Lk16 - 128)-row
   // boxes instead of 128-row ones (rows >= L are zero-filled by TMA either way).
+  // [r2] The all-ones tile shrank from one 2 KB block per 16-key step to two blocks (all keys real / the last, partly
+  // padded step), which leaves room for a THIRD Q / K stage up to 208 keys.  With the score MMA issued early the timeline
+  // shows a load landing 8 - 9.5 k cycles after its issue (every SM pulls its share of ~4.5 TB/s) and the issuer waiting
+  // ~1.1 k cycles per item for it -- yet the deeper ring measured the same (0.281 vs 0.279 ms per 1024 frames): the wait
+  // moves to the next link of the chain.  The depth is a kernel argument: 3 where it fits, else 2 (both are tested).
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   const int r1 = a.lk16 - 128;                          // rows of the second Q / K / V box (16..96)
   const uint32_t mat_bytes = (uint32_t)(128 + r1) * 128u;  // one of Q, K, V for one item
-  const uint32_t qk_base = base;                         // ring of 2 x [Q | K]
-  const uint32_t v_base = base + 4 * mat_bytes;          // ring of 2 x V
-  const uint32_t ones_base = base + 6 * mat_bytes;
+  const uint32_t qk_base = base;                                      // ring of qk_stages x [Q | K]
+  const uint32_t v_base = base + 2u * a.qk_stages * mat_bytes;        // ring of 2 x V
+  const uint32_t ones_base = v_base + 2 * mat_bytes;                  // block 0: ones; block 1: ones for keys < L of the last step
   const int nkk = a.lk16 / 16;  // 16-key steps of the PV MMA
-  const uint32_t ones_bytes = (uint32_t)nkk * 2048u;
-  const uint32_t bar_base = ones_base + ones_bytes;
-  auto qk_full = [&](int s) { return bar_base + 8u * s; };
-  auto qk_empty = [&](int s) { return bar_base + 16u + 8u * s; };
-  auto s_full = [&](int t) { return bar_base + 32u + 8u * t; };
-  auto pa_full = [&](int t) { return bar_base + 48u + 8u * t; };
-  auto pb_full = [&](int t) { return bar_base + 64u + 8u * t; };
-  auto o_full = [&](int t) { return bar_base + 80u + 8u * t; };
-  auto s_empty = [&](int t) { return bar_base + 96u + 8u * t; };
-  auto v_full = [&](int s) { return bar_base + 112u + 8u * s; };
-  auto v_empty = [&](int s) { return bar_base + 128u + 8u * s; };
-  const uint32_t tmem_ptr_addr = bar_base + 144u;
+  const uint32_t bar_base = ones_base + 4096u;
+  auto qk_full = [&](int s) { return bar_base + 8u * s; };            // 3
+  auto qk_empty = [&](int s) { return bar_base + 24u + 8u * s; };     // 3
+  auto s_full = [&](int t) { return bar_base + 48u + 8u * t; };       // scores of keys 0..63
+  auto sb_full = [&](int t) { return bar_base + 64u + 8u * t; };      // scores of keys 64..
+  auto pa_full = [&](int t) { return bar_base + 80u + 8u * t; };
+  auto pb_full = [&](int t) { return bar_base + 96u + 8u * t; };
+  auto o_full = [&](int t) { return bar_base + 112u + 8u * t; };
+  auto s_empty = [&](int t) { return bar_base + 128u + 8u * t; };
+  auto v_full = [&](int s) { return bar_base + 144u + 8u * s; };
+  auto v_empty = [&](int s) { return bar_base + 160u + 8u * s; };
+  const uint32_t tmem_ptr_addr = bar_base + 176u;
   volatile uint32_t* tmem_ptr_generic =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
-  float* mx_sh = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));  // SPLIT = 2: row stabilisers, [2][128]
 
-  constexpr int NSW = 8 * SPLIT;       // softmax warps 0 .. NSW-1, epilogue warps NSW .. NSW+3
-  constexpr int W_TMA = NSW + 4;       // then the TMA producer and one MMA issuer per query tile
-  constexpr int W_MMA = NSW + 5;
-  constexpr int NTHREADS = a5_threads(SPLIT);
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int n_my = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
 
-  // the all-ones "second MN atom" of the PV B operand (bf16 1.0 everywhere; any layout reads ones)
+  // the "second MN atom" of the PV B operand: bf16 1.0 for every real key.  One 128-byte row per key (the swizzle only
+  // permutes the 16-byte chunks inside a row, and every element of a row is the same), 16 rows per block.
   {
     uint4* ones = reinterpret_cast<uint4*>(smem_raw + (ones_base - raw_addr));
-    for (uint32_t i = tid; i < ones_bytes / 16; i += NTHREADS)
-      ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    const int last_valid = a.L - (nkk - 1) * 16;  // real keys of the last step (1..16)
+    for (uint32_t i = tid; i < 4096u / 16; i += A5B_THREADS) {
+      const int row = (int)(i >> 3) & 15;
+      const uint32_t one2 = (i < 128u || row < last_valid) ? 0x3F803F80u : 0u;
+      ones[i] = make_uint4(one2, one2, one2, one2);
+    }
     fence_proxy_async_smem();
   }
   if (tid == 0) {
     tma_prefetch_desc(&tm);
     tma_prefetch_desc(&tm1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(qk_full(i), 1);
       mbar_init(qk_empty(i), 2);  // one tcgen05.commit per tile's MMA issuer
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(v_full(i), 1);
       mbar_init(v_empty(i), 2);
       mbar_init(s_full(i), 1);
-      mbar_init(pa_full(i), 4 * SPLIT);  // one arrive per softmax warp of the tile
-      mbar_init(pb_full(i), 4 * SPLIT);
+      mbar_init(sb_full(i), 1);
+      mbar_init(pa_full(i), 4);  // one arrive per softmax warp of the tile
+      mbar_init(pb_full(i), 4);
       mbar_init(o_full(i), 1);
       mbar_init(s_empty(i), 4);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
-  if (warp == W_MMA) {
+  if (warp == 13) {
     tmem_alloc(tmem_ptr_addr, 512);
     tmem_relinquish();
   }
@@ -431,36 +418,45 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
   const uint32_t tmem_base = *tmem_ptr_generic;
   const int n_chunks = (a.lk16 + 31) / 32;  // 5..7
 
-  if (warp == W_TMA) {
-    // ===================== TMA producer: serves both rings, never blocks on one of them =====================
-    // (hot polling: a nanosleep between polls reacts in ~700 cycles and was measured neither faster nor slower)
+  if (warp == 12) {
+    // ===================== TMA producer =====================
+    // The rings are released in a fixed order -- Q/K of item k (both tiles' score MMAs retired), then V of item k (both PV
+    // MMAs), then Q/K of item k + 1 (its S_b needs the drained accumulators of item k) -- so the producer issues in that
+    // order and BLOCKS on the next release.  (Round 1 polled both barriers; measured the same: 0.294 vs 0.296 ms.)
     if (lane == 0) {
-      int kq = 0, kv = 0;
+      int kq = 0, kv = 0;          // next Q/K and V loads
+      int sq = 0;                  // Q/K ring slot and its use count parity
+      uint32_t pq = 0;
       while (kq < n_my || kv < n_my) {
-        if (kq < n_my && mbar_test_wait(qk_empty(kq & 1), (((uint32_t)kq >> 1) & 1u) ^ 1u)) {
+        const bool do_qk = kq < n_my && (kv >= n_my || kq < kv + a.qk_stages - 1);  // Q/K runs (stages - 1) items ahead of V
+        if (do_qk) {
+          mbar_wait(qk_empty(sq), pq ^ 1u);
           const int item = blockIdx.x + kq * gridDim.x;
           const int head = item % a.heads, frame = item / a.heads;
-          const int s = kq & 1;
-          const uint32_t q = qk_base + s * 2 * mat_bytes, kk_ = q + mat_bytes;
+          const uint32_t q = qk_base + sq * 2 * mat_bytes, kk_ = q + mat_bytes;
           VMC_DBG5(kq, 24);
-          if (VAR >= 4 && kq >= 2) {  // what-if: no loads after the first two items (ring contents reused): no HBM traffic
-            mbar_arrive(qk_full(s));
+          if (VAR >= 4 && VAR <= 5 && kq >= a.qk_stages) {  // what-if: ring contents reused, no HBM traffic
+            mbar_arrive(qk_full(sq));
           } else {
-            mbar_arrive_expect_tx(qk_full(s), 2 * mat_bytes);
-            tma_load_3d(q, &tm, qk_full(s), a.cq + head * a.chead, 0, frame);
-            tma_load_3d(q + TILE, &tm1, qk_full(s), a.cq + head * a.chead, 128, frame);
-            tma_load_3d(kk_, &tm, qk_full(s), a.ck + head * a.chead, 0, frame);
-            tma_load_3d(kk_ + TILE, &tm1, qk_full(s), a.ck + head * a.chead, 128, frame);
+            mbar_arrive_expect_tx(qk_full(sq), 2 * mat_bytes);
+            tma_load_3d(q, &tm, qk_full(sq), a.cq + head * a.chead, 0, frame);
+            tma_load_3d(q + TILE, &tm1, qk_full(sq), a.cq + head * a.chead, 128, frame);
+            tma_load_3d(kk_, &tm, qk_full(sq), a.ck + head * a.chead, 0, frame);
+            tma_load_3d(kk_ + TILE, &tm1, qk_full(sq), a.ck + head * a.chead, 128, frame);
           }
           ++kq;
-        }
-        if (kv < n_my && mbar_test_wait(v_empty(kv & 1), (((uint32_t)kv >> 1) & 1u) ^ 1u)) {
+          if (++sq == a.qk_stages) {
+            sq = 0;
+            pq ^= 1u;
+          }
+        } else {
+          const int s = kv & 1;
+          mbar_wait(v_empty(s), (((uint32_t)kv >> 1) & 1u) ^ 1u);
           const int item = blockIdx.x + kv * gridDim.x;
           const int head = item % a.heads, frame = item / a.heads;
-          const int s = kv & 1;
           const uint32_t v = v_base + s * mat_bytes;
           VMC_DBG5(kv, 26);
-          if (VAR >= 4 && kv >= 2) {
+          if (VAR >= 4 && VAR <= 5 && kv >= 2) {
             mbar_arrive(v_full(s));
           } else {
             mbar_arrive_expect_tx(v_full(s), mat_bytes);
@@ -472,63 +468,104 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == W_MMA || warp == W_MMA + 1) {
+  } else if (warp == 13 || warp == 14) {
     // ===================== MMA issuers: one warp per query tile =====================
     // Round 1 had ONE thread serve both tiles by polling their barriers round-robin with mbarrier.test_wait (~150 cycles
     // per probe, two to four probes per turn): every hand-over on a tile's S -> softmax -> PV -> drain chain waited for the
     // poller to come round, and an MMA burst for one tile delayed the other.  Each tile now has its own issuer that BLOCKS
     // on that tile's barriers (try_wait: the thread sleeps in hardware and wakes ~60 cycles after the arrive).  The shared
     // rings are released by both: qk_empty / v_empty count two arrivals, each issuer's tcgen05.commit covering its own MMAs.
-    const int t = warp - W_MMA;
+    //
+    // The chain  S MMA -> softmax -> PV -> accumulator drain -> next S MMA  still left the tile's four softmax warps idle
+    // for ~2 k cycles between their last probability chunk and the next item's scores (timeline: PV part B 0.4 k, drain
+    // 0.1 k, wait + issue 0.3 k, score MMA 0.7 - 1.3 k: its operands come from shared memory at ~100 B/clk next to the TMA
+    // writes).  The score MMA is therefore issued in two key ranges:
+    //   S_a (keys 0..63 -> columns [0, 64))    right after PV part A of the PREVIOUS item: those columns then hold only
+    //       P_a, which that MMA -- issued by this same thread, so ordered before S_a -- is the last to read;
+    //   S_b (keys 64..  -> columns [64, Lk16)) once the accumulator (columns 80..159) has been drained, as before.
+    // The softmax warps go from the last chunk of item k straight to chunks 0 and 1 of item k + 1, and PV part B, the
+    // drain and S_b run underneath those two chunks.
+    const int t = warp - 13;
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, a.lk16, 0, 0);
+      const uint32_t idesc_sa = umma_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_sb = umma_idesc_bf16(128, a.lk16 - 64, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 80, 0, 1);  // B = [V | ones], MN-major
       const int nka = nkk < 2 * A5_PA_CHUNKS ? nkk : 2 * A5_PA_CHUNKS;
+      const bool last_partial = (a.L & 15) != 0;
       const uint32_t tcol = tmem_base + uint32_t(t * 256);
+      int sq = 0;  // Q/K ring slot / parity of the next S_a
+      uint32_t pq = 0;
+      int sq_b = 0;  // ... of the next S_b (one item behind S_a in the steady state)
+      auto issue_sa = [&](int k) {
+        mbar_wait(qk_full(sq), pq);
+        tc_fence_after();
+        if (t == 0) VMC_DBG5(k, 25);
+        VMC_DBG5(k, 0 + t);
+        const uint32_t qst = qk_base + sq * 2 * mat_bytes;
+        const uint64_t dq = umma_desc_sw128(qst + t * TILE);
+        const uint64_t dk = umma_desc_sw128(qst + mat_bytes);
+#pragma unroll
+        for (int kq = 0; kq < HD / 16; ++kq)
+          umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_sa, kq != 0);
+        umma_commit(s_full(t));
+        if (++sq == a.qk_stages) {
+          sq = 0;
+          pq ^= 1u;
+        }
+      };
+      auto issue_sb = [&]() {
+        const uint32_t qst = qk_base + sq_b * 2 * mat_bytes;
+        const uint64_t dq = umma_desc_sw128(qst + t * TILE);
+        const uint64_t dk = umma_desc_sw128(qst + mat_bytes + 64u * 128u);  // K rows 64..: 8 KB further (swizzle-atom aligned)
+#pragma unroll
+        for (int kq = 0; kq < HD / 16; ++kq)
+          umma_ss(tcol + 64u, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_sb, kq != 0);
+        umma_commit(sb_full(t));
+        umma_commit(qk_empty(sq_b));  // second arrival (the other tile's issuer) frees Q and K
+        if (++sq_b == a.qk_stages) sq_b = 0;
+      };
+      if (n_my > 0) {
+        issue_sa(0);
+        issue_sb();
+      }
       for (int k = 0; k < n_my; ++k) {
         const int s = k & 1;
         const uint32_t par = (uint32_t)k & 1u;
         const uint32_t ring_par = ((uint32_t)k >> 1) & 1u;
         const uint32_t vst = v_base + s * mat_bytes;
-        // V descriptor: atom 0 = the TMA tile (64 head dims x 16 keys), atom 1 (N = 64..79) = LBO further = ones
-        const uint64_t dv0 = (umma_desc_sw128(vst) & ~(uint64_t(0x3FFF) << 16)) |
-                             (uint64_t((ones_base - vst) >> 4) << 16);
-        // ---- S = Q K^T ----
-        mbar_wait(qk_full(s), ring_par);
-        if (t == 0) VMC_DBG5(k, 25);
-        mbar_wait(s_empty(t), par ^ 1u);
-        tc_fence_after();
-        VMC_DBG5(k, 0 + t);
-        const uint32_t qst = qk_base + s * 2 * mat_bytes;
-        const uint64_t dq = umma_desc_sw128(qst + t * TILE);
-        const uint64_t dk = umma_desc_sw128(qst + mat_bytes);
-#pragma unroll
-        for (int kq = 0; kq < HD / 16; ++kq)
-          umma_ss(tcol, dq + uint64_t(2 * kq), dk + uint64_t(2 * kq), idesc_s, kq != 0);
-        umma_commit(s_full(t));
-        umma_commit(qk_empty(s));  // second arrival (the other tile's issuer) frees Q and K
+        // V descriptor of 16-key step kk: atom 0 = rows 16 kk.. of the TMA tile (64 head dims x 16 keys), atom 1 (N = 64..79)
+        // = the leading-dimension offset further = one of the two all-ones blocks
+        const uint64_t dv_base = umma_desc_sw128(vst) & ~(uint64_t(0x3FFF) << 16);
+        auto dv = [&](int kk) {
+          const uint32_t blk = ones_base + ((last_partial && kk == nkk - 1) ? 2048u : 0u);
+          return (dv_base + uint64_t(kk * 128)) | (uint64_t((blk - (vst + uint32_t(kk) * 2048u)) >> 4) << 16);
+        };
         // ---- O = P V, keys of part A (their probabilities are stored while the softmax still works on part B) ----
         mbar_wait(pa_full(t), par);
         mbar_wait(v_full(s), ring_par);
         tc_fence_after();
         VMC_DBG5(k, 2 + t);
-        for (int kk = 0; kk < nka; ++kk)
-          umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv0 + uint64_t(kk * 128), idesc_pv, kk != 0);
+        for (int kk = 0; kk < nka; ++kk) umma_ts(tcol + A5_OCOL, tcol + uint32_t(kk * 8), dv(kk), idesc_pv, kk != 0);
+        if (k + 1 < n_my) issue_sa(k + 1);
         // ---- part B ----
         mbar_wait(pb_full(t), par);
         tc_fence_after();
         VMC_DBG5(k, 4 + t);
         for (int kk = nka; kk < nkk; ++kk)
-          umma_ts(tcol + A5_OCOL, tcol + uint32_t((kk >> 1) * 32 + (kk & 1) * 8), dv0 + uint64_t(kk * 128),
-                  idesc_pv, 1u);
+          umma_ts(tcol + A5_OCOL, tcol + uint32_t((kk >> 1) * 32 + (kk & 1) * 8), dv(kk), idesc_pv, 1u);
         umma_commit(o_full(t));
         umma_commit(v_empty(s));  // second arrival frees V
+        if (k + 1 < n_my) {
+          mbar_wait(s_empty(t), par);  // accumulator of item k drained
+          tc_fence_after();
+          issue_sb();
+        }
       }
     }
     __syncwarp();
-  } else if (warp >= NSW) {
+  } else if (warp >= 8) {
     // ===================== epilogue warps: drain O, release the tile, write the rows =====================
-    const int q = warp - NSW;
+    const int q = warp - 8;
     for (int k = 0; k < n_my; ++k) {
       const int item = blockIdx.x + k * gridDim.x;
       const int head = item % a.heads;
@@ -583,70 +620,45 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
     }
   } else {
     // ===================== softmax warps =====================
-    const int t = (warp >> 2) & 1;
+    const int t = warp >> 2;
     const int q = warp & 3;
-    const int half = warp >> 3;  // SPLIT = 2: 0 = even chunks, 1 = odd chunks of the same rows
     const bool warp_active = (t * 128 + q * 32) < a.L;  // warp-uniform
     const uint32_t tb = tmem_base + uint32_t(t * 256) + (uint32_t(q * 32) << 16);
     const float sc = 0.125f * 1.4426950408889634f;
     const int n_full = a.L >> 5;           // chunks with 32 valid columns
     const int tail = a.L - (n_full << 5);  // valid columns of the last, partial chunk (0: none)
     auto pcol = [&](int c) { return tb + uint32_t(c < A5_PA_CHUNKS ? c * 16 : c * 32); };
+    constexpr int VX = VAR >= 4 ? 0 : VAR;
     for (int k = 0; k < n_my; ++k) {
       const uint32_t par = (uint32_t)k & 1u;
       mbar_wait(s_full(t), par);
       tc_fence_after();
-      if (q == 0 && half == 0 && lane == 0) VMC_DBG5(k, 8 + 8 * t);
+      if (q == 0 && lane == 0) VMC_DBG5(k, 8 + 8 * t);
       if (warp_active && (VAR == 1 || VAR == 5)) {
         if (lane == 0) mbar_arrive_relaxed(pa_full(t));
-      } else if (warp_active && SPLIT == 2) {
-        // Two warps per 32 rows.  With one softmax warp per scheduler and tile the exponentials of a row ran at well under half
-        // the MUFU rate (ncu: XU pipe 45 % busy, the warp alone on its scheduler for a third of the time), and the softmax is
-        // the longest link of the tile's S -> softmax -> PV -> drain chain.  Warp `half` takes chunks half, half + 2, ...; one
-        // register buffer per warp (the partner and the other tile's pair hide the TMEM latency).
-        // Hazards between the two warps: P of chunk c < 5 is stored over the scores of chunk c / 2, so P(1) (odd warp) lands on
-        // chunk 0 and P(2) (even warp) on chunk 1: both first loads are complete before either warp stores (named barrier of
-        // the pair, 64 threads); every later store lands on a chunk its own warp has already consumed.  The stabiliser (max
-        // of chunk 0) goes from the even to the odd warp through shared memory across the same barrier.
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tb + uint32_t(half * 32), r);
-        tmem_ld_wait();
-        float mxs = 0.f;
-        if (half == 0) {
-          mxs = chunk_max<false>(r, -INFINITY, 32) * sc;
-          mx_sh[t * 128 + q * 32 + lane] = mxs;
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + t * 4 + q) : "memory");
-        if (half == 1) mxs = mx_sh[t * 128 + q * 32 + lane];
-        for (int c = half; c < n_chunks; c += 2) {
-          if (c != half) tmem_ld_wait();
-          uint32_t pk[16];
-          if (c < n_full) chunk_exp_pack5<false, (VAR >= 4 ? 0 : VAR)>(r, sc, mxs, 32, pk);
-          else chunk_exp_pack5<true, (VAR >= 4 ? 0 : VAR)>(r, sc, mxs, tail, pk);
-          if (c + 2 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 2) * 32), r);  // r is dead: next chunk in flight during the store
-          tmem_st_32x32b_x16(pcol(c), pk);
-          if (c == A5_PA_CHUNKS - 1 - half) {
-            // this warp's last part-A chunk (4 for the even warp, 3 for the odd one) is stored
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_relaxed(pa_full(t));
-            if (q == 0 && half == 0 && lane == 0) VMC_DBG5(k, 9 + 8 * t);
-          }
-        }
-        tmem_st_wait();
       } else if (warp_active) {
         // single pass over the score row, 32-column chunks double-buffered in registers; stabiliser = max of
-        // the first 32 keys (<= row max, so the row sum is >= 1; argument clamped at +120), see v3
+        // the first 32 keys (<= row max, so the row sum is >= 1; argument clamped at +120), see v3.
+        // Chunks 0 and 1 (keys 0..63) come from S_a, which was computed while the previous item was being finished; the
+        // rest of the row (S_b) needs the drained accumulator and is waited for only after them.
         uint32_t r0[32], r1[32];
         tmem_ld_32x32b_x32(tb, r0);
+        tmem_ld_32x32b_x32(tb + 32u, r1);
         tmem_ld_wait();
         const float mxs = chunk_max<false>(r0, -INFINITY, 32) * sc;
-        for (int c = 0; c < n_chunks; c += 2) {
-          if (c != 0) tmem_ld_wait();
+        chunk_exp_store5<false, VX>(r0, sc, mxs, 32, pcol(0));
+        chunk_exp_store5<false, VX>(r1, sc, mxs, 32, pcol(1));
+        if (DBG && t == 0 && q == 0 && lane == 0) VMC_DBG5(k, 7);
+        mbar_wait(sb_full(t), par);
+        tc_fence_after();
+        if (DBG && t == 0 && q == 0 && lane == 0) VMC_DBG5(k, 6);
+        tmem_ld_32x32b_x32(tb + 64u, r0);
+        for (int c = 2; c < n_chunks; c += 2) {
+          tmem_ld_wait();
           if (c + 1 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 1) * 32), r1);
-          if (c < n_full) chunk_exp_store5<false, (VAR >= 4 ? 0 : VAR)>(r0, sc, mxs, 32, pcol(c));
-          else chunk_exp_store5<true, (VAR >= 4 ? 0 : VAR)>(r0, sc, mxs, tail, pcol(c));
+          if (c < n_full) chunk_exp_store5<false, VX>(r0, sc, mxs, 32, pcol(c));
+          else chunk_exp_store5<true, VX>(r0, sc, mxs, tail, pcol(c));
+          if (DBG && t == 0 && q == 0 && lane == 0) VMC_DBG5(k, 25 + c);  // chunks 2, 4, 6: slots 27, 29, 31
           if (c == A5_PA_CHUNKS - 1) {
             // chunks 0..4 (keys 0..159) are stored: release part A of the PV MMA.  The load of chunk 5
             // issued above reads columns >= 160, disjoint from P_a and the accumulator.
@@ -659,8 +671,9 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
           if (c + 1 < n_chunks) {
             tmem_ld_wait();
             if (c + 2 < n_chunks) tmem_ld_32x32b_x32(tb + uint32_t((c + 2) * 32), r0);
-            if (c + 1 < n_full) chunk_exp_store5<false, (VAR >= 4 ? 0 : VAR)>(r1, sc, mxs, 32, pcol(c + 1));
-            else chunk_exp_store5<true, (VAR >= 4 ? 0 : VAR)>(r1, sc, mxs, tail, pcol(c + 1));
+            if (c + 1 < n_full) chunk_exp_store5<false, VX>(r1, sc, mxs, 32, pcol(c + 1));
+            else chunk_exp_store5<true, VX>(r1, sc, mxs, tail, pcol(c + 1));
+            if (DBG && t == 0 && q == 0 && lane == 0) VMC_DBG5(k, 26 + c);  // chunks 3, 5: slots 28, 30
           }
         }
         tmem_st_wait();
@@ -670,13 +683,13 @@ attention_vit5_kernel(const __grid_constant__ CUtensorMap tm, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(pb_full(t));
-      if (q == 0 && half == 0 && lane == 0) VMC_DBG5(k, 10 + 8 * t);
+      if (q == 0 && lane == 0) VMC_DBG5(k, 10 + 8 * t);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == W_MMA) {
+  if (warp == 13) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -1613,16 +1626,11 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     var6 = impl - 100;
     impl = 6;
   }
-  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 9) || (impl >= 51 && impl <= 59), VMC_ERR_ARG,
-                "vmc_attention_vit: impl must be 2, 5, 6, 7, 8 or 9");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8) || (impl >= 51 && impl <= 58), VMC_ERR_ARG,
+                "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
 #else
-  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 9), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7, 8 or 9");
+  VMC_CHECK_ARG(impl == 2 || (impl >= 5 && impl <= 8), VMC_ERR_ARG, "vmc_attention_vit: impl must be 2, 5, 6, 7 or 8");
 #endif
-  bool v5_split = impl == 59;  // 9: v5 with 16 softmax warps (two per query tile and TMEM lane quarter)
-  if (impl == 9) {
-    v5_split = true;
-    impl = 5;
-  }
   const int d = heads * HD;
   if (impl == 8) {  // warp-level tensor path for short sequences (backward.cu)
     // (The same flash-attention-2 style kernel for 64 < L <= 272 -- scores / P / O in registers, keys in chunks of 64, two
@@ -1726,7 +1734,10 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
     CUtensorMap tm5b;  // second Q / K / V tile: rows 128 .. Lk16 - 1
     const uint32_t box5b[3] = {HD, (uint32_t)(a5.lk16 - 128), 1};
     VMC_TRY(vmc_encode_tmap_bf16(&tm5b, qkv, 3, dims5, strides5, box5b));
-    const uint32_t smem5 = 6u * (uint32_t)a5.lk16 * 128u + (uint32_t)(a5.lk16 / 16) * 2048u + 256 + 1024 /* row stabilisers */ + 1024;
+    // shared memory: qk_stages x [Q | K] + 2 x V + two all-ones blocks + barriers + alignment slack
+    auto smem5_for = [&](int stages) { return (uint32_t)(2 * stages + 2) * (uint32_t)a5.lk16 * 128u + 4096u + 256u + 1024u; };
+    a5.qk_stages = smem5_for(3) <= 227u * 1024u ? 3 : 2;
+    const uint32_t smem5 = smem5_for(a5.qk_stages);
     cudaStream_t st5 = reinterpret_cast<cudaStream_t>(stream);
     const int grid5 = a5.n_items < vmc_num_sms() ? a5.n_items : vmc_num_sms();
 #ifdef VMC_WHATIF
@@ -1738,15 +1749,13 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
                  : impl == 52 ? attention_vit5_kernel<2>
                  : impl == 53 ? attention_vit5_kernel<3>
                  : impl == 54 ? attention_vit5_kernel<1, true> : attention_vit5_kernel<0, true>;  // 54 / 55: timeline stamps
-    if (v5_split) kern5 = impl == 59 ? attention_vit5_kernel<0, true, 2> : attention_vit5_kernel<0, false, 2>;
 #else
-    auto kern5 = v5_split ? attention_vit5_kernel<0, false, 2> : attention_vit5_kernel<0>;
+    auto kern5 = attention_vit5_kernel<0>;
 #endif
-    const bool split5 = v5_split;
     VMC_CUDA(cudaFuncSetAttribute(kern5, cudaFuncAttributeMaxDynamicSharedMemorySize, smem5));
     {
       VmcProfScope prof(VMC_K_ATTN_VIT, st5, 4.0 * F * heads * (double)L * L * HD, 8.0 * F * L * d);
-      kern5<<<grid5, a5_threads(split5 ? 2 : 1), smem5, st5>>>(tm5, tm5b, a5);
+      kern5<<<grid5, A5B_THREADS, smem5, st5>>>(tm5, tm5b, a5);
     }
     VMC_LAUNCH_CHECK();
     vmc_count_launch();
