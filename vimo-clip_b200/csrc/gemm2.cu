@@ -22,6 +22,8 @@
 #include "common.cuh"
 #include "vimoclip_b200.h"
 
+long long vmc_get_option64(int option);
+
 namespace {
 
 using namespace vmc;
@@ -36,7 +38,12 @@ struct Gemm2Args {
   int tiles_m, tiles_n;  // pair tiles
   int a_mn, b_mn;        // operand given TRANSPOSED in memory ([K, M] / [K, N] row-major): MN-major UMMA operand
   vmc_gemm_epilogue epi;
+  long long* dbg;        // VMC_OPT_DEBUG_PTR: clock64 stamps of CTA 0's first 32 tiles, 8 slots each (tools/gemm_timeline.py)
 };
+#define VMC_DBG2(i_, slot)                                                                              \
+  do {                                                                                                  \
+    if (g.dbg != nullptr && blockIdx.x == 0 && (i_) < 32) g.dbg[(i_) * 8 + (slot)] = clock64();         \
+  } while (0)
 
 // MN-major SW128 operand: TMA boxes of 64 (MN, contiguous) x 64 (K) elements land as 64 rows of 128 bytes = the canonical
 // layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) with SBO = 1024 B between 8-row K groups and LBO = 8192 B between the
@@ -168,10 +175,36 @@ __device__ __forceinline__ void ln_row_stats(const vmc_gemm_epilogue& e, int m, 
   }
 }
 
+// The residual rows of a WHOLE tile part (32 rows x HALF_N columns of bf16 per warp: 8 x HALF_N / 32 uint2 per lane), requested
+// BEFORE the warp waits for the accumulator.  Round-2 timeline of attn.out_proj (K = 768): the epilogue took 9.4 - 10.7 k
+// cycles per tile against 8.5 k for the MMA main loop -- 2.5 k cycles per 32-column chunk, the latency of the residual loads
+// under load, which a one-chunk look-ahead does not cover.  The loads do not depend on the accumulator, so their latency now
+// overlaps the wait for it.
+template <int HALF_N>
+__device__ __forceinline__ void prefetch_resid16(const vmc_gemm_epilogue& e, int M, int N, int row0, int n_base, int lane,
+                                                 uint2 (&pre)[HALF_N / 32][8]) {
+  const int lr = lane >> 3, lc = lane & 7;
+  const int m_first = row0 + lr;
+  int nvalid = (M - m_first + 3) >> 2;
+  nvalid = nvalid < 0 ? 0 : (nvalid > 8 ? 8 : nvalid);
+  const char* rptr = reinterpret_cast<const char*>(e.resid) + ((long long)m_first * e.ldr + n_base + lc * 4) * 2;
+  const long long rstride = 4 * e.ldr * 2;
+#pragma unroll
+  for (int c = 0; c < HALF_N / 32; ++c) {
+    const char* rp = rptr + c * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      pre[c][i] = make_uint2(0u, 0u);
+      if (i < nvalid && n_base + c * 32 < N) pre[c][i] = *reinterpret_cast<const uint2*>(rp);
+      rp += rstride;
+    }
+  }
+}
+
 template <int MODE, int HALF_N, bool LNF = false, bool STATS = false, bool R16 = false>
 __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M, int N, int K, int row0,
                                               int n_base, uint32_t t_acc, uint8_t* stg, int lane, float rstd = 1.f,
-                                              float shift = 0.f) {
+                                              float shift = 0.f, const uint2 (*pre)[8] = nullptr) {
   const int lr = lane >> 3, lc = lane & 7;
   const int m_first = row0 + lr;
   int nvalid = (M - m_first + 3) >> 2;  // rows m_first + 4 i, i < nvalid, are inside the matrix
@@ -220,7 +253,7 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
     }
   };
   ResT res_next[8];
-  if constexpr (MODE == 3) {
+  if constexpr (MODE == 3 && !R16) {
     const char* rp = rptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -235,7 +268,7 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
     b4n = __ldg(reinterpret_cast<const float4*>(bptr));
     if constexpr (LNF) cs4n = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base + lc * 4));
   }
-#pragma unroll 1
+#pragma unroll(R16 ? HALF_N / 32 : 1)  // R16: unrolled, the prefetched residual registers are indexed by the chunk
   for (int c = 0; c < HALF_N / 32; ++c) {
     if (n_base + c * 32 >= N) break;  // warp-uniform
     uint32_t r[32];
@@ -247,7 +280,10 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
       if constexpr (LNF) cs4n = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base + (c + 1) * 32 + lc * 4));
     }
     ResT res[8];
-    if constexpr (MODE == 3) {
+    if constexpr (MODE == 3 && R16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[i] = pre[c][i];
+    } else if constexpr (MODE == 3) {
       // the residual rows of the NEXT chunk are requested while this one is processed: the epilogue of the
       // K = 768 residual GEMMs is bound by bytes in flight (8 warps x 4 KB per SM), not by HBM bandwidth
 #pragma unroll
@@ -524,6 +560,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       for (int i = 0; i < my_tiles; ++i) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        VMC_DBG2(i, 0);
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
@@ -543,6 +580,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           }
         }
         umma_commit_mc2(tfull_bar(acc));
+        VMC_DBG2(i, 1);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -568,12 +606,16 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int n_base = n_blk * BN + half * HALF_N;
       float ln_rstd = 1.f, ln_shift = 0.f;
       if constexpr (MODE == 6 || MODE == 7) ln_row_stats(e, row0 + lane, g.M, g.K, ln_rstd, ln_shift);  // before the wait
+      uint2 rpre[MODE == 8 ? HALF_N / 32 : 1][8];
+      if constexpr (MODE == 8) prefetch_resid16<HALF_N>(e, g.M, g.N, row0, n_base, lane, rpre);
+      if (ew == 0 && lane == 0) VMC_DBG2(i, 2);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (ew == 0 && lane == 0) VMC_DBG2(i, 3);
       const uint32_t t_acc =
           tmem_base + uint32_t(acc * BN + half * HALF_N) + (uint32_t(quarter * 32) << 16);
       if constexpr (MODE == 8) {
-        epilogue_fast<3, HALF_N, false, true, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
+        epilogue_fast<3, HALF_N, false, true, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane, 1.f, 0.f, rpre);
       } else if constexpr (MODE == 5) {
         epilogue_fast<3, HALF_N, false, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else if constexpr (MODE == 6 || MODE == 7) {
@@ -687,6 +729,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
+      if (lane == 0 && (ew == 0 || ew == 7)) VMC_DBG2(i, ew == 0 ? 4 : 5);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -736,6 +779,7 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
   g.tiles_m = (M + 2 * BM - 1) / (2 * BM);
   g.tiles_n = (N + BN - 1) / BN;
   g.epi = *epi;
+  g.dbg = reinterpret_cast<long long*>((uintptr_t)(unsigned long long)vmc_get_option64(VMC_OPT_DEBUG_PTR));
   VMC_CUDA(cudaFuncSetAttribute(gemm2_bf16_tcgen05_kernel<BN, MODE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int tiles = g.tiles_m * g.tiles_n;
