@@ -84,9 +84,23 @@ stats_in[0, :, 1] = (xf * xf).sum(1)
 del xf
 
 
+IMPLS = [int(v) for v in os.environ.get("GS_IMPLS", "0").split(",")]  # VMC_OPT_GEMM_IMPL values to time side by side (3 = LDS + STG epilogue)
+import vimoclip_b200 as vmc  # noqa: E402
+
+
 def case(name, a, N, K, **kw):
     if ONLY and not any(s in name for s in ONLY):
         return
+    if len(IMPLS) > 1 or IMPLS[0] != 0:
+        for impl in IMPLS:
+            ops.set_option(vmc._lib.OPT_GEMM_IMPL, impl)
+            _case(f"{name} [impl {impl}]", a, N, K, **dict(kw))
+        ops.set_option(vmc._lib.OPT_GEMM_IMPL, 0)
+        return
+    _case(name, a, N, K, **kw)
+
+
+def _case(name, a, N, K, **kw):
     w = (torch.randn(N, K, device=dev, generator=gen) * K**-0.5).to(torch.bfloat16)
     b = torch.randn(N, device=dev, generator=gen)
     if kw.pop("fold", False):
@@ -95,7 +109,7 @@ def case(name, a, N, K, **kw):
     if out is None:
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     ms, clk = sustained(lambda: ops.gemm(a, w, bias=b, out=out, **kw))
-    print(f"{name:34s} M={M} N={N:4d} K={K:4d}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:5.0f} TFLOP/s  [{clk}]", flush=True)
+    print(f"{name:38s} M={M} N={N:4d} K={K:4d}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:5.0f} TFLOP/s  [{clk}]", flush=True)
 
 
 case("qkv LN-fold", x, 3 * d, d, fold=True)
@@ -111,4 +125,4 @@ if os.environ.get("GS_CUBLAS", "0") == "1":
         w = (torch.randn(N, K, device=dev, generator=gen) * K**-0.5).to(torch.bfloat16)
         o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         ms, clk = sustained(lambda: torch.matmul(a, w.t(), out=o2))
-        print(f"{name:34s} M={M} N={N:4d} K={K:4d}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:5.0f} TFLOP/s  [{clk}]", flush=True)
+        print(f"{name:38s} M={M} N={N:4d} K={K:4d}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:5.0f} TFLOP/s  [{clk}]", flush=True)

@@ -22,6 +22,7 @@ stats_in = torch.zeros(1, M, 2, device=dev)
 stats_in[0, :, 0] = xf.sum(1)
 stats_in[0, :, 1] = (xf * xf).sum(1)
 del xf
+ops.set_option(vmc._lib.OPT_GEMM_IMPL, int(os.environ.get("GS_IMPL", "0")))
 names = ["mma:start", "mma:issued", "ep0:wait", "ep0:acc_ready", "ep0:done", "ep7:done"]
 
 
@@ -50,7 +51,8 @@ def case(name, a, N, K, **kw):
     ep7 = sum(int(t[i, 5]) - int(t[i, 3]) for i in range(8, 24)) / 16.0
     iss = sum(int(t[i, 1]) - int(t[i, 0]) for i in range(8, 24)) / 16.0
     wait = sum(int(t[i, 3]) - int(t[i, 2]) for i in range(8, 24)) / 16.0
-    print(f"  per tile: period {per:.0f} cycles, MMA issue span {iss:.0f}, epilogue warp 0 {ep:.0f} (warp 7 {ep7:.0f}), epilogue idle before the accumulator {wait:.0f}", flush=True)
+    starved = sum(int(t[i, 6]) for i in range(8, 24)) / 16.0
+    print(f"  per tile: period {per:.0f} cycles, MMA issue span {iss:.0f} (of which waiting for operands {starved:.0f}), epilogue warp 0 {ep:.0f} (warp 7 {ep7:.0f}), epilogue idle before the accumulator {wait:.0f}", flush=True)
 
 
 case("qkv LN-fold", x, 3 * d, d, fold=True)

@@ -1,8 +1,11 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x -k "gemm or tower or vit_" > gpurun_out/r02_pytest_gemm.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest_gemm.log
-tail -n 3 gpurun_out/r02_pytest_gemm.log
-timeout 300 python tools/gemm_timeline.py > gpurun_out/r02_gemm_timeline2.txt 2>&1
-grep "==\|per tile" gpurun_out/r02_gemm_timeline2.txt
-GS_ONLY=out_proj,c_proj,qkv timeout 300 python tools/gemm_shapes.py > gpurun_out/r02_gemm_shapes2.log 2>&1
-cat gpurun_out/r02_gemm_shapes2.log
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider -x > gpurun_out/r02_pytest_final3.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest_final3.log
+tail -n 4 gpurun_out/r02_pytest_final3.log
+python bench.py --steps 5 --warmup 3 --no-configs --no-strong > gpurun_out/r02_bench9.json 2> gpurun_out/r02_bench9.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02_bench9.json').read().strip().split('\n')[-1])
+print(d['ms_per_step'], d['value'], d['e2e']['value'], d['clocks'], d.get('ab_same_process'))
+print({k:round(v['ms'],2) for k,v in d['kernel_classes'].items()})
+PY

@@ -80,6 +80,9 @@ struct VmcProfScope {
 int vmc_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank,
                          const uint64_t* dims, const uint64_t* strides_bytes,
                          const uint32_t* box);
+// the same with the shared-memory swizzle of the box: 128, 64 (bytes) or 0 (none)
+int vmc_encode_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 // ----------------------------------------------------------------------------
 // Device-side PTX wrappers

@@ -23,6 +23,7 @@
 #include "vimoclip_b200.h"
 
 long long vmc_get_option64(int option);
+int vmc_get_option(int option);
 
 namespace {
 
@@ -38,6 +39,7 @@ struct Gemm2Args {
   int tiles_m, tiles_n;  // pair tiles
   int a_mn, b_mn;        // operand given TRANSPOSED in memory ([K, M] / [K, N] row-major): MN-major UMMA operand
   vmc_gemm_epilogue epi;
+  int store_tma;         // bf16 epilogues without a residual: the output leaves through tmC (TMA store)
   long long* dbg;        // VMC_OPT_DEBUG_PTR: clock64 stamps of CTA 0's first 32 tiles, 8 slots each (tools/gemm_timeline.py)
 };
 #define VMC_DBG2(i_, slot)                                                                              \
@@ -125,6 +127,15 @@ __device__ __forceinline__ void umma_commit_mc2(uint32_t bar) {
       "h"((uint16_t)3)
       : "memory");
 }
+
+// TMA store of one shared-memory box (bulk async-group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 __device__ __forceinline__ float act2(float v, int act) {
   switch (act) {
@@ -395,9 +406,14 @@ __device__ __forceinline__ void epilogue_fast(const vmc_gemm_epilogue& e, int M,
 // only the PACKED bf16 result is transposed: half the staging traffic, 4 + 4 shared-memory and 4 global instructions per
 // 32-column chunk instead of 8 + 8 + 8.
 //   stg (4 KB per warp): [0, 2048) swizzled 32 x 64-byte tile; [2048, 2560) bias of the warp's HALF_N columns; [2560, 3072) colsum
+// tmc != nullptr: the staged 32 x 32 bf16 tile leaves through ONE TMA store (the XOR pattern of the staging tile is the
+// tensor map's 64-byte swizzle) instead of 4 LDS.128 + 4 STG.128 per lane.  The tensor core's operand reads, the TMA writes
+// and every LSU access share the SM's shared-memory / L1 data pipe: the round-2 tile timeline shows the main loop stretching by
+// about one cycle per epilogue wavefront on that pipe (profiles/r02_gemm_tile_timeline.txt), and the bulk store reads the tile
+// once (16 wavefronts per chunk) where the LDS + STG pair moved it twice.  Out-of-range rows / columns are clipped by the map.
 template <int MODE, int HALF_N, bool LNF>
 __device__ __forceinline__ void epilogue_rowmajor(const vmc_gemm_epilogue& e, int M, int N, int row0, int n_base, uint32_t t_acc,
-                                                  uint8_t* stg, int lane, float rstd, float shift) {
+                                                  uint8_t* stg, int lane, float rstd, float shift, const CUtensorMap* tmc) {
   float* sb = reinterpret_cast<float*>(stg + 2048);
   float* scs = sb + 128;
   if (4 * lane < HALF_N && n_base + 4 * lane < N) {
@@ -441,10 +457,20 @@ __device__ __forceinline__ void epilogue_rowmajor(const vmc_gemm_epilogue& e, in
       pk[2 * q] = pack_bf16x2(v.x, v.y);
       pk[2 * q + 1] = pack_bf16x2(v.z, v.w);
     }
+    if (tmc != nullptr) {
+      if (lane == 0) bulk_wait_read0();  // the previous chunk's store has finished reading the tile
+      __syncwarp();
+    }
     // row `lane` of the 32 x 32 bf16 tile: four 16-byte chunks, chunk index XOR ((row >> 1) & 3): conflict-free both ways
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
       *reinterpret_cast<uint4*>(stg + lane * 64 + ((ch ^ sw) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+    if (tmc != nullptr) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(tmc, smem_u32(stg), n_base + c * 32, row0);
+      continue;
+    }
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -459,7 +485,7 @@ __device__ __forceinline__ void epilogue_rowmajor(const vmc_gemm_epilogue& e, in
 template <int BN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                          const __grid_constant__ CUtensorMap tmB, const Gemm2Args g) {
+                          const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const Gemm2Args g) {
   using C = Cfg2<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -494,6 +520,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.store_tma) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);   // leader's producer arrive (+ both CTAs' transaction bytes)
       mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
@@ -562,7 +589,13 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         tc_fence_after();
         VMC_DBG2(i, 0);
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        long long starved = 0;  // debug timeline: cycles this tile's issuer waited for operands that had not landed yet
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (g.dbg != nullptr && blockIdx.x == 0 && !mbar_test_wait(full_bar(stage), phase)) {
+            const long long w0 = clock64();
+            mbar_wait(full_bar(stage), phase);
+            starved += clock64() - w0;
+          }
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + stage * C::STAGE_BYTES;
@@ -581,6 +614,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         umma_commit_mc2(tfull_bar(acc));
         VMC_DBG2(i, 1);
+        if (g.dbg != nullptr && blockIdx.x == 0 && i < 32) g.dbg[i * 8 + 6] = starved;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -619,9 +653,9 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       } else if constexpr (MODE == 5) {
         epilogue_fast<3, HALF_N, false, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else if constexpr (MODE == 6 || MODE == 7) {
-        epilogue_rowmajor<MODE - 5, HALF_N, true>(e, g.M, g.N, row0, n_base, t_acc, stg, lane, ln_rstd, ln_shift);
+        epilogue_rowmajor<MODE - 5, HALF_N, true>(e, g.M, g.N, row0, n_base, t_acc, stg, lane, ln_rstd, ln_shift, g.store_tma ? &tmC : nullptr);
       } else if constexpr (MODE == 1 || MODE == 2) {
-        epilogue_rowmajor<MODE, HALF_N, false>(e, g.M, g.N, row0, n_base, t_acc, stg, lane, 1.f, 0.f);
+        epilogue_rowmajor<MODE, HALF_N, false>(e, g.M, g.N, row0, n_base, t_acc, stg, lane, 1.f, 0.f, g.store_tma ? &tmC : nullptr);
       } else if constexpr (MODE != 0) {
         epilogue_fast<MODE, HALF_N>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
       } else {
@@ -735,6 +769,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   }
 
+  if (g.store_tma && warp >= 2 && lane == 0) bulk_wait_read0();  // the staging tiles stay valid until the last store has read them
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {
@@ -776,6 +811,16 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
   g.K = K;
   g.a_mn = a_mn;
   g.b_mn = b_mn;
+  CUtensorMap tmC = tmA;  // placeholder when unused
+  g.store_tma = 0;
+  if ((MODE == 1 || MODE == 2 || MODE == 6 || MODE == 7) && (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0 && (epi->ldo % 8) == 0 &&
+      vmc_get_option(VMC_OPT_GEMM_IMPL) != 3) {  // option value 3: LDS + STG epilogue (A/B runs)
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)epi->ldo * 2};
+    const uint32_t box[2] = {32, 32};
+    VMC_TRY(vmc_encode_tmap_bf16_sw(&tmC, epi->out, 2, dims, strides, box, 64));
+    g.store_tma = 1;
+  }
   g.tiles_m = (M + 2 * BM - 1) / (2 * BM);
   g.tiles_n = (N + BN - 1) / BN;
   g.epi = *epi;
@@ -790,7 +835,7 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
     VmcProfScope prof(VMC_K_GEMM, stream, 2.0 * M * N * K,
                       2.0 * ((double)M * K + (double)N * K) + out_b + (epi->resid ? (epi->resid_bf16 ? 2.0 : 4.0) * M * N : 0.0) +
                           (epi->raw16_out ? 2.0 * M * N : 0.0));
-    gemm2_bf16_tcgen05_kernel<BN, MODE><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, g);
+    gemm2_bf16_tcgen05_kernel<BN, MODE><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, g);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();

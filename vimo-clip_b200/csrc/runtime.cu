@@ -89,6 +89,11 @@ static PFN_encodeTiled get_encode_fn() {
 
 int vmc_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return vmc_encode_tmap_bf16_sw(out, base, rank, dims, strides_bytes, box, 128);
+}
+
+int vmc_encode_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled fn = get_encode_fn();
   VMC_CHECK_ARG(fn != nullptr, VMC_ERR_DRIVER,
                 "cuTensorMapEncodeTiled not available from the CUDA driver");
@@ -109,7 +114,8 @@ int vmc_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uin
                   (unsigned long long)gstr[i]);
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
-                  gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VMC_CHECK_ARG(r == CUDA_SUCCESS, VMC_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d",
                 (int)r);
