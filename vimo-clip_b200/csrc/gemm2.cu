@@ -60,8 +60,15 @@ struct Cfg2 {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of B
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
-  static constexpr uint32_t STG_BYTES = 8 * 4096;
+  // Pipeline depth at BN = 256: 6, 5 and 4 stages measured the same on every tower shape (profiles/r02_gemm_stages.txt; the MMA
+  // issuer never waits for operands), so 4 it is, and the 64 KB go to the epilogue: 12 KB of staging per warp, which is
+  // what lets the bf16-residual epilogue keep a whole tile part of residual rows in flight (epilogue_rowmajor_resid).
+#ifndef VMC_G2_STAGES
+#define VMC_G2_STAGES 4
+#endif
+  static constexpr int STAGES = (BN == 256) ? VMC_G2_STAGES : 8;
+  static constexpr uint32_t STG_PER_WARP = (BN == 256) ? 12288 : 4096;
+  static constexpr uint32_t STG_BYTES = 8 * STG_PER_WARP;
   static constexpr uint32_t BAR_BYTES = 256;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -136,6 +143,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 __device__ __forceinline__ float act2(float v, int act) {
   switch (act) {
@@ -482,10 +490,80 @@ __device__ __forceinline__ void epilogue_rowmajor(const vmc_gemm_epilogue& e, in
   }
 }
 
+// bf16 residual stream (MODE 8) in the TMEM-native row layout, BN = 256.  A thread owns one accumulator row, so its row
+// statistics are two private registers (no shuffles) and nothing fp32 is staged.  The residual rows of the warp's whole tile
+// part arrive by FOUR TMA loads (32 x 32 bf16 boxes, 64-byte swizzle) issued by lane 0 before the warp waits for the
+// accumulator -- their latency overlaps that wait -- and complete on the warp's own mbarrier; each thread reads its row of a box
+// with four conflict-free LDS.128.  The result rows go out through a TMA store from one of two alternating 2 KB tiles.
+//   stg (12 KB per warp): [0, 8192) residual boxes of chunks 0..3; [8192, 12288) two output tiles
+// In-place use (out == resid) is safe: the warp's residual boxes have all landed before its first store is issued.
+template <int HALF_N>
+__device__ __forceinline__ void resid_rowmajor_prefetch(const CUtensorMap* tmr, uint32_t stg_addr, uint32_t rbar, int N, int row0,
+                                                        int n_base, int lane) {
+  if (lane == 0) {
+    int nb = 0;
+#pragma unroll
+    for (int c = 0; c < HALF_N / 32; ++c) nb += (n_base + c * 32 < N) ? 1 : 0;
+    mbar_arrive_expect_tx(rbar, (uint32_t)nb * 2048u);
+#pragma unroll
+    for (int c = 0; c < HALF_N / 32; ++c)
+      if (n_base + c * 32 < N) tma_load_2d(stg_addr + c * 2048u, tmr, rbar, n_base + c * 32, row0);
+  }
+}
+
+template <int HALF_N>
+__device__ __forceinline__ void epilogue_rowmajor_resid(const vmc_gemm_epilogue& e, int M, int N, int row0, int n_base, uint32_t t_acc,
+                                                        uint8_t* stg, uint32_t rbar, uint32_t rphase, int lane, const CUtensorMap* tmc) {
+  const int sw = (lane >> 1) & 3;
+  float psum = 0.f, psq = 0.f;
+  mbar_wait(rbar, rphase);
+#pragma unroll 1
+  for (int c = 0; c < HALF_N / 32; ++c) {
+    if (n_base + c * 32 >= N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_acc + uint32_t(c * 32), r);
+    uint4 rs[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) rs[ch] = *reinterpret_cast<const uint4*>(stg + c * 2048 + lane * 64 + ((ch ^ sw) << 4));
+    tmem_ld_wait();
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(rs);
+    uint32_t pk[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n_base + c * 32) + q);  // same address in every lane
+      const uint32_t w0 = rw[2 * q], w1 = rw[2 * q + 1];
+      const float v0 = __uint_as_float(r[4 * q]) + b4.x + __uint_as_float(w0 << 16);
+      const float v1 = __uint_as_float(r[4 * q + 1]) + b4.y + __uint_as_float(w0 & 0xFFFF0000u);
+      const float v2 = __uint_as_float(r[4 * q + 2]) + b4.z + __uint_as_float(w1 << 16);
+      const float v3 = __uint_as_float(r[4 * q + 3]) + b4.w + __uint_as_float(w1 & 0xFFFF0000u);
+      const uint32_t o0 = pack_bf16x2(v0, v1), o1 = pack_bf16x2(v2, v3);
+      pk[2 * q] = o0;
+      pk[2 * q + 1] = o1;
+      // statistics of the values the next GEMM will read
+      const float r0 = __uint_as_float(o0 << 16), r1 = __uint_as_float(o0 & 0xFFFF0000u);
+      const float r2 = __uint_as_float(o1 << 16), r3 = __uint_as_float(o1 & 0xFFFF0000u);
+      psum += (r0 + r1) + (r2 + r3);
+      psq += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
+    }
+    uint8_t* ot = stg + 8192 + (c & 1) * 2048;
+    if (lane == 0) bulk_wait_read1();  // the store issued two chunks ago has finished reading this tile
+    __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      *reinterpret_cast<uint4*>(ot + lane * 64 + ((ch ^ sw) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) tma_store_2d(tmc, smem_u32(ot), n_base + c * 32, row0);
+  }
+  if (row0 + lane < M && n_base < N)
+    reinterpret_cast<float2*>(e.stats_out)[(long long)(n_base / HALF_N) * e.stats_ld + row0 + lane] = make_float2(psum, psq);
+}
+
 template <int BN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                          const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const Gemm2Args g) {
+                          const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                          const __grid_constant__ CUtensorMap tmR, const Gemm2Args g) {
   using C = Cfg2<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -498,6 +576,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  auto resid_bar = [&](int ew) { return bar_base + 8u * (2 * STAGES + 5 + ew); };  // one per epilogue warp (MODE 8, BN = 256)
   volatile uint32_t* tmem_ptr_generic =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw_addr));
 
@@ -521,6 +600,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (g.store_tma) tma_prefetch_desc(&tmC);
+    if (g.store_tma && MODE == 8) tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);   // leader's producer arrive (+ both CTAs' transaction bytes)
       mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
@@ -529,6 +609,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_init(tfull_bar(a), 1);    // multicast tcgen05.commit
       mbar_init(tempty_bar(a), 16);  // 8 epilogue warps x 2 CTAs (used in the leader only)
     }
+    for (int w = 0; w < 8; ++w) mbar_init(resid_bar(w), 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -627,7 +708,7 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int half = ew >> 2;
     constexpr int HALF_N = BN / 2;
     const vmc_gemm_epilogue& e = g.epi;
-    uint8_t* stg = smem_raw + (stg_base - raw_addr) + ew * 4096;
+    uint8_t* stg = smem_raw + (stg_base - raw_addr) + ew * C::STG_PER_WARP;
     const int lr = lane >> 3;
     const int lc = lane & 7;
     const bool has_res = e.resid != nullptr;
@@ -640,15 +721,21 @@ gemm2_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int n_base = n_blk * BN + half * HALF_N;
       float ln_rstd = 1.f, ln_shift = 0.f;
       if constexpr (MODE == 6 || MODE == 7) ln_row_stats(e, row0 + lane, g.M, g.K, ln_rstd, ln_shift);  // before the wait
-      uint2 rpre[MODE == 8 ? HALF_N / 32 : 1][8];
-      if constexpr (MODE == 8) prefetch_resid16<HALF_N>(e, g.M, g.N, row0, n_base, lane, rpre);
+      constexpr bool RESID_TMA = MODE == 8 && BN == 256;  // row-layout epilogue, residual by TMA (needs the 12 KB staging)
+      uint2 rpre[(MODE == 8 && !RESID_TMA) ? HALF_N / 32 : 1][8];
+      if constexpr (RESID_TMA) {
+        if (g.store_tma) resid_rowmajor_prefetch<HALF_N>(&tmR, smem_u32(stg), resid_bar(ew), g.N, row0, n_base, lane);
+      }
+      if constexpr (MODE == 8 && !RESID_TMA) prefetch_resid16<HALF_N>(e, g.M, g.N, row0, n_base, lane, rpre);
       if (ew == 0 && lane == 0) VMC_DBG2(i, 2);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (ew == 0 && lane == 0) VMC_DBG2(i, 3);
       const uint32_t t_acc =
           tmem_base + uint32_t(acc * BN + half * HALF_N) + (uint32_t(quarter * 32) << 16);
-      if constexpr (MODE == 8) {
+      if constexpr (RESID_TMA) {
+        epilogue_rowmajor_resid<HALF_N>(e, g.M, g.N, row0, n_base, t_acc, stg, resid_bar(ew), (uint32_t)i & 1u, lane, &tmC);
+      } else if constexpr (MODE == 8) {
         epilogue_fast<3, HALF_N, false, true, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane, 1.f, 0.f, rpre);
       } else if constexpr (MODE == 5) {
         epilogue_fast<3, HALF_N, false, true>(e, g.M, g.N, g.K, row0, n_base, t_acc, stg, lane);
@@ -811,7 +898,7 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
   g.K = K;
   g.a_mn = a_mn;
   g.b_mn = b_mn;
-  CUtensorMap tmC = tmA;  // placeholder when unused
+  CUtensorMap tmC = tmA, tmR = tmA;  // placeholders when unused
   g.store_tma = 0;
   if ((MODE == 1 || MODE == 2 || MODE == 6 || MODE == 7) && (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0 && (epi->ldo % 8) == 0 &&
       vmc_get_option(VMC_OPT_GEMM_IMPL) != 3) {  // option value 3: LDS + STG epilogue (A/B runs)
@@ -819,6 +906,14 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
     const uint64_t strides[1] = {(uint64_t)epi->ldo * 2};
     const uint32_t box[2] = {32, 32};
     VMC_TRY(vmc_encode_tmap_bf16_sw(&tmC, epi->out, 2, dims, strides, box, 64));
+    g.store_tma = 1;
+  }
+  if (MODE == 8 && BN == 256) {  // row-layout bf16-residual epilogue: residual in, result out by TMA
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    const uint32_t box[2] = {32, 32};
+    const uint64_t so[1] = {(uint64_t)epi->ldo * 2}, sr[1] = {(uint64_t)epi->ldr * 2};
+    VMC_TRY(vmc_encode_tmap_bf16_sw(&tmC, epi->out, 2, dims, so, box, 64));
+    VMC_TRY(vmc_encode_tmap_bf16_sw(&tmR, epi->resid, 2, dims, sr, box, 64));
     g.store_tma = 1;
   }
   g.tiles_m = (M + 2 * BM - 1) / (2 * BM);
@@ -835,7 +930,7 @@ int launch_gemm2(const void* A, long long lda, const void* W, long long ldw, int
     VmcProfScope prof(VMC_K_GEMM, stream, 2.0 * M * N * K,
                       2.0 * ((double)M * K + (double)N * K) + out_b + (epi->resid ? (epi->resid_bf16 ? 2.0 : 4.0) * M * N : 0.0) +
                           (epi->raw16_out ? 2.0 * M * N : 0.0));
-    gemm2_bf16_tcgen05_kernel<BN, MODE><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, g);
+    gemm2_bf16_tcgen05_kernel<BN, MODE><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, g);
   }
   VMC_LAUNCH_CHECK();
   vmc_count_launch();
@@ -874,7 +969,12 @@ int vmc_gemm2_dispatch(const void* A, long long lda, const void* W, long long ld
                   VMC_ERR_ARG,
                   "vmc_gemm_bf16: the bf16 residual-stream epilogue needs bias, alpha 1, no activation, N a multiple of the "
                   "column slice (%d), stats_ld >= M and 8-byte aligned rows", big ? 128 : 64);
-    if (big) return launch_gemm2<256, 8>(A, lda, W, ldw, M, N, K, epi, stream, a_mn, b_mn);
+    if (big) {
+      VMC_CHECK_ARG((epi->ldr % 8) == 0 && (epi->ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(epi->resid) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0,
+                    VMC_ERR_ALIGN, "vmc_gemm_bf16: the bf16 residual-stream epilogue moves its rows by TMA: 16-byte aligned resid / out rows");
+      return launch_gemm2<256, 8>(A, lda, W, ldw, M, N, K, epi, stream, a_mn, b_mn);
+    }
     return launch_gemm2<128, 8>(A, lda, W, ldw, M, N, K, epi, stream, a_mn, b_mn);
   }
   if (epi->raw16_out != nullptr || epi->stats_out != nullptr) {
