@@ -1,11 +1,12 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider -x > gpurun_out/r02_pytest_final4.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest_final4.log
-tail -n 4 gpurun_out/r02_pytest_final4.log
-python bench.py --steps 5 --warmup 3 --no-configs --no-strong > gpurun_out/r02_bench10.json 2> gpurun_out/r02_bench10.err; echo "bench rc=$?"
+python bench.py --steps 10 --warmup 3 --no-configs --no-ab --strong-clips 32 > gpurun_out/r02_bench_strong32.json 2> gpurun_out/r02_bench_strong32.err; echo "rc=$?"
+python bench.py --steps 10 --warmup 3 --no-configs --no-ab --no-strong --clips 32 > gpurun_out/r02_bench_clips32.json 2> gpurun_out/r02_bench_clips32.err; echo "rc=$?"
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r02_bench10.json').read().strip().split('\n')[-1])
-print(d['ms_per_step'], d['value'], d['e2e']['value'], d['clocks'], d.get('ab_same_process'))
-print({k:round(v['ms'],2) for k,v in d['kernel_classes'].items()})
+d=json.loads(open('gpurun_out/r02_bench_strong32.json').read().strip().split('\n')[-1])
+print('strong32', d.get('strong'))
+d=json.loads(open('gpurun_out/r02_bench_clips32.json').read().strip().split('\n')[-1])
+print('clips32', d['ms_per_step'], d['value'], d['gpu_launches'], d['clocks'], d['e2e'])
+print({k:(round(v['ms'],2), v['launches']) for k,v in d['kernel_classes'].items()})
 PY
