@@ -30,9 +30,11 @@ const char* vmc_last_error(void);
 int vmc_abi_version(void);
 int vmc_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Implementation selectors (0 = default).  VMC_OPT_GEMM_IMPL: 0/2 = CTA-pair cta_group::2 kernel, 1 = single-CTA kernel
- * (kept as an independent cross-check for the tests).  VMC_OPT_ATTN_IMPL: 0 = by sequence length (7 for L <= 64, 5 for
- * 129..224, 6 for 225..257, else 2); 5 = persistent, split Q/K and V rings, event-driven MMA issuer, epilogue warps, row
- * sums from the tensor core; 6 = v5 on the patch tokens + the CLS token on mma.sync warps; 7 = two items per query tile;
+ * (kept as an independent cross-check for the tests), 3 = the CTA-pair kernel with the LDS + STG form of the bf16 epilogues
+ * instead of the TMA store (A/B runs).  VMC_OPT_ATTN_IMPL: 0 = by sequence length (7 for L <= 64, 5 for
+ * 129..224, 6 for 225..257, else 2); 5 = persistent, split Q/K and V rings, one MMA issuer per query tile, score MMA in two key
+ * ranges (the first issued one item ahead), epilogue warps, row sums from the tensor core; 6 = v5 (round-1 pipeline) on the
+ * patch tokens + the CLS token on mma.sync warps; 7 = two items per query tile;
  * 8 = warp-level mma.sync kernel for L <= 64; 2 = one CTA per (frame, head) with P in TMEM (any L <= 272). */
 /* vmc_set_option sets PROCESS-WIDE defaults (relaxed atomics; meant for tests, A/B runs and tools).  The per-model
  * selectors of vmc_vit_model take precedence, so two models in one process can run different variants concurrently. */
@@ -41,7 +43,7 @@ enum { VMC_OPT_ATTN_BWD_IMPL = 4 /* ViT attention backward, L <= 64: 0 = warp-le
                                      all tokens, but query, out_proj, ln_2 and the MLP on the F CLS rows only (default; the
                                      embeddings are the same numbers); 2 = the full last block */,
        VMC_OPT_ATTN_PREFETCH = 6 /* ViT attention: experiments, L <= 64 kernels: 1..8 = L2 prefetch distance of the v7 TMA producer in CTA iterations (measured slower; 0 = off, the default); 81 = impl 8 reads a head-major [F, heads, 3, L, 64] buffer (timing what-if only) */,
-       VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py), 0 = off */,
+       VMC_OPT_DEBUG_PTR = 7 /* device pointer of a clock64 timeline buffer (tools/attn_timeline.py with a WHATIF build, tools/gemm_timeline.py), 0 = off */,
        VMC_OPT_GEMM_IMPL = 0, VMC_OPT_ATTN_IMPL = 1, VMC_OPT_PROLOGUE_IMPL = 2 /* patch-matrix prologue: 0 = gather kernel (output-ordered, default), 1 = direct (input-ordered), 2 = band (smem-staged), 4 = gather with 16 pixels per item (uint8 sources; bit-identical, measured slower: experiment) */,
        VMC_OPT_LN_FUSE = 3 /* ViT tower variant (vmc_vit_model.ln_mode): 0 / 6 = bf16 residual stream, ln_1 and ln_2 FOLDED into
                               the qkv / c_fc GEMMs (default); 3 = fp32 residual stream + bf16 copy, both folded; 5 = fp32
