@@ -341,6 +341,49 @@ def test_layernorm(cuda_device, d):
     assert torch.allclose(stats[:, 1], (zr * zr).sum(1), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K,col0,pad", [(1000, 768, 256, 0, 0), (1000, 768, 256, 64, 200), (333, 2304, 128, 8, 8), (4097, 320, 192, 0, 8),
+                                            (70, 96, 64, 32, 40)])
+def test_gemm_tma_epilogues_strided_views(cuda_device, M, N, K, col0, pad):
+    """The bf16 epilogues move their rows by TMA (store; load + store for the bf16 residual stream): outputs and residuals that
+    are column slices of wider buffers (row stride > N, base offset), ragged last row tiles, out-of-place residual GEMMs with
+    different row strides, the untouched columns around the slice, and the LDS + STG fallback for strides TMA cannot take."""
+    gen = torch.Generator(device="cuda").manual_seed(M + N + col0)
+    a = torch.randn(M, K, device=cuda_device, generator=gen).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=cuda_device, generator=gen) * K**-0.5).to(torch.bfloat16)
+    b = torch.randn(N, device=cuda_device, generator=gen)
+    ref = a.float() @ w.float().t() + b
+    tol = 2e-2 * max(1.0, ref.abs().max().item())
+    for act in (ops.ACT_NONE, ops.ACT_QUICKGELU):
+        wide = torch.full((M, col0 + N + pad), 7.0, device=cuda_device, dtype=torch.bfloat16)
+        out = wide[:, col0:col0 + N]
+        ops.gemm(a, w, bias=b, act=act, out=out)
+        want = ref if act == ops.ACT_NONE else ref * torch.sigmoid(1.702 * ref)
+        assert (out.float() - want).abs().max().item() <= tol
+        assert torch.all(wide[:, :col0] == 7.0) and torch.all(wide[:, col0 + N:] == 7.0)  # nothing written outside the slice
+        ops.set_option(vmc._lib.OPT_GEMM_IMPL, 3)  # LDS + STG form of the same epilogue: same numbers
+        try:
+            chk = ops.gemm(a, w, bias=b, act=act)
+        finally:
+            ops.set_option(vmc._lib.OPT_GEMM_IMPL, 0)
+        assert torch.equal(chk, out.contiguous())
+    with pytest.raises(vmc._lib.VmcError):  # the C-ABI contract: 16-byte aligned output rows
+        ops.gemm(a, w, bias=b, out=torch.empty(M, N + 4, device=cuda_device, dtype=torch.bfloat16)[:, :N])
+    if N % 128 == 0:
+        # bf16 residual stream, out of place, residual and output with different row strides and offsets
+        x16 = (torch.randn(M, N + 24, device=cuda_device, generator=gen) * 2).to(torch.bfloat16)
+        resid = x16[:, 16:16 + N]
+        wide = torch.full((M, col0 + N + pad), 7.0, device=cuda_device, dtype=torch.bfloat16)
+        out = wide[:, col0:col0 + N]
+        stats = torch.zeros(ops.gemm_stats_parts(M, N), M, 2, device=cuda_device)
+        ops.gemm(a, w, bias=b, resid=resid, out=out, emit_stats=(None, stats))
+        want = ref + resid.float()
+        assert (out.float() - want).abs().max().item() <= 2.0 ** -7 * max(1.0, want.abs().max().item())
+        assert torch.all(wide[:, :col0] == 7.0) and torch.all(wide[:, col0 + N:] == 7.0)
+        st, xr = stats.sum(0), out.float()
+        assert torch.allclose(st[:, 0], xr.sum(1), rtol=1e-5, atol=1e-2)
+        assert torch.allclose(st[:, 1], (xr * xr).sum(1), rtol=1e-5, atol=1e-2)
+
+
 @pytest.mark.parametrize("M,d,N,act", [(394, 768, 2304, 0), (50000, 768, 3072, 1), (40000, 1024, 3072, 0), (700, 512, 1536, 1)])
 def test_gemm_layernorm_fold(cuda_device, M, d, N, act):
     """LayerNorm folded into the consuming GEMM: a producer GEMM (bias + fp32 residual) emits bf16 rows + partial row
