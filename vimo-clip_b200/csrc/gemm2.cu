@@ -14,9 +14,13 @@
 //               tcgen05.mma.cta_group::2 (UMMA 256 x BN x 16), commits multicast to both CTAs
 //   warps 2..9  epilogue in both CTAs on their own 128 TMEM lanes; accumulator-free signal goes to
 //               the leader's tempty barrier (remote mbarrier arrive)
-// Epilogue: tcgen05.ld gives a thread one accumulator ROW; the chunk is transposed through a private
-// XOR-swizzled 4 KB shared-memory tile so global loads (residual, bias) and stores are issued with 8
-// lanes per 128-byte row segment (4 full lines per warp instruction).
+// Epilogue: tcgen05.ld gives a thread one accumulator ROW.  The tower's modes (bf16 output with bias [+ QuickGELU]
+// [+ folded LayerNorm]; bf16 residual stream + row statistics) do all arithmetic in that row layout and move whole
+// 32 x 32 bf16 boxes between a private XOR-swizzled staging tile and global memory by TMA (epilogue_rowmajor,
+// epilogue_rowmajor_resid); the fp32-residual and generic modes transpose the fp32 chunk through the staging tile so
+// that global loads (residual, bias) and stores are issued with 8 lanes per 128-byte row segment (epilogue_fast).
+// Pipeline: 4 stages x 32 KB at BN = 256 (the MMA issuer is never short of operands: tools/gemm_timeline.py), 12 KB of
+// epilogue staging per warp.
 #include <type_traits>
 
 #include "common.cuh"
