@@ -118,6 +118,7 @@ case("c_fc LN-fold+QuickGELU", x, 4 * d, d, fold=True, act=ops.ACT_QUICKGELU)
 case("c_fc LN-fold (no act)", x, 4 * d, d, fold=True)
 case("c_fc plain+QuickGELU", x, 4 * d, d, act=ops.ACT_QUICKGELU)
 case("c_fc plain (no act)", x, 4 * d, d)
+case("out_proj shape, plain bias", x, d, d)
 case("out_proj bf16-resid+stats", x, d, d, resid=xs, out=xs, emit_stats=(None, stats))
 case("c_proj bf16-resid+stats", h, d, 4 * d, resid=xs, out=xs, emit_stats=(None, stats))
 if os.environ.get("GS_CUBLAS", "0") == "1":

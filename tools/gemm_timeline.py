@@ -59,5 +59,6 @@ case("qkv LN-fold", x, 3 * d, d, fold=True)
 case("qkv plain", x, 3 * d, d)
 case("c_fc LN-fold+QuickGELU", x, 4 * d, d, fold=True, act=ops.ACT_QUICKGELU)
 case("c_fc plain (no act)", x, 4 * d, d)
+case("out_proj shape, plain bias epilogue", x, d, d)
 case("out_proj bf16-resid+stats", x, d, d, resid=xs, out=xs, emit_stats=(None, stats))
 case("c_proj bf16-resid+stats", h, d, 4 * d, resid=xs, out=xs, emit_stats=(None, stats))
