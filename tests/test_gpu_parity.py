@@ -442,6 +442,20 @@ def test_attention_vit(cuda_device, L, heads, F_, impl):
     assert err < 2e-2, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("L,heads,F_", [(197, 12, 9), (50, 12, 33), (257, 16, 5), (1, 2, 3), (17, 1, 2), (8192, 1, 1)])
+def test_attention_cls_row(cuda_device, L, heads, F_):
+    """The last block's attention on the CLS query only (vmc_attention_cls) against fp32 softmax attention of that row."""
+    gen = torch.Generator(device="cuda").manual_seed(L + heads)
+    d = heads * 64
+    q = (torch.randn(F_, d, device=cuda_device, generator=gen) * 2).to(torch.bfloat16)
+    kv = (torch.randn(F_ * L, 2 * d, device=cuda_device, generator=gen) * 1.5).to(torch.bfloat16)
+    got = ops.attention_cls(q, kv, F_, L, heads).float().view(F_, heads, 64)
+    k, v = kv.float().view(F_, L, 2, heads, 64).unbind(2)
+    s = torch.einsum("fhd,fmhd->fhm", q.float().view(F_, heads, 64), k) / 8.0
+    ref = torch.einsum("fhm,fmhd->fhd", torch.softmax(s, -1), v)
+    assert (got - ref).abs().max().item() < 2e-2
+
+
 @pytest.mark.parametrize("impl,L", [(5, 197), (5, 224), (5, 160), (2, 197), (6, 257), (6, 197), (7, 50), (8, 50)])
 def test_attention_vit_peaky_and_shifted_scores(cuda_device, impl, L):
     """Large score spread and a large common offset: the single-pass softmax (stabiliser = max of the

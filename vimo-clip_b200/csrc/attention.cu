@@ -1559,20 +1559,43 @@ attention_masked_kernel(const float* __restrict__ q, long long ldq, const float*
 __global__ void __launch_bounds__(128)
 attention_cls_kernel(const __nv_bfloat16* __restrict__ qcls, const __nv_bfloat16* __restrict__ kv,
                      __nv_bfloat16* __restrict__ out, int L, int heads) {
+  // One CTA per (frame, head); the CLS query against all L keys.  [r2] 16-byte loads: 8 lanes cover one 128-byte head row,
+  // so a warp instruction fetches FOUR key (or value) rows and a score costs 3 shuffles instead of 5 -- the first version read
+  // one row per warp instruction (4 bytes per lane) and ran at a third of the HBM rate (ncu launch list: 2.07 TB/s).
   extern __shared__ float s_sc[];  // [L] scores -> probabilities
   __shared__ float s_red[4];
-  __shared__ float s_o[2][HD];
+  __shared__ float s_o[16][HD];
   const int f = blockIdx.y, h = blockIdx.x;
   const int d = heads * HD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __nv_bfloat162 q2 = reinterpret_cast<const __nv_bfloat162*>(qcls + (size_t)f * d + h * HD)[lane];
-  const float qx = __low2float(q2), qy = __high2float(q2);
-  const __nv_bfloat16* kbase = kv + (size_t)f * L * 2 * d + h * HD;
+  const int sub = tid & 7;   // 16-byte chunk (8 head dims) of a row
+  const int grp = tid >> 3;  // row within a 16-row step
+  float q[8];
+  {
+    const uint4 qv = *reinterpret_cast<const uint4*>(qcls + (size_t)f * d + h * HD + sub * 8);
+    const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      q[2 * i] = __uint_as_float(w[i] << 16);
+      q[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  const __nv_bfloat16* kbase = kv + (size_t)f * L * 2 * d + h * HD + sub * 8;
   const __nv_bfloat16* vbase = kbase + d;
-  for (int j = warp; j < L; j += 4) {
-    const __nv_bfloat162 k2 = reinterpret_cast<const __nv_bfloat162*>(kbase + (size_t)j * 2 * d)[lane];
-    const float s = warp_sum(qx * __low2float(k2) + qy * __high2float(k2));
-    if (lane == 0) s_sc[j] = s * 0.125f;
+#pragma unroll 4
+  for (int j0 = 0; j0 < L; j0 += 16) {
+    const int j = j0 + grp;
+    float s = 0.f;
+    if (j < L) {
+      const uint4 kv4 = __ldg(reinterpret_cast<const uint4*>(kbase + (size_t)j * 2 * d));
+      const uint32_t w[4] = {kv4.x, kv4.y, kv4.z, kv4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s = fmaf(q[2 * i], __uint_as_float(w[i] << 16), fmaf(q[2 * i + 1], __uint_as_float(w[i] & 0xFFFF0000u), s));
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0 && j < L) s_sc[j] = s * 0.125f;
   }
   __syncthreads();
   float mx = -INFINITY;
@@ -1592,13 +1615,30 @@ attention_cls_kernel(const __nv_bfloat16* __restrict__ qcls, const __nv_bfloat16
   if (lane == 0) s_red[warp] = sum;
   __syncthreads();
   const float inv = 1.0f / ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3]));
-  // O[dim] = sum_j p_j v_j[dim]: 64 dims x 2 key halves
-  const int dim = tid & 63, half = tid >> 6;
-  float acc = 0.f;
-  for (int j = half; j < L; j += 2) acc = fmaf(s_sc[j], __bfloat162float(vbase[(size_t)j * 2 * d + dim]), acc);
-  s_o[half][dim] = acc;
+  // O[dim] = sum_j p_j v_j[dim]: 16 row groups x 8 chunks of 8 dims
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+  for (int j = grp; j < L; j += 16) {
+    const float p = s_sc[j];
+    const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(vbase + (size_t)j * 2 * d));
+    const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fmaf(p, __uint_as_float(w[i] << 16), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(p, __uint_as_float(w[i] & 0xFFFF0000u), acc[2 * i + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_o[grp][sub * 8 + i] = acc[i];
   __syncthreads();
-  if (tid < HD) out[(size_t)f * d + h * HD + tid] = __float2bfloat16_rn((s_o[0][tid] + s_o[1][tid]) * inv);
+  if (tid < HD) {
+    float o = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) o += s_o[g][tid];
+    out[(size_t)f * d + h * HD + tid] = __float2bfloat16_rn(o * inv);
+  }
 }
 
 uint32_t pow2_at_least(uint32_t v) {
@@ -1799,6 +1839,8 @@ int vmc_attention_vit_impl(const void* qkv, void* out, int F, int L, int heads, 
 int vmc_attention_cls(const void* q_cls, const void* kv, void* out, int F, int L, int heads, void* stream) {
   VMC_CHECK_ARG(q_cls && kv && out, VMC_ERR_ARG, "vmc_attention_cls: null pointer");
   VMC_CHECK_ARG(F > 0 && F <= 65535 && heads > 0 && L > 0 && L <= 8192, VMC_ERR_SHAPE, "vmc_attention_cls: bad shape F=%d L=%d", F, L);
+  VMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(q_cls) | reinterpret_cast<uintptr_t>(kv)) & 15) == 0, VMC_ERR_ALIGN,
+                "vmc_attention_cls: q_cls and kv must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   {
     VmcProfScope prof(VMC_K_ATTN_VIT, st, 4.0 * F * heads * (double)L * HD, 4.0 * F * (double)L * heads * HD);

@@ -254,6 +254,20 @@ def attention_vit(qkv: torch.Tensor, F_: int, L: int, heads: int, impl: int = 5)
     return out
 
 
+def attention_cls(q_cls: torch.Tensor, kv: torch.Tensor, F_: int, L: int, heads: int) -> torch.Tensor:
+    """q_cls bf16 [F, heads*64] (the CLS query rows), kv bf16 [F*L, 2*heads*64] = [k | v] of every token ->
+    bf16 [F, heads*64]: softmax(q k^T / 8) v of the CLS row only (last block of the tower)."""
+    _need_cuda(q_cls, kv)
+    d = heads * 64
+    if q_cls.dtype != torch.bfloat16 or kv.dtype != torch.bfloat16 or tuple(q_cls.shape) != (F_, d) or tuple(kv.shape) != (F_ * L, 2 * d) \
+            or not q_cls.is_contiguous() or not kv.is_contiguous():
+        raise ValueError("attention_cls: q_cls must be contiguous bf16 [F, d] and kv contiguous bf16 [F*L, 2*d]")
+    out = torch.empty((F_, d), dtype=torch.bfloat16, device=q_cls.device)
+    with torch.cuda.device(q_cls.device):
+        _lib.check(_lib.lib().vmc_attention_cls(_p(q_cls), _p(kv), _p(out), F_, L, heads, _stream()), "vmc_attention_cls")
+    return out
+
+
 def attention_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_valid, B: int, Tq: int, Tk: int, heads: int,
                      out_dtype=torch.bfloat16, prob_mask=None) -> torch.Tensor:
     """q [B*Tq, *], k/v [B*Tk, *] fp32 views (row-major, heads*64 columns) -> bf16 or fp32 [B*Tq, heads*64].
