@@ -163,6 +163,12 @@ __device__ __forceinline__ float act2(float v, int act) {
 }
 
 // x * sigmoid(1.702 x) with sigmoid(z) = 0.5 + 0.5 tanh(z / 2): one MUFU per element instead of two
+// the same from h = x / 2: h + h tanh(1.702 h)
+__device__ __forceinline__ float quickgelu_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(1.702f * h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float quickgelu_fast(float x) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
@@ -428,10 +434,17 @@ __device__ __forceinline__ void epilogue_rowmajor(const vmc_gemm_epilogue& e, in
                                                   uint8_t* stg, int lane, float rstd, float shift, const CUtensorMap* tmc) {
   float* sb = reinterpret_cast<float*>(stg + 2048);
   float* scs = sb + 128;
+  // QuickGELU(v) = v sigmoid(1.702 v) = h + h tanh(1.702 h) with h = v / 2: the halving is folded into the per-row scalars and
+  // the shared bias copy (exact: powers of two), which leaves FMUL + MUFU.TANH + FFMA per element
+  constexpr float HS = MODE == 2 ? 0.5f : 1.0f;
   if (4 * lane < HALF_N && n_base + 4 * lane < N) {
-    *reinterpret_cast<float4*>(sb + 4 * lane) = __ldg(reinterpret_cast<const float4*>(e.bias + n_base) + lane);
+    float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n_base) + lane);
+    bv.x *= HS, bv.y *= HS, bv.z *= HS, bv.w *= HS;
+    *reinterpret_cast<float4*>(sb + 4 * lane) = bv;
     if constexpr (LNF) *reinterpret_cast<float4*>(scs + 4 * lane) = __ldg(reinterpret_cast<const float4*>(e.colsum + n_base) + lane);
   }
+  rstd *= HS;
+  shift *= HS;
   __syncwarp();
   const int sw = (lane >> 1) & 3;           // write side: this thread's row = lane
   const int rrow = lane >> 2, rch = lane & 3;  // read side: rows 8 i + rrow, 16-byte chunk rch
@@ -454,6 +467,11 @@ __device__ __forceinline__ void epilogue_rowmajor(const vmc_gemm_epilogue& e, in
         v.y = fmaf(v.y, rstd, fmaf(shift, cs4.y, b4.y));
         v.z = fmaf(v.z, rstd, fmaf(shift, cs4.z, b4.z));
         v.w = fmaf(v.w, rstd, fmaf(shift, cs4.w, b4.w));
+      } else if constexpr (MODE == 2) {
+        v.x = fmaf(v.x, HS, b4.x);
+        v.y = fmaf(v.y, HS, b4.y);
+        v.z = fmaf(v.z, HS, b4.z);
+        v.w = fmaf(v.w, HS, b4.w);
       } else {
         v.x += b4.x;
         v.y += b4.y;
@@ -461,10 +479,10 @@ __device__ __forceinline__ void epilogue_rowmajor(const vmc_gemm_epilogue& e, in
         v.w += b4.w;
       }
       if constexpr (MODE == 2) {
-        v.x = quickgelu_fast(v.x);
-        v.y = quickgelu_fast(v.y);
-        v.z = quickgelu_fast(v.z);
-        v.w = quickgelu_fast(v.w);
+        v.x = quickgelu_half(v.x);
+        v.y = quickgelu_half(v.y);
+        v.z = quickgelu_half(v.z);
+        v.w = quickgelu_half(v.w);
       }
       pk[2 * q] = pack_bf16x2(v.x, v.y);
       pk[2 * q + 1] = pack_bf16x2(v.z, v.w);
