@@ -136,7 +136,9 @@ typedef struct vmc_gemm_epilogue {
   /* bf16 RESIDUAL STREAM (ViT tower default): resid_bf16 = 1 means `resid` points to bf16 rows.  With out_bf16 = 1, bias,
    * no activation and stats_out set, the epilogue writes out = bf16(acc + bias + resid) -- the residual stream AND the A
    * operand of the next (LayerNorm-folded) GEMM in one buffer, may alias resid -- plus the per-row partial statistics of
-   * the ROUNDED values (raw16_out must be NULL).  With an fp32 out it is only a dtype switch of the residual read. */
+   * the ROUNDED values (raw16_out must be NULL); for N >= 256 the residual and result rows move by TMA: resid / out 16-byte
+   * aligned with ldr, ldo multiples of 8 elements.  With an fp32 out it is only a dtype switch of the residual read.
+   * (All bf16 outputs: out 16-byte aligned, ldo % 8 == 0.) */
   int resid_bf16;
 } vmc_gemm_epilogue;
 /* number of column slices (partials per row) a producer GEMM of this shape writes to stats_out */
