@@ -223,10 +223,11 @@ def gemm_stats_parts(M: int, N: int) -> int:
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5, want32: bool = False,
               want16: bool = True, out32: torch.Tensor | None = None, split16: bool = False, stats: torch.Tensor | None = None,
-              stats_rounded: bool = False):
+              stats_rounded: bool = False, cls_row: torch.Tensor | None = None, cls_every: int = 0):
     """x fp32 or bf16 [rows, d] -> (y32 | None, y16 | None).  split16: y16 is the [rows, 3d] split operand [hi|lo|hi].
-    stats fp32 [rows, 2]: (sum, sum of squares) of the output row (of its bf16 rounding when stats_rounded)."""
-    _need_cuda(x, gamma, beta, out32, stats)
+    stats fp32 [rows, 2]: (sum, sum of squares) of the output row (of its bf16 rounding when stats_rounded).
+    cls_row fp32 [d] with cls_every > 0: rows r % cls_every == 0 take their input from cls_row (the CLS token under ln_pre)."""
+    _need_cuda(x, gamma, beta, out32, stats, cls_row)
     if x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("layernorm input must be fp32 or bf16 [rows, d] row-major")
     rows, d = x.shape
@@ -236,7 +237,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
         _lib.check(
             _lib.lib().vmc_layernorm_ex(_p(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), _p(gamma), _p(beta), eps, _p(y32),
                                         0 if y32 is None else y32.stride(0), _p(y16), 0 if y16 is None else y16.stride(0),
-                                        1 if split16 else 0, rows, d, None, 0, _p(stats), 1 if stats_rounded else 0, _stream()),
+                                        1 if split16 else 0, rows, d, _p(cls_row), cls_every, _p(stats), 1 if stats_rounded else 0, _stream()),
             "vmc_layernorm",
         )
     return y32, y16
