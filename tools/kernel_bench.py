@@ -74,7 +74,7 @@ if "attn" in which:
         d = heads * 64
         Fa = F_ if L != 257 else F_ // 2
         qkv = torch.randn(Fa * L, 3 * d, device=dev, generator=gen).to(torch.bfloat16)
-        for impl in [int(x) for x in os.environ.get("KB_ATTN_IMPLS", "5,9,2").split(",")]:
+        for impl in [int(x) for x in os.environ.get("KB_ATTN_IMPLS", "5,2").split(",")]:
             ms = timeit(lambda: ops.attention_vit(qkv, Fa, L, heads, impl=impl))
             fl = 4.0 * Fa * heads * L * L * 64
             print(f"attn impl={impl} L={L} heads={heads} F={Fa}: {ms:.3f} ms  {fl / ms / 1e9:.0f} TFLOP/s  "
