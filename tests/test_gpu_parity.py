@@ -384,6 +384,43 @@ def test_gemm_tma_epilogues_strided_views(cuda_device, M, N, K, col0, pad):
         assert torch.allclose(st[:, 1], (xr * xr).sum(1), rtol=1e-5, atol=1e-2)
 
 
+def test_gemm_tma_epilogues_deterministic_at_scale(cuda_device):
+    """Many tiles per CTA pair (the staging tiles and residual boxes are reused every 32-column chunk): the TMA epilogues give
+    the same bits run to run, the same bits as the LDS + STG form, and the in-place residual GEMM the same as out of place."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    M, d = 150001, 768
+    x = torch.randn(M, d, device=cuda_device, generator=gen).to(torch.bfloat16)
+    stats = torch.zeros(ops.gemm_stats_parts(M, d), M, 2, device=cuda_device)
+    xf = x.float()
+    st_in = torch.stack([xf.sum(1), (xf * xf).sum(1)], 1)[None].contiguous()
+    del xf
+    for N, act in ((2304, ops.ACT_NONE), (3072, ops.ACT_QUICKGELU)):
+        w = (torch.randn(N, d, device=cuda_device, generator=gen) * d**-0.5).to(torch.bfloat16)
+        b = torch.randn(N, device=cuda_device, generator=gen)
+        cs = w.float().sum(1)
+        first = ops.gemm(x, w, bias=b, act=act, fold=(st_in, cs, 1e-5))
+        for _ in range(2):
+            assert torch.equal(first, ops.gemm(x, w, bias=b, act=act, fold=(st_in, cs, 1e-5)))
+        ops.set_option(vmc._lib.OPT_GEMM_IMPL, 3)
+        try:
+            assert torch.equal(first, ops.gemm(x, w, bias=b, act=act, fold=(st_in, cs, 1e-5)))
+        finally:
+            ops.set_option(vmc._lib.OPT_GEMM_IMPL, 0)
+        del first
+    for K in (768, 3072):
+        a = torch.randn(M, K, device=cuda_device, generator=gen).to(torch.bfloat16)
+        w = (torch.randn(d, K, device=cuda_device, generator=gen) * K**-0.5).to(torch.bfloat16)
+        b = torch.randn(d, device=cuda_device, generator=gen)
+        out = torch.empty_like(x)
+        ops.gemm(a, w, bias=b, resid=x, out=out, emit_stats=(None, stats))
+        st0 = stats.clone()
+        for _ in range(2):
+            xs = x.clone()
+            ops.gemm(a, w, bias=b, resid=xs, out=xs, emit_stats=(None, stats))  # in place
+            assert torch.equal(xs, out) and torch.equal(stats, st0)
+        del a, out
+
+
 @pytest.mark.parametrize("M,d,N,act", [(394, 768, 2304, 0), (50000, 768, 3072, 1), (40000, 1024, 3072, 0), (700, 512, 1536, 1)])
 def test_gemm_layernorm_fold(cuda_device, M, d, N, act):
     """LayerNorm folded into the consuming GEMM: a producer GEMM (bias + fp32 residual) emits bf16 rows + partial row
