@@ -24,7 +24,36 @@ __device__ __forceinline__ float gelu_erf(float v) {
 template <int NC>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ xt, const float* __restrict__ wt, int K,
                                           int N, int n0, float (&acc)[NC][RT]) {
-  for (int k = 0; k < K; ++k) {
+  // weights of KU k-steps are requested before the first of them is used: the loop was bound by the L2 latency of one weight
+  // load per k-step (0.34 ms per clip CTA at ~10 % of the FMA rate)
+  constexpr int KU = 8;
+  int k = 0;
+  for (; k + KU <= K; k += KU) {
+    float w[KU][NC];
+#pragma unroll
+    for (int u = 0; u < KU; ++u)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int n = n0 + c * blockDim.x;
+        w[u][c] = n < N ? __ldg(wt + (size_t)(k + u) * N + n) : 0.f;
+      }
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+      const float4* xr = reinterpret_cast<const float4*>(xt + (k + u) * RT);
+#pragma unroll
+      for (int q = 0; q < RT / 4; ++q) {
+        const float4 x4 = xr[q];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          acc[c][4 * q + 0] = fmaf(x4.x, w[u][c], acc[c][4 * q + 0]);
+          acc[c][4 * q + 1] = fmaf(x4.y, w[u][c], acc[c][4 * q + 1]);
+          acc[c][4 * q + 2] = fmaf(x4.z, w[u][c], acc[c][4 * q + 2]);
+          acc[c][4 * q + 3] = fmaf(x4.w, w[u][c], acc[c][4 * q + 3]);
+        }
+      }
+    }
+  }
+  for (; k < K; ++k) {
     float w[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
