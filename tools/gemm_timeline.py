@@ -28,7 +28,7 @@ names = ["mma:start", "mma:issued", "ep0:wait", "ep0:acc_ready", "ep0:done", "ep
 
 def case(name, a, N, K, **kw):
     w = (torch.randn(N, K, device=dev, generator=gen) * K**-0.5).to(torch.bfloat16)
-    b = torch.randn(N, device=dev, generator=gen)
+    b = None if kw.pop("nobias", False) else torch.randn(N, device=dev, generator=gen)
     if kw.pop("fold", False):
         kw["fold"] = (stats_in, torch.randn(N, device=dev, generator=gen), 1e-5)
     out = kw.pop("out", None)
@@ -55,6 +55,12 @@ def case(name, a, N, K, **kw):
     print(f"  per tile: period {per:.0f} cycles, MMA issue span {iss:.0f} (of which waiting for operands {starved:.0f}), epilogue warp 0 {ep:.0f} (warp 7 {ep7:.0f}), epilogue idle before the accumulator {wait:.0f}", flush=True)
 
 
+n_tok = 196
+pe_rows = (M // 197) * n_tok
+pos = torch.randn(197, d, device=dev, generator=gen)
+pe_out = torch.zeros((M // 197) * 197, d, device=dev)
+if os.environ.get("GS_PATCH", "1") == "1":
+    case("patch embed (generic: row remap + pos-emb, fp32 out)", x[:pe_rows], d, d, resid=pos, out=pe_out, row_group=n_tok, nobias=True)
 case("qkv LN-fold", x, 3 * d, d, fold=True)
 case("qkv plain", x, 3 * d, d)
 case("c_fc LN-fold+QuickGELU", x, 4 * d, d, fold=True, act=ops.ACT_QUICKGELU)
